@@ -1,0 +1,135 @@
+/* vettore_b200.h — C ABI of the B200-native scan path of Vettore.
+ *
+ * This is the drop-in boundary: every entry point below is what an erl_nif (or any
+ * FFI) binding for the reference's scan path would call instead of the Rust code in
+ * native/vettore/src/{flat,search,multi_vector,distances}.rs. Plain pointers and
+ * sizes only. Citations are relative to /root/reference/.
+ *
+ * Conventions (nifs.rs: `Result<T, String>` => {:ok, T} | {:error, msg}):
+ *   - every call returns VB_OK (0) or a non-zero status; on failure vb_last_error()
+ *     (thread-local) holds the message. VB_ERR messages are the reference's own strings,
+ *     byte for byte ("dimension mismatch", "vector must not be empty",
+ *     "vector contains a non-finite value", "metric overflow", "score overflow",
+ *     "unknown metric", "invalid prefix dimensions", "dimensions must be positive",
+ *     "vectors must not be empty"). VB_ERR_CUDA messages start with "cuda: ".
+ *   - the caller owns every input buffer; nothing is borrowed past the call.
+ *   - results are returned as vb_hits objects owned by the caller (vb_hits_free).
+ *   - ids are arbitrary byte strings (UTF-8 binaries on the BEAM), passed as one blob
+ *     plus n+1 offsets; ragged float / u64 lists are passed as values plus n+1 offsets
+ *     (in elements), so validation errors the reference raises for ragged input
+ *     ("dimension mismatch") are reproducible.
+ *   - all handles are safe for concurrent use: searches share, mutations exclude
+ *     (nifs.rs:266-309 RwLock discipline).
+ *   - the library has no CPU fallback: without a CUDA device every compute call fails
+ *     with VB_ERR_CUDA.
+ */
+#ifndef VETTORE_B200_H
+#define VETTORE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_OK 0
+#define VB_ERR 1      /* reference-visible error string */
+#define VB_ERR_CUDA 2 /* device/runtime failure, "cuda: ..." */
+
+/* Metric codes, distances.rs:25-38 / collection.ex:1306-1315. */
+#define VB_METRIC_L2 0
+#define VB_METRIC_L2_SQUARED 1
+#define VB_METRIC_COSINE 2
+#define VB_METRIC_INNER_PRODUCT 3
+#define VB_METRIC_NEGATIVE_INNER_PRODUCT 4
+#define VB_METRIC_MANHATTAN 5
+#define VB_METRIC_CHEBYSHEV 6
+#define VB_METRIC_HAMMING 7
+#define VB_METRIC_JACCARD 8
+
+typedef struct vb_flat vb_flat; /* replaces FlatResource, flat.rs:131-134 */
+typedef struct vb_hits vb_hits; /* a sorted Vec<(String, f32)> */
+
+const char* vb_last_error(void);
+const char* vb_version(void);
+/* Number of visible CUDA devices (0 when none; never fails). */
+int vb_device_count(void);
+
+/* ---- hits: Vec<(String, f32)> as returned by flat_search / *_top_k ------------- */
+size_t vb_hits_len(const vb_hits* h);
+/* Id bytes of hit i (not NUL-terminated); *len receives the byte length. */
+const char* vb_hits_id(const vb_hits* h, size_t i, size_t* len);
+/* Raw metric value (flat/vector/binary) or MaxSim score (multi-vector) of hit i. */
+float vb_hits_value(const vb_hits* h, size_t i);
+/* Position of hit i in the caller's input batch (by-value calls) or its device row. */
+uint64_t vb_hits_index(const vb_hits* h, size_t i);
+void vb_hits_free(vb_hits* h);
+
+/* ---- resident flat index: Nifs.flat_* ------------------------------------------ */
+/* flat_new_<metric>/0, nifs.rs:200-257. The index lives on the current CUDA device. */
+int vb_flat_new(int metric_code, vb_flat** out);
+/* Resource destructor (BEAM GC of the last reference). Frees the HBM matrix. */
+void vb_flat_free(vb_flat* index);
+/* flat_insert/3, nifs.rs:259-271 -> FlatIndex::insert, flat.rs:59-66. */
+int vb_flat_insert(vb_flat* index, const char* id, size_t id_len, const float* vector, size_t len);
+/* flat_insert_many/2, nifs.rs:273-284 -> FlatIndex::insert_many, flat.rs:69-85.
+ * All-or-nothing validation; duplicate ids in a batch: last wins. */
+int vb_flat_insert_many(vb_flat* index, size_t n, const char* ids, const uint64_t* id_off,
+                        const float* values, const uint64_t* value_off);
+/* flat_delete/2, nifs.rs:286-295 -> FlatIndex::delete, flat.rs:88-93. */
+int vb_flat_delete(vb_flat* index, const char* id, size_t id_len);
+/* flat_search/3, nifs.rs:297-309 -> FlatIndex::search, flat.rs:96-124.
+ * Hits ascend by (rank.total_cmp, id bytes); values are the raw metric. */
+int vb_flat_search(vb_flat* index, const float* query, size_t len, size_t limit, vb_hits** out);
+/* Additive: nq searches in one call (same semantics per query); out[nq]. */
+int vb_flat_search_batch(vb_flat* index, const float* queries, size_t nq, size_t len, size_t limit,
+                         vb_hits** out);
+/* Additive: row count and dimension (dimension 0 == None, flat.rs:16). */
+int vb_flat_info(vb_flat* index, size_t* rows, size_t* dimension);
+/* Additive (funnel_search stage over the resident matrix instead of store.all + by-value
+ * vector_top_k, collection.ex:674-691): vector_top_k semantics (search.rs:38-73: prefix
+ * `dimensions`, true f64 cosine when metric_code is cosine) over the resident rows whose
+ * ids are listed (n_ids == SIZE_MAX: every row). Unknown ids are skipped. */
+int vb_flat_prefix_top_k(vb_flat* index, size_t n_ids, const char* ids, const uint64_t* id_off,
+                         const float* query, size_t len, int metric_code, size_t dimensions,
+                         size_t limit, vb_hits** out);
+
+/* Device-level entry (inputs already in HBM; used for kernel-only timing and by the
+ * row-sharded multi-GPU path). Queries: nq rows of `q_stride` floats (q_stride % 4 == 0,
+ * zero padded) in device memory. Writes, per query, k = min(limit, rows) sorted entries:
+ * keys (rank-order key << 32 | id rank), raw values and device rows. No host sync;
+ * `stream` is a cudaStream_t. limit must be <= 1024 here. */
+int vb_flat_search_device(vb_flat* index, const float* d_queries, size_t nq, size_t q_stride,
+                          size_t limit, uint64_t* d_keys, float* d_values, uint32_t* d_rows,
+                          uint32_t* d_counts, void* stream);
+/* Overrides the id tie-break ranks of the resident rows (row-sharded corpora: ranks must
+ * be comparable across shards). ranks[row] for row < rows, in insertion (device row) order. */
+int vb_flat_set_id_ranks(vb_flat* index, const uint32_t* ranks, size_t n);
+/* K7: merges `lists` sorted top-k lists per query into the best k_out per query (the
+ * final select after the shards' lists were all-gathered over NVLink). All pointers are
+ * device memory. List l holds arrays [nq][k_in] of keys / values / rows and [nq] counts
+ * starting `l * list_stride_bytes` bytes after the given base pointers (an all-gather of
+ * one packed record per shard has exactly this shape). Outputs are [nq][k_out];
+ * d_rows_out receives (list << 32 | row). */
+int vb_topk_merge_device(const uint64_t* d_keys, const float* d_values, const uint32_t* d_rows,
+                         const uint32_t* d_counts, size_t list_stride_bytes, size_t nq, size_t lists,
+                         size_t k_in, size_t k_out, uint64_t* d_keys_out, float* d_values_out,
+                         uint64_t* d_rows_out, uint32_t* d_counts_out, void* stream);
+
+/* ---- by-value batched helpers: Nifs.vector_top_k / binary_top_k / multi_vector_* -- */
+/* vector_top_k/5, nifs.rs:151-162 -> search::vector_top_k, search.rs:38-73. */
+int vb_vector_top_k(size_t n, const char* ids, const uint64_t* id_off, const float* values,
+                    const uint64_t* value_off, const float* query, size_t len, int metric_code,
+                    size_t dimensions, size_t limit, vb_hits** out);
+/* binary_top_k/4, nifs.rs:164-175 -> search::binary_top_k, search.rs:76-92. */
+int vb_binary_top_k(size_t n, const char* ids, const uint64_t* id_off, const uint64_t* words,
+                    const uint64_t* word_off, const uint64_t* query, size_t query_words,
+                    size_t dimensions, size_t limit, vb_hits** out);
+/* compress_sign_bits/1, nifs.rs:125-129 -> distances.rs:413-423. words[ceil(len/64)]. */
+int vb_compress_sign_bits(const float* vector, size_t len, uint64_t* words);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VETTORE_B200_H */

@@ -1,0 +1,288 @@
+// api.cu — the extern "C" boundary declared in include/vettore_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "../../include/vettore_b200.h"
+#include "flat_index.h"
+#include "hamming.h"
+#include "runtime.h"
+#include "scan_driver.h"
+#include "select.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int finish(const vb::Status& s) {
+    if (s.ok()) return VB_OK;
+    g_last_error = s.msg;
+    return s.code;
+}
+
+bool all_finite(const float* v, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (!std::isfinite(v[i])) return false;
+    return true;
+}
+
+// Ranks of a by-value id batch: position in byte-lexicographic order (stable, so duplicate
+// ids still get distinct keys).
+std::vector<uint32_t> id_ranks(size_t n, const char* ids, const uint64_t* id_off) {
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        size_t la = id_off[a + 1] - id_off[a], lb = id_off[b + 1] - id_off[b];
+        int c = std::memcmp(ids + id_off[a], ids + id_off[b], std::min(la, lb));
+        return c != 0 ? c < 0 : la < lb;
+    });
+    std::vector<uint32_t> rank(n);
+    for (size_t i = 0; i < n; ++i) rank[order[i]] = (uint32_t)i;
+    return rank;
+}
+
+void emit_hits(vb::Hits* h, const char* ids, const uint64_t* id_off, const uint32_t* rows, const float* vals,
+               size_t cnt) {
+    for (size_t i = 0; i < cnt; ++i) {
+        uint32_t r = rows[i];
+        h->ids.emplace_back(ids + id_off[r], ids + id_off[r + 1]);
+        h->values.push_back(vals[i]);
+        h->index.push_back(r);
+    }
+}
+
+int no_device() {
+    g_last_error = "cuda: no CUDA device available (vettore_b200 has no CPU fallback)";
+    return VB_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vb_last_error(void) { return g_last_error.c_str(); }
+const char* vb_version(void) { return "vettore_b200 0.1.0 (sm_100a)"; }
+
+int vb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+size_t vb_hits_len(const vb_hits* h) { return h ? h->ids.size() : 0; }
+const char* vb_hits_id(const vb_hits* h, size_t i, size_t* len) {
+    *len = h->ids[i].size();
+    return h->ids[i].data();
+}
+float vb_hits_value(const vb_hits* h, size_t i) { return h->values[i]; }
+uint64_t vb_hits_index(const vb_hits* h, size_t i) { return h->index[i]; }
+void vb_hits_free(vb_hits* h) { delete h; }
+
+// ---------------------------------------------------------------- resident flat index
+int vb_flat_new(int metric_code, vb_flat** out) {
+    *out = nullptr;
+    if (metric_code < 0 || metric_code > 8) return finish(vb::Status::Ref("unknown metric"));
+    if (vb_device_count() <= 0) return no_device();
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return no_device();
+    *out = new vb_flat{new vb::FlatIndex(metric_code, dev)};
+    return VB_OK;
+}
+
+void vb_flat_free(vb_flat* index) {
+    if (!index) return;
+    delete index->impl;
+    delete index;
+}
+
+int vb_flat_insert(vb_flat* index, const char* id, size_t id_len, const float* vector, size_t len) {
+    const uint64_t id_off[2] = {0, id_len}, val_off[2] = {0, len};
+    return finish(index->impl->insert_many(1, id, id_off, vector, val_off, true));
+}
+
+int vb_flat_insert_many(vb_flat* index, size_t n, const char* ids, const uint64_t* id_off, const float* values,
+                        const uint64_t* value_off) {
+    return finish(index->impl->insert_many(n, ids, id_off, values, value_off, false));
+}
+
+int vb_flat_delete(vb_flat* index, const char* id, size_t id_len) {
+    return finish(index->impl->remove(id, id_len));
+}
+
+int vb_flat_search(vb_flat* index, const float* query, size_t len, size_t limit, vb_hits** out) {
+    *out = nullptr;
+    std::vector<vb::Hits> hits;
+    vb::Status s = index->impl->search(query, 1, len, limit, &hits);
+    if (!s.ok()) return finish(s);
+    *out = new vb_hits{std::move(hits[0])};
+    return VB_OK;
+}
+
+int vb_flat_search_batch(vb_flat* index, const float* queries, size_t nq, size_t len, size_t limit,
+                         vb_hits** out) {
+    for (size_t q = 0; q < nq; ++q) out[q] = nullptr;
+    std::vector<vb::Hits> hits;
+    vb::Status s = index->impl->search(queries, nq, len, limit, &hits);
+    if (!s.ok()) return finish(s);
+    for (size_t q = 0; q < nq; ++q) out[q] = new vb_hits{std::move(hits[q])};
+    return VB_OK;
+}
+
+int vb_flat_info(vb_flat* index, size_t* rows, size_t* dimension) {
+    index->impl->info(rows, dimension);
+    return VB_OK;
+}
+
+int vb_flat_prefix_top_k(vb_flat* index, size_t n_ids, const char* ids, const uint64_t* id_off,
+                         const float* query, size_t len, int metric_code, size_t dimensions, size_t limit,
+                         vb_hits** out) {
+    *out = nullptr;
+    vb::Hits hits;
+    vb::Status s = index->impl->prefix_top_k(n_ids == SIZE_MAX, n_ids == SIZE_MAX ? 0 : n_ids, ids, id_off, query,
+                                             len, metric_code, dimensions, limit, &hits);
+    if (!s.ok()) return finish(s);
+    *out = new vb_hits{std::move(hits)};
+    return VB_OK;
+}
+
+int vb_flat_search_device(vb_flat* index, const float* d_queries, size_t nq, size_t q_stride, size_t limit,
+                          uint64_t* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, void* stream) {
+    return finish(index->impl->search_device(d_queries, nq, q_stride, limit,
+                                             reinterpret_cast<vb::u64*>(d_keys), d_values, d_rows, d_counts,
+                                             static_cast<cudaStream_t>(stream)));
+}
+
+int vb_flat_set_id_ranks(vb_flat* index, const uint32_t* ranks, size_t n) {
+    return finish(index->impl->set_id_ranks(ranks, n));
+}
+
+int vb_topk_merge_device(const uint64_t* d_keys, const float* d_values, const uint32_t* d_rows,
+                         const uint32_t* d_counts, size_t list_stride_bytes, size_t nq, size_t lists, size_t k_in,
+                         size_t k_out, uint64_t* d_keys_out, float* d_values_out, uint64_t* d_rows_out, uint32_t* d_counts_out,
+                         void* stream) {
+    return finish(vb::topk_merge_device(reinterpret_cast<const vb::u64*>(d_keys), d_values, d_rows, d_counts,
+                                        list_stride_bytes, nq, lists, k_in, k_out, reinterpret_cast<vb::u64*>(d_keys_out), d_values_out,
+                                        reinterpret_cast<vb::u64*>(d_rows_out), d_counts_out,
+                                        static_cast<cudaStream_t>(stream)));
+}
+
+// ---------------------------------------------------------------- by-value helpers
+int vb_vector_top_k(size_t n, const char* ids, const uint64_t* id_off, const float* values,
+                    const uint64_t* value_off, const float* query, size_t len, int metric_code, size_t dimensions,
+                    size_t limit, vb_hits** out) {
+    *out = nullptr;
+    // search.rs:38-55 validation order.
+    if (metric_code < 0 || metric_code > 8) return finish(vb::Status::Ref("unknown metric"));
+    if (dimensions == 0 || dimensions > len) return finish(vb::Status::Ref("invalid prefix dimensions"));
+    if (!all_finite(query, dimensions)) return finish(vb::Status::Ref("vector contains a non-finite value"));
+    size_t good = n;  // rows before the first one the reference would reject
+    const char* bad_msg = nullptr;
+    for (size_t r = 0; r < n; ++r) {
+        const size_t rl = value_off[r + 1] - value_off[r];
+        if (dimensions > rl) { good = r; bad_msg = "dimension mismatch"; break; }
+        if (!all_finite(values + value_off[r], dimensions)) {
+            good = r;
+            bad_msg = "vector contains a non-finite value";
+            break;
+        }
+    }
+    vb::Hits hits;
+    if (good > 0) {
+        if (good >= (1ull << 32) - 1) return finish(vb::Status::Cuda("batch too large"));
+        if (vb_device_count() <= 0) return no_device();
+        vb::CtxLease ctx;
+        vb::Status s = ctx.get();
+        if (!s.ok()) return finish(s);
+        // Stage only the scored prefix: [good, stride] fp32, zero padded to 16-byte rows.
+        const size_t stride = (dimensions + 3) & ~(size_t)3;
+        vb::PinnedBuf hb;
+        s = hb.reserve(good * stride * sizeof(float) + good * sizeof(uint32_t));
+        if (!s.ok()) return finish(s);
+        float* hrows = hb.as<float>();
+        uint32_t* hrank = reinterpret_cast<uint32_t*>(hrows + good * stride);
+        for (size_t r = 0; r < good; ++r) {
+            std::memcpy(hrows + r * stride, values + value_off[r], dimensions * sizeof(float));
+            for (size_t c = dimensions; c < stride; ++c) hrows[r * stride + c] = 0.0f;
+        }
+        std::vector<uint32_t> rank = id_ranks(good, ids, id_off);
+        std::memcpy(hrank, rank.data(), good * sizeof(uint32_t));
+        s = ctx->staging.reserve(good * stride * sizeof(float));
+        if (s.ok()) s = ctx->staging_rank.reserve(good * sizeof(uint32_t));
+        if (s.ok()) {
+            cudaError_t e = cudaMemcpyAsync(ctx->staging.p, hrows, good * stride * sizeof(float),
+                                            cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(ctx->staging_rank.p, hrank, good * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                    ctx->stream);
+            if (e != cudaSuccess) s = vb::Status::Cuda(cudaGetErrorString(e));
+        }
+        vb::ScanResult res;
+        if (s.ok()) {
+            vb::ScanJob job;
+            job.metric = metric_code == vb::kCosine ? vb::kCosineTrue : metric_code;   // search.rs:56-60
+            job.d_rows = ctx->staging.as<float>();
+            job.row_stride = stride;
+            job.d_id_rank = ctx->staging_rank.as<uint32_t>();
+            job.n = (uint32_t)good;
+            job.dims = (uint32_t)dimensions;
+            job.h_queries = query;
+            job.nq = 1;
+            job.q_len = len;
+            job.k = std::max<size_t>(1, std::min(limit, good));
+            s = vb::run_scan(*ctx.ctx, job, &res);
+        }
+        hb.release();
+        if (!s.ok()) return finish(s);
+        if (res.err_rows[0] != vb::kNoError) return finish(vb::Status::Ref("metric overflow"));
+        if (!bad_msg && limit > 0) emit_hits(&hits, ids, id_off, res.rows.data(), res.raws.data(), res.counts[0]);
+    }
+    if (bad_msg) return finish(vb::Status::Ref(bad_msg));
+    *out = new vb_hits{std::move(hits)};
+    return VB_OK;
+}
+
+int vb_binary_top_k(size_t n, const char* ids, const uint64_t* id_off, const uint64_t* words,
+                    const uint64_t* word_off, const uint64_t* query, size_t query_words, size_t dimensions,
+                    size_t limit, vb_hits** out) {
+    *out = nullptr;
+    // search.rs:84 -> distances.rs:459-470: the query is validated even for an empty batch.
+    const size_t nw = (dimensions + 63) / 64;
+    if (dimensions == 0) return finish(vb::Status::Ref("dimensions must be positive"));
+    if (query_words != nw) return finish(vb::Status::Ref("dimension mismatch"));
+    size_t good = n;
+    for (size_t r = 0; r < n; ++r)
+        if (word_off[r + 1] - word_off[r] != nw) { good = r; break; }
+    vb::Hits hits;
+    if (good > 0 && limit > 0 && good == n) {
+        if (good >= (1ull << 32) - 1) return finish(vb::Status::Cuda("batch too large"));
+        if (vb_device_count() <= 0) return no_device();
+        vb::CtxLease ctx;
+        vb::Status s = ctx.get();
+        if (!s.ok()) return finish(s);
+        std::vector<uint32_t> rank = id_ranks(good, ids, id_off);
+        std::vector<uint32_t> rows;
+        std::vector<float> vals;
+        // Codes of a well-formed batch are contiguous: words[word_off[0] ..].
+        s = vb::hamming_top_k_host(*ctx.ctx, words + word_off[0], good, nw, dimensions, rank.data(), query,
+                                   std::min(limit, good), &rows, &vals);
+        if (!s.ok()) return finish(s);
+        emit_hits(&hits, ids, id_off, rows.data(), vals.data(), rows.size());
+    }
+    if (good < n) return finish(vb::Status::Ref("dimension mismatch"));
+    *out = new vb_hits{std::move(hits)};
+    return VB_OK;
+}
+
+int vb_compress_sign_bits(const float* vector, size_t len, uint64_t* words) {
+    const size_t nw = (len + 63) / 64;
+    for (size_t w = 0; w < nw; ++w) words[w] = 0;
+    for (size_t i = 0; i < len; ++i)
+        if (vector[i] >= 0.0f) words[i / 64] |= 1ull << (i % 64);   // distances.rs:416-420
+    return VB_OK;
+}
+
+}  // extern "C"

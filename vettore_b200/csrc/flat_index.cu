@@ -1,0 +1,362 @@
+// flat_index.cu — see flat_index.h. Validation order and messages follow the reference
+// (flat.rs:59-144, search.rs:38-73) so errors are indistinguishable at the NIF boundary.
+#include "flat_index.h"
+
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+
+namespace vb {
+
+namespace {
+
+constexpr uint64_t kRankSpace = 1ull << 32;
+constexpr uint64_t kAppendStep = 16;
+constexpr size_t kStageBytes = 64u << 20;
+
+bool all_finite(const float* v, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (!std::isfinite(v[i])) return false;
+    return true;
+}
+
+// flat.rs:136-144
+const char* validate_vector(const float* v, size_t len, size_t expected /*0 == None*/) {
+    if (len == 0) return "vector must not be empty";
+    if (expected != 0 && len != expected) return "dimension mismatch";
+    if (!all_finite(v, len)) return "vector contains a non-finite value";
+    return nullptr;
+}
+
+}  // namespace
+
+FlatIndex::~FlatIndex() {
+    cudaSetDevice(device_);
+    if (dev_ctx_) {
+        cudaDeviceSynchronize();
+        dev_ctx_->destroy();
+        delete dev_ctx_;
+    }
+    if (d_rows_) cudaFree(d_rows_);
+    if (d_rank_) cudaFree(d_rank_);
+}
+
+void FlatIndex::info(size_t* rows, size_t* dim) {
+    std::shared_lock<std::shared_mutex> g(mu_);
+    *rows = n_;
+    *dim = dim_;
+}
+
+Status FlatIndex::grow(size_t need_rows) {
+    if (need_rows <= cap_) return Status::Ok();
+    size_t new_cap = std::max<size_t>(need_rows, std::max<size_t>(cap_ * 2, 1024));
+    float* rows = nullptr;
+    uint32_t* rank = nullptr;
+    cudaError_t e = cudaMalloc(&rows, new_cap * stride_ * sizeof(float));
+    if (e != cudaSuccess && new_cap > need_rows) {  // retry without head-room
+        cudaGetLastError();
+        new_cap = need_rows;
+        e = cudaMalloc(&rows, new_cap * stride_ * sizeof(float));
+    }
+    if (e != cudaSuccess) return Status::Cuda(cudaGetErrorString(e));
+    e = cudaMalloc(&rank, new_cap * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        cudaFree(rows);
+        return Status::Cuda(cudaGetErrorString(e));
+    }
+    if (n_ > 0) {
+        VB_CUDA(cudaMemcpy(rows, d_rows_, n_ * stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
+        VB_CUDA(cudaMemcpy(rank, d_rank_, n_ * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+    }
+    if (d_rows_) cudaFree(d_rows_);
+    if (d_rank_) cudaFree(d_rank_);
+    d_rows_ = rows;
+    d_rank_ = rank;
+    cap_ = new_cap;
+    return Status::Ok();
+}
+
+Status FlatIndex::relabel_all() {
+    const uint64_t spacing = std::max<uint64_t>(1, std::min<uint64_t>(kRankSpace / (n_ + 1), 1u << 20));
+    uint64_t r = 0;
+    for (auto& kv : id_row_) {
+        r += spacing;
+        h_rank_[kv.second] = (uint32_t)std::min<uint64_t>(r, kRankSpace - 1);
+    }
+    if (n_ > 0) VB_CUDA(cudaMemcpy(d_rank_, h_rank_.data(), n_ * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return Status::Ok();
+}
+
+// Order-maintenance label for a freshly inserted id: strictly between its neighbours.
+Status FlatIndex::assign_rank(std::map<std::string, uint32_t>::iterator it, uint32_t row, bool* relabel_needed) {
+    if (external_ranks_ || *relabel_needed) { h_rank_[row] = row; return Status::Ok(); }
+    int64_t lo = -1;
+    int64_t hi = (int64_t)kRankSpace;
+    if (it != id_row_.begin()) lo = h_rank_[std::prev(it)->second];
+    auto nx = std::next(it);
+    const bool at_end = nx == id_row_.end();
+    if (!at_end) hi = h_rank_[nx->second];
+    int64_t r;
+    if (at_end && lo + (int64_t)kAppendStep < hi) r = lo + (int64_t)kAppendStep;
+    else if (hi - lo >= 2) r = lo + (hi - lo) / 2;
+    else { *relabel_needed = true; r = row; }
+    h_rank_[row] = (uint32_t)r;
+    return Status::Ok();
+}
+
+Status FlatIndex::insert_many(size_t n, const char* ids, const uint64_t* id_off, const float* values,
+                              const uint64_t* value_off, bool single) {
+    (void)single;
+    std::unique_lock<std::shared_mutex> g(mu_);
+    VB_CUDA(cudaSetDevice(device_));
+    // flat.rs:70-76: validate the whole batch against the index dimension (or the first row's).
+    size_t expected = dim_;
+    if (expected == 0 && n > 0) expected = value_off[1] - value_off[0];
+    for (size_t i = 0; i < n; ++i) {
+        const char* e = validate_vector(values + value_off[i], value_off[i + 1] - value_off[i], expected);
+        if (e) return Status::Ref(e);
+    }
+    if (n == 0) return Status::Ok();
+    if (n_ + n >= kRankSpace - 1) return Status::Cuda("index row limit (2^32) exceeded");
+    if (dev_ctx_) VB_CUDA(cudaDeviceSynchronize());
+
+    if (dim_ == 0) {
+        dim_ = expected;
+        stride_ = (dim_ + 3) & ~(size_t)3;
+    }
+    VB_TRY(grow(n_ + n));
+
+    const size_t row_bytes = stride_ * sizeof(float);
+    const size_t stage_rows = std::max<size_t>(1, std::min<size_t>(n, kStageBytes / row_bytes));
+    PinnedBuf stage;
+    VB_TRY(stage.reserve(stage_rows * row_bytes + row_bytes));
+    float* sbuf = stage.as<float>();
+    float* one = sbuf + stage_rows * stride_;  // scratch row for in-place replacement
+    size_t staged = 0;                         // rows in sbuf
+    size_t flushed_to = n_;                    // device row where sbuf[0] lands
+    const size_t n_before = n_;
+    bool relabel_needed = false;
+    Status st = Status::Ok();
+
+    auto flush = [&]() -> Status {
+        if (staged == 0) return Status::Ok();
+        VB_CUDA(cudaMemcpy(d_rows_ + flushed_to * stride_, sbuf, staged * row_bytes, cudaMemcpyHostToDevice));
+        flushed_to += staged;
+        staged = 0;
+        return Status::Ok();
+    };
+    auto fill_row = [&](float* dst, size_t i) {
+        std::memcpy(dst, values + value_off[i], dim_ * sizeof(float));
+        for (size_t c = dim_; c < stride_; ++c) dst[c] = 0.0f;
+    };
+
+    for (size_t i = 0; i < n && st.ok(); ++i) {
+        std::string id(ids + id_off[i], ids + id_off[i + 1]);
+        auto hint = id_row_.end();
+        if (!id_row_.empty() && std::prev(hint)->first < id) {
+            // ascending append (rebuild_index feeds ids sorted, collection.ex:426-433): O(1) insert
+        } else {
+            hint = id_row_.lower_bound(id);
+        }
+        if (hint != id_row_.end() && hint->first == id) {
+            // upsert of an existing id (flat.rs:64 / :79): replace the row in place
+            const uint32_t row = hint->second;
+            if (row >= flushed_to) {
+                fill_row(sbuf + (row - flushed_to) * stride_, i);  // still staged (duplicate id in this batch)
+            } else {
+                fill_row(one, i);
+                cudaError_t e = cudaMemcpy(d_rows_ + (size_t)row * stride_, one, row_bytes, cudaMemcpyHostToDevice);
+                if (e != cudaSuccess) st = Status::Cuda(cudaGetErrorString(e));
+            }
+            continue;
+        }
+        const uint32_t row = (uint32_t)n_;
+        auto it = id_row_.emplace_hint(hint, id, row);
+        row_id_.push_back(std::move(id));
+        h_rank_.push_back(0);
+        ++n_;
+        st = assign_rank(it, row, &relabel_needed);
+        if (staged == stage_rows && st.ok()) st = flush();
+        fill_row(sbuf + staged * stride_, i);
+        ++staged;
+    }
+    if (st.ok()) st = flush();
+    if (st.ok()) {
+        if (relabel_needed) st = relabel_all();
+        else if (n_ > n_before) {
+            cudaError_t e = cudaMemcpy(d_rank_ + n_before, h_rank_.data() + n_before,
+                                       (n_ - n_before) * sizeof(uint32_t), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) st = Status::Cuda(cudaGetErrorString(e));
+        }
+    }
+    stage.release();
+    return st;
+}
+
+void FlatIndex::reset_if_empty() {
+    if (n_ != 0) return;
+    dim_ = 0;  // flat.rs:90-92: dimension resets to None
+    stride_ = 0;
+    cap_ = 0;
+    if (d_rows_) cudaFree(d_rows_);
+    if (d_rank_) cudaFree(d_rank_);
+    d_rows_ = nullptr;
+    d_rank_ = nullptr;
+    external_ranks_ = false;
+}
+
+Status FlatIndex::remove(const char* id, size_t id_len) {
+    std::unique_lock<std::shared_mutex> g(mu_);
+    auto it = id_row_.find(std::string(id, id + id_len));
+    if (it == id_row_.end()) return Status::Ok();
+    VB_CUDA(cudaSetDevice(device_));
+    if (dev_ctx_) VB_CUDA(cudaDeviceSynchronize());
+    const uint32_t row = it->second;
+    const uint32_t last = (uint32_t)(n_ - 1);
+    id_row_.erase(it);
+    if (row != last) {  // move the last row into the hole; its rank label travels with it
+        VB_CUDA(cudaMemcpy(d_rows_ + (size_t)row * stride_, d_rows_ + (size_t)last * stride_,
+                           stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
+        VB_CUDA(cudaMemcpy(d_rank_ + row, d_rank_ + last, sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+        row_id_[row] = std::move(row_id_[last]);
+        h_rank_[row] = h_rank_[last];
+        id_row_[row_id_[row]] = row;
+    }
+    row_id_.pop_back();
+    h_rank_.pop_back();
+    --n_;
+    reset_if_empty();
+    return Status::Ok();
+}
+
+Status FlatIndex::search(const float* queries, size_t nq, size_t len, size_t limit, std::vector<Hits>* out) {
+    out->assign(nq, Hits{});
+    if (limit == 0 || nq == 0) return Status::Ok();  // flat.rs:97-99: before any validation
+    std::shared_lock<std::shared_mutex> g(mu_);
+    for (size_t q = 0; q < nq; ++q) {
+        const char* e = validate_vector(queries + q * len, len, dim_);  // flat.rs:101
+        if (e) return Status::Ref(e);
+    }
+    if (n_ == 0) return Status::Ok();
+    VB_CUDA(cudaSetDevice(device_));
+    CtxLease ctx;
+    VB_TRY(ctx.get());
+    ScanJob job;
+    job.metric = metric_;
+    job.d_rows = d_rows_;
+    job.row_stride = stride_;
+    job.d_id_rank = d_rank_;
+    job.n = (uint32_t)n_;
+    job.dims = (uint32_t)dim_;
+    job.h_queries = queries;
+    job.nq = (uint32_t)nq;
+    job.q_len = len;
+    job.k = std::min(limit, n_);
+    ScanResult res;
+    VB_TRY(run_scan(*ctx.ctx, job, &res));
+    for (size_t q = 0; q < nq; ++q)
+        if (res.err_rows[q] != kNoError) return Status::Ref("metric overflow");  // flat.rs:105 `?`
+    for (size_t q = 0; q < nq; ++q) {
+        Hits& h = (*out)[q];
+        const uint32_t cnt = res.counts[q];
+        h.ids.reserve(cnt);
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t row = res.rows[q * res.k + i];
+            h.ids.push_back(row_id_[row]);
+            h.values.push_back(res.raws[q * res.k + i]);
+            h.index.push_back(row);
+        }
+    }
+    return Status::Ok();
+}
+
+Status FlatIndex::prefix_top_k(bool all_rows, size_t n_ids, const char* ids, const uint64_t* id_off,
+                               const float* query, size_t len, int metric_code, size_t dimensions, size_t limit,
+                               Hits* out) {
+    *out = Hits{};
+    if (metric_code < 0 || metric_code > 8) return Status::Ref("unknown metric");            // nifs.rs:160
+    if (dimensions == 0 || dimensions > len) return Status::Ref("invalid prefix dimensions");  // search.rs:45-47
+    if (!all_finite(query, dimensions)) return Status::Ref("vector contains a non-finite value");
+    std::shared_lock<std::shared_mutex> g(mu_);
+    std::vector<uint32_t> sel;
+    if (!all_rows) {
+        sel.reserve(n_ids);
+        for (size_t i = 0; i < n_ids; ++i) {
+            auto it = id_row_.find(std::string(ids + id_off[i], ids + id_off[i + 1]));
+            if (it != id_row_.end()) sel.push_back(it->second);
+        }
+    }
+    const size_t cand = all_rows ? n_ : sel.size();
+    if (cand == 0) return Status::Ok();
+    if (dimensions > dim_) return Status::Ref("dimension mismatch");                          // search.rs:52-54
+    VB_CUDA(cudaSetDevice(device_));
+    CtxLease ctx;
+    VB_TRY(ctx.get());
+    ScanJob job;
+    job.metric = metric_code == kCosine ? kCosineTrue : metric_code;                          // search.rs:56-60
+    job.d_rows = d_rows_;
+    job.row_stride = stride_;
+    job.d_id_rank = d_rank_;
+    job.n = (uint32_t)cand;
+    job.dims = (uint32_t)dimensions;
+    job.h_queries = query;
+    job.nq = 1;
+    job.q_len = len;
+    job.k = std::max<size_t>(1, std::min(limit, cand));
+    if (!all_rows) {
+        VB_TRY(ctx->row_sel.reserve(sel.size() * sizeof(uint32_t)));
+        VB_CUDA(cudaMemcpyAsync(ctx->row_sel.p, sel.data(), sel.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                ctx->stream));
+        VB_CUDA(cudaStreamSynchronize(ctx->stream));  // `sel` is pageable: finish before it can go away
+        job.d_row_sel = ctx->row_sel.as<uint32_t>();
+    }
+    ScanResult res;
+    VB_TRY(run_scan(*ctx.ctx, job, &res));
+    if (res.err_rows[0] != kNoError) return Status::Ref("metric overflow");
+    if (limit == 0) return Status::Ok();
+    for (uint32_t i = 0; i < res.counts[0]; ++i) {
+        const uint32_t row = res.rows[i];
+        out->ids.push_back(row_id_[row]);
+        out->values.push_back(res.raws[i]);
+        out->index.push_back(row);
+    }
+    return Status::Ok();
+}
+
+Status FlatIndex::search_device(const float* d_queries, size_t nq, size_t q_stride, size_t limit, u64* d_keys,
+                                float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream) {
+    if (limit == 0 || nq == 0) return Status::Cuda("device search needs limit >= 1 and nq >= 1");
+    std::unique_lock<std::shared_mutex> g(mu_);  // owns dev_ctx_; device-level calls are stream-ordered
+    if (n_ == 0) return Status::Cuda("device search on an empty index");
+    if (q_stride < stride_ || (q_stride & 3)) return Status::Ref("dimension mismatch");
+    VB_CUDA(cudaSetDevice(device_));
+    if (!dev_ctx_) {
+        dev_ctx_ = new SearchCtx();
+        dev_ctx_->device = device_;
+        VB_CUDA(cudaStreamCreateWithFlags(&dev_ctx_->stream, cudaStreamNonBlocking));
+    }
+    ScanJob job;
+    job.metric = metric_;
+    job.d_rows = d_rows_;
+    job.row_stride = stride_;
+    job.d_id_rank = d_rank_;
+    job.n = (uint32_t)n_;
+    job.dims = (uint32_t)dim_;
+    job.nq = (uint32_t)nq;
+    job.k = std::min(limit, n_);
+    return run_scan_device(*dev_ctx_, job, d_queries, q_stride, nullptr, d_keys, d_values, d_rows, d_counts,
+                           stream);
+}
+
+Status FlatIndex::set_id_ranks(const uint32_t* ranks, size_t n) {
+    std::unique_lock<std::shared_mutex> g(mu_);
+    if (n != n_) return Status::Ref("dimension mismatch");
+    VB_CUDA(cudaSetDevice(device_));
+    if (dev_ctx_) VB_CUDA(cudaDeviceSynchronize());
+    std::copy(ranks, ranks + n, h_rank_.begin());
+    if (n > 0) VB_CUDA(cudaMemcpy(d_rank_, h_rank_.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    external_ranks_ = true;
+    return Status::Ok();
+}
+
+}  // namespace vb

@@ -1,0 +1,71 @@
+// flat_index.h — DeviceFlatIndex: the HBM-resident replacement of the reference's
+// FlatIndex (flat.rs:13-129, a HashMap<String, Vec<f32>> walked row by row).
+//
+// Layout in HBM: one row-major [capacity, stride] fp32 matrix (stride = dimension rounded
+// up to 4 floats so every row is 16-byte aligned, padding zero) plus one u32 id-rank per
+// row. Host side: an ordered id -> row map (byte-lexicographic, the reference's id.cmp)
+// and the row -> id table. The id rank is an order-maintenance label: rank order == id
+// byte order, so the device can break rank ties exactly like flat.rs:34-40 without ever
+// seeing a string. Deletes move the last row into the hole (ranks stay valid), ascending
+// appends take the next label, out-of-order inserts bisect the neighbouring labels and
+// fall back to an even relabel when a gap is exhausted.
+#pragma once
+#include <map>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "runtime.h"
+#include "scan_driver.h"
+
+namespace vb {
+
+class FlatIndex {
+  public:
+    explicit FlatIndex(int metric, int device) : metric_(metric), device_(device) {}
+    ~FlatIndex();
+
+    // flat.rs:59-85 (single insert == batch of one). Ragged input: row i is
+    // values[value_off[i] .. value_off[i+1]).
+    Status insert_many(size_t n, const char* ids, const uint64_t* id_off, const float* values,
+                       const uint64_t* value_off, bool single);
+    Status remove(const char* id, size_t id_len);                                    // flat.rs:88-93
+    Status search(const float* queries, size_t nq, size_t len, size_t limit, std::vector<Hits>* out);  // flat.rs:96-124
+    // search.rs:38-73 over resident rows (all rows, or the listed ids).
+    Status prefix_top_k(bool all_rows, size_t n_ids, const char* ids, const uint64_t* id_off, const float* query,
+                        size_t len, int metric_code, size_t dimensions, size_t limit, Hits* out);
+    Status search_device(const float* d_queries, size_t nq, size_t q_stride, size_t limit, u64* d_keys,
+                         float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream);
+    Status set_id_ranks(const uint32_t* ranks, size_t n);
+    void info(size_t* rows, size_t* dim);
+
+    // Resident matrix view for sibling indexes (valid under the caller's own lock discipline).
+    const float* device_rows() const { return d_rows_; }
+    size_t stride() const { return stride_; }
+
+  private:
+    Status grow(size_t need_rows);
+    Status relabel_all();
+    Status assign_rank(std::map<std::string, uint32_t>::iterator it, uint32_t row, bool* relabel_needed);
+    void reset_if_empty();
+
+    const int metric_;
+    const int device_;
+    std::shared_mutex mu_;
+    size_t dim_ = 0;        // 0 == None (flat.rs:16)
+    size_t stride_ = 0;     // floats per device row
+    size_t n_ = 0, cap_ = 0;
+    float* d_rows_ = nullptr;
+    uint32_t* d_rank_ = nullptr;
+    std::vector<std::string> row_id_;
+    std::vector<uint32_t> h_rank_;
+    std::map<std::string, uint32_t> id_row_;
+    bool external_ranks_ = false;
+    SearchCtx* dev_ctx_ = nullptr;  // workspace of the stream-ordered device-level entry
+};
+
+}  // namespace vb
+
+struct vb_flat {
+    vb::FlatIndex* impl;
+};

@@ -1,0 +1,120 @@
+// flat_scan.cu — variant selection and launch of the K1/K4 scan kernels.
+#include "flat_scan.cuh"
+#include "flat_scan.h"
+
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
+namespace vb {
+
+#define VB_DECL(M) ScanKernel flat_scan_kernel_metric_##M(int nv, int r);
+VB_DECL(0) VB_DECL(1) VB_DECL(2) VB_DECL(3) VB_DECL(4) VB_DECL(5) VB_DECL(6) VB_DECL(7) VB_DECL(8) VB_DECL(9)
+#undef VB_DECL
+
+static ScanKernel lookup(int metric, int nv, int r) {
+    switch (metric) {
+        case 0: return flat_scan_kernel_metric_0(nv, r);
+        case 1: return flat_scan_kernel_metric_1(nv, r);
+        case 2: return flat_scan_kernel_metric_2(nv, r);
+        case 3: return flat_scan_kernel_metric_3(nv, r);
+        case 4: return flat_scan_kernel_metric_4(nv, r);
+        case 5: return flat_scan_kernel_metric_5(nv, r);
+        case 6: return flat_scan_kernel_metric_6(nv, r);
+        case 7: return flat_scan_kernel_metric_7(nv, r);
+        case 8: return flat_scan_kernel_metric_8(nv, r);
+        case 9: return flat_scan_kernel_metric_9(nv, r);
+    }
+    return nullptr;
+}
+
+int device_sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev != cached_dev) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+        cached = prop.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : dflt;
+}
+
+static uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 32;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+Status plan_flat_scan(int metric, uint32_t dims, uint32_t n, uint32_t k, bool dump, ScanPlan* plan) {
+    if (metric < 0 || metric > 9) return Status::Ref("unknown metric");
+    if (dims == 0 || n == 0) return Status::Cuda("empty scan");
+    const uint32_t nvec = (dims + 3) / 4;
+    const uint32_t need = (nvec + 31) / 32;
+    int nv, r;
+    if (need <= 1) { nv = 1; r = 4; }
+    else if (need <= 2) { nv = 2; r = 4; }
+    else if (need <= 3) { nv = 3; r = 4; }
+    else if (need <= 4) { nv = 4; r = 4; }
+    else if (need <= 6) { nv = 6; r = 2; }
+    else if (need <= 8) { nv = 8; r = 2; }
+    else if (need <= 12) { nv = 12; r = 1; }
+    else { nv = 0; r = 2; }
+    const int r_env = env_int("VB_SCAN_R", 0);
+    if (r_env > 0 && lookup(metric, nv, r_env)) r = r_env;
+    ScanKernel kernel = lookup(metric, nv, r);
+    if (!kernel) return Status::Cuda("no scan kernel variant");
+
+    if (!dump && k > (uint32_t)kMaxFusedK) return Status::Cuda("k beyond fused collector");
+    const uint32_t slack = kSyncEvery * kScanWarps * r;
+    const uint32_t kk = dump ? 1 : k;
+    const uint32_t cap = next_pow2(std::max(2 * kk, kk + slack));
+    const size_t smem = (size_t)cap * 16;
+
+    static std::mutex mu;
+    static std::map<std::pair<const void*, size_t>, int> occ_cache;
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto key = std::make_pair((const void*)kernel, smem);
+        auto it = occ_cache.find(key);
+        if (it == occ_cache.end()) {
+            if (smem > 48 * 1024)
+                VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kScanThreads, smem));
+            if (per_sm < 1) return Status::Cuda("scan kernel does not fit on an SM");
+            occ_cache[key] = per_sm;
+        } else {
+            per_sm = it->second;
+        }
+    }
+    const int per_sm_env = env_int("VB_SCAN_CTAS_PER_SM", 0);
+    if (per_sm_env > 0 && per_sm_env < per_sm) per_sm = per_sm_env;
+    const int sms = device_sm_count();
+    if (sms <= 0) return Status::Cuda("no CUDA device");
+    const uint32_t tile_rows = kScanWarps * r;
+    const uint32_t tiles = (n + tile_rows - 1) / tile_rows;
+    plan->kernel = kernel;
+    plan->nv = nv;
+    plan->r = r;
+    plan->grid_x = std::min<uint32_t>(tiles, (uint32_t)(sms * per_sm));
+    plan->cap = cap;
+    plan->smem = smem;
+    return Status::Ok();
+}
+
+Status run_flat_scan(const ScanPlan& plan, ScanParams params, uint32_t nq, cudaStream_t stream) {
+    params.cap = plan.cap;
+    dim3 grid(plan.grid_x, nq);
+    plan.kernel<<<grid, kScanThreads, plan.smem, stream>>>(params);
+    VB_CUDA(cudaGetLastError());
+    return Status::Ok();
+}
+
+}  // namespace vb

@@ -1,0 +1,225 @@
+// scan_driver.cu — see scan_driver.h.
+#include "scan_driver.h"
+
+#include <cmath>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "flat_scan.cuh"
+#include "flat_scan.h"
+
+namespace vb {
+
+static Status prepare_workspace(SearchCtx& ctx, const ScanPlan& plan, uint32_t nq, size_t k) {
+    VB_TRY(ctx.arm_ctrl(nq));
+    const size_t lists = (size_t)nq * plan.grid_x;
+    VB_TRY(ctx.cand_keys.reserve(lists * k * sizeof(u64)));
+    VB_TRY(ctx.cand_pays.reserve(lists * k * sizeof(u64)));
+    VB_TRY(ctx.cand_counts.reserve(lists * sizeof(uint32_t)));
+    VB_TRY(ctx.out_keys.reserve((size_t)nq * k * sizeof(u64)));
+    // result block: pays[nq][k] u64 | counts[nq] u32 | err[nq] u32
+    VB_TRY(ctx.result.reserve((size_t)nq * k * sizeof(u64) + (size_t)nq * 8));
+    return Status::Ok();
+}
+
+static void fill_params(const SearchCtx& ctx, const ScanJob& job, const float* d_queries, size_t q_stride,
+                        const double* d_q_norms, size_t k, ScanParams* p) {
+    p->rows = job.d_rows;
+    p->row_stride = job.row_stride;
+    p->row_sel = job.d_row_sel;
+    p->id_rank = job.d_id_rank;
+    p->n = job.n;
+    p->dims = job.dims;
+    p->queries = d_queries;
+    p->q_stride = (uint32_t)q_stride;
+    p->q_norms = d_q_norms;
+    p->cap = 0;
+    p->ws.k = (uint32_t)k;
+    p->ws.cand_keys = ctx.cand_keys.as<u64>();
+    p->ws.cand_pays = ctx.cand_pays.as<u64>();
+    p->ws.cand_counts = ctx.cand_counts.as<uint32_t>();
+    p->ws.done = ctx.done();
+    p->ws.g_thresh = ctx.g_thresh();
+    p->err_row = ctx.err_row();
+    p->ws.out_keys = ctx.out_keys.as<u64>();
+    p->ws.out_pays = ctx.result.as<u64>();
+    p->ws.out_counts = reinterpret_cast<uint32_t*>(ctx.result.as<u64>() + (size_t)job.nq * k);
+    p->dump_keys = nullptr;
+    p->dump_pays = nullptr;
+}
+
+// Copies err_row into the result block and re-arms it (one thread per query).
+__global__ void collect_err_kernel(uint32_t* err_row, uint32_t* out_err, uint32_t nq) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) { out_err[i] = err_row[i]; err_row[i] = kNoError; }
+}
+
+__global__ void unpack_results_kernel(const u64* keys, const u64* pays, const uint32_t* counts, uint32_t nq,
+                                      uint32_t k, u64* out_keys, float* out_values, uint32_t* out_rows,
+                                      uint32_t* out_counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq * k) {
+        uint32_t q = i / k, j = i - q * k;
+        bool valid = j < counts[q];
+        u64 pay = valid ? pays[i] : 0;
+        if (out_keys) out_keys[i] = valid ? keys[i] : kKeyMax;
+        if (out_values) out_values[i] = __uint_as_float((uint32_t)(pay >> 32));
+        if (out_rows) out_rows[i] = (uint32_t)pay;
+    }
+    if (i < nq && out_counts) out_counts[i] = counts[i];
+}
+
+static Status stage_queries(SearchCtx& ctx, const ScanJob& job, size_t* q_stride_out) {
+    const size_t q_stride = ((size_t)job.dims + 3) & ~(size_t)3;
+    const bool need_norm = job.metric == kCosineTrue;
+    VB_TRY(ctx.h_queries.reserve(job.nq * q_stride * sizeof(float) + job.nq * sizeof(double)));
+    VB_TRY(ctx.queries.reserve(job.nq * q_stride * sizeof(float)));
+    float* hq = ctx.h_queries.as<float>();
+    double* hn = reinterpret_cast<double*>(hq + job.nq * q_stride);
+    for (uint32_t q = 0; q < job.nq; ++q) {
+        const float* src = job.h_queries + (size_t)q * job.q_len;
+        float* dst = hq + (size_t)q * q_stride;
+        std::memcpy(dst, src, job.dims * sizeof(float));
+        for (size_t i = job.dims; i < q_stride; ++i) dst[i] = 0.0f;
+        if (need_norm) {  // reference distances.rs:165: f64_dot(left, left).sqrt()
+            double s = 0.0;
+            for (uint32_t i = 0; i < job.dims; ++i) s += (double)src[i] * (double)src[i];
+            hn[q] = std::sqrt(s);
+        }
+    }
+    VB_CUDA(cudaMemcpyAsync(ctx.queries.p, hq, job.nq * q_stride * sizeof(float), cudaMemcpyHostToDevice,
+                            ctx.stream));
+    if (need_norm) {
+        VB_TRY(ctx.q_norms.reserve(job.nq * sizeof(double)));
+        VB_CUDA(cudaMemcpyAsync(ctx.q_norms.p, hn, job.nq * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    }
+    *q_stride_out = q_stride;
+    return Status::Ok();
+}
+
+// k beyond the fused collector: every key/payload to HBM, then a device radix sort.
+static Status run_scan_dump(SearchCtx& ctx, const ScanJob& job, size_t q_stride, ScanResult* out) {
+    ScanPlan plan;
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.n, 1, /*dump=*/true, &plan));
+    VB_TRY(prepare_workspace(ctx, plan, 1, 1));
+    const size_t n = job.n, k = job.k;
+    VB_TRY(ctx.dump_keys.reserve(n * sizeof(u64)));
+    VB_TRY(ctx.dump_pays.reserve(n * sizeof(u64)));
+    VB_TRY(ctx.dump_keys2.reserve(n * sizeof(u64)));
+    VB_TRY(ctx.dump_pays2.reserve(n * sizeof(u64)));
+    size_t tmp_bytes = 0;
+    VB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx.dump_keys.as<u64>(), ctx.dump_keys2.as<u64>(),
+                                            ctx.dump_pays.as<u64>(), ctx.dump_pays2.as<u64>(), (int64_t)n, 0, 64,
+                                            ctx.stream));
+    VB_TRY(ctx.sort_tmp.reserve(tmp_bytes));
+    VB_TRY(ctx.h_result.reserve(k * sizeof(u64) + 8));
+    out->k = k;
+    out->counts.assign(job.nq, 0);
+    out->rows.assign((size_t)job.nq * k, 0);
+    out->raws.assign((size_t)job.nq * k, 0.0f);
+    out->err_rows.assign(job.nq, kNoError);
+    for (uint32_t q = 0; q < job.nq; ++q) {
+        ScanJob one = job;
+        one.nq = 1;
+        ScanParams p;
+        fill_params(ctx, one, ctx.queries.as<float>() + (size_t)q * q_stride, q_stride,
+                    job.metric == kCosineTrue ? ctx.q_norms.as<double>() + q : nullptr, 1, &p);
+        p.dump_keys = ctx.dump_keys.as<u64>();
+        p.dump_pays = ctx.dump_pays.as<u64>();
+        VB_TRY(run_flat_scan(plan, p, 1, ctx.stream));
+        VB_CUDA(cub::DeviceRadixSort::SortPairs(ctx.sort_tmp.p, tmp_bytes, ctx.dump_keys.as<u64>(),
+                                                ctx.dump_keys2.as<u64>(), ctx.dump_pays.as<u64>(),
+                                                ctx.dump_pays2.as<u64>(), (int64_t)n, 0, 64, ctx.stream));
+        uint32_t* h_err = reinterpret_cast<uint32_t*>(ctx.h_result.as<u64>() + k);
+        collect_err_kernel<<<1, 32, 0, ctx.stream>>>(ctx.err_row(), ctx.err_row() + 1, 1);  // slot 1 = scratch
+        VB_CUDA(cudaMemcpyAsync(ctx.h_result.p, ctx.dump_pays2.p, k * sizeof(u64), cudaMemcpyDeviceToHost,
+                                ctx.stream));
+        VB_CUDA(cudaMemcpyAsync(h_err, ctx.err_row() + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
+        VB_CUDA(cudaStreamSynchronize(ctx.stream));
+        // slot 1 was used as scratch for the error word: re-arm it
+        const uint32_t no_err = kNoError;
+        VB_CUDA(cudaMemcpyAsync(ctx.err_row() + 1, &no_err, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx.stream));
+        VB_CUDA(cudaStreamSynchronize(ctx.stream));
+        const u64* pays = ctx.h_result.as<u64>();
+        out->counts[q] = (uint32_t)k;
+        out->err_rows[q] = *h_err;
+        for (size_t i = 0; i < k; ++i) {
+            uint32_t bits = (uint32_t)(pays[i] >> 32);
+            std::memcpy(&out->raws[(size_t)q * k + i], &bits, 4);
+            out->rows[(size_t)q * k + i] = (uint32_t)pays[i];
+        }
+    }
+    return Status::Ok();
+}
+
+Status run_scan(SearchCtx& ctx, const ScanJob& job, ScanResult* out) {
+    if (job.n == 0 || job.k == 0 || job.nq == 0) return Status::Cuda("empty scan job");
+    size_t q_stride = 0;
+    VB_TRY(stage_queries(ctx, job, &q_stride));
+    const size_t k = std::min<size_t>(job.k, job.n);
+    if (k > (size_t)kMaxFusedK) {
+        ScanJob j2 = job;
+        j2.k = k;
+        Status s = run_scan_dump(ctx, j2, q_stride, out);
+        if (!s.ok()) ctx.poison();
+        return s;
+    }
+
+    ScanPlan plan;
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.n, (uint32_t)k, false, &plan));
+    VB_TRY(prepare_workspace(ctx, plan, job.nq, k));
+    ScanParams p;
+    fill_params(ctx, job, ctx.queries.as<float>(), q_stride,
+                job.metric == kCosineTrue ? ctx.q_norms.as<double>() : nullptr, k, &p);
+    Status s = run_flat_scan(plan, p, job.nq, ctx.stream);
+    if (!s.ok()) { ctx.poison(); return s; }
+    uint32_t* d_err = p.ws.out_counts + job.nq;
+    collect_err_kernel<<<(job.nq + 127) / 128, 128, 0, ctx.stream>>>(ctx.err_row(), d_err, job.nq);
+    const size_t bytes = (size_t)job.nq * k * sizeof(u64) + (size_t)job.nq * 8;
+    VB_TRY(ctx.h_result.reserve(bytes));
+    cudaError_t e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, bytes, cudaMemcpyDeviceToHost, ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx.stream);
+    if (e != cudaSuccess) {
+        ctx.poison();
+        return Status::Cuda(cudaGetErrorString(e));
+    }
+    const u64* pays = ctx.h_result.as<u64>();
+    const uint32_t* counts = reinterpret_cast<const uint32_t*>(pays + (size_t)job.nq * k);
+    const uint32_t* errs = counts + job.nq;
+    out->k = k;
+    out->counts.assign(counts, counts + job.nq);
+    out->err_rows.assign(errs, errs + job.nq);
+    out->rows.resize((size_t)job.nq * k);
+    out->raws.resize((size_t)job.nq * k);
+    for (size_t i = 0; i < (size_t)job.nq * k; ++i) {
+        uint32_t bits = (uint32_t)(pays[i] >> 32);
+        std::memcpy(&out->raws[i], &bits, 4);
+        out->rows[i] = (uint32_t)pays[i];
+    }
+    return Status::Ok();
+}
+
+Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_queries, size_t q_stride,
+                       const double* d_q_norms, u64* d_keys, float* d_values, uint32_t* d_rows,
+                       uint32_t* d_counts, cudaStream_t stream) {
+    if (job.n == 0 || job.k == 0 || job.nq == 0) return Status::Cuda("empty scan job");
+    const size_t k = std::min<size_t>(job.k, job.n);
+    if (k > (size_t)kMaxFusedK) return Status::Cuda("limit beyond the fused collector (1024)");
+    ScanPlan plan;
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.n, (uint32_t)k, false, &plan));
+    cudaStream_t saved = ctx.stream;
+    ctx.stream = stream;  // workspace arming must be ordered on the caller's stream
+    Status s = prepare_workspace(ctx, plan, job.nq, k);
+    ctx.stream = saved;
+    VB_TRY(s);
+    ScanParams p;
+    fill_params(ctx, job, d_queries, q_stride, d_q_norms, k, &p);
+    s = run_flat_scan(plan, p, job.nq, stream);
+    if (!s.ok()) { ctx.poison(); return s; }
+    const uint32_t total = job.nq * (uint32_t)k;
+    unpack_results_kernel<<<(std::max(total, job.nq) + 255) / 256, 256, 0, stream>>>(
+        p.ws.out_keys, p.ws.out_pays, p.ws.out_counts, job.nq, (uint32_t)k, d_keys, d_values, d_rows, d_counts);
+    VB_CUDA(cudaGetLastError());
+    return Status::Ok();
+}
+
+}  // namespace vb

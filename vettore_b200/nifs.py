@@ -1,0 +1,227 @@
+"""Function-for-function mirror of ``Vettore.Nifs`` (reference lib/vettore_nifs.ex:16-258)
+for the scan path, bound to the CUDA library through the C ABI.
+
+Same names, argument order and result shapes as the reference NIFs:
+``{:ok, value}`` -> ``("ok", value)``, ``{:error, msg}`` -> ``("error", msg)`` with the
+reference's exact strings; ``flat_new_*`` return the bare resource like nifs.rs:200-257;
+``Result<(), String>`` successes are ``("ok", ())`` like ``{:ok, {}}``.
+Ids are ``str`` (UTF-8 binaries on the BEAM) or ``bytes``.
+
+HNSW, MUVERA, the pairwise metric helpers and the normalisers stay on the reference
+path (out of scope) and are not defined here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import SIZE_MAX, lib
+
+METRICS = ["l2", "l2_squared", "cosine", "inner_product", "negative_inner_product",
+           "manhattan", "chebyshev", "hamming", "jaccard"]  # distances.rs:25-38
+METRIC_CODE = {m: i for i, m in enumerate(METRICS)}
+
+_f32p, _u64p, _u32p = C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+
+
+def _err():
+    return ("error", _lib.last_error())
+
+
+def _f32(v) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(-1))
+
+
+def _ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+def _enc(i) -> bytes:
+    return i.encode("utf-8") if isinstance(i, str) else bytes(i)
+
+
+def _ids_blob(ids: Sequence) -> tuple[bytes, np.ndarray]:
+    enc = [_enc(i) for i in ids]
+    off = np.zeros(len(enc) + 1, dtype=np.uint64)
+    if enc:
+        off[1:] = np.cumsum(np.fromiter((len(e) for e in enc), dtype=np.uint64, count=len(enc)))
+    return b"".join(enc), off
+
+
+def _ragged(rows: Iterable, dtype) -> tuple[np.ndarray, np.ndarray]:
+    if isinstance(rows, np.ndarray) and rows.ndim == 2:
+        n, d = rows.shape
+        vals = np.ascontiguousarray(rows, dtype=dtype).reshape(-1)
+        off = np.arange(n + 1, dtype=np.uint64) * np.uint64(d)
+        return vals, off
+    if dtype == np.uint64:
+        rows = [np.asarray([int(x) for x in r], dtype=np.uint64).reshape(-1) for r in rows]
+    else:
+        rows = [np.asarray(r, dtype=dtype).reshape(-1) for r in rows]
+    off = np.zeros(len(rows) + 1, dtype=np.uint64)
+    if rows:
+        off[1:] = np.cumsum(np.fromiter((r.size for r in rows), dtype=np.uint64, count=len(rows)))
+    vals = np.concatenate(rows) if rows else np.zeros(0, dtype=dtype)
+    return np.ascontiguousarray(vals, dtype=dtype), off
+
+
+def _take_hits(handle: C.c_void_p, as_str: bool = True) -> list[tuple]:
+    L = lib()
+    try:
+        n = L.vb_hits_len(handle)
+        out = []
+        ln = C.c_size_t()
+        for i in range(n):
+            p = L.vb_hits_id(handle, i, C.byref(ln))
+            raw = C.string_at(p, ln.value)
+            out.append((raw.decode("utf-8") if as_str else raw, float(L.vb_hits_value(handle, i))))
+        return out
+    finally:
+        L.vb_hits_free(handle)
+
+
+class FlatRef:
+    """Opaque resource handle (the BEAM ``reference()`` of flat_new_*). Freed on GC."""
+
+    def __init__(self, handle: C.c_void_p, metric: str):
+        self._h = handle
+        self.metric = metric
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().vb_flat_free(h)
+            except Exception:
+                pass
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if not self._h:
+            raise ValueError("flat index resource already released")
+        return self._h
+
+
+def _flat_new(metric: str) -> FlatRef:
+    h = C.c_void_p()
+    rc = lib().vb_flat_new(METRIC_CODE[metric], C.byref(h))
+    if rc:
+        # the reference constructors cannot fail; a missing device must be loud, not silent
+        raise RuntimeError(_lib.last_error())
+    return FlatRef(h, metric)
+
+
+def flat_new_l2(): return _flat_new("l2")
+def flat_new_l2_squared(): return _flat_new("l2_squared")
+def flat_new_cosine(): return _flat_new("cosine")
+def flat_new_inner_product(): return _flat_new("inner_product")
+def flat_new_negative_inner_product(): return _flat_new("negative_inner_product")
+def flat_new_manhattan(): return _flat_new("manhattan")
+def flat_new_chebyshev(): return _flat_new("chebyshev")
+def flat_new_hamming(): return _flat_new("hamming")
+def flat_new_jaccard(): return _flat_new("jaccard")
+
+
+def flat_insert(index: FlatRef, id, vector):
+    """nifs.rs:259-271."""
+    v = _f32(vector)
+    b = _enc(id)
+    rc = lib().vb_flat_insert(index.handle, b, len(b), _ptr(v, _f32p), v.size)
+    return _err() if rc else ("ok", ())
+
+
+def flat_insert_many(index: FlatRef, vectors: Sequence[tuple]):
+    """nifs.rs:273-284. ``vectors`` is a list of ``(id, vector)``."""
+    ids = [v[0] for v in vectors]
+    vals, off = _ragged([v[1] for v in vectors], np.float32)
+    blob, ioff = _ids_blob(ids)
+    rc = lib().vb_flat_insert_many(index.handle, len(ids), blob, _ptr(ioff, _u64p), _ptr(vals, _f32p), _ptr(off, _u64p))
+    return _err() if rc else ("ok", ())
+
+
+def flat_insert_matrix(index: FlatRef, ids: Sequence, matrix: np.ndarray):
+    """Same C entry as flat_insert_many for a dense ``[n, d]`` float32 matrix (no per-row Python objects)."""
+    vals, off = _ragged(np.asarray(matrix), np.float32)
+    blob, ioff = _ids_blob(ids)
+    rc = lib().vb_flat_insert_many(index.handle, len(ids), blob, _ptr(ioff, _u64p), _ptr(vals, _f32p), _ptr(off, _u64p))
+    return _err() if rc else ("ok", ())
+
+
+def flat_delete(index: FlatRef, id):
+    """nifs.rs:286-295."""
+    b = _enc(id)
+    rc = lib().vb_flat_delete(index.handle, b, len(b))
+    return _err() if rc else ("ok", ())
+
+
+def flat_search(index: FlatRef, query, limit: int):
+    """nifs.rs:297-309: ``("ok", [(id, raw)])`` ascending by (rank, id)."""
+    q = _f32(query)
+    h = C.c_void_p()
+    rc = lib().vb_flat_search(index.handle, _ptr(q, _f32p), q.size, min(int(limit), SIZE_MAX), C.byref(h))
+    return _err() if rc else ("ok", _take_hits(h))
+
+
+def flat_search_batch(index: FlatRef, queries: np.ndarray, limit: int):
+    """Additive: one call for ``[nq, d]`` queries; ``("ok", [hits per query])``."""
+    q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
+    nq, d = q.shape
+    hs = (C.c_void_p * nq)()
+    rc = lib().vb_flat_search_batch(index.handle, _ptr(q, _f32p), nq, d, int(limit), hs)
+    return _err() if rc else ("ok", [_take_hits(C.c_void_p(h)) for h in hs])
+
+
+def flat_info(index: FlatRef) -> tuple[int, int | None]:
+    rows, dim = C.c_size_t(), C.c_size_t()
+    lib().vb_flat_info(index.handle, C.byref(rows), C.byref(dim))
+    return rows.value, (dim.value or None)
+
+
+def flat_prefix_top_k(index: FlatRef, ids: Sequence | None, query, metric_code: int, dimensions: int, limit: int):
+    """Additive resident form of vector_top_k (search.rs:38-73) over the index's own rows:
+    ``ids=None`` scores every row, else only the listed ids (unknown ids are skipped)."""
+    q = _f32(query)
+    h = C.c_void_p()
+    if ids is None:
+        rc = lib().vb_flat_prefix_top_k(index.handle, SIZE_MAX, None, None, _ptr(q, _f32p), q.size, int(metric_code),
+                                        int(dimensions), int(limit), C.byref(h))
+    else:
+        blob, ioff = _ids_blob(ids)
+        rc = lib().vb_flat_prefix_top_k(index.handle, len(ids), blob, _ptr(ioff, _u64p), _ptr(q, _f32p), q.size,
+                                        int(metric_code), int(dimensions), int(limit), C.byref(h))
+    return _err() if rc else ("ok", _take_hits(h))
+
+
+def vector_top_k(vectors: Sequence[tuple], query, metric_code: int, dimensions: int, limit: int):
+    """nifs.rs:151-162."""
+    ids = [v[0] for v in vectors]
+    vals, off = _ragged([v[1] for v in vectors], np.float32)
+    blob, ioff = _ids_blob(ids)
+    q = _f32(query)
+    h = C.c_void_p()
+    rc = lib().vb_vector_top_k(len(ids), blob, _ptr(ioff, _u64p), _ptr(vals, _f32p), _ptr(off, _u64p), _ptr(q, _f32p),
+                               q.size, int(metric_code), int(dimensions), min(int(limit), SIZE_MAX), C.byref(h))
+    return _err() if rc else ("ok", _take_hits(h))
+
+
+def binary_top_k(vectors: Sequence[tuple], query: Sequence[int], dimensions: int, limit: int):
+    """nifs.rs:164-175."""
+    ids = [v[0] for v in vectors]
+    vals, off = _ragged([v[1] for v in vectors], np.uint64)
+    blob, ioff = _ids_blob(ids)
+    q = np.asarray([int(x) for x in query], dtype=np.uint64)
+    h = C.c_void_p()
+    rc = lib().vb_binary_top_k(len(ids), blob, _ptr(ioff, _u64p), _ptr(vals, _u64p), _ptr(off, _u64p), _ptr(q, _u64p),
+                               q.size, int(dimensions), min(int(limit), SIZE_MAX), C.byref(h))
+    return _err() if rc else ("ok", _take_hits(h))
+
+
+def compress_sign_bits(vector) -> list[int]:
+    """nifs.rs:125-129: bare list of u64 words."""
+    v = _f32(vector)
+    words = np.zeros((v.size + 63) // 64, dtype=np.uint64)
+    lib().vb_compress_sign_bits(_ptr(v, _f32p), v.size, _ptr(words, _u64p))
+    return [int(w) for w in words]
