@@ -64,6 +64,10 @@ const char* vb_hits_id(const vb_hits* h, size_t i, size_t* len);
 float vb_hits_value(const vb_hits* h, size_t i);
 /* Position of hit i in the caller's input batch (by-value calls) or its device row. */
 uint64_t vb_hits_index(const vb_hits* h, size_t i);
+/* Whole result in one call: id blob + len+1 offsets, values, indexes (valid until
+ * vb_hits_free). Returns the number of hits. */
+size_t vb_hits_export(const vb_hits* h, const char** id_blob, const uint64_t** id_off,
+                      const float** values, const uint64_t** index);
 void vb_hits_free(vb_hits* h);
 
 /* ---- resident flat index: Nifs.flat_* ------------------------------------------ */

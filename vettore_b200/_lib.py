@@ -25,6 +25,7 @@ SIGNATURES = {
     "vb_hits_id": (C.POINTER(C.c_char), [_vp, _sz, C.POINTER(_sz)]),
     "vb_hits_value": (C.c_float, [_vp, _sz]),
     "vb_hits_index": (C.c_uint64, [_vp, _sz]),
+    "vb_hits_export": (_sz, [_vp, C.POINTER(C.c_void_p), C.POINTER(_u64p), C.POINTER(_f32p), C.POINTER(_u64p)]),
     "vb_hits_free": (None, [_vp]),
     "vb_flat_new": (C.c_int, [C.c_int, _vpp]),
     "vb_flat_free": (None, [_vp]),

@@ -46,9 +46,7 @@ void emit_hits(vb::Hits* h, const char* ids, const uint64_t* id_off, const uint3
                size_t cnt) {
     for (size_t i = 0; i < cnt; ++i) {
         uint32_t r = rows[i];
-        h->ids.emplace_back(ids + id_off[r], ids + id_off[r + 1]);
-        h->values.push_back(vals[i]);
-        h->index.push_back(r);
+        h->add(ids + id_off[r], id_off[r + 1] - id_off[r], vals[i], r);
     }
 }
 
@@ -73,10 +71,19 @@ int vb_device_count(void) {
     return n;
 }
 
-size_t vb_hits_len(const vb_hits* h) { return h ? h->ids.size() : 0; }
+size_t vb_hits_len(const vb_hits* h) { return h ? h->size() : 0; }
 const char* vb_hits_id(const vb_hits* h, size_t i, size_t* len) {
-    *len = h->ids[i].size();
-    return h->ids[i].data();
+    *len = h->off[i + 1] - h->off[i];
+    return h->blob.data() + h->off[i];
+}
+size_t vb_hits_export(const vb_hits* h, const char** id_blob, const uint64_t** id_off, const float** values,
+                      const uint64_t** index) {
+    if (!h) return 0;
+    *id_blob = h->blob.data();
+    *id_off = h->off.data();
+    *values = h->values.data();
+    *index = h->index.data();
+    return h->size();
 }
 float vb_hits_value(const vb_hits* h, size_t i) { return h->values[i]; }
 uint64_t vb_hits_index(const vb_hits* h, size_t i) { return h->index[i]; }
@@ -229,6 +236,7 @@ int vb_vector_top_k(size_t n, const char* ids, const uint64_t* id_off, const flo
             job.d_id_rank = ctx->staging_rank.as<uint32_t>();
             job.n = (uint32_t)good;
             job.dims = (uint32_t)dimensions;
+            job.whole_rows = true;  // staged rows hold the prefix only, zero padded
             job.h_queries = query;
             job.nq = 1;
             job.q_len = len;

@@ -248,6 +248,7 @@ Status FlatIndex::search(const float* queries, size_t nq, size_t len, size_t lim
     job.d_id_rank = d_rank_;
     job.n = (uint32_t)n_;
     job.dims = (uint32_t)dim_;
+    job.whole_rows = true;
     job.h_queries = queries;
     job.nq = (uint32_t)nq;
     job.q_len = len;
@@ -259,12 +260,9 @@ Status FlatIndex::search(const float* queries, size_t nq, size_t len, size_t lim
     for (size_t q = 0; q < nq; ++q) {
         Hits& h = (*out)[q];
         const uint32_t cnt = res.counts[q];
-        h.ids.reserve(cnt);
         for (uint32_t i = 0; i < cnt; ++i) {
             const uint32_t row = res.rows[q * res.k + i];
-            h.ids.push_back(row_id_[row]);
-            h.values.push_back(res.raws[q * res.k + i]);
-            h.index.push_back(row);
+            h.add(row_id_[row].data(), row_id_[row].size(), res.raws[q * res.k + i], row);
         }
     }
     return Status::Ok();
@@ -299,6 +297,7 @@ Status FlatIndex::prefix_top_k(bool all_rows, size_t n_ids, const char* ids, con
     job.d_id_rank = d_rank_;
     job.n = (uint32_t)cand;
     job.dims = (uint32_t)dimensions;
+    job.whole_rows = dimensions == dim_;
     job.h_queries = query;
     job.nq = 1;
     job.q_len = len;
@@ -316,9 +315,7 @@ Status FlatIndex::prefix_top_k(bool all_rows, size_t n_ids, const char* ids, con
     if (limit == 0) return Status::Ok();
     for (uint32_t i = 0; i < res.counts[0]; ++i) {
         const uint32_t row = res.rows[i];
-        out->ids.push_back(row_id_[row]);
-        out->values.push_back(res.raws[i]);
-        out->index.push_back(row);
+        out->add(row_id_[row].data(), row_id_[row].size(), res.raws[i], row);
     }
     return Status::Ok();
 }
@@ -342,6 +339,7 @@ Status FlatIndex::search_device(const float* d_queries, size_t nq, size_t q_stri
     job.d_id_rank = d_rank_;
     job.n = (uint32_t)n_;
     job.dims = (uint32_t)dim_;
+    job.whole_rows = true;
     job.nq = (uint32_t)nq;
     job.k = std::min(limit, n_);
     return run_scan_device(*dev_ctx_, job, d_queries, q_stride, nullptr, d_keys, d_values, d_rows, d_counts,

@@ -8,7 +8,9 @@
 
 namespace vb {
 
-#define VB_DECL(M) ScanKernel flat_scan_kernel_metric_##M(int nv, int r);
+#define VB_DECL(M)                                         \
+    ScanKernel flat_scan_kernel_metric_##M(int nv, int r); \
+    StreamKernel flat_stream_kernel_metric_##M(int nv, int rpw, int warps);
 VB_DECL(0) VB_DECL(1) VB_DECL(2) VB_DECL(3) VB_DECL(4) VB_DECL(5) VB_DECL(6) VB_DECL(7) VB_DECL(8) VB_DECL(9)
 #undef VB_DECL
 
@@ -24,6 +26,22 @@ static ScanKernel lookup(int metric, int nv, int r) {
         case 7: return flat_scan_kernel_metric_7(nv, r);
         case 8: return flat_scan_kernel_metric_8(nv, r);
         case 9: return flat_scan_kernel_metric_9(nv, r);
+    }
+    return nullptr;
+}
+
+static StreamKernel lookup_stream(int metric, int nv, int rpw, int warps) {
+    switch (metric) {
+        case 0: return flat_stream_kernel_metric_0(nv, rpw, warps);
+        case 1: return flat_stream_kernel_metric_1(nv, rpw, warps);
+        case 2: return flat_stream_kernel_metric_2(nv, rpw, warps);
+        case 3: return flat_stream_kernel_metric_3(nv, rpw, warps);
+        case 4: return flat_stream_kernel_metric_4(nv, rpw, warps);
+        case 5: return flat_stream_kernel_metric_5(nv, rpw, warps);
+        case 6: return flat_stream_kernel_metric_6(nv, rpw, warps);
+        case 7: return flat_stream_kernel_metric_7(nv, rpw, warps);
+        case 8: return flat_stream_kernel_metric_8(nv, rpw, warps);
+        case 9: return flat_stream_kernel_metric_9(nv, rpw, warps);
     }
     return nullptr;
 }
@@ -52,7 +70,59 @@ static uint32_t next_pow2(uint32_t v) {
     return p;
 }
 
-Status plan_flat_scan(int metric, uint32_t dims, uint32_t n, uint32_t k, bool dump, ScanPlan* plan) {
+// Kernel B: whole contiguous rows streamed through a shared-memory ring by TMA bulk copies.
+static Status plan_stream(int metric, int nv, size_t row_stride, uint32_t n, uint32_t k, ScanPlan* plan,
+                          bool* taken) {
+    *taken = false;
+    int rpw = nv <= 2 ? 4 : (nv <= 4 ? 2 : 1);
+    int warps = nv >= 12 ? 8 : 16;
+    const int rpw_env = env_int("VB_STREAM_RPW", 0), warps_env = env_int("VB_STREAM_WARPS", 0);
+    if ((rpw_env > 0 || warps_env > 0) &&
+        lookup_stream(metric, nv, rpw_env > 0 ? rpw_env : rpw, warps_env > 0 ? warps_env : warps)) {
+        if (rpw_env > 0) rpw = rpw_env;
+        if (warps_env > 0) warps = warps_env;
+    }
+    StreamKernel kernel = lookup_stream(metric, nv, rpw, warps);
+    if (!kernel) return Status::Ok();
+    const uint32_t tile_rows = warps * rpw;
+    const uint32_t tile_bytes = (uint32_t)(((size_t)tile_rows * row_stride * 4 + 127) & ~(size_t)127);
+    const uint32_t groups_per_sync = std::max(1, kStreamSyncEvery / (kGroupRows / rpw));
+    const uint32_t slack = groups_per_sync * kGroupRows * warps;
+    const uint32_t cap = next_pow2(std::max(2 * k, k + slack));
+    const size_t budget = 200 * 1024;
+    if ((size_t)cap * 16 + 2 * (size_t)tile_bytes > budget) return Status::Ok();
+    uint32_t stages = (uint32_t)std::min<size_t>(kStreamMaxStages, (budget - (size_t)cap * 16) / tile_bytes);
+    const int stages_env = env_int("VB_STREAM_STAGES", 0);
+    if (stages_env >= 2 && (uint32_t)stages_env < stages) stages = stages_env;
+    const size_t smem = (size_t)stages * tile_bytes + (size_t)cap * 16;
+    static std::mutex mu;
+    static std::map<const void*, size_t> attr_cache;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = attr_cache.find((const void*)kernel);
+        if (it == attr_cache.end() || it->second < smem) {
+            VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+            attr_cache[(const void*)kernel] = budget;
+        }
+    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return Status::Cuda("no CUDA device");
+    const uint32_t tiles = (n + tile_rows - 1) / tile_rows;
+    plan->stream_kernel = kernel;
+    plan->nv = nv;
+    plan->r = rpw;
+    plan->stream_threads = warps * 32 + 32;
+    plan->grid_x = std::min<uint32_t>(tiles, (uint32_t)sms);
+    plan->cap = cap;
+    plan->smem = smem;
+    plan->stages = stages;
+    plan->tile_bytes = tile_bytes;
+    *taken = true;
+    return Status::Ok();
+}
+
+Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, bool contiguous, uint32_t n, uint32_t k,
+                      bool dump, ScanPlan* plan) {
     if (metric < 0 || metric > 9) return Status::Ref("unknown metric");
     if (dims == 0 || n == 0) return Status::Cuda("empty scan");
     const uint32_t nvec = (dims + 3) / 4;
@@ -72,6 +142,12 @@ Status plan_flat_scan(int metric, uint32_t dims, uint32_t n, uint32_t k, bool du
     if (!kernel) return Status::Cuda("no scan kernel variant");
 
     if (!dump && k > (uint32_t)kMaxFusedK) return Status::Cuda("k beyond fused collector");
+    *plan = ScanPlan{};
+    if (!dump && contiguous && nv > 0 && (size_t)nvec * 4 == row_stride && !env_int("VB_SCAN_NO_STREAM", 0)) {
+        bool taken = false;
+        VB_TRY(plan_stream(metric, nv, row_stride, n, k, plan, &taken));
+        if (taken) return Status::Ok();
+    }
     const uint32_t slack = kSyncEvery * kScanWarps * r;
     const uint32_t kk = dump ? 1 : k;
     const uint32_t cap = next_pow2(std::max(2 * kk, kk + slack));
@@ -112,7 +188,12 @@ Status plan_flat_scan(int metric, uint32_t dims, uint32_t n, uint32_t k, bool du
 Status run_flat_scan(const ScanPlan& plan, ScanParams params, uint32_t nq, cudaStream_t stream) {
     params.cap = plan.cap;
     dim3 grid(plan.grid_x, nq);
-    plan.kernel<<<grid, kScanThreads, plan.smem, stream>>>(params);
+    if (plan.stream_kernel) {
+        StreamGeom geom{plan.stages, plan.tile_bytes};
+        plan.stream_kernel<<<grid, plan.stream_threads, plan.smem, stream>>>(params, geom);
+    } else {
+        plan.kernel<<<grid, kScanThreads, plan.smem, stream>>>(params);
+    }
     VB_CUDA(cudaGetLastError());
     return Status::Ok();
 }

@@ -6,24 +6,32 @@
 //
 // Shape of the work: an N x D fp32 stream read exactly once per query (N*D*4 algorithmic
 // bytes), 2 flops per element -> HBM-bound. Design:
-//   - persistent grid (SM count x resident CTAs), 8 warps per CTA, each warp owns R whole
-//     rows per step; a lane owns float4 slots {lane + 32 j}: every warp-level load is one
-//     fully coalesced 512-byte segment, 128-bit per lane, read-only/no-L1-allocate;
-//   - the query lives in registers (NV float4 per lane), all R*NV loads of a step are
-//     issued before the first FMA so each lane keeps R*NV 16-byte requests in flight;
+//   - flat_stream_kernel (whole rows, the FlatIndex::search case): one persistent CTA per
+//     SM; a producer warp streams contiguous row tiles HBM -> shared memory with TMA bulk
+//     copies (cp.async.bulk + mbarrier complete_tx) through a multi-stage ring, so the bytes
+//     in flight per SM are the ring size (~190 KB), independent of warp scheduling; eight
+//     consumer warps read their rows back with conflict-free 128-bit LDS and score them
+//     against the query held in registers;
+//   - flat_scan_kernel (prefix scoring, row lists, dump mode): persistent grid, 8 warps per
+//     CTA, each warp owns R whole rows per step, lane owns float4 slots {lane + 32 j}
+//     (coalesced 512-byte segments, 128-bit read-only/no-L1-allocate loads), all R*NV loads
+//     of a step issued before the first FMA;
 //   - the score never goes back to HBM: rank key + id rank go straight into the CTA's
 //     shared-memory collector (topk.cuh); the last CTA to finish merges the per-CTA
 //     lists, so one launch per query returns the sorted top-k;
 //   - non-finite f32 results are recomputed in f64 from the registers already loaded
 //     (reference distances.rs:59-98); unrepresentable ones flag "metric overflow".
 #pragma once
+#include <type_traits>
+
 #include "topk.cuh"
 
 namespace vb {
 
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kSyncEvery = 4;  // steps between collector checks (power of two)
+constexpr int kSyncEvery = 8;         // kernel A: steps between collector checks (power of two)
+constexpr int kStreamSyncEvery = 16;  // kernel B: tiles between collector checks (power of two)
 
 struct ScanParams {
     const float* rows;        // [*, row_stride] fp32, rows 16-byte aligned
@@ -36,6 +44,7 @@ struct ScanParams {
     uint32_t q_stride;        // floats, multiple of 4
     const double* q_norms;    // [nq] f64 L2 norm of the query prefix (kCosineTrue only)
     uint32_t cap;             // collector capacity (entries, power of two)
+    uint32_t debug;           // tuning experiments only (VB_SCAN_DEBUG): 1 no emit, 2 no scoring, 4 no checkpoint
     TopkWorkspace ws;         // per-query candidate lists / threshold / output (ws.k = results)
     uint32_t* err_row;        // [nq] smallest logical row with an unrecoverable overflow
     // dump mode (limit beyond the fused collector): every row's key/payload to HBM
@@ -176,11 +185,52 @@ __device__ __forceinline__ void mask_tail(float4& b, uint32_t rem) {
 }
 
 // ---------------------------------------------------------------------------------------
-// NV > 0: query and R rows in registers (dims <= 128 * NV). NV == 0: generic loop (any dims).
+// Scores one row held in registers (b[NV]) against the query (q[NV]) and, when the f32
+// result is non-finite, recomputes it in f64 from the same registers. Warp-wide.
+template <int M, int NV>
+__device__ __forceinline__ float score_row_regs(const float4 (&q)[NV], float4 (&b)[NV], double q_norm,
+                                                bool& fatal) {
+    Scorer<M> sc;
+    sc.init();
+#pragma unroll
+    for (int j = 0; j < NV; ++j) sc.accum(q[j], b[j]);
+    bool bad;
+    float raw = sc.finish(q_norm, bad, fatal);
+    if constexpr (kCanOverflow<M>) {
+        if (bad) {  // warp-uniform cold path
+            Recover<M> rc;
+            rc.init();
+#pragma unroll
+            for (int j = 0; j < NV; ++j) rc.accum(q[j], b[j]);
+            raw = rc.finish(fatal);
+        }
+    }
+    return raw;
+}
+
+// Lane 0: turn a raw value into (key, payload) and hand it to the collector / dump arrays.
+template <int M>
+__device__ __forceinline__ void emit_row(const ScanParams& p, Collector& col, uint32_t qi, bool dump, u64 T,
+                                         float raw, uint32_t row, uint32_t drow) {
+    const uint32_t rk = order_key(rank_value(M, raw));
+    if (rk > (uint32_t)(T >> 32)) return;
+    const uint32_t idr = p.id_rank ? __ldg(p.id_rank + drow) : drow;
+    const u64 key = ((u64)rk << 32) | idr;
+    const u64 pay = ((u64)__float_as_uint(raw) << 32) | drow;
+    if (dump) {
+        p.dump_keys[(size_t)qi * p.n + row] = key;
+        p.dump_pays[(size_t)qi * p.n + row] = pay;
+    } else if (key < T) {
+        col.push(key, pay);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel A. NV > 0: query and R rows in registers (dims <= 128 * NV). NV == 0: generic loop.
 template <int M, int NV, int R>
 __global__ void __launch_bounds__(kScanThreads, (NV * R <= 12) ? 2 : 1)
 flat_scan_kernel(const ScanParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ u64 s_thresh;
     __shared__ uint32_t s_count;
     __shared__ int s_last;
@@ -196,6 +246,7 @@ flat_scan_kernel(const ScanParams p) {
     const uint32_t nvec = (p.dims + 3u) >> 2;           // float4 slots in the prefix
     const uint32_t tail_idx = nvec - 1u;                // slot holding the prefix tail
     const uint32_t tail_rem = p.dims - 4u * tail_idx;   // valid components in it (1..4)
+    const bool need_mask = tail_rem != 4u;              // uniform: rows carry data beyond dims
     const float4* q4 = reinterpret_cast<const float4*>(p.queries + (size_t)qi * p.q_stride);
     const double q_norm = (M == kCosineTrue) ? p.q_norms[qi] : 0.0;
 
@@ -213,6 +264,7 @@ flat_scan_kernel(const ScanParams p) {
     const uint32_t num_tiles = (p.n + kTileRows - 1u) / kTileRows;
     const uint32_t slack = kSyncEvery * kTileRows;
     uint32_t step = 0;
+    u64 g_prefetch = kKeyMax;
 
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++step) {
         const uint32_t r0 = tile * kTileRows + warp * R;
@@ -227,42 +279,27 @@ flat_scan_kernel(const ScanParams p) {
         }
 
         float raw[R];
-        bool fatal_any = false;
-
         if constexpr (NV > 0) {
             float4 b[R][NV];
+            // issue every load of the step before anything consumes one
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const bool valid = (r0 + r) < p.n;
 #pragma unroll
                 for (int j = 0; j < NV; ++j) {
-                    uint32_t idx = lane + 32u * j;
-                    if (valid && idx < nvec) {
-                        b[r][j] = ldg_stream(rp[r] + idx);
-                        if (idx == tail_idx) mask_tail(b[r][j], tail_rem);
-                    } else {
-                        b[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    const uint32_t idx = lane + 32u * j;
+                    b[r][j] = (valid && idx < nvec) ? ldg_stream(rp[r] + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                Scorer<M> sc;
-                sc.init();
+                if (need_mask) {
 #pragma unroll
-                for (int j = 0; j < NV; ++j) sc.accum(q[j], b[r][j]);
-                bool bad, fatal;
-                raw[r] = sc.finish(q_norm, bad, fatal);
-                if constexpr (kCanOverflow<M>) {
-                    if (bad) {  // warp-uniform cold path
-                        Recover<M> rc;
-                        rc.init();
-#pragma unroll
-                        for (int j = 0; j < NV; ++j) rc.accum(q[j], b[r][j]);
-                        raw[r] = rc.finish(fatal);
-                    }
+                    for (int j = 0; j < NV; ++j)
+                        if (lane + 32u * j == tail_idx) mask_tail(b[r][j], tail_rem);
                 }
-                fatal_any |= fatal && ((r0 + r) < p.n);
+                bool fatal;
+                raw[r] = score_row_regs<M, NV>(q, b[r], q_norm, fatal);
                 if (fatal && (r0 + r) < p.n && lane == 0) atomicMin(p.err_row + qi, r0 + r);
             }
         } else {
@@ -295,33 +332,302 @@ flat_scan_kernel(const ScanParams p) {
                 if (fatal && valid && lane == 0) atomicMin(p.err_row + qi, r0 + r);
             }
         }
-        (void)fatal_any;
 
         if (lane == 0) {
             const u64 T = dump ? kKeyMax : col.threshold();
-            const uint32_t t_hi = (uint32_t)(T >> 32);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t row = r0 + r;
-                if (row >= p.n) continue;
-                const uint32_t rk = order_key(rank_value(M, raw[r]));
-                if (rk > t_hi) continue;
-                const uint32_t idr = p.id_rank ? __ldg(p.id_rank + drow[r]) : drow[r];
-                const u64 key = ((u64)rk << 32) | idr;
-                const u64 pay = ((u64)__float_as_uint(raw[r]) << 32) | drow[r];
-                if (dump) {
-                    p.dump_keys[(size_t)qi * p.n + row] = key;
-                    p.dump_pays[(size_t)qi * p.n + row] = pay;
-                } else if (key < T) {
-                    col.push(key, pay);
-                }
-            }
+            for (int r = 0; r < R; ++r)
+                if (r0 + r < p.n) emit_row<M>(p, col, qi, dump, T, raw[r], r0 + r, drow[r]);
         }
 
-        if (!dump && (step & (kSyncEvery - 1)) == kSyncEvery - 1) collector_checkpoint(col, p.ws, qi, slack);
+        if (!dump && (step & (kSyncEvery - 1)) == kSyncEvery - 1)
+            collector_checkpoint(col, p.ws, qi, slack, g_prefetch);
     }
     if (dump) return;
 
+    collector_publish_and_merge(col, p.ws, qi, &s_last);
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel B: TMA-staged whole-row stream. 8 consumer warps + 1 producer warp.
+constexpr int kStreamMaxStages = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (complete_tx::bytes).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct StreamGeom {
+    uint32_t stages;      // ring depth
+    uint32_t tile_bytes;  // bytes per stage (tile_rows * row_stride * 4), multiple of 128
+};
+
+// Per-lane partial state of one row, reduced across the warp only once per group of rows.
+template <int M>
+struct PartialTraits {
+    static constexpr bool kIsDouble = (M == kCosineTrue);
+    static constexpr bool kIsCount = (M == kHamming || M == kJaccard);
+    static constexpr bool kIsMax = (M == kChebyshev);
+    static constexpr int kComps = (M == kJaccard || M == kCosineTrue) ? 2 : 1;
+    using T = typename std::conditional<kIsDouble, double,
+                                        typename std::conditional<kIsCount, uint32_t, float>::type>::type;
+    __device__ static __forceinline__ T zero() { return T(0); }
+    __device__ static __forceinline__ T op(T a, T b) {
+        if constexpr (kIsMax) return fmaxf(a, b);
+        else return a + b;
+    }
+    // lane-local partial of one row from the Scorer accumulators
+    __device__ static __forceinline__ void from_scorer(const Scorer<M>& sc, T (&out)[kComps]) {
+        if constexpr (kIsDouble) { out[0] = sc.d0; out[1] = sc.d1; }
+        else if constexpr (M == kJaccard) { out[0] = sc.c0; out[1] = sc.c1; }
+        else if constexpr (M == kHamming) { out[0] = sc.c0; }
+        else if constexpr (kIsMax) { out[0] = fmaxf(fmaxf(sc.s0, sc.s1), fmaxf(sc.s2, sc.s3)); }
+        else { out[0] = (sc.s0 + sc.s1) + (sc.s2 + sc.s3); }
+    }
+    // warp-reduced partial -> raw metric value (the tail of Scorer::finish)
+    __device__ static __forceinline__ float finalize(const T (&v)[kComps], double q_norm, bool& bad, bool& fatal) {
+        bad = false;
+        fatal = false;
+        float r;
+        if constexpr (M == kCosine || M == kInnerProduct || M == kL2Squared || M == kManhattan || M == kChebyshev) {
+            r = v[0];
+            bad = !isfinite(r);
+        } else if constexpr (M == kNegativeInnerProduct) {
+            r = -v[0];
+            bad = !isfinite(r);
+        } else if constexpr (M == kL2) {
+            bad = !isfinite(v[0]);
+            r = sqrtf(v[0]);
+        } else if constexpr (M == kHamming) {
+            r = (float)v[0];
+        } else if constexpr (M == kJaccard) {
+            r = v[1] == 0u ? 0.0f : __fsub_rn(1.0f, __fdiv_rn((float)v[0], (float)v[1]));
+        } else {
+            const double rn = sqrt(v[1]);
+            if (q_norm == 0.0 || rn == 0.0) {
+                r = 0.0f;
+            } else {
+                double s = v[0] / (q_norm * rn);
+                if (!isfinite(s)) { fatal = true; s = 0.0; }
+                s = s < -1.0 ? -1.0 : (s > 1.0 ? 1.0 : s);
+                r = (float)s;
+            }
+        }
+        return r;
+    }
+};
+
+constexpr int kGroupRows = 8;  // rows whose partials one warp reduces with a single butterfly
+
+// Reduces 8 per-lane partial rows across the warp with 4+2+1+1+1 = 9 shuffles per component
+// (instead of 8 x 5). Afterwards v[0] of lane L holds the total of row slot_of_lane(L).
+template <typename Tr, typename T, int C>
+__device__ __forceinline__ void butterfly8(T (&v)[kGroupRows][C], int lane) {
+    bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            T send = hi ? v[i][c] : v[i + 4][c], keep = hi ? v[i + 4][c] : v[i][c];
+            v[i][c] = Tr::op(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+        }
+    hi = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            T send = hi ? v[i][c] : v[i + 2][c], keep = hi ? v[i + 2][c] : v[i][c];
+            v[i][c] = Tr::op(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+        }
+    hi = (lane & 4) != 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        T send = hi ? v[0][c] : v[1][c], keep = hi ? v[1][c] : v[0][c];
+        v[0][c] = Tr::op(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+        v[0][c] = Tr::op(v[0][c], __shfl_xor_sync(0xffffffffu, v[0][c], 2));
+        v[0][c] = Tr::op(v[0][c], __shfl_xor_sync(0xffffffffu, v[0][c], 1));
+    }
+}
+__device__ __forceinline__ int slot_of_lane(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+
+// Rows must be whole (dims covers the stride's float4 slots) and contiguous (no row_sel).
+// W consumer warps + 1 producer warp; every consumer warp owns RPW rows of each tile and
+// defers the cross-lane reduction until it has kGroupRows row partials.
+template <int M, int NV, int RPW, int W>
+__global__ void __launch_bounds__(W * 32 + 32, 1)
+flat_stream_kernel(const ScanParams p, const StreamGeom geom) {
+    using Tr = PartialTraits<M>;
+    using T = typename Tr::T;
+    constexpr int C = Tr::kComps;
+    static_assert(kGroupRows % RPW == 0, "RPW must divide the group size");
+    constexpr int kTilesPerGroup = kGroupRows / RPW;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[kStreamMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStreamMaxStages];
+    __shared__ u64 s_thresh;
+    __shared__ uint32_t s_count;
+    __shared__ int s_last;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t qi = blockIdx.y;
+    constexpr uint32_t kTileRows = W * RPW;
+    const uint32_t num_tiles = (p.n + kTileRows - 1u) / kTileRows;
+    const uint32_t row_bytes = (uint32_t)p.row_stride * 4u;
+    unsigned char* ring = smem;
+    unsigned char* col_mem = smem + (size_t)geom.stages * geom.tile_bytes;
+
+    Collector col;
+    col.init(col_mem, &s_thresh, &s_count, p.cap, p.ws.k, W * 32, 1);
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < geom.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], W);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == W) {
+        // ===== producer: one elected lane streams this CTA's tiles through the ring =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t s = it % geom.stages, ph = (it / geom.stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                const uint32_t row0 = tile * kTileRows;
+                const uint32_t rows = min(kTileRows, p.n - row0);
+                const uint32_t bytes = rows * row_bytes;
+                mbar_arrive_expect_tx(&full_bar[s], bytes);
+                tma_bulk_g2s(ring + (size_t)s * geom.tile_bytes, p.rows + (size_t)row0 * p.row_stride, bytes,
+                             &full_bar[s]);
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const uint32_t nvec = (uint32_t)p.row_stride >> 2;
+    const float4* q4 = reinterpret_cast<const float4*>(p.queries + (size_t)qi * p.q_stride);
+    const double q_norm = (M == kCosineTrue) ? p.q_norms[qi] : 0.0;
+    float4 q[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        uint32_t idx = lane + 32u * j;
+        q[j] = idx < nvec ? q4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // Reduce + emit the current group: slot s = tile_in_group * RPW + r.
+    T part[kGroupRows][C];
+
+    auto flush_group = [&](uint32_t tile0) {
+        butterfly8<Tr, T, C>(part, lane);
+        const int slot = slot_of_lane(lane);
+        const uint32_t tile = tile0 + (uint32_t)(slot / RPW) * gridDim.x;
+        const uint32_t row = tile * kTileRows + (uint32_t)warp * RPW + (uint32_t)(slot % RPW);
+        const bool owner = (lane & 3) == 0 && tile < num_tiles && row < p.n;
+        bool bad = false, fatal = false;
+        float raw = Tr::finalize(part[0], q_norm, bad, fatal);
+        if constexpr (kCanOverflow<M>) {
+            // cold path: recompute overflowed rows in f64 straight from HBM, one row at a time
+            uint32_t todo = __ballot_sync(0xffffffffu, owner && bad);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t rrow = __shfl_sync(0xffffffffu, row, src);
+                const float4* rp = reinterpret_cast<const float4*>(p.rows + (size_t)rrow * p.row_stride);
+                Recover<M> rc;
+                rc.init();
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    const uint32_t idx = lane + 32u * j;
+                    if (idx < nvec) rc.accum(q[j], ldg_stream(rp + idx));
+                }
+                bool f2;
+                const float rec = rc.finish(f2);
+                if (lane == src) { raw = rec; fatal = f2; }
+            }
+        }
+        if (owner) {
+            if (fatal) atomicMin(p.err_row + qi, row);
+            emit_row<M>(p, col, qi, false, col.threshold(), raw, row, row);
+        }
+    };
+
+    constexpr uint32_t kGroupsPerSync = kStreamSyncEvery / kTilesPerGroup > 0 ? kStreamSyncEvery / kTilesPerGroup : 1;
+    uint32_t it = 0, grp = 0;
+    u64 g_prefetch = kKeyMax;
+    for (uint32_t tile0 = blockIdx.x; tile0 < num_tiles; tile0 += gridDim.x * kTilesPerGroup, ++grp) {
+#pragma unroll
+        for (int g = 0; g < kGroupRows; ++g)
+#pragma unroll
+            for (int c = 0; c < C; ++c) part[g][c] = Tr::zero();
+#pragma unroll
+        for (int t = 0; t < kTilesPerGroup; ++t) {
+            const uint32_t tile = tile0 + (uint32_t)t * gridDim.x;
+            if (tile >= num_tiles) break;  // CTA-uniform
+            const uint32_t s = it % geom.stages, ph = (it / geom.stages) & 1u;
+            ++it;
+            if (lane == 0) mbar_wait(&full_bar[s], ph);
+            __syncwarp();
+            const float4* tile4 = reinterpret_cast<const float4*>(ring + (size_t)s * geom.tile_bytes);
+            const uint32_t r0 = tile * kTileRows + warp * RPW;
+            float4 b[RPW][NV];
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                const bool valid = (r0 + r) < p.n;
+                const float4* rp = tile4 + (size_t)(warp * RPW + r) * nvec;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    const uint32_t idx = lane + 32u * j;
+                    b[r][j] = (valid && idx < nvec) ? rp[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                Scorer<M> sc;
+                sc.init();
+                if (!(p.debug & 2u)) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) sc.accum(q[j], b[r][j]);
+                }
+                Tr::from_scorer(sc, part[t * RPW + r]);
+            }
+            // every lane's shared-memory reads have been consumed: hand the slot back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+        if (!(p.debug & 1u)) flush_group(tile0);
+        if (!(p.debug & 4u) && (grp & (kGroupsPerSync - 1)) == kGroupsPerSync - 1)
+            collector_checkpoint(col, p.ws, qi, kGroupsPerSync * kGroupRows * W, g_prefetch);
+    }
     collector_publish_and_merge(col, p.ws, qi, &s_last);
 }
 

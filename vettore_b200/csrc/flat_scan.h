@@ -5,20 +5,29 @@
 namespace vb {
 
 struct ScanParams;
+struct StreamGeom;
 typedef void (*ScanKernel)(const ScanParams);
+typedef void (*StreamKernel)(const ScanParams, const StreamGeom);
 
 struct ScanPlan {
-    ScanKernel kernel = nullptr;
+    ScanKernel kernel = nullptr;          // kernel A (register-staged loads)
+    StreamKernel stream_kernel = nullptr; // kernel B (TMA-staged ring), when eligible
     int nv = 0, r = 0;
     uint32_t grid_x = 0;     // CTAs per query
     uint32_t cap = 0;        // collector capacity (entries)
     size_t smem = 0;         // dynamic shared memory bytes
+    uint32_t stages = 0, tile_bytes = 0;  // kernel B ring geometry
+    uint32_t stream_threads = 0;          // kernel B block size (consumer warps + producer warp)
 };
 
 // Picks the kernel variant, grid and collector capacity for `n` rows of `dims` scored
-// elements and k results (k <= kMaxFusedK unless dump). Env knobs for tuning runs:
-// VB_SCAN_R (rows per warp step), VB_SCAN_CTAS_PER_SM.
-Status plan_flat_scan(int metric, uint32_t dims, uint32_t n, uint32_t k, bool dump, ScanPlan* plan);
+// elements (row stride `row_stride` floats) and k results (k <= kMaxFusedK unless dump).
+// `contiguous` = no row list and no data beyond `dims` in a row: such scans take the
+// TMA-staged kernel B.
+// Env knobs for tuning runs: VB_SCAN_R, VB_SCAN_CTAS_PER_SM, VB_SCAN_NO_STREAM,
+// VB_STREAM_STAGES, VB_STREAM_RPW, VB_STREAM_WARPS.
+Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, bool contiguous, uint32_t n, uint32_t k,
+                      bool dump, ScanPlan* plan);
 
 // Launches plan.kernel over grid (plan.grid_x, nq). ScanParams.k/.cap are taken from the plan.
 Status run_flat_scan(const ScanPlan& plan, ScanParams params, uint32_t nq, cudaStream_t stream);

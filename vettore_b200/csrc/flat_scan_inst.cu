@@ -26,4 +26,18 @@ ScanKernel VB_CAT(flat_scan_kernel_metric_, VB_METRIC)(int nv, int r) {
     return nullptr;
 }
 
+#define VB_STREAM_VARIANT(NV, RPW, W) \
+    if (nv == NV && rpw == RPW && warps == W) return flat_stream_kernel<VB_METRIC, NV, RPW, W>;
+
+StreamKernel VB_CAT(flat_stream_kernel_metric_, VB_METRIC)(int nv, int rpw, int warps) {
+    VB_STREAM_VARIANT(1, 4, 16)
+    VB_STREAM_VARIANT(2, 4, 16)
+    VB_STREAM_VARIANT(3, 2, 16)
+    VB_STREAM_VARIANT(4, 2, 16) VB_STREAM_VARIANT(4, 1, 16)
+    VB_STREAM_VARIANT(6, 1, 16) VB_STREAM_VARIANT(6, 2, 8) VB_STREAM_VARIANT(6, 1, 8) VB_STREAM_VARIANT(6, 2, 16)
+    VB_STREAM_VARIANT(8, 1, 16)
+    VB_STREAM_VARIANT(12, 1, 8)
+    return nullptr;
+}
+
 }  // namespace vb

@@ -16,6 +16,7 @@ namespace vb {
 constexpr int kHamThreads = 256;
 constexpr int kHamWarps = kHamThreads / 32;
 constexpr int kHamUnroll = 4;
+constexpr uint32_t kHamSlackRows = 1024;  // rows scanned per CTA between collector checks
 
 struct HammingParams {
     const u64* codes;          // [n, nw]
@@ -23,6 +24,7 @@ struct HammingParams {
     const uint32_t* id_rank;   // optional
     const u64* queries;        // [nq, nw]
     uint32_t g;                // lanes per row (power of two)
+    uint32_t sync_every;       // steps between collector checks (power of two)
     uint32_t cap;
     TopkWorkspace ws;
     u64* dump_keys;            // dump mode: [n] keys / pays, no collector
@@ -61,7 +63,9 @@ __global__ void __launch_bounds__(kHamThreads, 4) hamming_scan_kernel(const Hamm
 
     const uint32_t rows_per_step = kHamWarps * rpw * kHamUnroll;
     const uint32_t steps = (p.n + rows_per_step - 1u) / rows_per_step;
-    for (uint32_t step = blockIdx.x; step < steps; step += gridDim.x) {
+    u64 g_prefetch = kKeyMax;
+    uint32_t it = 0;
+    for (uint32_t step = blockIdx.x; step < steps; step += gridDim.x, ++it) {
         const uint32_t base = step * rows_per_step + warp * rpw * kHamUnroll + sub;
         uint32_t dist[kHamUnroll];
         // first chunk pass: all U loads issued back to back
@@ -127,7 +131,8 @@ __global__ void __launch_bounds__(kHamThreads, 4) hamming_scan_kernel(const Hamm
                 }
             }
         }
-        if (!dump) collector_checkpoint(col, p.ws, qi, rows_per_step);
+        if (!dump && (it & (p.sync_every - 1)) == p.sync_every - 1)
+            collector_checkpoint(col, p.ws, qi, p.sync_every * rows_per_step, g_prefetch);
     }
     if (dump) return;
     collector_publish_and_merge(col, p.ws, qi, &s_last);
@@ -146,7 +151,8 @@ static Status launch_hamming(SearchCtx& ctx, HammingParams p, uint32_t nq, uint3
     p.g = std::min<uint32_t>(32, pow2_at_least(cpr, 1));
     const uint32_t rows_per_step = kHamWarps * (32 / p.g) * kHamUnroll;
     const uint32_t kk = dump ? 1 : k;
-    p.cap = pow2_at_least(std::max(2 * kk, kk + rows_per_step), 256);
+    p.sync_every = std::max<uint32_t>(1, kHamSlackRows / rows_per_step);  // both are powers of two
+    p.cap = pow2_at_least(std::max(2 * kk, kk + p.sync_every * rows_per_step), 256);
     const size_t smem = (size_t)p.cap * 16;
     auto kernel = wide ? hamming_scan_kernel<true> : hamming_scan_kernel<false>;
     if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -178,6 +184,8 @@ static Status launch_hamming(SearchCtx& ctx, HammingParams p, uint32_t nq, uint3
         p.ws.out_keys = ctx.out_keys.as<u64>();
         p.ws.out_pays = ctx.result.as<u64>();
         p.ws.out_counts = reinterpret_cast<uint32_t*>(ctx.result.as<u64>() + (size_t)nq * k);
+        p.ws.err_row = nullptr;
+        p.ws.out_err = nullptr;
     } else {
         p.ws = TopkWorkspace{};
         p.ws.k = 1;

@@ -67,10 +67,19 @@ struct CtxLease {
 };
 
 // Sorted Vec<(String, f32)> handed to the caller (opaque vb_hits in the C ABI).
+// Ids are one blob plus n+1 offsets so a binding can take the whole result in one read.
 struct Hits {
-    std::vector<std::string> ids;
+    std::string blob;
+    std::vector<uint64_t> off{0};
     std::vector<float> values;
     std::vector<uint64_t> index;
+    size_t size() const { return values.size(); }
+    void add(const char* id, size_t len, float value, uint64_t idx) {
+        blob.append(id, len);
+        off.push_back(blob.size());
+        values.push_back(value);
+        index.push_back(idx);
+    }
 };
 
 }  // namespace vb

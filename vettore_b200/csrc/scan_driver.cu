@@ -2,6 +2,7 @@
 #include "scan_driver.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "flat_scan.cuh"
@@ -33,6 +34,7 @@ static void fill_params(const SearchCtx& ctx, const ScanJob& job, const float* d
     p->q_stride = (uint32_t)q_stride;
     p->q_norms = d_q_norms;
     p->cap = 0;
+    { const char* dbg = std::getenv("VB_SCAN_DEBUG"); p->debug = dbg ? (uint32_t)std::atoi(dbg) : 0u; }
     p->ws.k = (uint32_t)k;
     p->ws.cand_keys = ctx.cand_keys.as<u64>();
     p->ws.cand_pays = ctx.cand_pays.as<u64>();
@@ -43,6 +45,8 @@ static void fill_params(const SearchCtx& ctx, const ScanJob& job, const float* d
     p->ws.out_keys = ctx.out_keys.as<u64>();
     p->ws.out_pays = ctx.result.as<u64>();
     p->ws.out_counts = reinterpret_cast<uint32_t*>(ctx.result.as<u64>() + (size_t)job.nq * k);
+    p->ws.err_row = ctx.err_row();
+    p->ws.out_err = p->ws.out_counts + job.nq;
     p->dump_keys = nullptr;
     p->dump_pays = nullptr;
 }
@@ -99,7 +103,7 @@ static Status stage_queries(SearchCtx& ctx, const ScanJob& job, size_t* q_stride
 // k beyond the fused collector: every key/payload to HBM, then a device radix sort.
 static Status run_scan_dump(SearchCtx& ctx, const ScanJob& job, size_t q_stride, ScanResult* out) {
     ScanPlan plan;
-    VB_TRY(plan_flat_scan(job.metric, job.dims, job.n, 1, /*dump=*/true, &plan));
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, job.d_row_sel == nullptr && job.whole_rows, job.n, 1, /*dump=*/true, &plan));
     VB_TRY(prepare_workspace(ctx, plan, 1, 1));
     const size_t n = job.n, k = job.k;
     VB_TRY(ctx.dump_keys.reserve(n * sizeof(u64)));
@@ -165,15 +169,13 @@ Status run_scan(SearchCtx& ctx, const ScanJob& job, ScanResult* out) {
     }
 
     ScanPlan plan;
-    VB_TRY(plan_flat_scan(job.metric, job.dims, job.n, (uint32_t)k, false, &plan));
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, job.d_row_sel == nullptr && job.whole_rows, job.n, (uint32_t)k, false, &plan));
     VB_TRY(prepare_workspace(ctx, plan, job.nq, k));
     ScanParams p;
     fill_params(ctx, job, ctx.queries.as<float>(), q_stride,
                 job.metric == kCosineTrue ? ctx.q_norms.as<double>() : nullptr, k, &p);
     Status s = run_flat_scan(plan, p, job.nq, ctx.stream);
     if (!s.ok()) { ctx.poison(); return s; }
-    uint32_t* d_err = p.ws.out_counts + job.nq;
-    collect_err_kernel<<<(job.nq + 127) / 128, 128, 0, ctx.stream>>>(ctx.err_row(), d_err, job.nq);
     const size_t bytes = (size_t)job.nq * k * sizeof(u64) + (size_t)job.nq * 8;
     VB_TRY(ctx.h_result.reserve(bytes));
     cudaError_t e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, bytes, cudaMemcpyDeviceToHost, ctx.stream);
@@ -205,7 +207,7 @@ Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_querie
     const size_t k = std::min<size_t>(job.k, job.n);
     if (k > (size_t)kMaxFusedK) return Status::Cuda("limit beyond the fused collector (1024)");
     ScanPlan plan;
-    VB_TRY(plan_flat_scan(job.metric, job.dims, job.n, (uint32_t)k, false, &plan));
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, job.d_row_sel == nullptr && job.whole_rows, job.n, (uint32_t)k, false, &plan));
     cudaStream_t saved = ctx.stream;
     ctx.stream = stream;  // workspace arming must be ordered on the caller's stream
     Status s = prepare_workspace(ctx, plan, job.nq, k);

@@ -16,6 +16,7 @@ struct ScanJob {
     const uint32_t* d_id_rank = nullptr;
     uint32_t n = 0;                     // logical rows
     uint32_t dims = 0;                  // scored prefix
+    bool whole_rows = false;            // dims covers every non-zero element of a row (no data beyond it)
     const float* h_queries = nullptr;   // host, nq rows of q_len floats (q_len >= dims)
     uint32_t nq = 1;
     size_t q_len = 0;

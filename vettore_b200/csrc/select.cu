@@ -20,9 +20,18 @@ topk_merge_kernel(const u64* keys, const float* values, const uint32_t* rows, co
     auto at = [list_stride](const void* base, uint32_t l) {
         return reinterpret_cast<const unsigned char*>(base) + (size_t)l * list_stride;
     };
+    // A list that holds >= k_out entries bounds the global k_out-th key from above.
+    for (uint32_t l = threadIdx.x; l < lists; l += blockDim.x) {
+        const uint32_t cnt = min(reinterpret_cast<const uint32_t*>(at(counts, l))[qi], k_in);
+        if (cnt >= k_out) {
+            const u64 kth = reinterpret_cast<const u64*>(at(keys, l))[(size_t)qi * k_in + k_out - 1];
+            if (kth != kKeyMax) atomicMin(col.thresh, kth + 1);
+        }
+    }
+    __syncthreads();
     collector_merge_lists(
-        col, lists,
-        [&](uint32_t l) { return min(reinterpret_cast<const uint32_t*>(at(counts, l))[qi], k_in); },
+        col, lists, k_in,
+        [&](uint32_t l) { return reinterpret_cast<const uint32_t*>(at(counts, l))[qi]; },
         [&](uint32_t l, uint32_t i) { return reinterpret_cast<const u64*>(at(keys, l))[(size_t)qi * k_in + i]; },
         [&](uint32_t l, uint32_t i) { return ((u64)l << 32) | i; });
     const uint32_t total = *col.count;

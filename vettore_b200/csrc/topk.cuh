@@ -21,16 +21,34 @@ struct Collector {
     uint32_t* count;    // smem
     uint32_t cap;       // power of two
     uint32_t k;
+    uint32_t nthreads;  // threads taking part (threadIdx.x < nthreads), multiple of 32
+    uint32_t bar_id;    // hardware barrier they synchronise on (0 == __syncthreads when all do)
 
     __device__ __forceinline__ void init(unsigned char* smem, u64* s_thresh, uint32_t* s_count,
-                                         uint32_t cap_, uint32_t k_) {
+                                         uint32_t cap_, uint32_t k_, uint32_t nthreads_ = 0,
+                                         uint32_t bar_id_ = 0) {
         keys = reinterpret_cast<u64*>(smem);
         pays = keys + cap_;
         thresh = s_thresh;
         count = s_count;
         cap = cap_;
         k = k_;
+        nthreads = nthreads_ ? nthreads_ : blockDim.x;
+        bar_id = bar_id_;
         if (threadIdx.x == 0) { *thresh = kKeyMax; *count = 0; }
+    }
+
+    __device__ __forceinline__ void sync() const {
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    }
+    // Barrier + OR-reduction of a predicate over the participating threads.
+    __device__ __forceinline__ bool sync_or(bool pred) const {
+        uint32_t res;
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\t"
+            "selp.u32 %0, 1, 0, q;\n\t}"
+            : "=r"(res) : "r"((uint32_t)pred), "r"(bar_id), "r"(nthreads) : "memory");
+        return res != 0;
     }
 
     __device__ __forceinline__ u64 threshold() const { return *reinterpret_cast<volatile u64*>(thresh); }
@@ -44,15 +62,15 @@ struct Collector {
     // Block-wide (every thread of the CTA must call). Sorts the buffer ascending, keeps the
     // best k and tightens the threshold. Returns the number of retained entries.
     __device__ uint32_t compact() {
-        __syncthreads();
+        sync();
         uint32_t n = min(*count, cap);
         uint32_t p2 = 32;
         while (p2 < n) p2 <<= 1;
-        for (uint32_t i = n + threadIdx.x; i < p2; i += blockDim.x) { keys[i] = kKeyMax; pays[i] = 0; }
-        __syncthreads();
+        for (uint32_t i = n + threadIdx.x; i < p2; i += nthreads) { keys[i] = kKeyMax; pays[i] = 0; }
+        sync();
         for (uint32_t size = 2; size <= p2; size <<= 1) {
             for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-                for (uint32_t t = threadIdx.x; t < (p2 >> 1); t += blockDim.x) {
+                for (uint32_t t = threadIdx.x; t < (p2 >> 1); t += nthreads) {
                     uint32_t lo = 2 * t - (t & (stride - 1));
                     uint32_t hi = lo + stride;
                     bool up = (lo & size) == 0;
@@ -62,7 +80,7 @@ struct Collector {
                         u64 pa = pays[lo]; pays[lo] = pays[hi]; pays[hi] = pa;
                     }
                 }
-                __syncthreads();
+                sync();
             }
         }
         uint32_t kept = min(n, k);
@@ -70,41 +88,70 @@ struct Collector {
             *count = kept;
             if (n >= k) atomicMin(thresh, keys[k - 1]);
         }
-        __syncthreads();
+        sync();
         return kept;
     }
 };
 
+constexpr uint32_t kMergeChunk = 1024;  // lists whose counts are staged in shared memory at once
+
 // Merges `lists` candidate lists (global memory, written by other CTAs or other GPUs) into
-// the collector. Block-wide. List l holds list_len(l) <= k entries; key_at(l, i) / pay_at(l, i)
-// fetch entry i of list l.
+// the collector. Block-wide. List l holds list_len(l) <= list_cap entries; key_at(l, i) /
+// pay_at(l, i) fetch entry i of list l. The collector's threshold may be pre-tightened by
+// the caller (entries must be < threshold to matter).
+//
+// Counts are staged in shared memory and the candidates are walked as one flat index space,
+// so no thread ever chases a dependent chain of global loads. First an optimistic single
+// pass (with a tight threshold almost nothing survives the filter); only if that would
+// overflow the buffer it is redone in windows that cannot overflow.
 template <typename CountFn, typename KeyFn, typename PayFn>
-__device__ void collector_merge_lists(Collector& c, uint32_t lists, CountFn list_len, KeyFn key_at, PayFn pay_at) {
-    // Each round appends at most (cap - k) surviving candidates, so push never overflows.
+__device__ void collector_merge_lists(Collector& c, uint32_t lists, uint32_t list_cap, CountFn list_len,
+                                      KeyFn key_at, PayFn pay_at) {
+    __shared__ uint32_t s_cnt[kMergeChunk];
+    __shared__ int s_overflow;
     const uint32_t room = c.cap - c.k;
-    for (uint32_t l0 = 0; l0 < lists;) {
-        // take as many whole lists as fit in `room` candidates (a list holds <= room entries)
-        uint32_t l1 = l0, total = 0;
-        while (l1 < lists) {
-            uint32_t len = list_len(l1);
-            if (total + len > room) break;
-            total += len;
-            ++l1;
+    for (uint32_t chunk0 = 0; chunk0 < lists; chunk0 += kMergeChunk) {
+        const uint32_t nl = min(kMergeChunk, lists - chunk0);
+        for (uint32_t l = threadIdx.x; l < nl; l += c.nthreads) s_cnt[l] = min(list_len(chunk0 + l), list_cap);
+        if (threadIdx.x == 0) s_overflow = 0;
+        c.sync();
+        const uint32_t base = *c.count;  // <= k: left by the previous chunk's compaction
+        const uint32_t slots = nl * list_cap;
+        const u64 T = c.threshold();
+        c.sync();
+        for (uint32_t s = threadIdx.x; s < slots; s += c.nthreads) {
+            const uint32_t l = s / list_cap, i = s - l * list_cap;
+            if (i >= s_cnt[l]) continue;
+            const u64 key = key_at(chunk0 + l, i);
+            if (key >= T) continue;
+            const uint32_t slot = atomicAdd(c.count, 1u);
+            if (slot < c.cap) { c.keys[slot] = key; c.pays[slot] = pay_at(chunk0 + l, i); }
+            else s_overflow = 1;
         }
-        if (l1 == l0) ++l1;  // unreachable while list_len <= room; keeps the loop total
-        u64 T = c.threshold();
-        for (uint32_t l = l0; l < l1; ++l) {
-            uint32_t len = list_len(l);
-            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
-                u64 key = key_at(l, i);
-                if (key < T) c.push(key, pay_at(l, i));
+        c.sync();
+        const bool overflow = s_overflow != 0;
+        c.sync();
+        if (!overflow) {
+            c.compact();
+            continue;
+        }
+        // safe path: drop the partial pass, then windows of `room` slots (cannot overflow)
+        if (threadIdx.x == 0) *c.count = base;
+        c.sync();
+        for (uint32_t w0 = 0; w0 < slots; w0 += room) {
+            const u64 Tw = c.threshold();
+            const uint32_t w1 = min(slots, w0 + room);
+            for (uint32_t s = w0 + threadIdx.x; s < w1; s += c.nthreads) {
+                const uint32_t l = s / list_cap, i = s - l * list_cap;
+                if (i >= s_cnt[l]) continue;
+                const u64 key = key_at(chunk0 + l, i);
+                if (key < Tw) c.push(key, pay_at(chunk0 + l, i));
             }
+            c.sync();
+            const uint32_t filled = *c.count;
+            c.sync();  // everyone has read `filled` before the next window's pushes
+            if (filled + room > c.cap || w1 == slots) c.compact();
         }
-        __syncthreads();
-        const uint32_t filled = *c.count;
-        __syncthreads();  // everyone has read `filled` before the next round's pushes
-        if (filled + room > c.cap || l1 == lists) c.compact();
-        l0 = l1;
     }
 }
 
@@ -123,24 +170,26 @@ struct TopkWorkspace {
     u64* out_keys;          // [nq][k] sorted ascending
     u64* out_pays;
     uint32_t* out_counts;   // [nq]
+    uint32_t* err_row;      // [nq] optional: first overflowing row (atomicMin by any CTA)
+    uint32_t* out_err;      // [nq] optional: err_row snapshot taken by the last CTA (err_row re-armed)
     uint32_t k;
 };
 
 // Block-wide, called at a CTA-uniform cadence: adopts the grid-wide threshold, and when
 // the buffer could overflow within the next `slack` pushes compacts it and publishes the
-// CTA's own k-th key.
+// CTA's own k-th key. `g_prefetch` (meaningful in thread 0) carries the grid-wide threshold
+// loaded one cadence earlier, so the global-memory round trip overlaps the scan instead of
+// stalling the CTA at the barrier; it is re-issued here for the next call.
 __device__ __forceinline__ void collector_checkpoint(Collector& col, const TopkWorkspace& ws, uint32_t qi,
-                                                     uint32_t slack) {
-    if (threadIdx.x == 0) {
-        u64 g = ld_volatile_u64(ws.g_thresh + qi);
-        if (g < col.threshold()) atomicMin(col.thresh, g);
-    }
-    const bool need = __syncthreads_or(
+                                                     uint32_t slack, u64& g_prefetch) {
+    if (threadIdx.x == 0 && g_prefetch < col.threshold()) atomicMin(col.thresh, g_prefetch);
+    const bool need = col.sync_or(
         (threadIdx.x & 31) == 0 && *reinterpret_cast<volatile uint32_t*>(col.count) + slack > col.cap);
     if (need) {
         col.compact();
         if (threadIdx.x == 0 && *col.thresh != kKeyMax) atomicMin(ws.g_thresh + qi, *col.thresh);
     }
+    if (threadIdx.x == 0) g_prefetch = ld_volatile_u64(ws.g_thresh + qi);
 }
 
 // Block-wide epilogue of a fused scan: publishes this CTA's best k; the last CTA of the
@@ -149,39 +198,50 @@ __device__ __forceinline__ void collector_checkpoint(Collector& col, const TopkW
 __device__ __forceinline__ void collector_publish_and_merge(Collector& col, const TopkWorkspace& ws, uint32_t qi,
                                                             int* s_last) {
     const uint32_t kept = col.compact();
+    if (threadIdx.x == 0 && *col.thresh != kKeyMax) atomicMin(ws.g_thresh + qi, *col.thresh);
     const size_t slot = (size_t)qi * gridDim.x + blockIdx.x;
-    for (uint32_t i = threadIdx.x; i < kept; i += blockDim.x) {
+    for (uint32_t i = threadIdx.x; i < kept; i += col.nthreads) {
         ws.cand_keys[slot * ws.k + i] = col.keys[i];
         ws.cand_pays[slot * ws.k + i] = col.pays[i];
     }
     if (threadIdx.x == 0) ws.cand_counts[slot] = kept;
     __threadfence();
-    __syncthreads();
+    col.sync();
     if (threadIdx.x == 0) {
         uint32_t ticket = atomicAdd(ws.done + qi, 1u);
         *s_last = (ticket == gridDim.x - 1u);
     }
-    __syncthreads();
+    col.sync();
     if (!*s_last) return;
     __threadfence();
 
-    if (threadIdx.x == 0) { *col.thresh = kKeyMax; *col.count = 0; }
-    __syncthreads();
+    // Every list's k-th key was folded into g_thresh: nothing above the smallest of them can be
+    // in the global top-k. Keys are unique, so "<= g" is "< g + 1".
+    if (threadIdx.x == 0) {
+        const u64 g = ld_volatile_u64(ws.g_thresh + qi);
+        *col.thresh = g == kKeyMax ? kKeyMax : g + 1;
+        *col.count = 0;
+    }
+    col.sync();
     const uint32_t* counts = ws.cand_counts + (size_t)qi * gridDim.x;
     const u64* gk = ws.cand_keys + (size_t)qi * gridDim.x * ws.k;
     const u64* gp = ws.cand_pays + (size_t)qi * gridDim.x * ws.k;
     const uint32_t stride = ws.k;
     collector_merge_lists(
-        col, gridDim.x, [counts](uint32_t l) { return __ldcg(counts + l); },
+        col, gridDim.x, ws.k, [counts](uint32_t l) { return __ldcg(counts + l); },
         [gk, stride](uint32_t l, uint32_t i) { return __ldcg(gk + (size_t)l * stride + i); },
         [gp, stride](uint32_t l, uint32_t i) { return __ldcg(gp + (size_t)l * stride + i); });
     const uint32_t total = *col.count;
-    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+    for (uint32_t i = threadIdx.x; i < total; i += col.nthreads) {
         ws.out_keys[(size_t)qi * ws.k + i] = col.keys[i];
         ws.out_pays[(size_t)qi * ws.k + i] = col.pays[i];
     }
     if (threadIdx.x == 0) {
         ws.out_counts[qi] = total;
+        if (ws.out_err) {
+            ws.out_err[qi] = __ldcg(ws.err_row + qi);
+            ws.err_row[qi] = kNoError;
+        }
         ws.done[qi] = 0u;
         ws.g_thresh[qi] = kKeyMax;
     }

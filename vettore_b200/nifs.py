@@ -71,14 +71,15 @@ def _ragged(rows: Iterable, dtype) -> tuple[np.ndarray, np.ndarray]:
 def _take_hits(handle: C.c_void_p, as_str: bool = True) -> list[tuple]:
     L = lib()
     try:
-        n = L.vb_hits_len(handle)
-        out = []
-        ln = C.c_size_t()
-        for i in range(n):
-            p = L.vb_hits_id(handle, i, C.byref(ln))
-            raw = C.string_at(p, ln.value)
-            out.append((raw.decode("utf-8") if as_str else raw, float(L.vb_hits_value(handle, i))))
-        return out
+        blob, off, vals, idx = C.c_void_p(), _u64p(), _f32p(), _u64p()
+        n = L.vb_hits_export(handle, C.byref(blob), C.byref(off), C.byref(vals), C.byref(idx))
+        if n == 0:
+            return []
+        offs = off[: n + 1]
+        raw = C.string_at(blob.value, offs[n])
+        if as_str:
+            return [(raw[offs[i]:offs[i + 1]].decode("utf-8"), vals[i]) for i in range(n)]
+        return [(raw[offs[i]:offs[i + 1]], vals[i]) for i in range(n)]
     finally:
         L.vb_hits_free(handle)
 
