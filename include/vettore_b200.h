@@ -130,6 +130,29 @@ int vb_vector_top_k(size_t n, const char* ids, const uint64_t* id_off, const flo
 int vb_binary_top_k(size_t n, const char* ids, const uint64_t* id_off, const uint64_t* words,
                     const uint64_t* word_off, const uint64_t* query, size_t query_words,
                     size_t dimensions, size_t limit, vb_hits** out);
+/* multi_vector_top_k/4, nifs.rs:188-198 -> multi_vector::top_k, multi_vector.rs:90-132.
+ * Tokens are one ragged list (tok_vals, tok_off[ntok+1]); document i owns tokens
+ * [doc_tok[i], doc_tok[i+1]). Hits descend by score (total order), ids ascending on ties. */
+int vb_multi_vector_top_k(size_t ndocs, const char* ids, const uint64_t* id_off, const float* tok_vals,
+                          const uint64_t* tok_off, const uint64_t* doc_tok, const float* q_vals,
+                          const uint64_t* q_off, size_t tq, int metric_code, size_t limit, vb_hits** out);
+/* multi_vector_score/3, nifs.rs:177-186 -> multi_vector::score, multi_vector.rs:40-63. */
+int vb_multi_vector_score(const float* q_vals, const uint64_t* q_off, size_t tq, const float* d_vals,
+                          const uint64_t* d_off, size_t td, int metric_code, float* out);
+
+/* ---- additive: HBM-resident multi-vector collection (multi_vector_search without
+ * store.all + by-value marshalling, collection.ex:313-323). Same scoring and ordering as
+ * vb_multi_vector_top_k; documents are upserted by id like the flat index. ---------------- */
+typedef struct vb_mv vb_mv;
+int vb_mv_new(int metric_code, vb_mv** out);
+void vb_mv_free(vb_mv* index);
+int vb_mv_insert_many(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off,
+                      const float* tok_vals, const uint64_t* tok_off, const uint64_t* doc_tok);
+int vb_mv_delete(vb_mv* index, const char* id, size_t id_len);
+int vb_mv_search(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit,
+                 vb_hits** out);
+int vb_mv_info(vb_mv* index, size_t* docs, size_t* tokens, size_t* dimension);
+
 /* compress_sign_bits/1, nifs.rs:125-129 -> distances.rs:413-423. words[ceil(len/64)]. */
 int vb_compress_sign_bits(const float* vector, size_t len, uint64_t* words);
 

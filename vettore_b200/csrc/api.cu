@@ -7,6 +7,7 @@
 #include "../../include/vettore_b200.h"
 #include "flat_index.h"
 #include "hamming.h"
+#include "maxsim.h"
 #include "runtime.h"
 #include "scan_driver.h"
 #include "select.h"
@@ -282,6 +283,171 @@ int vb_binary_top_k(size_t n, const char* ids, const uint64_t* id_off, const uin
     }
     if (good < n) return finish(vb::Status::Ref("dimension mismatch"));
     *out = new vb_hits{std::move(hits)};
+    return VB_OK;
+}
+
+// ---- multi-vector (MaxSim) ---------------------------------------------------------------
+namespace {
+
+// multi_vector.rs:144-152 over tokens [t0, t1) of a ragged token list
+const char* validate_tokens(const float* vals, const uint64_t* off, size_t t0, size_t t1, size_t dim) {
+    for (size_t t = t0; t < t1; ++t) {
+        const size_t len = off[t + 1] - off[t];
+        if (len != dim) return "dimension mismatch";
+        if (!all_finite(vals + off[t], len)) return "vector contains a non-finite value";
+    }
+    return nullptr;
+}
+// multi_vector.rs:134-142
+const char* validate_standalone(const float* vals, const uint64_t* off, size_t t0, size_t t1) {
+    if (t0 == t1) return nullptr;
+    const size_t first = off[t0 + 1] - off[t0];
+    if (first == 0) return "vectors must not be empty";
+    return validate_tokens(vals, off, t0, t1, first);
+}
+
+// Scores documents [0, ndocs) (already validated, every token `dim` long) on the device.
+vb::Status maxsim_by_value(size_t ndocs, const float* tok_vals, const uint64_t* tok_off, const uint64_t* doc_tok,
+                           const uint32_t* ranks, const float* q_vals, size_t tq, size_t dim, int metric_code,
+                           size_t k, vb::MaxSimResult* res) {
+    vb::CtxLease ctx;
+    VB_TRY(ctx.get());
+    const size_t stride = (dim + 3) & ~(size_t)3;
+    const size_t ntok = doc_tok[ndocs] - doc_tok[0];
+    if (ntok >= 0xFFFFFFFFull || ndocs >= 0xFFFFFFFEull) return vb::Status::Cuda("batch too large");
+    vb::PinnedBuf hb;
+    VB_TRY(hb.reserve(std::max<size_t>(ntok, 1) * stride * sizeof(float) + (2 * ndocs + 1) * sizeof(uint32_t)));
+    float* hrows = hb.as<float>();
+    uint32_t* hoff = reinterpret_cast<uint32_t*>(hrows + std::max<size_t>(ntok, 1) * stride);
+    uint32_t* hrank = hoff + ndocs + 1;
+    for (size_t t = 0; t < ntok; ++t) {
+        std::memcpy(hrows + t * stride, tok_vals + tok_off[doc_tok[0] + t], dim * sizeof(float));
+        for (size_t c = dim; c < stride; ++c) hrows[t * stride + c] = 0.0f;
+    }
+    for (size_t d = 0; d <= ndocs; ++d) hoff[d] = (uint32_t)(doc_tok[d] - doc_tok[0]);
+    std::memcpy(hrank, ranks, ndocs * sizeof(uint32_t));
+    VB_TRY(ctx->staging.reserve(std::max<size_t>(ntok, 1) * stride * sizeof(float)));
+    VB_TRY(ctx->staging_rank.reserve((2 * ndocs + 1) * sizeof(uint32_t)));
+    VB_CUDA(cudaMemcpyAsync(ctx->staging.p, hrows, ntok * stride * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    VB_CUDA(cudaMemcpyAsync(ctx->staging_rank.p, hoff, (2 * ndocs + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    vb::MaxSimJob job;
+    job.metric = metric_code == vb::kCosine ? vb::kCosineTrue : metric_code;   // multi_vector.rs:74-75
+    job.d_tokens = ctx->staging.as<float>();
+    job.stride = stride;
+    job.d_doc_off = ctx->staging_rank.as<uint32_t>();
+    job.d_doc_rank = job.d_doc_off + ndocs + 1;
+    job.ndocs = ndocs;
+    job.dims = (uint32_t)dim;
+    job.h_query = q_vals;
+    job.tq = (uint32_t)tq;
+    job.k = k;
+    vb::Status s = vb::maxsim_top_k(*ctx.ctx, job, res);
+    hb.release();
+    return s;
+}
+
+}  // namespace
+
+int vb_multi_vector_top_k(size_t ndocs, const char* ids, const uint64_t* id_off, const float* tok_vals,
+                          const uint64_t* tok_off, const uint64_t* doc_tok, const float* q_vals,
+                          const uint64_t* q_off, size_t tq, int metric_code, size_t limit, vb_hits** out) {
+    *out = nullptr;
+    if (metric_code < 0 || metric_code > 8) return finish(vb::Status::Ref("unknown metric"));   // nifs.rs:196
+    if (const char* e = validate_standalone(q_vals, q_off, 0, tq)) return finish(vb::Status::Ref(e));   // :96
+    const size_t qdim = tq ? (size_t)(q_off[1] - q_off[0]) : 0;
+    size_t good = ndocs;
+    const char* bad_msg = nullptr;
+    for (size_t d = 0; d < ndocs && !bad_msg; ++d) {                      // multi_vector.rs:100-111
+        const size_t t0 = doc_tok[d], t1 = doc_tok[d + 1];
+        const char* e = nullptr;
+        if (tq == 0) e = validate_standalone(tok_vals, tok_off, t0, t1);
+        else if (t0 != t1) e = validate_tokens(tok_vals, tok_off, t0, t1, qdim);
+        if (e) { good = d; bad_msg = e; }
+    }
+    vb::Hits hits;
+    if (good > 0) {
+        std::vector<uint32_t> rank = id_ranks(good, ids, id_off);
+        const size_t ntok = doc_tok[good] - doc_tok[0];
+        if (tq == 0 || ntok == 0) {
+            // every score is 0.0 (:102-106): the best `limit` are simply the smallest ids
+            if (!bad_msg && limit > 0) {
+                std::vector<uint32_t> by_rank(good);
+                for (size_t d = 0; d < good; ++d) by_rank[rank[d]] = (uint32_t)d;
+                for (size_t i = 0; i < std::min(limit, good); ++i) {
+                    const uint32_t d = by_rank[i];
+                    hits.add(ids + id_off[d], id_off[d + 1] - id_off[d], 0.0f, d);
+                }
+            }
+        } else {
+            if (vb_device_count() <= 0) return no_device();
+            vb::MaxSimResult res;
+            vb::Status s = maxsim_by_value(good, tok_vals, tok_off, doc_tok, rank.data(), q_vals + q_off[0], tq, qdim,
+                                           metric_code, std::max<size_t>(1, std::min(limit, good)), &res);
+            if (!s.ok()) return finish(s);
+            if (res.err != vb::kNoError)
+                return finish(vb::Status::Ref((res.err & 1u) ? "score overflow" : "metric overflow"));
+            if (!bad_msg && limit > 0) emit_hits(&hits, ids, id_off, res.rows.data(), res.scores.data(), res.rows.size());
+        }
+    }
+    if (bad_msg) return finish(vb::Status::Ref(bad_msg));
+    *out = new vb_hits{std::move(hits)};
+    return VB_OK;
+}
+
+int vb_multi_vector_score(const float* q_vals, const uint64_t* q_off, size_t tq, const float* d_vals,
+                          const uint64_t* d_off, size_t td, int metric_code, float* out) {
+    *out = 0.0f;
+    if (metric_code < 0 || metric_code > 8) return finish(vb::Status::Ref("unknown metric"));   // nifs.rs:184
+    if (tq == 0) {                                                       // multi_vector.rs:45-48
+        if (const char* e = validate_standalone(d_vals, d_off, 0, td)) return finish(vb::Status::Ref(e));
+        return VB_OK;
+    }
+    const size_t dim = q_off[1] - q_off[0];
+    if (dim == 0) return finish(vb::Status::Ref("vectors must not be empty"));
+    if (const char* e = validate_tokens(q_vals, q_off, 0, tq, dim)) return finish(vb::Status::Ref(e));
+    if (td == 0) return VB_OK;
+    if (const char* e = validate_tokens(d_vals, d_off, 0, td, dim)) return finish(vb::Status::Ref(e));
+    if (vb_device_count() <= 0) return no_device();
+    const uint64_t doc_tok[2] = {0, td};
+    const uint32_t rank0 = 0;
+    vb::MaxSimResult res;
+    vb::Status s = maxsim_by_value(1, d_vals, d_off, doc_tok, &rank0, q_vals + q_off[0], tq, dim, metric_code, 1, &res);
+    if (!s.ok()) return finish(s);
+    if (res.err != vb::kNoError) return finish(vb::Status::Ref((res.err & 1u) ? "score overflow" : "metric overflow"));
+    *out = res.scores.empty() ? 0.0f : res.scores[0];
+    return VB_OK;
+}
+
+int vb_mv_new(int metric_code, vb_mv** out) {
+    *out = nullptr;
+    if (metric_code < 0 || metric_code > 8) return finish(vb::Status::Ref("unknown metric"));
+    if (vb_device_count() <= 0) return no_device();
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return no_device();
+    *out = new vb_mv{new vb::MvIndex(metric_code, dev)};
+    return VB_OK;
+}
+void vb_mv_free(vb_mv* index) {
+    if (!index) return;
+    delete index->impl;
+    delete index;
+}
+int vb_mv_insert_many(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off, const float* tok_vals,
+                      const uint64_t* tok_off, const uint64_t* doc_tok) {
+    return finish(index->impl->insert_many(ndocs, ids, id_off, tok_vals, tok_off, doc_tok));
+}
+int vb_mv_delete(vb_mv* index, const char* id, size_t id_len) { return finish(index->impl->remove(id, id_len)); }
+int vb_mv_search(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, vb_hits** out) {
+    *out = nullptr;
+    vb::Hits hits;
+    vb::Status s = index->impl->search(q_vals, q_off, tq, limit, &hits);
+    if (!s.ok()) return finish(s);
+    *out = new vb_hits{std::move(hits)};
+    return VB_OK;
+}
+int vb_mv_info(vb_mv* index, size_t* docs, size_t* tokens, size_t* dimension) {
+    index->impl->info(docs, tokens, dimension);
     return VB_OK;
 }
 

@@ -1,0 +1,73 @@
+// maxsim.h — K5: MaxSim scoring + top-k over a device-resident token matrix
+// (reference multi_vector.rs:65-132), and the HBM-resident multi-vector index built on it.
+#pragma once
+#include <map>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "runtime.h"
+
+namespace vb {
+
+struct MaxSimJob {
+    int metric = 0;                        // kernel metric (kCosineTrue when the NIF metric is cosine)
+    const float* d_tokens = nullptr;       // [ntok, stride] device
+    size_t stride = 0;                     // floats, multiple of 4
+    const uint32_t* d_doc_off = nullptr;   // [ndocs + 1]
+    const uint32_t* d_doc_rank = nullptr;  // [ndocs] id ranks (0xFFFFFFFF = deleted) or null (= doc index)
+    size_t ndocs = 0;
+    uint32_t dims = 0;
+    const float* h_query = nullptr;        // host [tq, dims]
+    uint32_t tq = 0;
+    size_t k = 0;
+};
+
+struct MaxSimResult {
+    std::vector<uint32_t> rows;   // document indices, best first
+    std::vector<float> scores;
+    uint32_t err = 0xFFFFFFFFu;   // kNoError or (doc << 1 | kind): 0 metric overflow, 1 score overflow
+};
+
+Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out);
+
+// HBM-resident multi-vector collection: token matrix + document offsets + id ranks.
+// Upserts append a fresh copy and tombstone the old one; the matrix is compacted when
+// tombstones outweigh live tokens.
+class MvIndex {
+  public:
+    MvIndex(int metric, int device) : metric_(metric), device_(device) {}
+    ~MvIndex();
+    // Documents: doc i owns tokens [doc_tok[i], doc_tok[i+1]) of the ragged token list.
+    Status insert_many(size_t ndocs, const char* ids, const uint64_t* id_off, const float* tok_vals,
+                       const uint64_t* tok_off, const uint64_t* doc_tok);
+    Status remove(const char* id, size_t id_len);
+    Status search(const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, Hits* out);
+    void info(size_t* docs, size_t* tokens, size_t* dim);
+
+  private:
+    Status reserve_tokens(size_t need);
+    Status reserve_docs(size_t need);
+    Status relabel();
+    Status compact();
+
+    const int metric_;
+    const int device_;
+    std::shared_mutex mu_;
+    size_t dim_ = 0, stride_ = 0;
+    size_t ntok_ = 0, tok_cap_ = 0, dead_tok_ = 0;
+    size_t ndocs_ = 0, doc_cap_ = 0;       // doc slots used (live + tombstoned)
+    float* d_tokens_ = nullptr;
+    uint32_t* d_doc_off_ = nullptr;        // [doc_cap + 1]
+    uint32_t* d_doc_rank_ = nullptr;       // [doc_cap]
+    std::vector<uint32_t> h_doc_off_{0};
+    std::vector<uint32_t> h_rank_;
+    std::vector<std::string> doc_id_;      // slot -> id ("" for tombstones)
+    std::map<std::string, uint32_t> id_doc_;
+};
+
+}  // namespace vb
+
+struct vb_mv {
+    vb::MvIndex* impl;
+};

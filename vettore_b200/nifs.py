@@ -226,3 +226,108 @@ def compress_sign_bits(vector) -> list[int]:
     words = np.zeros((v.size + 63) // 64, dtype=np.uint64)
     lib().vb_compress_sign_bits(_ptr(v, _f32p), v.size, _ptr(words, _u64p))
     return [int(w) for w in words]
+
+
+# ------------------------------------------------------------------ multi-vector (MaxSim)
+def _tokens(docs: Sequence[Sequence[Sequence[float]]]):
+    """Flattens [[token vectors] per doc] into one ragged token list + per-doc token offsets."""
+    toks, doc_tok = [], np.zeros(len(docs) + 1, dtype=np.uint64)
+    for i, vs in enumerate(docs):
+        if isinstance(vs, np.ndarray) and vs.ndim == 2:
+            toks.extend(vs)
+        else:
+            toks.extend(vs)
+        doc_tok[i + 1] = len(toks)
+    vals, off = _ragged(toks, np.float32)
+    return vals, off, doc_tok
+
+
+def multi_vector_score(query_vectors, document_vectors, metric_code: int):
+    """nifs.rs:177-186."""
+    qv, qoff = _ragged(list(query_vectors), np.float32)
+    dv, doff = _ragged(list(document_vectors), np.float32)
+    out = C.c_float()
+    rc = lib().vb_multi_vector_score(_ptr(qv, _f32p), _ptr(qoff, _u64p), len(qoff) - 1, _ptr(dv, _f32p),
+                                     _ptr(doff, _u64p), len(doff) - 1, int(metric_code), C.byref(out))
+    return _err() if rc else ("ok", out.value)
+
+
+def multi_vector_top_k(documents: Sequence[tuple], query_vectors, metric_code: int, limit: int):
+    """nifs.rs:188-198. ``documents`` is a list of ``(id, [token vectors])``."""
+    ids = [d[0] for d in documents]
+    dv, doff, doc_tok = _tokens([d[1] for d in documents])
+    qv, qoff = _ragged(list(query_vectors), np.float32)
+    blob, ioff = _ids_blob(ids)
+    h = C.c_void_p()
+    rc = lib().vb_multi_vector_top_k(len(ids), blob, _ptr(ioff, _u64p), _ptr(dv, _f32p), _ptr(doff, _u64p),
+                                     _ptr(doc_tok, _u64p), _ptr(qv, _f32p), _ptr(qoff, _u64p), len(qoff) - 1,
+                                     int(metric_code), min(int(limit), SIZE_MAX), C.byref(h))
+    return _err() if rc else ("ok", _take_hits(h))
+
+
+class MvRef:
+    """Handle of an HBM-resident multi-vector collection (additive; see include/vettore_b200.h)."""
+
+    def __init__(self, metric: str):
+        h = C.c_void_p()
+        if lib().vb_mv_new(METRIC_CODE[metric], C.byref(h)):
+            raise RuntimeError(_lib.last_error())
+        self._h, self.metric = h, metric
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().vb_mv_free(h)
+            except Exception:
+                pass
+
+    @property
+    def handle(self):
+        return self._h
+
+
+def mv_new(metric: str) -> MvRef:
+    return MvRef(metric)
+
+
+def mv_insert_many(index: MvRef, documents: Sequence[tuple]):
+    ids = [d[0] for d in documents]
+    dv, doff, doc_tok = _tokens([d[1] for d in documents])
+    blob, ioff = _ids_blob(ids)
+    rc = lib().vb_mv_insert_many(index.handle, len(ids), blob, _ptr(ioff, _u64p), _ptr(dv, _f32p), _ptr(doff, _u64p),
+                                 _ptr(doc_tok, _u64p))
+    return _err() if rc else ("ok", ())
+
+
+def mv_insert_tensor(index: MvRef, ids: Sequence, tokens: np.ndarray):
+    """Dense ``[ndocs, tokens_per_doc, dim]`` float32 ingest through the same C entry."""
+    t = np.ascontiguousarray(tokens, dtype=np.float32)
+    nd, tp, d = t.shape
+    vals = t.reshape(-1)
+    off = np.arange(nd * tp + 1, dtype=np.uint64) * np.uint64(d)
+    doc_tok = np.arange(nd + 1, dtype=np.uint64) * np.uint64(tp)
+    blob, ioff = _ids_blob(ids)
+    rc = lib().vb_mv_insert_many(index.handle, nd, blob, _ptr(ioff, _u64p), _ptr(vals, _f32p), _ptr(off, _u64p),
+                                 _ptr(doc_tok, _u64p))
+    return _err() if rc else ("ok", ())
+
+
+def mv_delete(index: MvRef, id):
+    b = _enc(id)
+    rc = lib().vb_mv_delete(index.handle, b, len(b))
+    return _err() if rc else ("ok", ())
+
+
+def mv_search(index: MvRef, query_vectors, limit: int):
+    qv, qoff = _ragged(list(query_vectors) if not isinstance(query_vectors, np.ndarray) else query_vectors, np.float32)
+    h = C.c_void_p()
+    rc = lib().vb_mv_search(index.handle, _ptr(qv, _f32p), _ptr(qoff, _u64p), len(qoff) - 1, min(int(limit), SIZE_MAX),
+                            C.byref(h))
+    return _err() if rc else ("ok", _take_hits(h))
+
+
+def mv_info(index: MvRef):
+    docs, toks, dim = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    lib().vb_mv_info(index.handle, C.byref(docs), C.byref(toks), C.byref(dim))
+    return docs.value, toks.value, (dim.value or None)
