@@ -99,6 +99,21 @@ int vb_flat_prefix_top_k(vb_flat* index, size_t n_ids, const char* ids, const ui
                          const float* query, size_t len, int metric_code, size_t dimensions,
                          size_t limit, vb_hits** out);
 
+/* Additive: funnel_search (collection.ex:244-260, 674-691) run entirely on the resident
+ * matrix. Stage s keeps the best `candidates` rows of the previous stage's survivors under
+ * vector_top_k semantics at prefix stages[s]; the last step is the exact rerank at the full
+ * query length with `limit`. One host synchronisation in total. candidates <= 1024. */
+int vb_flat_funnel_search(vb_flat* index, const float* query, size_t len, int metric_code,
+                          const size_t* stages, size_t n_stages, size_t candidates, size_t limit,
+                          vb_hits** out);
+/* Additive: quantized_search (collection.ex:266-295) on the resident index: the sign-bit
+ * codes of the rows (packed on the device, distances.rs:413-423) are scanned by Hamming
+ * distance for the best `candidates` (distance, then id; bit-exact with binary_top_k,
+ * search.rs:76-92), which are then reranked exactly (vector_top_k at full length).
+ * candidates <= 1024. */
+int vb_flat_quantized_search(vb_flat* index, const float* query, size_t len, int metric_code,
+                             size_t candidates, size_t limit, vb_hits** out);
+
 /* Device-level entry (inputs already in HBM; used for kernel-only timing and by the
  * row-sharded multi-GPU path). Queries: nq rows of `q_stride` floats (q_stride % 4 == 0,
  * zero padded) in device memory. Writes, per query, k = min(limit, rows) sorted entries:

@@ -36,6 +36,8 @@ SIGNATURES = {
     "vb_flat_search_batch": (C.c_int, [_vp, _f32p, _sz, _sz, _sz, _vpp]),
     "vb_flat_info": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "vb_flat_prefix_top_k": (C.c_int, [_vp, _sz, C.c_char_p, _u64p, _f32p, _sz, C.c_int, _sz, _sz, _vpp]),
+    "vb_flat_funnel_search": (C.c_int, [_vp, _f32p, _sz, C.c_int, C.POINTER(_sz), _sz, _sz, _sz, _vpp]),
+    "vb_flat_quantized_search": (C.c_int, [_vp, _f32p, _sz, C.c_int, _sz, _sz, _vpp]),
     "vb_flat_search_device": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "vb_flat_set_id_ranks": (C.c_int, [_vp, _u32p, _sz]),
     "vb_topk_merge_device": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),

@@ -157,6 +157,26 @@ int vb_flat_prefix_top_k(vb_flat* index, size_t n_ids, const char* ids, const ui
     return VB_OK;
 }
 
+int vb_flat_funnel_search(vb_flat* index, const float* query, size_t len, int metric_code, const size_t* stages,
+                          size_t n_stages, size_t candidates, size_t limit, vb_hits** out) {
+    *out = nullptr;
+    vb::Hits hits;
+    vb::Status s = index->impl->funnel_search(query, len, metric_code, stages, n_stages, candidates, limit, &hits);
+    if (!s.ok()) return finish(s);
+    *out = new vb_hits{std::move(hits)};
+    return VB_OK;
+}
+
+int vb_flat_quantized_search(vb_flat* index, const float* query, size_t len, int metric_code, size_t candidates,
+                             size_t limit, vb_hits** out) {
+    *out = nullptr;
+    vb::Hits hits;
+    vb::Status s = index->impl->quantized_search(query, len, metric_code, candidates, limit, &hits);
+    if (!s.ok()) return finish(s);
+    *out = new vb_hits{std::move(hits)};
+    return VB_OK;
+}
+
 int vb_flat_search_device(vb_flat* index, const float* d_queries, size_t nq, size_t q_stride, size_t limit,
                           uint64_t* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, void* stream) {
     return finish(index->impl->search_device(d_queries, nq, q_stride, limit,

@@ -2,6 +2,8 @@
 // (flat.rs:59-144, search.rs:38-73) so errors are indistinguishable at the NIF boundary.
 #include "flat_index.h"
 
+#include "hamming.h"
+
 #include <algorithm>
 #include <cmath>
 #include <mutex>
@@ -39,6 +41,7 @@ FlatIndex::~FlatIndex() {
     }
     if (d_rows_) cudaFree(d_rows_);
     if (d_rank_) cudaFree(d_rank_);
+    if (d_codes_) cudaFree(d_codes_);
 }
 
 void FlatIndex::info(size_t* rows, size_t* dim) {
@@ -68,12 +71,34 @@ Status FlatIndex::grow(size_t need_rows) {
         VB_CUDA(cudaMemcpy(rows, d_rows_, n_ * stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
         VB_CUDA(cudaMemcpy(rank, d_rank_, n_ * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
     }
+    if (d_codes_) {
+        u64* codes = nullptr;
+        VB_CUDA(cudaMalloc(&codes, new_cap * code_words_ * sizeof(u64)));
+        if (n_ > 0) VB_CUDA(cudaMemcpy(codes, d_codes_, n_ * code_words_ * sizeof(u64), cudaMemcpyDeviceToDevice));
+        cudaFree(d_codes_);
+        d_codes_ = codes;
+    }
     if (d_rows_) cudaFree(d_rows_);
     if (d_rank_) cudaFree(d_rank_);
     d_rows_ = rows;
     d_rank_ = rank;
     cap_ = new_cap;
     return Status::Ok();
+}
+
+Status FlatIndex::pack_rows(size_t row0, size_t rows) {
+    if (!d_codes_ || rows == 0) return Status::Ok();
+    VB_TRY(sign_pack_device(d_rows_ + row0 * stride_, stride_, (uint32_t)rows, (uint32_t)dim_,
+                            d_codes_ + row0 * code_words_, nullptr));
+    VB_CUDA(cudaStreamSynchronize(nullptr));
+    return Status::Ok();
+}
+
+Status FlatIndex::ensure_codes() {
+    if (d_codes_ || n_ == 0) return Status::Ok();
+    code_words_ = (dim_ + 63) / 64;
+    VB_CUDA(cudaMalloc(&d_codes_, cap_ * code_words_ * sizeof(u64)));
+    return pack_rows(0, n_);
 }
 
 Status FlatIndex::relabel_all() {
@@ -167,6 +192,7 @@ Status FlatIndex::insert_many(size_t n, const char* ids, const uint64_t* id_off,
                 fill_row(one, i);
                 cudaError_t e = cudaMemcpy(d_rows_ + (size_t)row * stride_, one, row_bytes, cudaMemcpyHostToDevice);
                 if (e != cudaSuccess) st = Status::Cuda(cudaGetErrorString(e));
+                else st = pack_rows(row, 1);
             }
             continue;
         }
@@ -181,6 +207,7 @@ Status FlatIndex::insert_many(size_t n, const char* ids, const uint64_t* id_off,
         ++staged;
     }
     if (st.ok()) st = flush();
+    if (st.ok()) st = pack_rows(n_before, n_ - n_before);
     if (st.ok()) {
         if (relabel_needed) st = relabel_all();
         else if (n_ > n_before) {
@@ -200,8 +227,11 @@ void FlatIndex::reset_if_empty() {
     cap_ = 0;
     if (d_rows_) cudaFree(d_rows_);
     if (d_rank_) cudaFree(d_rank_);
+    if (d_codes_) cudaFree(d_codes_);
     d_rows_ = nullptr;
     d_rank_ = nullptr;
+    d_codes_ = nullptr;
+    code_words_ = 0;
     external_ranks_ = false;
 }
 
@@ -218,6 +248,9 @@ Status FlatIndex::remove(const char* id, size_t id_len) {
         VB_CUDA(cudaMemcpy(d_rows_ + (size_t)row * stride_, d_rows_ + (size_t)last * stride_,
                            stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
         VB_CUDA(cudaMemcpy(d_rank_ + row, d_rank_ + last, sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+        if (d_codes_)
+            VB_CUDA(cudaMemcpy(d_codes_ + (size_t)row * code_words_, d_codes_ + (size_t)last * code_words_,
+                               code_words_ * sizeof(u64), cudaMemcpyDeviceToDevice));
         row_id_[row] = std::move(row_id_[last]);
         h_rank_[row] = h_rank_[last];
         id_row_[row_id_[row]] = row;
@@ -311,6 +344,125 @@ Status FlatIndex::prefix_top_k(bool all_rows, size_t n_ids, const char* ids, con
     }
     ScanResult res;
     VB_TRY(run_scan(*ctx.ctx, job, &res));
+    if (res.err_rows[0] != kNoError) return Status::Ref("metric overflow");
+    if (limit == 0) return Status::Ok();
+    for (uint32_t i = 0; i < res.counts[0]; ++i) {
+        const uint32_t row = res.rows[i];
+        out->add(row_id_[row].data(), row_id_[row].size(), res.raws[i], row);
+    }
+    return Status::Ok();
+}
+
+Status FlatIndex::funnel_search(const float* query, size_t len, int metric_code, const size_t* stages,
+                                size_t nstages, size_t candidates, size_t limit, Hits* out) {
+    *out = Hits{};
+    if (metric_code < 0 || metric_code > 8) return Status::Ref("unknown metric");
+    // Every stage is one vector_top_k call (search.rs:38-73): validate them all up front in
+    // the order the reference would meet them (collection.ex:674-691, then exact_rerank).
+    for (size_t s = 0; s <= nstages; ++s) {
+        const size_t d = s < nstages ? stages[s] : len;
+        if (d == 0 || d > len) return Status::Ref("invalid prefix dimensions");
+        if (!all_finite(query, d)) return Status::Ref("vector contains a non-finite value");
+    }
+    std::shared_lock<std::shared_mutex> g(mu_);
+    if (n_ == 0) return Status::Ok();
+    for (size_t s = 0; s <= nstages; ++s)
+        if ((s < nstages ? stages[s] : len) > dim_) return Status::Ref("dimension mismatch");
+    if (candidates == 0 || std::min(candidates, n_) > (size_t)kMaxFusedK)
+        return Status::Cuda("funnel candidates must be in 1..1024 for the resident pipeline");
+    VB_CUDA(cudaSetDevice(device_));
+    CtxLease ctx;
+    VB_TRY(ctx.get());
+    const uint32_t nslots = (uint32_t)nstages + 1;
+    VB_TRY(ctx->h_misc.reserve(nslots * sizeof(uint32_t)));
+    uint32_t* h_err = ctx->h_misc.as<uint32_t>();
+    for (uint32_t s = 0; s < nslots; ++s) h_err[s] = kNoError;
+    ScanJob job;
+    job.metric = metric_code == kCosine ? kCosineTrue : metric_code;
+    job.d_rows = d_rows_;
+    job.row_stride = stride_;
+    job.d_id_rank = d_rank_;
+    job.h_queries = query;
+    job.nq = 1;
+    job.q_len = len;
+    size_t survivors = n_;
+    for (size_t s = 0; s < nstages; ++s) {
+        job.n = (uint32_t)survivors;
+        job.dims = (uint32_t)stages[s];
+        job.whole_rows = stages[s] == dim_;
+        job.d_row_sel = s == 0 ? nullptr : ctx->row_sel.as<uint32_t>();
+        job.k = std::min(candidates, survivors);
+        VB_TRY(run_scan_to_rows(*ctx.ctx, job, (uint32_t)s, nslots, h_err + s));
+        survivors = job.k;
+    }
+    job.n = (uint32_t)survivors;
+    job.dims = (uint32_t)len;
+    job.whole_rows = len == dim_;
+    job.d_row_sel = nstages == 0 ? nullptr : ctx->row_sel.as<uint32_t>();
+    job.k = std::max<size_t>(1, std::min(limit, survivors));
+    if (job.k > (size_t)kMaxFusedK) return Status::Cuda("limit beyond the fused collector (1024)");
+    ScanResult res;
+    VB_TRY(run_scan_final(*ctx.ctx, job, (uint32_t)nstages, nslots, &res));
+    for (size_t s = 0; s < nstages; ++s)
+        if (h_err[s] != kNoError) return Status::Ref("metric overflow");
+    if (res.err_rows[0] != kNoError) return Status::Ref("metric overflow");
+    if (limit == 0) return Status::Ok();
+    for (uint32_t i = 0; i < res.counts[0]; ++i) {
+        const uint32_t row = res.rows[i];
+        out->add(row_id_[row].data(), row_id_[row].size(), res.raws[i], row);
+    }
+    return Status::Ok();
+}
+
+Status FlatIndex::quantized_search(const float* query, size_t len, int metric_code, size_t candidates, size_t limit,
+                                   Hits* out) {
+    *out = Hits{};
+    if (metric_code < 0 || metric_code > 8) return Status::Ref("unknown metric");
+    if (len == 0) return Status::Ref("vector must not be empty");
+    if (!all_finite(query, len)) return Status::Ref("vector contains a non-finite value");
+    {
+        std::unique_lock<std::shared_mutex> g(mu_);   // first use builds the code mirror
+        if (n_ > 0 && !d_codes_) {
+            VB_CUDA(cudaSetDevice(device_));
+            VB_TRY(ensure_codes());
+        }
+    }
+    std::shared_lock<std::shared_mutex> g(mu_);
+    if (n_ == 0) return Status::Ok();
+    if (len != dim_) return Status::Ref("dimension mismatch");
+    const size_t cand = std::min(candidates, n_);
+    if (cand == 0 || cand > (size_t)kMaxFusedK)
+        return Status::Cuda("quantized candidates must be in 1..1024 for the resident pipeline");
+    VB_CUDA(cudaSetDevice(device_));
+    CtxLease ctx;
+    VB_TRY(ctx.get());
+    // query sign code (distances.rs:413-423), host scalar
+    const size_t nw = code_words_;
+    VB_TRY(ctx->h_misc.reserve(nw * sizeof(u64) + 16));
+    u64* hq = ctx->h_misc.as<u64>();
+    for (size_t w = 0; w < nw; ++w) hq[w] = 0;
+    for (size_t i = 0; i < len; ++i)
+        if (query[i] >= 0.0f) hq[i / 64] |= 1ull << (i % 64);
+    VB_TRY(ctx->staging.reserve(nw * sizeof(u64)));
+    VB_CUDA(cudaMemcpyAsync(ctx->staging.p, hq, nw * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    VB_TRY(hamming_scan_device(*ctx.ctx, d_codes_, (uint32_t)n_, (uint32_t)nw, (uint32_t)dim_, d_rank_,
+                               ctx->staging.as<u64>(), 1, (uint32_t)cand, ctx->stream));
+    VB_TRY(extract_rows(*ctx.ctx, ctx->result.as<u64>(), (uint32_t)cand));
+    ScanJob job;
+    job.metric = metric_code == kCosine ? kCosineTrue : metric_code;   // exact_rerank -> vector_top_k
+    job.d_rows = d_rows_;
+    job.row_stride = stride_;
+    job.d_id_rank = d_rank_;
+    job.d_row_sel = ctx->row_sel.as<uint32_t>();
+    job.n = (uint32_t)cand;
+    job.dims = (uint32_t)dim_;
+    job.whole_rows = true;
+    job.h_queries = query;
+    job.nq = 1;
+    job.q_len = len;
+    job.k = std::max<size_t>(1, std::min(limit, cand));
+    ScanResult res;
+    VB_TRY(run_scan_final(*ctx.ctx, job, 0, 1, &res));
     if (res.err_rows[0] != kNoError) return Status::Ref("metric overflow");
     if (limit == 0) return Status::Ok();
     for (uint32_t i = 0; i < res.counts[0]; ++i) {

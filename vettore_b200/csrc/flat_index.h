@@ -34,6 +34,15 @@ class FlatIndex {
     // search.rs:38-73 over resident rows (all rows, or the listed ids).
     Status prefix_top_k(bool all_rows, size_t n_ids, const char* ids, const uint64_t* id_off, const float* query,
                         size_t len, int metric_code, size_t dimensions, size_t limit, Hits* out);
+    // funnel_search (collection.ex:244-260) on the resident matrix: every stage is a
+    // vector_top_k over the survivors of the previous one, then the exact rerank; one host
+    // synchronisation for the whole pipeline.
+    Status funnel_search(const float* query, size_t len, int metric_code, const size_t* stages, size_t nstages,
+                         size_t candidates, size_t limit, Hits* out);
+    // quantized_search (collection.ex:266-295): sign-code Hamming candidates over the code
+    // mirror of the rows (K3), then the exact rerank of those rows (K4).
+    Status quantized_search(const float* query, size_t len, int metric_code, size_t candidates, size_t limit,
+                            Hits* out);
     Status search_device(const float* d_queries, size_t nq, size_t q_stride, size_t limit, u64* d_keys,
                          float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream);
     Status set_id_ranks(const uint32_t* ranks, size_t n);
@@ -45,6 +54,8 @@ class FlatIndex {
 
   private:
     Status grow(size_t need_rows);
+    Status ensure_codes();                       // builds the sign-code mirror on first use (K6)
+    Status pack_rows(size_t row0, size_t rows);  // (re)packs rows [row0, row0 + rows)
     Status relabel_all();
     Status assign_rank(std::map<std::string, uint32_t>::iterator it, uint32_t row, bool* relabel_needed);
     void reset_if_empty();
@@ -57,6 +68,8 @@ class FlatIndex {
     size_t n_ = 0, cap_ = 0;
     float* d_rows_ = nullptr;
     uint32_t* d_rank_ = nullptr;
+    u64* d_codes_ = nullptr;   // [cap, code_words_] sign codes of the rows, kept in sync once built
+    size_t code_words_ = 0;
     std::vector<std::string> row_id_;
     std::vector<uint32_t> h_rank_;
     std::map<std::string, uint32_t> id_row_;

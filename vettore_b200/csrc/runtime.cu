@@ -49,7 +49,7 @@ Status SearchCtx::arm_ctrl(uint32_t nq) {
 void SearchCtx::destroy() {
     cudaSetDevice(device);
     DeviceBuf* dbufs[] = {&queries, &q_norms, &cand_keys, &cand_pays, &cand_counts, &ctrl, &out_keys, &result,
-                          &row_sel, &staging, &staging_rank, &dump_keys, &dump_pays, &dump_keys2, &dump_pays2,
+                          &row_sel, &row_sel2, &staging, &staging_rank, &dump_keys, &dump_pays, &dump_keys2, &dump_pays2,
                           &sort_tmp};
     for (DeviceBuf* b : dbufs) b->release();
     h_queries.release();

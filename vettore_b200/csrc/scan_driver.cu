@@ -200,6 +200,100 @@ Status run_scan(SearchCtx& ctx, const ScanJob& job, ScanResult* out) {
     return Status::Ok();
 }
 
+__global__ void extract_rows_kernel(const u64* pays, uint32_t n, uint32_t* rows) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rows[i] = (uint32_t)pays[i];
+}
+
+Status extract_rows(SearchCtx& ctx, const u64* d_pays, uint32_t n) {
+    VB_TRY(ctx.row_sel2.reserve((size_t)n * sizeof(uint32_t)));
+    extract_rows_kernel<<<(n + 255) / 256, 256, 0, ctx.stream>>>(d_pays, n, ctx.row_sel2.as<uint32_t>());
+    VB_CUDA(cudaGetLastError());
+    std::swap(ctx.row_sel, ctx.row_sel2);   // the new list becomes the current one
+    return Status::Ok();
+}
+
+// Pipeline stages run back to back without host synchronisation, so every stage gets its
+// own slot of the pinned / device query buffers (an async H2D copy reads the pinned source
+// when it executes, not when it is enqueued). Slot layout: round4(q_len) floats | f64 norm.
+static Status stage_query_slot(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_t nslots,
+                               const float** d_q, size_t* q_stride, const double** d_norm) {
+    const size_t full = ((size_t)job.q_len + 3) & ~(size_t)3;
+    const size_t slot_floats = full + 4;
+    VB_TRY(ctx.h_queries.reserve(nslots * slot_floats * sizeof(float)));   // no-op after the first stage
+    VB_TRY(ctx.queries.reserve(nslots * slot_floats * sizeof(float)));
+    float* hq = ctx.h_queries.as<float>() + slot * slot_floats;
+    float* dq = ctx.queries.as<float>() + slot * slot_floats;
+    const size_t stride = ((size_t)job.dims + 3) & ~(size_t)3;
+    std::memcpy(hq, job.h_queries, job.dims * sizeof(float));
+    for (size_t i = job.dims; i < full; ++i) hq[i] = 0.0f;
+    double s = 0.0;
+    for (uint32_t i = 0; i < job.dims; ++i) s += (double)job.h_queries[i] * (double)job.h_queries[i];
+    *reinterpret_cast<double*>(hq + full) = std::sqrt(s);
+    VB_CUDA(cudaMemcpyAsync(dq, hq, slot_floats * sizeof(float), cudaMemcpyHostToDevice, ctx.stream));
+    *d_q = dq;
+    *q_stride = stride;
+    *d_norm = reinterpret_cast<const double*>(dq + full);
+    return Status::Ok();
+}
+
+Status run_scan_to_rows(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_t nslots, uint32_t* h_err) {
+    if (job.n == 0 || job.k == 0 || job.nq != 1) return Status::Cuda("bad pipeline stage");
+    const size_t k = std::min<size_t>(job.k, job.n);
+    if (k > (size_t)kMaxFusedK) return Status::Cuda("stage candidates beyond the fused collector (1024)");
+    size_t q_stride = 0;
+    const float* d_q = nullptr;
+    const double* d_norm = nullptr;
+    VB_TRY(stage_query_slot(ctx, job, slot, nslots, &d_q, &q_stride, &d_norm));
+    ScanPlan plan;
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, job.d_row_sel == nullptr && job.whole_rows, job.n,
+                          (uint32_t)k, false, &plan));
+    VB_TRY(prepare_workspace(ctx, plan, 1, k));
+    ScanParams p;
+    fill_params(ctx, job, d_q, q_stride, d_norm, k, &p);
+    Status s = run_flat_scan(plan, p, 1, ctx.stream);
+    if (!s.ok()) { ctx.poison(); return s; }
+    VB_CUDA(cudaMemcpyAsync(h_err, p.ws.out_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
+    return extract_rows(ctx, p.ws.out_pays, (uint32_t)k);
+}
+
+// Final stage of a pipeline: like run_scan for one query, but staged in its own query slot.
+Status run_scan_final(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_t nslots, ScanResult* out) {
+    if (job.n == 0 || job.k == 0 || job.nq != 1) return Status::Cuda("bad pipeline stage");
+    const size_t k = std::min<size_t>(job.k, job.n);
+    if (k > (size_t)kMaxFusedK) return Status::Cuda("limit beyond the fused collector (1024)");
+    size_t q_stride = 0;
+    const float* d_q = nullptr;
+    const double* d_norm = nullptr;
+    VB_TRY(stage_query_slot(ctx, job, slot, nslots, &d_q, &q_stride, &d_norm));
+    ScanPlan plan;
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, job.d_row_sel == nullptr && job.whole_rows, job.n,
+                          (uint32_t)k, false, &plan));
+    VB_TRY(prepare_workspace(ctx, plan, 1, k));
+    ScanParams p;
+    fill_params(ctx, job, d_q, q_stride, d_norm, k, &p);
+    Status s = run_flat_scan(plan, p, 1, ctx.stream);
+    if (!s.ok()) { ctx.poison(); return s; }
+    const size_t bytes = k * sizeof(u64) + 8;
+    VB_TRY(ctx.h_result.reserve(bytes));
+    cudaError_t e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, bytes, cudaMemcpyDeviceToHost, ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx.stream);
+    if (e != cudaSuccess) { ctx.poison(); return Status::Cuda(cudaGetErrorString(e)); }
+    const u64* pays = ctx.h_result.as<u64>();
+    const uint32_t* tail = reinterpret_cast<const uint32_t*>(pays + k);
+    out->k = k;
+    out->counts.assign(1, tail[0]);
+    out->err_rows.assign(1, tail[1]);
+    out->rows.resize(k);
+    out->raws.resize(k);
+    for (size_t i = 0; i < k; ++i) {
+        uint32_t bits = (uint32_t)(pays[i] >> 32);
+        std::memcpy(&out->raws[i], &bits, 4);
+        out->rows[i] = (uint32_t)pays[i];
+    }
+    return Status::Ok();
+}
+
 Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_queries, size_t q_stride,
                        const double* d_q_norms, u64* d_keys, float* d_values, uint32_t* d_rows,
                        uint32_t* d_counts, cudaStream_t stream) {

@@ -33,6 +33,16 @@ struct ScanResult {
 
 Status run_scan(SearchCtx& ctx, const ScanJob& job, ScanResult* out);
 
+// Pipeline stage: same scan, but the k = min(job.k, job.n) winning device rows stay on the
+// device (ctx.row_sel[0..k)) to drive the next stage as its row list; the stage's overflow
+// word is copied asynchronously into *h_err (pinned). No host synchronisation.
+Status run_scan_to_rows(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_t nslots, uint32_t* h_err);
+// Last stage: results come back to the host (one synchronisation for the whole pipeline).
+Status run_scan_final(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_t nslots, ScanResult* out);
+
+// Copies the rows (low 32 bits) of `n` payloads into ctx.row_sel on the stream.
+Status extract_rows(SearchCtx& ctx, const u64* d_pays, uint32_t n);
+
 // Device-resident variant: queries already on the device, sorted results stay on the device.
 Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_queries, size_t q_stride,
                        const double* d_q_norms, u64* d_keys, float* d_values, uint32_t* d_rows,

@@ -196,6 +196,25 @@ def flat_prefix_top_k(index: FlatRef, ids: Sequence | None, query, metric_code: 
     return _err() if rc else ("ok", _take_hits(h))
 
 
+def flat_funnel_search(index: FlatRef, query, metric_code: int, stages: Sequence[int], candidates: int, limit: int):
+    """Additive: the whole funnel pipeline (collection.ex:244-260) on the resident matrix."""
+    q = _f32(query)
+    st = (C.c_size_t * len(stages))(*[int(s) for s in stages])
+    h = C.c_void_p()
+    rc = lib().vb_flat_funnel_search(index.handle, _ptr(q, _f32p), q.size, int(metric_code), st, len(stages),
+                                     int(candidates), int(limit), C.byref(h))
+    return _err() if rc else ("ok", _take_hits(h))
+
+
+def flat_quantized_search(index: FlatRef, query, metric_code: int, candidates: int, limit: int):
+    """Additive: Hamming candidates over the resident sign codes + exact rerank (collection.ex:266-295)."""
+    q = _f32(query)
+    h = C.c_void_p()
+    rc = lib().vb_flat_quantized_search(index.handle, _ptr(q, _f32p), q.size, int(metric_code), int(candidates),
+                                        int(limit), C.byref(h))
+    return _err() if rc else ("ok", _take_hits(h))
+
+
 def vector_top_k(vectors: Sequence[tuple], query, metric_code: int, dimensions: int, limit: int):
     """nifs.rs:151-162."""
     ids = [v[0] for v in vectors]
