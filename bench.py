@@ -300,14 +300,19 @@ def run_b200(args):
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": args.steps * sharded.launches_per_search,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "flat_scan_kernel<cosine,NV=6> (+2 us unpack kernel inside the timed launch pair)",
+                         "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed
+                         # ncu --set full capture (profiles/r1_flat_stream_ncu_summary.txt); default shape only
+                         "traffic": 3.0802e9 if (n, d, k) == (1_000_000, 768, 10) else None,
+                         "peak_source": peak_src,
+                         "kernel": "vb::flat_stream_kernel<cosine, NV=6, RPW=1, W=16> (TMA-staged ring; the timed "
+                                   "launch pair also holds the ~3 us unpack kernel)",
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
         }
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             threads = os.cpu_count() or 1
-            nq = 2 * threads
+            nq = 4 * threads
             secs, _ = oracle.flat_scan_timed("cosine", host_rows, q_host[:nq].numpy() if nq <= args.queries
                                              else np.tile(q_host.numpy(), (nq // args.queries + 1, 1))[:nq], k, threads)
             line["cpu_baseline"] = {"value": nq / secs, "unit": "queries/s", "cores": threads, "kind": "port",
