@@ -125,3 +125,45 @@ def test_resident_index_matches_by_value_and_handles_mutation():
     assert_hits_match(ok(nifs.mv_search(idx, q, 10)), ok(oracle.multi_vector_top_k(docs2, q, 3, 10)))
     assert err(nifs.mv_search(idx, q[:, :5], 10)) == "dimension mismatch"
     assert ok(nifs.mv_search(idx, [], 3)) == ok(oracle.multi_vector_top_k(docs2, [], 3, 3))
+
+
+# ------------------------------------------------------------------ tensor-core path (uniform documents)
+def _uniform_docs(ndocs, td, dim, seed, normalise=True):
+    rng = np.random.default_rng(seed)
+    t = rng.standard_normal((ndocs, td, dim)).astype(np.float32)
+    if normalise:
+        t = (t / np.linalg.norm(t.astype(np.float64), axis=2, keepdims=True)).astype(np.float32)
+    ids = [f"doc-{(i * 7919) % ndocs:06d}" for i in range(ndocs)]
+    return ids, t
+
+
+@pytest.mark.parametrize("metric", ["inner_product", "negative_inner_product", "cosine"])
+@pytest.mark.parametrize("ndocs,td,dim,tq", [(700, 128, 128, 32), (1000, 64, 64, 7), (900, 32, 96, 1), (333, 128, 32, 20)])
+def test_tensor_core_maxsim_matches_oracle(metric, ndocs, td, dim, tq):
+    ids, toks = _uniform_docs(ndocs, td, dim, seed=ndocs + td, normalise=(metric != "cosine"))
+    rng = np.random.default_rng(11)
+    q = rng.standard_normal((tq, dim)).astype(np.float32)
+    if metric != "cosine":
+        q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    idx = nifs.mv_new(metric)
+    assert nifs.mv_insert_tensor(idx, ids, toks) == ("ok", ())
+    docs = [(ids[i], toks[i]) for i in range(ndocs)]
+    code = nifs.METRIC_CODE[metric]
+    for limit in (1, 10, 100):
+        assert_hits_match(ok(nifs.mv_search(idx, q, limit)), ok(oracle.multi_vector_top_k(docs, q, code, limit)))
+    # deleting and upserting keeps the uniform layout (tombstones are skipped by the epilogue)
+    best = ok(nifs.mv_search(idx, q, 1))[0][0]
+    assert nifs.mv_delete(idx, best) == ("ok", ())
+    docs2 = [d for d in docs if d[0] != best]
+    assert_hits_match(ok(nifs.mv_search(idx, q, 10)), ok(oracle.multi_vector_top_k(docs2, q, code, 10)))
+
+
+def test_tensor_core_and_general_kernels_agree(monkeypatch):
+    ids, toks = _uniform_docs(512, 128, 128, seed=3)
+    q = _uniform_docs(1, 32, 128, seed=4)[1][0]
+    idx = nifs.mv_new("inner_product")
+    assert nifs.mv_insert_tensor(idx, ids, toks) == ("ok", ())
+    tc = ok(nifs.mv_search(idx, q, 50))
+    monkeypatch.setenv("VB_MAXSIM_NO_TC", "1")
+    general = ok(nifs.mv_search(idx, q, 50))
+    assert_hits_match(tc, general)

@@ -10,6 +10,8 @@
 // register-tiled blocks (each thread a 4 x 4 patch) from shared-memory chunks of 32 dims.
 #include "maxsim.h"
 
+#include <cstdlib>
+
 #include "topk.cuh"
 
 namespace vb {
@@ -229,6 +231,8 @@ Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out) {
     if (job.ndocs == 0 || job.k == 0 || job.tq == 0) return Status::Cuda("empty maxsim job");
     const uint32_t k = (uint32_t)std::min<size_t>(job.k, job.ndocs);
     if (k > (uint32_t)kMaxFusedK) return Status::Cuda("multi-vector limit beyond the fused collector (1024)");
+    if (maxsim_tc_eligible(job, job.uniform_td) && (job.metric != kCosineTrue || job.d_inv_dnorm))
+        return maxsim_tc_top_k(ctx, job, job.uniform_td, job.d_inv_dnorm, out);
     MaxSimKernel kernel = maxsim_lookup(job.metric);
     if (!kernel) return Status::Ref("unknown metric");
 

@@ -21,6 +21,8 @@ struct MaxSimJob {
     const float* h_query = nullptr;        // host [tq, dims]
     uint32_t tq = 0;
     size_t k = 0;
+    uint32_t uniform_td = 0;               // every document slot has exactly this many tokens (0 = ragged)
+    const float* d_inv_dnorm = nullptr;    // [ntok] 1/|token| (device), enables the tensor-core cosine path
 };
 
 struct MaxSimResult {
@@ -30,6 +32,11 @@ struct MaxSimResult {
 };
 
 Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out);
+
+// Tensor-core path (maxsim_tc.cu): inner-product family, uniform documents of 32/64/128
+// tokens, dims a multiple of 32 up to 128, at most 32 query tokens.
+bool maxsim_tc_eligible(const MaxSimJob& job, uint32_t uniform_td);
+Status maxsim_tc_top_k(SearchCtx& ctx, const MaxSimJob& job, uint32_t td, const float* d_inv_dnorm, MaxSimResult* out);
 
 // HBM-resident multi-vector collection: token matrix + document offsets + id ranks.
 // Upserts append a fresh copy and tombstone the old one; the matrix is compacted when
@@ -58,6 +65,9 @@ class MvIndex {
     size_t ntok_ = 0, tok_cap_ = 0, dead_tok_ = 0;
     size_t ndocs_ = 0, doc_cap_ = 0;       // doc slots used (live + tombstoned)
     float* d_tokens_ = nullptr;
+    float* d_inv_norm_ = nullptr;          // [tok_cap] 1/|token| in f32 (0 for zero tokens)
+    uint32_t uniform_td_ = 0;              // tokens per document while all slots agree, else 0
+    bool uniform_known_ = false;
     uint32_t* d_doc_off_ = nullptr;        // [doc_cap + 1]
     uint32_t* d_doc_rank_ = nullptr;       // [doc_cap]
     std::vector<uint32_t> h_doc_off_{0};

@@ -1,0 +1,373 @@
+// maxsim_tc.cu — K5 on the 5th-gen tensor cores: ColBERT MaxSim for the inner-product
+// family (inner product, negative inner product, renormalising cosine) over uniform-length
+// documents, as a 3xTF32 tcgen05 contraction with the max-reduce + sum + top-k fused into
+// the epilogue (reference multi_vector.rs:65-132).
+//
+// Shape of the work (C5: 1M docs x 128 tokens x 128 dims, 32 query tokens): the token matrix
+// is streamed once (tokens * D * 4 bytes, HBM-bound at 16 flop/B), every 128-token tile is a
+// [128 x D] . [D x 32] product. Per SM, one persistent CTA of 10 warps:
+//   warp 8      producer: TMA 2D tiled loads (128-byte swizzle) of token tiles into a 2-stage ring
+//   warps 4-7   split: each thread owns one token row (= one TMEM lane), reads it from the
+//               swizzled tile (conflict-free 128-bit LDS), splits x = hi + lo and writes both
+//               halves into TMEM with tcgen05.st (A operand from TMEM: no second smem round trip)
+//   warp 9      MMA issuer: per tile 3 * D/8 tcgen05.mma kind::tf32 (A in TMEM, B = query
+//               tokens resident in shared memory in the UMMA K-major SWIZZLE_128B layout),
+//               fp32 accumulators in TMEM (4 buffers of 32 columns)
+//   warps 0-3   epilogue: tcgen05.ld the [128 x 32] tile, similarity transform, per-query max
+//               over each document's tokens (31-shuffle transpose butterfly + shared memory
+//               across warps), f32 sum in query order, collector push (topk.cuh)
+#include "maxsim.h"
+#include "tc.cuh"
+#include "topk.cuh"
+
+namespace vb {
+
+constexpr int kTcEpiWarps = 4, kTcSplitWarps = 4;
+constexpr int kTcThreads = (kTcEpiWarps + kTcSplitWarps + 2) * 32;   // + producer + MMA issuer
+constexpr int kTcStages = 2;
+constexpr int kTcAccBufs = 4;
+constexpr int kTcTile = 128;    // tokens per tile (UMMA M)
+constexpr int kTcN = 32;        // query tokens (UMMA N), zero padded
+
+struct MaxSimTcParams {
+    uint32_t ndocs, td, dims, tq;
+    int metric;                   // kInnerProduct, kNegativeInnerProduct or kCosineTrue
+    const uint32_t* doc_rank;     // [ndocs] or null
+    const float* inv_dnorm;       // [ndocs * td] 1/|token| (0 for zero tokens), cosine only
+    const float* query;           // [tq, dims]
+    const float* inv_qnorm;       // [tq], cosine only
+    uint32_t cap;
+    uint32_t* err;
+    TopkWorkspace ws;
+};
+
+// Max over the 32 lanes of a warp for 32 per-lane values at once: after the butterfly lane q
+// holds max_l v_l[q]. 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_transpose_max(float (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool hi = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = hi ? v[i] : v[i + half];
+            const float keep = hi ? v[i + half] : v[i];
+            v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, half));
+        }
+    }
+    return v[0];   // lane q: query index = bit-reversal-free mapping below
+}
+// The butterfly above leaves in lane L the value of index idx(L) = sum over steps of
+// (L & half ? half : 0) = L itself (each step keeps the upper half in lanes with the bit set).
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages];
+    __shared__ __align__(8) uint64_t a_ready, a_free, d_full[kTcAccBufs], d_free[kTcAccBufs];
+    __shared__ uint32_t tmem_slot;
+    __shared__ u64 s_thresh;
+    __shared__ uint32_t s_count;
+    __shared__ int s_last;
+    __shared__ float s_part[kTcAccBufs][4][kTcN];
+    __shared__ float s_invq[kTcN];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t KB = p.dims / 32;                        // 128-byte K blocks per row
+    const uint32_t stage_bytes = KB * 16384u;               // [128 rows x 128 B] per K block
+    unsigned char* ring = smem;
+    unsigned char* b_hi = ring + (size_t)kTcStages * stage_bytes;   // KB x [32 rows x 128 B]
+    unsigned char* b_lo = b_hi + (size_t)KB * 4096;
+    unsigned char* col_mem = b_lo + (size_t)KB * 4096;
+
+    Collector col;
+    col.init(col_mem, &s_thresh, &s_count, p.cap, p.ws.k, kTcEpiWarps * 32, 2);
+    if (tid == 0) {
+        for (int s = 0; s < kTcStages; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], kTcSplitWarps);
+        }
+        tc::mbar_init(&a_ready, kTcSplitWarps);
+        tc::mbar_init(&a_free, 1);
+        for (int b = 0; b < kTcAccBufs; ++b) {
+            tc::mbar_init(&d_full[b], 1);
+            tc::mbar_init(&d_free[b], kTcEpiWarps);
+        }
+        tc::mbar_fence_init();
+    }
+    if (warp == 9) tc::tmem_alloc(&tmem_slot, 512);
+    if (tid < kTcN) s_invq[tid] = (p.inv_qnorm && (uint32_t)tid < p.tq) ? p.inv_qnorm[tid] : 0.0f;
+    // B operand: the query tokens, split hi/lo, UMMA K-major SWIZZLE_128B layout; rows >= tq are zero.
+    for (uint32_t idx = tid; idx < (uint32_t)kTcN * p.dims; idx += kTcThreads) {
+        const uint32_t n = idx / p.dims, k = idx % p.dims;
+        const float x = n < p.tq ? p.query[(size_t)n * p.dims + k] : 0.0f;
+        const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        const uint32_t off = (k / 32u) * 4096u + tc::sw128_offset(n, k % 32u);
+        *reinterpret_cast<float*>(b_hi + off) = hi;
+        *reinterpret_cast<float*>(b_lo + off) = x - hi;
+    }
+    tc::fence_proxy_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+
+    const uint32_t ntok = p.ndocs * p.td;
+    const uint32_t num_tiles = (ntok + kTcTile - 1) / kTcTile;
+    const uint32_t docs_per_tile = kTcTile / p.td;          // td in {32, 64, 128}
+
+    if (warp == 8) {
+        // ===== producer =====
+        if (lane == 0) {
+            tc::tma_prefetch_desc(&tmap);
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+                tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+                tc::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                for (uint32_t kb = 0; kb < KB; ++kb)
+                    tc::tma_load_2d(ring + (size_t)s * stage_bytes + (size_t)kb * 16384, &tmap, kb * 32, tile * kTcTile,
+                                    &full_bar[s]);
+            }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = tc::umma_idesc_tf32(kTcTile, kTcN);
+            const uint32_t b_hi_addr = tc::smem_addr(b_hi), b_lo_addr = tc::smem_addr(b_lo);
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t b = it % kTcAccBufs;
+                tc::mbar_wait(&a_ready, it & 1u);
+                tc::mbar_wait(&d_free[b], ((it / kTcAccBufs) & 1u) ^ 1u);
+                tc::fence_after_sync();
+                const uint32_t d_tmem = tbase + 256u + b * kTcN;
+                uint32_t acc = 0;
+                for (uint32_t kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 4; ++ks) {
+                        const uint64_t bh = tc::umma_smem_desc_sw128(b_hi_addr + kb * 4096u + ks * 32u);
+                        const uint64_t bl = tc::umma_smem_desc_sw128(b_lo_addr + kb * 4096u + ks * 32u);
+                        const uint32_t ah = tbase + kb * 32u + ks * 8u, al = ah + 128u;
+                        tc::umma_tf32_ts(d_tmem, ah, bh, idesc, acc);
+                        acc = 1;
+                        tc::umma_tf32_ts(d_tmem, ah, bl, idesc, 1);
+                        tc::umma_tf32_ts(d_tmem, al, bh, idesc, 1);
+                    }
+                }
+                tc::umma_commit(&a_free);      // the A operand may be overwritten
+                tc::umma_commit(&d_full[b]);   // the accumulator is complete
+            }
+        }
+    } else if (warp >= kTcEpiWarps) {
+        // ===== split warps: smem tile -> (hi, lo) -> TMEM =====
+        const uint32_t quarter = warp & 3u;
+        const uint32_t row = quarter * 32u + lane;            // token row within the tile == TMEM lane
+        const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+            tc::mbar_wait(&full_bar[s], ph);
+            tc::mbar_wait(&a_free, (it & 1u) ^ 1u);           // MMAs of the previous tile have read A
+            tc::fence_after_sync();
+            const unsigned char* tile_base = ring + (size_t)s * stage_bytes;
+            for (uint32_t kb = 0; kb < KB; ++kb) {
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) {
+                    const float4 v = *reinterpret_cast<const float4*>(tile_base + (size_t)kb * 16384 + row * 128u +
+                                                                      ((c ^ (row & 7u)) << 4));
+                    const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t h = __float_as_uint(xs[e]) & 0xFFFFE000u;
+                        hi[c * 4 + e] = h;
+                        lo[c * 4 + e] = __float_as_uint(xs[e] - __uint_as_float(h));
+                    }
+                }
+                tc::tmem_st32(lane_addr + kb * 32u, hi);
+                tc::tmem_st32(lane_addr + 128u + kb * 32u, lo);
+            }
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                tc::mbar_arrive(&a_ready);
+                tc::mbar_arrive(&empty_bar[s]);   // this warp's rows of the stage are consumed
+            }
+        }
+    } else {
+        // ===== epilogue warps 0-3 =====
+        const uint32_t quarter = warp;                        // TMEM lanes [32 * warp, +32)
+        const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
+        const uint32_t warps_per_doc = p.td / 32u;            // 1, 2 or 4
+        u64 g_prefetch = kKeyMax;
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t b = it % kTcAccBufs;
+            const uint32_t token = tile * kTcTile + quarter * 32u + lane;
+            float inv_dn = 1.0f;
+            if (p.metric == kCosineTrue) inv_dn = token < ntok ? __ldg(p.inv_dnorm + token) : 0.0f;
+            tc::mbar_wait(&d_full[b], (it / kTcAccBufs) & 1u);
+            tc::fence_after_sync();
+            uint32_t r[32];
+            tc::tmem_ld32(lane_addr + 256u + b * kTcN, r);
+            tc::tmem_ld_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&d_free[b]);
+            float v[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                float sdot = __uint_as_float(r[q]);
+                float sim;
+                if (p.metric == kCosineTrue) {
+                    sim = sdot * s_invq[q] * inv_dn;                       // distances.rs:170-172
+                    sim = fminf(1.0f, fmaxf(-1.0f, sim));
+                } else if (p.metric == kNegativeInnerProduct) {
+                    sim = sdot;                                             // similarity(-raw) with raw = -dot
+                } else {
+                    sim = sdot;
+                }
+                v[q] = token < ntok ? sim : -INFINITY;
+            }
+            const float wmax = warp_transpose_max(v, lane);                // lane q: max over this warp's tokens
+            s_part[b][quarter][lane] = wmax;
+            col.sync();                                                      // 4 epilogue warps
+            // document leaders: the first warp of each document combines its warps and sums over queries
+            if ((quarter % warps_per_doc) == 0) {
+                float m = wmax;
+                for (uint32_t w = 1; w < warps_per_doc; ++w) m = fmaxf(m, s_part[b][quarter + w][lane]);
+                const uint32_t doc = tile * docs_per_tile + quarter / warps_per_doc;
+                float total = 0.0f;
+                bool overflow = false;
+                for (uint32_t q = 0; q < p.tq; ++q) {                       // multi_vector.rs:81-84
+                    total += __shfl_sync(0xffffffffu, m, q);
+                    overflow |= !isfinite(total);
+                }
+                if (lane == 0 && doc < p.ndocs) {
+                    const uint32_t rank = p.doc_rank ? __ldg(p.doc_rank + doc) : doc;
+                    if (rank != 0xFFFFFFFFu) {
+                        if (overflow) { atomicMin(p.err, (doc << 1) | 1u); total = 0.0f; }
+                        const u64 key = ((u64)(~order_key(total)) << 32) | rank;
+                        if (key < col.threshold()) col.push(key, ((u64)__float_as_uint(total) << 32) | doc);
+                    }
+                }
+            }
+            if ((it & 15u) == 15u) collector_checkpoint(col, p.ws, 0, 16 * 4, g_prefetch);
+        }
+        collector_publish_and_merge(col, p.ws, 0, &s_last);
+    }
+    // teardown: every role is done with TMEM before it is released
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 9) tc::tmem_dealloc(tbase, 512);
+}
+
+bool maxsim_tc_eligible(const MaxSimJob& job, uint32_t uniform_td) {
+    if (std::getenv("VB_MAXSIM_NO_TC")) return false;
+    if (job.metric != kInnerProduct && job.metric != kNegativeInnerProduct && job.metric != kCosineTrue) return false;
+    if (job.dims % 32 != 0 || job.dims > 128 || job.stride != job.dims) return false;
+    if (job.tq == 0 || job.tq > (uint32_t)kTcN) return false;
+    if (uniform_td != 32 && uniform_td != 64 && uniform_td != 128) return false;
+    if (std::min<size_t>(job.k, job.ndocs) > (size_t)kMaxFusedK) return false;
+    return true;
+}
+
+Status maxsim_tc_top_k(SearchCtx& ctx, const MaxSimJob& job, uint32_t td, const float* d_inv_dnorm,
+                       MaxSimResult* out) {
+    out->rows.clear();
+    out->scores.clear();
+    out->err = kNoError;
+    const uint32_t k = (uint32_t)std::min<size_t>(job.k, job.ndocs);
+    const uint32_t KB = job.dims / 32;
+    // query tokens + their inverse norms (f64 norm, reference distances.rs:165)
+    const size_t qbytes = (size_t)job.tq * job.dims * sizeof(float);
+    VB_TRY(ctx.h_queries.reserve(qbytes + kTcN * sizeof(float)));
+    VB_TRY(ctx.queries.reserve(qbytes + kTcN * sizeof(float)));
+    float* hq = ctx.h_queries.as<float>();
+    std::memcpy(hq, job.h_query, qbytes);
+    float* hinv = hq + (size_t)job.tq * job.dims;
+    for (uint32_t q = 0; q < (uint32_t)kTcN; ++q) {
+        double s = 0.0;
+        if (q < job.tq)
+            for (uint32_t i = 0; i < job.dims; ++i) {
+                const double x = job.h_query[(size_t)q * job.dims + i];
+                s += x * x;
+            }
+        hinv[q] = s > 0.0 ? (float)(1.0 / std::sqrt(s)) : 0.0f;
+    }
+    VB_CUDA(cudaMemcpyAsync(ctx.queries.p, hq, qbytes + kTcN * sizeof(float), cudaMemcpyHostToDevice, ctx.stream));
+
+    CUtensorMap tmap;
+    VB_TRY(make_tmap_rows_sw128(job.d_tokens, (uint64_t)job.ndocs * td, job.stride, kTcTile, &tmap));
+
+    uint32_t cap = 256;
+    while (cap < 2 * k || cap < k + 64) cap <<= 1;
+    const size_t smem = (size_t)kTcStages * KB * 16384 + 2 * (size_t)KB * 4096 + (size_t)cap * 16 + 1024;
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(maxsim_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    });
+    if (attr_err != cudaSuccess) return Status::Cuda(cudaGetErrorString(attr_err));
+    if (smem > 220 * 1024) return Status::Cuda("maxsim tensor-core kernel: shared memory budget exceeded");
+    int dev = 0, sms = 0;
+    VB_CUDA(cudaGetDevice(&dev));
+    VB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const uint32_t tiles = (uint32_t)(((uint64_t)job.ndocs * td + kTcTile - 1) / kTcTile);
+    const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)sms);
+
+    VB_TRY(ctx.arm_ctrl(1));
+    VB_TRY(ctx.cand_keys.reserve((size_t)grid * k * sizeof(u64)));
+    VB_TRY(ctx.cand_pays.reserve((size_t)grid * k * sizeof(u64)));
+    VB_TRY(ctx.cand_counts.reserve((size_t)grid * sizeof(uint32_t)));
+    VB_TRY(ctx.out_keys.reserve((size_t)k * sizeof(u64)));
+    VB_TRY(ctx.result.reserve((size_t)k * sizeof(u64) + 8));
+
+    MaxSimTcParams p{};
+    p.ndocs = (uint32_t)job.ndocs;
+    p.td = td;
+    p.dims = job.dims;
+    p.tq = job.tq;
+    p.metric = job.metric;
+    p.doc_rank = job.d_doc_rank;
+    p.inv_dnorm = d_inv_dnorm;
+    p.query = ctx.queries.as<float>();
+    p.inv_qnorm = ctx.queries.as<float>() + (size_t)job.tq * job.dims;
+    p.cap = cap;
+    p.err = ctx.err_row();
+    p.ws.k = k;
+    p.ws.cand_keys = ctx.cand_keys.as<u64>();
+    p.ws.cand_pays = ctx.cand_pays.as<u64>();
+    p.ws.cand_counts = ctx.cand_counts.as<uint32_t>();
+    p.ws.done = ctx.done();
+    p.ws.g_thresh = ctx.g_thresh();
+    p.ws.out_keys = ctx.out_keys.as<u64>();
+    p.ws.out_pays = ctx.result.as<u64>();
+    p.ws.out_counts = reinterpret_cast<uint32_t*>(ctx.result.as<u64>() + k);
+    p.ws.err_row = ctx.err_row();
+    p.ws.out_err = p.ws.out_counts + 1;
+    maxsim_tc_kernel<<<grid, kTcThreads, smem, ctx.stream>>>(tmap, p);
+    cudaError_t e = cudaGetLastError();
+    const size_t bytes = (size_t)k * sizeof(u64) + 8;
+    if (e == cudaSuccess && !ctx.h_result.reserve(bytes).ok()) e = cudaErrorMemoryAllocation;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, bytes, cudaMemcpyDeviceToHost, ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx.stream);
+    if (e != cudaSuccess) {
+        ctx.poison();
+        return Status::Cuda(cudaGetErrorString(e));
+    }
+    const u64* pays = ctx.h_result.as<u64>();
+    const uint32_t* tail = reinterpret_cast<const uint32_t*>(pays + k);
+    out->err = tail[1];
+    out->rows.resize(tail[0]);
+    out->scores.resize(tail[0]);
+    for (uint32_t i = 0; i < tail[0]; ++i) {
+        uint32_t bits = (uint32_t)(pays[i] >> 32);
+        std::memcpy(&out->scores[i], &bits, 4);
+        out->rows[i] = (uint32_t)pays[i];
+    }
+    return Status::Ok();
+}
+
+}  // namespace vb

@@ -19,6 +19,7 @@ constexpr uint32_t kDead = 0xFFFFFFFFu;
 MvIndex::~MvIndex() {
     cudaSetDevice(device_);
     if (d_tokens_) cudaFree(d_tokens_);
+    if (d_inv_norm_) cudaFree(d_inv_norm_);
     if (d_doc_off_) cudaFree(d_doc_off_);
     if (d_doc_rank_) cudaFree(d_doc_rank_);
 }
@@ -41,9 +42,16 @@ Status MvIndex::reserve_tokens(size_t need) {
         e = cudaMalloc(&t, cap * stride_ * sizeof(float));
     }
     if (e != cudaSuccess) return Status::Cuda(cudaGetErrorString(e));
-    if (ntok_) VB_CUDA(cudaMemcpy(t, d_tokens_, ntok_ * stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
+    float* inv = nullptr;
+    VB_CUDA(cudaMalloc(&inv, cap * sizeof(float)));
+    if (ntok_) {
+        VB_CUDA(cudaMemcpy(t, d_tokens_, ntok_ * stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
+        VB_CUDA(cudaMemcpy(inv, d_inv_norm_, ntok_ * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
     if (d_tokens_) cudaFree(d_tokens_);
+    if (d_inv_norm_) cudaFree(d_inv_norm_);
     d_tokens_ = t;
+    d_inv_norm_ = inv;
     tok_cap_ = cap;
     return Status::Ok();
 }
@@ -72,8 +80,10 @@ Status MvIndex::relabel() {
 Status MvIndex::compact() {
     // Rebuild the token matrix without tombstoned documents (device-side gather per document).
     float* fresh = nullptr;
+    float* fresh_inv = nullptr;
     const size_t live = ntok_ - dead_tok_;
     VB_CUDA(cudaMalloc(&fresh, std::max<size_t>(live, 1) * stride_ * sizeof(float)));
+    VB_CUDA(cudaMalloc(&fresh_inv, std::max<size_t>(live, 1) * sizeof(float)));
     std::vector<uint32_t> off{0};
     std::vector<uint32_t> rank;
     std::vector<std::string> ids;
@@ -81,9 +91,11 @@ Status MvIndex::compact() {
     for (size_t d = 0; d < ndocs_; ++d) {
         if (h_rank_[d] == kDead) continue;
         const size_t t0 = h_doc_off_[d], cnt = h_doc_off_[d + 1] - t0;
-        if (cnt)
+        if (cnt) {
             VB_CUDA(cudaMemcpy(fresh + cursor * stride_, d_tokens_ + t0 * stride_, cnt * stride_ * sizeof(float),
                                cudaMemcpyDeviceToDevice));
+            VB_CUDA(cudaMemcpy(fresh_inv + cursor, d_inv_norm_ + t0, cnt * sizeof(float), cudaMemcpyDeviceToDevice));
+        }
         cursor += cnt;
         id_doc_[doc_id_[d]] = (uint32_t)ids.size();
         ids.push_back(std::move(doc_id_[d]));
@@ -91,7 +103,10 @@ Status MvIndex::compact() {
         off.push_back((uint32_t)cursor);
     }
     cudaFree(d_tokens_);
+    cudaFree(d_inv_norm_);
     d_tokens_ = fresh;
+    d_inv_norm_ = fresh_inv;
+    uniform_known_ = false;   // recomputed from the surviving documents below
     tok_cap_ = std::max<size_t>(live, 1);
     ntok_ = live;
     dead_tok_ = 0;
@@ -99,6 +114,11 @@ Status MvIndex::compact() {
     doc_id_ = std::move(ids);
     h_rank_ = std::move(rank);
     h_doc_off_ = std::move(off);
+    for (size_t d = 0; d < ndocs_; ++d) {
+        const uint32_t cnt = h_doc_off_[d + 1] - h_doc_off_[d];
+        if (!uniform_known_) { uniform_td_ = cnt; uniform_known_ = true; }
+        else if (uniform_td_ != cnt) uniform_td_ = 0;
+    }
     return Status::Ok();
 }
 
@@ -133,16 +153,22 @@ Status MvIndex::insert_many(size_t ndocs, const char* ids, const uint64_t* id_of
         const size_t chunk_rows = std::max<size_t>(1, std::min<size_t>(new_tok, (64u << 20) / (stride_ * sizeof(float))));
         VB_TRY(stage.reserve(chunk_rows * stride_ * sizeof(float)));
         float* sb = stage.as<float>();
+        std::vector<float> inv(chunk_rows);
         size_t done = 0;
         while (done < new_tok) {
             const size_t n = std::min(chunk_rows, new_tok - done);
             for (size_t i = 0; i < n; ++i) {
                 const size_t t = doc_tok[0] + done + i;
-                std::memcpy(sb + i * stride_, tok_vals + tok_off[t], dim_ * sizeof(float));
+                const float* src = tok_vals + tok_off[t];
+                std::memcpy(sb + i * stride_, src, dim_ * sizeof(float));
                 for (size_t c = dim_; c < stride_; ++c) sb[i * stride_ + c] = 0.0f;
+                double s = 0.0;   // distances.rs:166: f64_dot(right, right).sqrt()
+                for (size_t c = 0; c < dim_; ++c) s += (double)src[c] * (double)src[c];
+                inv[i] = s > 0.0 ? (float)(1.0 / std::sqrt(s)) : 0.0f;
             }
             VB_CUDA(cudaMemcpy(d_tokens_ + (ntok_ + done) * stride_, sb, n * stride_ * sizeof(float),
                                cudaMemcpyHostToDevice));
+            VB_CUDA(cudaMemcpy(d_inv_norm_ + ntok_ + done, inv.data(), n * sizeof(float), cudaMemcpyHostToDevice));
             done += n;
         }
         stage.release();
@@ -161,6 +187,11 @@ Status MvIndex::insert_many(size_t ndocs, const char* ids, const uint64_t* id_of
         }
         doc_id_.push_back(std::move(id));
         h_rank_.push_back(0);
+        {
+            const uint32_t cnt = (uint32_t)(doc_tok[d + 1] - doc_tok[d]);
+            if (!uniform_known_) { uniform_td_ = cnt; uniform_known_ = true; }
+            else if (uniform_td_ != cnt) uniform_td_ = 0;
+        }
         ntok_ += doc_tok[d + 1] - doc_tok[d];
         h_doc_off_.push_back((uint32_t)ntok_);
         ++ndocs_;
@@ -189,7 +220,11 @@ Status MvIndex::remove(const char* id, size_t id_len) {
         ntok_ = dead_tok_ = tok_cap_ = 0;
         ndocs_ = 0;
         if (d_tokens_) cudaFree(d_tokens_);
+        if (d_inv_norm_) cudaFree(d_inv_norm_);
         d_tokens_ = nullptr;
+        d_inv_norm_ = nullptr;
+        uniform_known_ = false;
+        uniform_td_ = 0;
         h_doc_off_.assign(1, 0);
         h_rank_.clear();
         doc_id_.clear();
@@ -239,6 +274,8 @@ Status MvIndex::search(const float* q_vals, const uint64_t* q_off, size_t tq, si
     job.h_query = q_vals + q_off[0];
     job.tq = (uint32_t)tq;
     job.k = k;
+    job.uniform_td = uniform_known_ ? uniform_td_ : 0;
+    job.d_inv_dnorm = d_inv_norm_;
     MaxSimResult res;
     VB_TRY(maxsim_top_k(*ctx.ctx, job, &res));
     if (res.err != kNoError) return Status::Ref((res.err & 1u) ? "score overflow" : "metric overflow");
