@@ -163,6 +163,13 @@ int vb_mv_new(int metric_code, vb_mv** out);
 void vb_mv_free(vb_mv* index);
 int vb_mv_insert_many(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off,
                       const float* tok_vals, const uint64_t* tok_off, const uint64_t* doc_tok);
+/* Pre-sizes the HBM arrays so a large corpus can be streamed in without realloc + copy. */
+int vb_mv_reserve(vb_mv* index, size_t docs, size_t tokens, size_t dimension);
+/* Uniform documents (tokens_per_doc each) whose tokens already sit in device memory as a
+ * row-major [ndocs * tokens_per_doc, dimension] fp32 matrix (e.g. produced by an encoder on
+ * the same GPU). Validation (finite values) and the per-token norms run on the device. */
+int vb_mv_insert_many_device(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off,
+                             const float* d_tokens, size_t tokens_per_doc, size_t dimension);
 int vb_mv_delete(vb_mv* index, const char* id, size_t id_len);
 int vb_mv_search(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit,
                  vb_hits** out);

@@ -457,6 +457,13 @@ int vb_mv_insert_many(vb_mv* index, size_t ndocs, const char* ids, const uint64_
                       const uint64_t* tok_off, const uint64_t* doc_tok) {
     return finish(index->impl->insert_many(ndocs, ids, id_off, tok_vals, tok_off, doc_tok));
 }
+int vb_mv_reserve(vb_mv* index, size_t docs, size_t tokens, size_t dimension) {
+    return finish(index->impl->reserve(docs, tokens, dimension));
+}
+int vb_mv_insert_many_device(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off,
+                             const float* d_tokens, size_t tokens_per_doc, size_t dimension) {
+    return finish(index->impl->insert_many_device(ndocs, ids, id_off, d_tokens, tokens_per_doc, dimension));
+}
 int vb_mv_delete(vb_mv* index, const char* id, size_t id_len) { return finish(index->impl->remove(id, id_len)); }
 int vb_mv_search(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, vb_hits** out) {
     *out = nullptr;

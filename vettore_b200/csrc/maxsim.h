@@ -49,6 +49,11 @@ class MvIndex {
     Status insert_many(size_t ndocs, const char* ids, const uint64_t* id_off, const float* tok_vals,
                        const uint64_t* tok_off, const uint64_t* doc_tok);
     Status remove(const char* id, size_t id_len);
+    // Pre-sizes the HBM arrays (no realloc + copy while a large corpus is streamed in).
+    Status reserve(size_t docs, size_t tokens, size_t dim);
+    // Uniform documents whose tokens are already in device memory: [ndocs * td, dim] fp32.
+    Status insert_many_device(size_t ndocs, const char* ids, const uint64_t* id_off, const float* d_tokens,
+                              size_t td, size_t dim);
     Status search(const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, Hits* out);
     void info(size_t* docs, size_t* tokens, size_t* dim);
 

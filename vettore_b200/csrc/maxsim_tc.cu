@@ -5,14 +5,14 @@
 //
 // Shape of the work (C5: 1M docs x 128 tokens x 128 dims, 32 query tokens): the token matrix
 // is streamed once (tokens * D * 4 bytes, HBM-bound at 16 flop/B), every 128-token tile is a
-// [128 x D] . [D x 32] product. Per SM, one persistent CTA of 10 warps:
-//   warp 8      producer: TMA 2D tiled loads (128-byte swizzle) of token tiles into a 2-stage ring
-//   warps 4-7   split: each thread owns one token row (= one TMEM lane), reads it from the
+// [128 x D] . [D x 32] product. Per SM, one persistent CTA of 14 warps:
+//   warp 12     producer: TMA 2D tiled loads (128-byte swizzle) of token chunks into a 4-stage ring
+//   warps 4-11  split: each thread owns one token row (= one TMEM lane), reads it from the
 //               swizzled tile (conflict-free 128-bit LDS), splits x = hi + lo and writes both
 //               halves into TMEM with tcgen05.st (A operand from TMEM: no second smem round trip)
-//   warp 9      MMA issuer: per tile 3 * D/8 tcgen05.mma kind::tf32 (A in TMEM, B = query
+//   warp 13     MMA issuer: per tile 3 * D/8 tcgen05.mma kind::tf32 (A in TMEM, B = query
 //               tokens resident in shared memory in the UMMA K-major SWIZZLE_128B layout),
-//               fp32 accumulators in TMEM (4 buffers of 32 columns)
+//               fp32 accumulators in TMEM (2 buffers x 4 independent partial accumulators)
 //   warps 0-3   epilogue: tcgen05.ld the [128 x 32] tile, similarity transform, per-query max
 //               over each document's tokens (31-shuffle transpose butterfly + shared memory
 //               across warps), f32 sum in query order, collector push (topk.cuh)
@@ -22,12 +22,18 @@
 
 namespace vb {
 
-constexpr int kTcEpiWarps = 4, kTcSplitWarps = 4;
-constexpr int kTcThreads = (kTcEpiWarps + kTcSplitWarps + 2) * 32;   // + producer + MMA issuer
-constexpr int kTcStages = 2;
-constexpr int kTcAccBufs = 4;
-constexpr int kTcTile = 128;    // tokens per tile (UMMA M)
-constexpr int kTcN = 32;        // query tokens (UMMA N), zero padded
+constexpr int kTcEpiWarps = 4, kTcSplitWarps = 8;
+constexpr int kTcProducerWarp = kTcEpiWarps + kTcSplitWarps, kTcMmaWarp = kTcProducerWarp + 1;
+constexpr int kTcThreads = (kTcMmaWarp + 1) * 32;
+constexpr int kTcStages = 4;     // ring stages of one chunk (<= 2 K blocks = 32 KB) each
+constexpr int kTcAccBufs = 2;     // accumulator buffers (MMA <-> epilogue double buffering)
+constexpr int kTcChains = 4;      // independent accumulators per buffer: consecutive MMAs never depend on each other
+constexpr int kTcTile = 128;     // tokens per tile (UMMA M)
+constexpr int kTcN = 32;         // query tokens (UMMA N), zero padded
+constexpr uint32_t kTcChunkBytes = 2 * 16384;   // 2 K blocks of [128 rows x 128 B]
+// TMEM columns: A operand double-buffered per chunk, buffer u at [128 u, +128): hi [0,64) lo [64,128);
+// accumulator buffer b at 256 + 128 b: kTcChains partial accumulators of 32 columns (summed by the epilogue).
+constexpr uint32_t kTcAccCol = 256;
 
 struct MaxSimTcParams {
     uint32_t ndocs, td, dims, tq;
@@ -42,7 +48,7 @@ struct MaxSimTcParams {
 };
 
 // Max over the 32 lanes of a warp for 32 per-lane values at once: after the butterfly lane q
-// holds max_l v_l[q]. 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
+// holds max over lanes of v[q]. 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
 __device__ __forceinline__ float warp_transpose_max(float (&v)[32], int lane) {
 #pragma unroll
     for (int half = 16; half >= 1; half >>= 1) {
@@ -54,28 +60,26 @@ __device__ __forceinline__ float warp_transpose_max(float (&v)[32], int lane) {
             v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, half));
         }
     }
-    return v[0];   // lane q: query index = bit-reversal-free mapping below
+    return v[0];
 }
-// The butterfly above leaves in lane L the value of index idx(L) = sum over steps of
-// (L & half ? half : 0) = L itself (each step keeps the upper half in lanes with the bit set).
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages];
-    __shared__ __align__(8) uint64_t a_ready, a_free, d_full[kTcAccBufs], d_free[kTcAccBufs];
+    __shared__ __align__(8) uint64_t a_ready[2], a_free[2], d_full[kTcAccBufs], d_free[kTcAccBufs];
     __shared__ uint32_t tmem_slot;
     __shared__ u64 s_thresh;
     __shared__ uint32_t s_count;
     __shared__ int s_last;
-    __shared__ float s_part[kTcAccBufs][4][kTcN];
+    __shared__ __align__(16) float s_part[kTcAccBufs][4][kTcN];
     __shared__ float s_invq[kTcN];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t KB = p.dims / 32;                        // 128-byte K blocks per row
-    const uint32_t stage_bytes = KB * 16384u;               // [128 rows x 128 B] per K block
+    const uint32_t KB = p.dims / 32;                        // 128-byte K blocks per row (1..4)
+    const uint32_t chunks_per_tile = (KB + 1) / 2;          // a chunk = up to 2 K blocks
     unsigned char* ring = smem;
-    unsigned char* b_hi = ring + (size_t)kTcStages * stage_bytes;   // KB x [32 rows x 128 B]
+    unsigned char* b_hi = ring + (size_t)kTcStages * kTcChunkBytes;   // KB x [32 rows x 128 B]
     unsigned char* b_lo = b_hi + (size_t)KB * 4096;
     unsigned char* col_mem = b_lo + (size_t)KB * 4096;
 
@@ -86,15 +90,17 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
             tc::mbar_init(&full_bar[s], 1);
             tc::mbar_init(&empty_bar[s], kTcSplitWarps);
         }
-        tc::mbar_init(&a_ready, kTcSplitWarps);
-        tc::mbar_init(&a_free, 1);
+        for (int u = 0; u < 2; ++u) {
+            tc::mbar_init(&a_ready[u], kTcSplitWarps);
+            tc::mbar_init(&a_free[u], 1);
+        }
         for (int b = 0; b < kTcAccBufs; ++b) {
             tc::mbar_init(&d_full[b], 1);
             tc::mbar_init(&d_free[b], kTcEpiWarps);
         }
         tc::mbar_fence_init();
     }
-    if (warp == 9) tc::tmem_alloc(&tmem_slot, 512);
+    if (warp == kTcMmaWarp) tc::tmem_alloc(&tmem_slot, 512);
     if (tid < kTcN) s_invq[tid] = (p.inv_qnorm && (uint32_t)tid < p.tq) ? p.inv_qnorm[tid] : 0.0f;
     // B operand: the query tokens, split hi/lo, UMMA K-major SWIZZLE_128B layout; rows >= tq are zero.
     for (uint32_t idx = tid; idx < (uint32_t)kTcN * p.dims; idx += kTcThreads) {
@@ -115,84 +121,104 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
     const uint32_t num_tiles = (ntok + kTcTile - 1) / kTcTile;
     const uint32_t docs_per_tile = kTcTile / p.td;          // td in {32, 64, 128}
 
-    if (warp == 8) {
-        // ===== producer =====
+    if (warp == kTcProducerWarp) {
+        // ===== producer: one chunk (<= 2 K blocks of the tile) per ring stage =====
         if (lane == 0) {
             tc::tma_prefetch_desc(&tmap);
-            uint32_t it = 0;
-            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
-                tc::mbar_wait(&empty_bar[s], ph ^ 1u);
-                tc::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-                for (uint32_t kb = 0; kb < KB; ++kb)
-                    tc::tma_load_2d(ring + (size_t)s * stage_bytes + (size_t)kb * 16384, &tmap, kb * 32, tile * kTcTile,
-                                    &full_bar[s]);
+            uint32_t cc = 0;
+            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (uint32_t j = 0; j < chunks_per_tile; ++j, ++cc) {
+                    const uint32_t s = cc % kTcStages, ph = (cc / kTcStages) & 1u;
+                    const uint32_t blocks = min(2u, KB - 2u * j);
+                    tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+                    tc::mbar_arrive_expect_tx(&full_bar[s], blocks * 16384u);
+                    for (uint32_t h = 0; h < blocks; ++h)
+                        tc::tma_load_2d(ring + (size_t)s * kTcChunkBytes + (size_t)h * 16384, &tmap, (2u * j + h) * 32u,
+                                        tile * kTcTile, &full_bar[s]);
+                }
             }
         }
-    } else if (warp == 9) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = tc::umma_idesc_tf32(kTcTile, kTcN);
-            const uint32_t b_hi_addr = tc::smem_addr(b_hi), b_lo_addr = tc::smem_addr(b_lo);
-            uint32_t it = 0;
-            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const uint32_t b = it % kTcAccBufs;
-                tc::mbar_wait(&a_ready, it & 1u);
-                tc::mbar_wait(&d_free[b], ((it / kTcAccBufs) & 1u) ^ 1u);
+    } else if (warp == kTcMmaWarp) {
+        // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues =====
+        const uint32_t idesc = tc::umma_idesc_tf32(kTcTile, kTcN);
+        const uint64_t bh0 = tc::umma_smem_desc_sw128(tc::smem_addr(b_hi));
+        const uint64_t bl0 = tc::umma_smem_desc_sw128(tc::smem_addr(b_lo));
+        uint32_t cc = 0, it = 0;
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t b = it % kTcAccBufs;
+            const uint32_t d_tmem = tbase + kTcAccCol + b * (kTcChains * kTcN);
+            for (uint32_t j = 0; j < chunks_per_tile; ++j, ++cc) {
+                const uint32_t u = cc & 1u;
+                const uint32_t blocks = min(2u, KB - 2u * j);
+                tc::mbar_wait(&a_ready[u], (cc >> 1) & 1u);
+                if (j == 0) tc::mbar_wait(&d_free[b], ((it / kTcAccBufs) & 1u) ^ 1u);
                 tc::fence_after_sync();
-                const uint32_t d_tmem = tbase + 256u + b * kTcN;
-                uint32_t acc = 0;
-                for (uint32_t kb = 0; kb < KB; ++kb) {
+                // The 4 k-steps of a block feed 4 different partial accumulators, so back-to-back
+                // MMAs never wait on each other's result; the epilogue adds the partials.
+                // Descriptor start-address field counts 16-byte units: K block = 256, k-step = 2.
+                const uint32_t a0 = tbase + u * 128u;
+                const uint64_t kbo = (uint64_t)(2u * j) * 256u;
+                if (tc::elect_one()) {
 #pragma unroll
-                    for (uint32_t ks = 0; ks < 4; ++ks) {
-                        const uint64_t bh = tc::umma_smem_desc_sw128(b_hi_addr + kb * 4096u + ks * 32u);
-                        const uint64_t bl = tc::umma_smem_desc_sw128(b_lo_addr + kb * 4096u + ks * 32u);
-                        const uint32_t ah = tbase + kb * 32u + ks * 8u, al = ah + 128u;
-                        tc::umma_tf32_ts(d_tmem, ah, bh, idesc, acc);
-                        acc = 1;
-                        tc::umma_tf32_ts(d_tmem, ah, bl, idesc, 1);
-                        tc::umma_tf32_ts(d_tmem, al, bh, idesc, 1);
+                    for (uint32_t h = 0; h < 2; ++h) {
+                        if (h < blocks) {
+                            const uint32_t first = (j | h) == 0u ? 0u : 1u;
+#pragma unroll
+                            for (uint32_t term = 0; term < 3; ++term) {
+#pragma unroll
+                                for (uint32_t ks = 0; ks < 4; ++ks) {
+                                    const uint64_t bdesc = (term == 1 ? bl0 : bh0) + kbo + (uint64_t)(h * 256u + ks * 2u);
+                                    const uint32_t a_addr = a0 + h * 32u + ks * 8u + (term == 2 ? 64u : 0u);
+                                    tc::umma_tf32_ts(d_tmem + ks * kTcN, a_addr, bdesc, idesc, term == 0 ? first : 1u);
+                                }
+                            }
+                        }
                     }
+                    tc::umma_commit(&a_free[u]);                                 // this A buffer may be overwritten
+                    if (j + 1 == chunks_per_tile) tc::umma_commit(&d_full[b]);   // the accumulator is complete
                 }
-                tc::umma_commit(&a_free);      // the A operand may be overwritten
-                tc::umma_commit(&d_full[b]);   // the accumulator is complete
+                __syncwarp();
             }
         }
     } else if (warp >= kTcEpiWarps) {
-        // ===== split warps: smem tile -> (hi, lo) -> TMEM =====
-        const uint32_t quarter = warp & 3u;
+        // ===== split warps: smem chunk -> (hi, lo) -> TMEM. Two warps per TMEM lane quarter, =====
+        // ===== one K block of the chunk each.                                               =====
+        const uint32_t sw = warp - kTcEpiWarps;
+        const uint32_t quarter = warp & 3u, h = sw >> 2;      // warps 4..7 -> block 0, 8..11 -> block 1
         const uint32_t row = quarter * 32u + lane;            // token row within the tile == TMEM lane
         const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
-        uint32_t it = 0;
-        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
-            tc::mbar_wait(&full_bar[s], ph);
-            tc::mbar_wait(&a_free, (it & 1u) ^ 1u);           // MMAs of the previous tile have read A
-            tc::fence_after_sync();
-            const unsigned char* tile_base = ring + (size_t)s * stage_bytes;
-            for (uint32_t kb = 0; kb < KB; ++kb) {
-                uint32_t hi[32], lo[32];
+        uint32_t cc = 0;
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (uint32_t j = 0; j < chunks_per_tile; ++j, ++cc) {
+                const uint32_t s = cc % kTcStages, ph = (cc / kTcStages) & 1u, u = cc & 1u;
+                const uint32_t blocks = min(2u, KB - 2u * j);
+                tc::mbar_wait(&full_bar[s], ph);
+                tc::mbar_wait(&a_free[u], ((cc >> 1) & 1u) ^ 1u);   // MMAs that read this A buffer are done
+                tc::fence_after_sync();
+                if (h < blocks) {
+                    const unsigned char* blk = ring + (size_t)s * kTcChunkBytes + (size_t)h * 16384 + row * 128u;
+                    uint32_t hi[32], lo[32];
 #pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) {
-                    const float4 v = *reinterpret_cast<const float4*>(tile_base + (size_t)kb * 16384 + row * 128u +
-                                                                      ((c ^ (row & 7u)) << 4));
-                    const float xs[4] = {v.x, v.y, v.z, v.w};
+                    for (uint32_t c = 0; c < 8; ++c) {
+                        const float4 v = *reinterpret_cast<const float4*>(blk + ((c ^ (row & 7u)) << 4));
+                        const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t h = __float_as_uint(xs[e]) & 0xFFFFE000u;
-                        hi[c * 4 + e] = h;
-                        lo[c * 4 + e] = __float_as_uint(xs[e] - __uint_as_float(h));
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t hbits = __float_as_uint(xs[e]) & 0xFFFFE000u;
+                            hi[c * 4 + e] = hbits;
+                            lo[c * 4 + e] = __float_as_uint(xs[e] - __uint_as_float(hbits));
+                        }
                     }
+                    tc::tmem_st32(lane_addr + u * 128u + h * 32u, hi);
+                    tc::tmem_st32(lane_addr + u * 128u + 64u + h * 32u, lo);
+                    tc::tmem_st_wait();
                 }
-                tc::tmem_st32(lane_addr + kb * 32u, hi);
-                tc::tmem_st32(lane_addr + 128u + kb * 32u, lo);
-            }
-            tc::tmem_st_wait();
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) {
-                tc::mbar_arrive(&a_ready);
-                tc::mbar_arrive(&empty_bar[s]);   // this warp's rows of the stage are consumed
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    tc::mbar_arrive(&a_ready[u]);
+                    tc::mbar_arrive(&empty_bar[s]);   // this warp's share of the stage is consumed
+                }
             }
         }
     } else {
@@ -209,45 +235,62 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
             if (p.metric == kCosineTrue) inv_dn = token < ntok ? __ldg(p.inv_dnorm + token) : 0.0f;
             tc::mbar_wait(&d_full[b], (it / kTcAccBufs) & 1u);
             tc::fence_after_sync();
-            uint32_t r[32];
-            tc::tmem_ld32(lane_addr + 256u + b * kTcN, r);
-            tc::tmem_ld_wait();
+            float v[32];
+            {
+                uint32_t r0[32], r1[32];
+                const uint32_t acc = lane_addr + kTcAccCol + b * (kTcChains * kTcN);
+                tc::tmem_ld32(acc, r0);
+                tc::tmem_ld32(acc + kTcN, r1);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r0[q]) + __uint_as_float(r1[q]);
+                tc::tmem_ld32(acc + 2 * kTcN, r0);
+                tc::tmem_ld32(acc + 3 * kTcN, r1);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] += __uint_as_float(r0[q]) + __uint_as_float(r1[q]);
+            }
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&d_free[b]);
-            float v[32];
+            // similarity_value: inner product -> dot; negative inner product -> -(-dot) = dot; cosine ->
+            // dot / (|q| |d|) clamped (distances.rs:170-172). Scaling by 1/|q| >= 0 and clamping are
+            // monotonic, so they are applied once per query after the max instead of per pair.
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
-                float sdot = __uint_as_float(r[q]);
-                float sim;
-                if (p.metric == kCosineTrue) {
-                    sim = sdot * s_invq[q] * inv_dn;                       // distances.rs:170-172
-                    sim = fminf(1.0f, fmaxf(-1.0f, sim));
-                } else if (p.metric == kNegativeInnerProduct) {
-                    sim = sdot;                                             // similarity(-raw) with raw = -dot
-                } else {
-                    sim = sdot;
-                }
+                float sim = v[q];
+                if (p.metric == kCosineTrue) sim *= inv_dn;
                 v[q] = token < ntok ? sim : -INFINITY;
             }
-            const float wmax = warp_transpose_max(v, lane);                // lane q: max over this warp's tokens
+            float wmax = warp_transpose_max(v, lane);                      // lane q: max over this warp's tokens
+            if (p.metric == kCosineTrue) wmax = fminf(1.0f, fmaxf(-1.0f, wmax * s_invq[lane]));
             s_part[b][quarter][lane] = wmax;
-            col.sync();                                                      // 4 epilogue warps
-            // document leaders: the first warp of each document combines its warps and sums over queries
+            col.sync();                                                      // the 4 epilogue warps
+            // document leaders: the first warp of each document combines its warps; one lane then adds
+            // the per-query maxima in query order (multi_vector.rs:81-84) straight from shared memory
+            // (32 pipelined loads + 32 dependent adds instead of a 32-deep shuffle chain).
             if ((quarter % warps_per_doc) == 0) {
                 float m = wmax;
                 for (uint32_t w = 1; w < warps_per_doc; ++w) m = fmaxf(m, s_part[b][quarter + w][lane]);
+                s_part[b][quarter][lane] = m;
+                __syncwarp();
                 const uint32_t doc = tile * docs_per_tile + quarter / warps_per_doc;
-                float total = 0.0f;
-                bool overflow = false;
-                for (uint32_t q = 0; q < p.tq; ++q) {                       // multi_vector.rs:81-84
-                    total += __shfl_sync(0xffffffffu, m, q);
-                    overflow |= !isfinite(total);
-                }
                 if (lane == 0 && doc < p.ndocs) {
                     const uint32_t rank = p.doc_rank ? __ldg(p.doc_rank + doc) : doc;
                     if (rank != 0xFFFFFFFFu) {
-                        if (overflow) { atomicMin(p.err, (doc << 1) | 1u); total = 0.0f; }
+                        const float4* mv = reinterpret_cast<const float4*>(&s_part[b][quarter][0]);
+                        float mq[kTcN];
+#pragma unroll
+                        for (int i = 0; i < kTcN / 4; ++i) {
+                            const float4 t4 = mv[i];
+                            mq[4 * i] = t4.x; mq[4 * i + 1] = t4.y; mq[4 * i + 2] = t4.z; mq[4 * i + 3] = t4.w;
+                        }
+                        float total = 0.0f;
+#pragma unroll
+                        for (int q = 0; q < kTcN; ++q)
+                            if ((uint32_t)q < p.tq) total += mq[q];
+                        // a non-finite running sum can never become finite again, so one check suffices
+                        if (!isfinite(total)) { atomicMin(p.err, (doc << 1) | 1u); total = 0.0f; }
                         const u64 key = ((u64)(~order_key(total)) << 32) | rank;
                         if (key < col.threshold()) col.push(key, ((u64)__float_as_uint(total) << 32) | doc);
                     }
@@ -260,7 +303,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
     // teardown: every role is done with TMEM before it is released
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 9) tc::tmem_dealloc(tbase, 512);
+    if (warp == kTcMmaWarp) tc::tmem_dealloc(tbase, 512);
 }
 
 bool maxsim_tc_eligible(const MaxSimJob& job, uint32_t uniform_td) {
@@ -303,7 +346,7 @@ Status maxsim_tc_top_k(SearchCtx& ctx, const MaxSimJob& job, uint32_t td, const 
 
     uint32_t cap = 256;
     while (cap < 2 * k || cap < k + 64) cap <<= 1;
-    const size_t smem = (size_t)kTcStages * KB * 16384 + 2 * (size_t)KB * 4096 + (size_t)cap * 16 + 1024;
+    const size_t smem = (size_t)kTcStages * kTcChunkBytes + 2 * (size_t)KB * 4096 + (size_t)cap * 16 + 1024;
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {

@@ -204,6 +204,105 @@ Status MvIndex::insert_many(size_t ndocs, const char* ids, const uint64_t* id_of
     return Status::Ok();
 }
 
+// 1/|token| in f32 from an f64 norm (distances.rs:166), one warp per token; flags non-finite input.
+__global__ void token_inv_norm_kernel(const float* tokens, size_t stride, uint32_t dim, uint32_t ntok, float* inv,
+                                      uint32_t* bad) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t t = warp; t < ntok; t += warps) {
+        double s = 0.0;
+        bool finite = true;
+        for (uint32_t c = lane; c < dim; c += 32) {
+            const float v = tokens[t * stride + c];
+            finite &= isfinite(v);
+            s = fma((double)v, (double)v, s);
+        }
+        s = warp_sum(s);
+        if (!__all_sync(0xffffffffu, finite)) { if (lane == 0) atomicOr(bad, 1u); }
+        if (lane == 0) inv[t] = s > 0.0 ? (float)(1.0 / sqrt(s)) : 0.0f;
+    }
+}
+
+Status MvIndex::reserve(size_t docs, size_t tokens, size_t dim) {
+    std::unique_lock<std::shared_mutex> g(mu_);
+    VB_CUDA(cudaSetDevice(device_));
+    if (dim == 0) return Status::Ref("vectors must not be empty");
+    if (dim_ != 0 && dim != dim_) return Status::Ref("dimension mismatch");
+    if (dim_ == 0) {
+        dim_ = dim;
+        stride_ = (dim + 3) & ~(size_t)3;
+    }
+    VB_TRY(reserve_tokens(tokens));
+    if (docs > doc_cap_) {
+        VB_TRY(reserve_docs(docs));
+        if (ndocs_) {
+            VB_CUDA(cudaMemcpy(d_doc_off_, h_doc_off_.data(), (ndocs_ + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            VB_CUDA(cudaMemcpy(d_doc_rank_, h_rank_.data(), ndocs_ * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+    }
+    return Status::Ok();
+}
+
+Status MvIndex::insert_many_device(size_t ndocs, const char* ids, const uint64_t* id_off, const float* d_tokens,
+                                   size_t td, size_t dim) {
+    std::unique_lock<std::shared_mutex> g(mu_);
+    VB_CUDA(cudaSetDevice(device_));
+    if (ndocs == 0) return Status::Ok();
+    if (dim == 0 || td == 0) return Status::Ref("vectors must not be empty");
+    if (dim_ != 0 && dim != dim_) return Status::Ref("dimension mismatch");
+    if (dim % 4 != 0) return Status::Cuda("device ingest needs a dimension that is a multiple of 4");
+    const size_t new_tok = ndocs * td;
+    if (ntok_ + new_tok >= 0xFFFFFFFFull || ndocs_ + ndocs >= 0xFFFFFFFEull)
+        return Status::Cuda("multi-vector index limit (2^32 tokens) exceeded");
+    if (dim_ == 0) {
+        dim_ = dim;
+        stride_ = dim;
+    }
+    VB_TRY(reserve_tokens(ntok_ + new_tok));
+    // validate + norms on the device, then one D2D copy
+    uint32_t* d_bad = nullptr;
+    VB_CUDA(cudaMalloc(&d_bad, sizeof(uint32_t)));
+    VB_CUDA(cudaMemset(d_bad, 0, sizeof(uint32_t)));
+    token_inv_norm_kernel<<<148 * 8, 256>>>(d_tokens, dim, (uint32_t)dim, (uint32_t)new_tok, d_inv_norm_ + ntok_, d_bad);
+    uint32_t bad = 0;
+    cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) return Status::Cuda(cudaGetErrorString(e));
+    if (bad) return Status::Ref("vector contains a non-finite value");
+    VB_CUDA(cudaMemcpy(d_tokens_ + ntok_ * stride_, d_tokens, new_tok * stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
+    for (size_t d = 0; d < ndocs; ++d) {
+        std::string id(ids + id_off[d], ids + id_off[d + 1]);
+        auto hint = id_doc_.end();
+        if (id_doc_.empty() || std::prev(hint)->first < id) {
+            id_doc_.emplace_hint(hint, id, (uint32_t)ndocs_);
+        } else {
+            auto it = id_doc_.find(id);
+            if (it != id_doc_.end()) {
+                const uint32_t old = it->second;
+                dead_tok_ += h_doc_off_[old + 1] - h_doc_off_[old];
+                h_rank_[old] = kDead;
+                doc_id_[old].clear();
+                it->second = (uint32_t)ndocs_;
+            } else {
+                id_doc_.emplace(id, (uint32_t)ndocs_);
+            }
+        }
+        doc_id_.push_back(std::move(id));
+        h_rank_.push_back(0);
+        if (!uniform_known_) { uniform_td_ = (uint32_t)td; uniform_known_ = true; }
+        else if (uniform_td_ != td) uniform_td_ = 0;
+        ntok_ += td;
+        h_doc_off_.push_back((uint32_t)ntok_);
+        ++ndocs_;
+    }
+    VB_TRY(relabel());
+    if (ndocs_ > doc_cap_) VB_TRY(reserve_docs(ndocs_));
+    VB_CUDA(cudaMemcpy(d_doc_off_, h_doc_off_.data(), (ndocs_ + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    VB_CUDA(cudaMemcpy(d_doc_rank_, h_rank_.data(), ndocs_ * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return Status::Ok();
+}
+
 Status MvIndex::remove(const char* id, size_t id_len) {
     std::unique_lock<std::shared_mutex> g(mu_);
     auto it = id_doc_.find(std::string(id, id + id_len));

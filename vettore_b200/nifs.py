@@ -332,6 +332,20 @@ def mv_insert_tensor(index: MvRef, ids: Sequence, tokens: np.ndarray):
     return _err() if rc else ("ok", ())
 
 
+def mv_reserve(index: MvRef, docs: int, tokens: int, dimension: int):
+    rc = lib().vb_mv_reserve(index.handle, int(docs), int(tokens), int(dimension))
+    return _err() if rc else ("ok", ())
+
+
+def mv_insert_device(index: MvRef, ids: Sequence, device_ptr: int, tokens_per_doc: int, dimension: int):
+    """Uniform documents whose tokens are already in device memory (``device_ptr`` = address of a
+    row-major ``[len(ids) * tokens_per_doc, dimension]`` float32 matrix)."""
+    blob, ioff = _ids_blob(ids)
+    rc = lib().vb_mv_insert_many_device(index.handle, len(ids), blob, _ptr(ioff, _u64p), C.c_void_p(device_ptr),
+                                        int(tokens_per_doc), int(dimension))
+    return _err() if rc else ("ok", ())
+
+
 def mv_delete(index: MvRef, id):
     b = _enc(id)
     rc = lib().vb_mv_delete(index.handle, b, len(b))
