@@ -88,7 +88,7 @@ static Status plan_stream(int metric, int nv, size_t row_stride, uint32_t n, uin
     const uint32_t tile_bytes = (uint32_t)(((size_t)tile_rows * row_stride * 4 + 127) & ~(size_t)127);
     const uint32_t groups_per_sync = std::max(1, kStreamSyncEvery / (kGroupRows / rpw));
     const uint32_t slack = groups_per_sync * kGroupRows * warps;
-    const uint32_t cap = next_pow2(std::max(2 * k, k + slack));
+    const uint32_t cap = next_pow2(2 * k + slack);
     const size_t budget = 200 * 1024;
     if ((size_t)cap * 16 + 2 * (size_t)tile_bytes > budget) return Status::Ok();
     uint32_t stages = (uint32_t)std::min<size_t>(kStreamMaxStages, (budget - (size_t)cap * 16) / tile_bytes);
@@ -150,7 +150,7 @@ Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, bool contigu
     }
     const uint32_t slack = kSyncEvery * kScanWarps * r;
     const uint32_t kk = dump ? 1 : k;
-    const uint32_t cap = next_pow2(std::max(2 * kk, kk + slack));
+    const uint32_t cap = next_pow2(2 * kk + slack);
     const size_t smem = (size_t)cap * 16;
 
     static std::mutex mu;

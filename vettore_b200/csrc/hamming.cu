@@ -9,13 +9,14 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include "select.h"
 #include "topk.cuh"
 
 namespace vb {
 
 constexpr int kHamThreads = 256;
 constexpr int kHamWarps = kHamThreads / 32;
-constexpr int kHamUnroll = 4;
+constexpr int kHamUnroll = 8;
 constexpr uint32_t kHamSlackRows = 1024;  // rows scanned per CTA between collector checks
 
 struct HammingParams {
@@ -152,7 +153,7 @@ static Status launch_hamming(SearchCtx& ctx, HammingParams p, uint32_t nq, uint3
     const uint32_t rows_per_step = kHamWarps * (32 / p.g) * kHamUnroll;
     const uint32_t kk = dump ? 1 : k;
     p.sync_every = std::max<uint32_t>(1, kHamSlackRows / rows_per_step);  // both are powers of two
-    p.cap = pow2_at_least(std::max(2 * kk, kk + p.sync_every * rows_per_step), 256);
+    p.cap = pow2_at_least(2 * kk + p.sync_every * rows_per_step, 256);
     const size_t smem = (size_t)p.cap * 16;
     auto kernel = wide ? hamming_scan_kernel<true> : hamming_scan_kernel<false>;
     if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -186,12 +187,14 @@ static Status launch_hamming(SearchCtx& ctx, HammingParams p, uint32_t nq, uint3
         p.ws.out_counts = reinterpret_cast<uint32_t*>(ctx.result.as<u64>() + (size_t)nq * k);
         p.ws.err_row = nullptr;
         p.ws.out_err = nullptr;
+        p.ws.defer_merge = merge_tree_wanted(grid_x, k) ? 1u : 0u;
     } else {
         p.ws = TopkWorkspace{};
         p.ws.k = 1;
     }
     kernel<<<dim3(grid_x, nq), kHamThreads, smem, stream>>>(p);
     VB_CUDA(cudaGetLastError());
+    if (!dump && p.ws.defer_merge) VB_TRY(run_merge_tree(p.ws, nq, grid_x, ctx.sort_tmp, stream));
     return Status::Ok();
 }
 
@@ -317,3 +320,64 @@ Status sign_pack_device(const float* d_rows, size_t row_stride, uint32_t n, uint
 }
 
 }  // namespace vb
+
+// ---------------------------------------------------------------------------------------
+// Measurement entry (not part of the drop-in ABI): K3 over n synthetic codes generated on the
+// device (splitmix64 of the word index), `iters` timed scans with CUDA events. Used by
+// tools/bench_hamming.py for the C4 shape (100M x 1024 bits) where no host copy can exist.
+namespace vb {
+__global__ void fill_codes_kernel(u64* codes, size_t total, u64 seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        u64 z = (i + seed) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        codes[i] = z ^ (z >> 31);
+    }
+}
+}  // namespace vb
+
+extern "C" int vb_debug_hamming_bench(size_t n, size_t dims, size_t k, int iters, float* ms_per_scan,
+                                      uint32_t* top_rows, float* top_dist) {
+    using namespace vb;
+    const size_t nw = (dims + 63) / 64;
+    u64 *d_codes = nullptr, *d_q = nullptr;
+    if (cudaMalloc(&d_codes, n * nw * sizeof(u64)) != cudaSuccess) return -1;
+    cudaMalloc(&d_q, nw * sizeof(u64));
+    fill_codes_kernel<<<148 * 8, 256>>>(d_codes, n * nw, 1);
+    fill_codes_kernel<<<1, 32>>>(d_q, nw, 0xABCDEF);
+    SearchCtx ctx;
+    cudaGetDevice(&ctx.device);
+    cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking);
+    cudaDeviceSynchronize();
+    int rc = 0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3 && rc == 0; ++i)
+        if (!hamming_scan_device(ctx, d_codes, (uint32_t)n, (uint32_t)nw, (uint32_t)dims, nullptr, d_q, 1, (uint32_t)k,
+                                 ctx.stream).ok()) rc = -2;
+    cudaEventRecord(e0, ctx.stream);
+    for (int i = 0; i < iters && rc == 0; ++i)
+        if (!hamming_scan_device(ctx, d_codes, (uint32_t)n, (uint32_t)nw, (uint32_t)dims, nullptr, d_q, 1, (uint32_t)k,
+                                 ctx.stream).ok()) rc = -2;
+    cudaEventRecord(e1, ctx.stream);
+    if (cudaStreamSynchronize(ctx.stream) != cudaSuccess) rc = -3;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_per_scan = ms / (iters > 0 ? iters : 1);
+    if (rc == 0) {
+        std::vector<u64> pays(k);
+        cudaMemcpy(pays.data(), ctx.result.p, k * sizeof(u64), cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < k; ++i) {
+            uint32_t bits = (uint32_t)(pays[i] >> 32);
+            std::memcpy(&top_dist[i], &bits, 4);
+            top_rows[i] = (uint32_t)pays[i];
+        }
+    }
+    ctx.destroy();
+    cudaFree(d_codes);
+    cudaFree(d_q);
+    return rc;
+}

@@ -7,6 +7,7 @@
 
 #include "flat_scan.cuh"
 #include "flat_scan.h"
+#include "select.h"
 
 namespace vb {
 
@@ -47,6 +48,7 @@ static void fill_params(const SearchCtx& ctx, const ScanJob& job, const float* d
     p->ws.out_counts = reinterpret_cast<uint32_t*>(ctx.result.as<u64>() + (size_t)job.nq * k);
     p->ws.err_row = ctx.err_row();
     p->ws.out_err = p->ws.out_counts + job.nq;
+    p->ws.defer_merge = 0;
     p->dump_keys = nullptr;
     p->dump_pays = nullptr;
 }
@@ -174,7 +176,9 @@ Status run_scan(SearchCtx& ctx, const ScanJob& job, ScanResult* out) {
     ScanParams p;
     fill_params(ctx, job, ctx.queries.as<float>(), q_stride,
                 job.metric == kCosineTrue ? ctx.q_norms.as<double>() : nullptr, k, &p);
+    p.ws.defer_merge = merge_tree_wanted(plan.grid_x, k) ? 1u : 0u;
     Status s = run_flat_scan(plan, p, job.nq, ctx.stream);
+    if (s.ok() && p.ws.defer_merge) s = run_merge_tree(p.ws, job.nq, plan.grid_x, ctx.sort_tmp, ctx.stream);
     if (!s.ok()) { ctx.poison(); return s; }
     const size_t bytes = (size_t)job.nq * k * sizeof(u64) + (size_t)job.nq * 8;
     VB_TRY(ctx.h_result.reserve(bytes));
@@ -251,7 +255,9 @@ Status run_scan_to_rows(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint3
     VB_TRY(prepare_workspace(ctx, plan, 1, k));
     ScanParams p;
     fill_params(ctx, job, d_q, q_stride, d_norm, k, &p);
+    p.ws.defer_merge = merge_tree_wanted(plan.grid_x, k) ? 1u : 0u;
     Status s = run_flat_scan(plan, p, 1, ctx.stream);
+    if (s.ok() && p.ws.defer_merge) s = run_merge_tree(p.ws, 1, plan.grid_x, ctx.sort_tmp, ctx.stream);
     if (!s.ok()) { ctx.poison(); return s; }
     VB_CUDA(cudaMemcpyAsync(h_err, p.ws.out_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
     return extract_rows(ctx, p.ws.out_pays, (uint32_t)k);
@@ -272,7 +278,9 @@ Status run_scan_final(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_
     VB_TRY(prepare_workspace(ctx, plan, 1, k));
     ScanParams p;
     fill_params(ctx, job, d_q, q_stride, d_norm, k, &p);
+    p.ws.defer_merge = merge_tree_wanted(plan.grid_x, k) ? 1u : 0u;
     Status s = run_flat_scan(plan, p, 1, ctx.stream);
+    if (s.ok() && p.ws.defer_merge) s = run_merge_tree(p.ws, 1, plan.grid_x, ctx.sort_tmp, ctx.stream);
     if (!s.ok()) { ctx.poison(); return s; }
     const size_t bytes = k * sizeof(u64) + 8;
     VB_TRY(ctx.h_result.reserve(bytes));
@@ -309,7 +317,9 @@ Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_querie
     VB_TRY(s);
     ScanParams p;
     fill_params(ctx, job, d_queries, q_stride, d_q_norms, k, &p);
+    p.ws.defer_merge = merge_tree_wanted(plan.grid_x, k) ? 1u : 0u;
     s = run_flat_scan(plan, p, job.nq, stream);
+    if (s.ok() && p.ws.defer_merge) s = run_merge_tree(p.ws, job.nq, plan.grid_x, ctx.sort_tmp, stream);
     if (!s.ok()) { ctx.poison(); return s; }
     const uint32_t total = job.nq * (uint32_t)k;
     unpack_results_kernel<<<(std::max(total, job.nq) + 255) / 256, 256, 0, stream>>>(

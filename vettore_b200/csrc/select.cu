@@ -2,6 +2,8 @@
 // through the shared-memory collector; payload = position of the entry in the input, so
 // values and rows are gathered once for the k_out survivors.
 #include "select.h"
+
+#include "runtime.h"
 #include "topk.cuh"
 
 namespace vb {
@@ -70,6 +72,100 @@ Status topk_merge_device(const u64* d_keys, const float* d_values, const uint32_
                                                           (uint32_t)k_in, (uint32_t)k_out, cap, d_keys_out,
                                                           d_values_out, d_rows_out, d_counts_out);
     VB_CUDA(cudaGetLastError());
+    return Status::Ok();
+}
+
+constexpr uint32_t kTreeGroup = 16;
+
+// One CTA merges `group` consecutive lists of query blockIdx.y into list blockIdx.x of the output.
+__global__ void __launch_bounds__(256)
+topk_tree_merge_kernel(const u64* keys_in, const u64* pays_in, const uint32_t* counts_in, uint32_t lists_in,
+                       uint32_t k, uint32_t cap, u64* keys_out, u64* pays_out, uint32_t* counts_out,
+                       uint32_t lists_out, uint32_t* err_row, uint32_t* out_err, u64* g_thresh) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ u64 s_thresh;
+    __shared__ uint32_t s_count;
+    const uint32_t qi = blockIdx.y, og = blockIdx.x;
+    const uint32_t l0 = og * kTreeGroup, nl = min(kTreeGroup, lists_in - l0);
+    Collector col;
+    col.init(smem, &s_thresh, &s_count, cap, k);
+    __syncthreads();
+    const u64* qk = keys_in + ((size_t)qi * lists_in + l0) * k;
+    const u64* qp = pays_in + ((size_t)qi * lists_in + l0) * k;
+    const uint32_t* qc = counts_in + (size_t)qi * lists_in + l0;
+    // a full list bounds the k-th key of the merged result from above
+    for (uint32_t l = threadIdx.x; l < nl; l += blockDim.x)
+        if (qc[l] >= k) {
+            const u64 kth = qk[(size_t)l * k + k - 1];
+            if (kth != kKeyMax) atomicMin(col.thresh, kth + 1);
+        }
+    __syncthreads();
+    collector_merge_lists(
+        col, nl, k, [qc](uint32_t l) { return qc[l]; },
+        [qk, k](uint32_t l, uint32_t i) { return qk[(size_t)l * k + i]; },
+        [qp, k](uint32_t l, uint32_t i) { return qp[(size_t)l * k + i]; });
+    const uint32_t total = *col.count;
+    const size_t o = ((size_t)qi * lists_out + og) * k;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        keys_out[o + i] = col.keys[i];
+        pays_out[o + i] = col.pays[i];
+    }
+    if (threadIdx.x == 0) {
+        counts_out[(size_t)qi * lists_out + og] = total;
+        if (lists_out == 1) {   // final level: finish what the last CTA of the scan would have done
+            if (out_err) { out_err[qi] = err_row[qi]; err_row[qi] = kNoError; }
+            if (g_thresh) g_thresh[qi] = kKeyMax;
+        }
+    }
+}
+
+Status run_merge_tree(const TopkWorkspace& ws, uint32_t nq, uint32_t lists, DeviceBuf& scratch, cudaStream_t stream) {
+    const uint32_t k = ws.k;
+    uint32_t cap = 256;
+    while (cap < 2 * k + 64) cap <<= 1;
+    const size_t smem = (size_t)cap * 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VB_CUDA(cudaFuncSetAttribute(topk_tree_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    // scratch: two ping-pong levels of at most ceil(lists / group) lists each
+    const uint32_t l1 = (lists + kTreeGroup - 1) / kTreeGroup;
+    const size_t level_entries = (size_t)nq * l1 * k;
+    const size_t level_bytes = level_entries * 16 + (size_t)nq * l1 * 4;
+    VB_TRY(scratch.reserve(2 * ((level_bytes + 255) & ~(size_t)255)));
+    unsigned char* base[2] = {scratch.as<unsigned char>(),
+                              scratch.as<unsigned char>() + ((level_bytes + 255) & ~(size_t)255)};
+    const u64* kin = ws.cand_keys;
+    const u64* pin = ws.cand_pays;
+    const uint32_t* cin = ws.cand_counts;
+    uint32_t lin = lists;
+    int level = 0;
+    for (;;) {
+        const uint32_t lout = (lin + kTreeGroup - 1) / kTreeGroup;
+        u64 *kout, *pout;
+        uint32_t* cout;
+        if (lout == 1) {
+            kout = ws.out_keys;
+            pout = ws.out_pays;
+            cout = ws.out_counts;
+        } else {
+            unsigned char* b = base[level & 1];
+            kout = reinterpret_cast<u64*>(b);
+            pout = kout + (size_t)nq * lout * k;
+            cout = reinterpret_cast<uint32_t*>(pout + (size_t)nq * lout * k);
+        }
+        topk_tree_merge_kernel<<<dim3(lout, nq), 256, smem, stream>>>(kin, pin, cin, lin, k, cap, kout, pout, cout, lout,
+                                                                      ws.err_row, lout == 1 ? ws.out_err : nullptr,
+                                                                      lout == 1 ? ws.g_thresh : nullptr);
+        VB_CUDA(cudaGetLastError());
+        if (lout == 1) break;
+        kin = kout;
+        pin = pout;
+        cin = cout;
+        lin = lout;
+        ++level;
+    }
     return Status::Ok();
 }
 

@@ -10,4 +10,13 @@ Status topk_merge_device(const u64* d_keys, const float* d_values, const uint32_
                          size_t list_stride, size_t nq, size_t lists, size_t k_in, size_t k_out, u64* d_keys_out, float* d_values_out,
                          u64* d_rows_out, uint32_t* d_counts_out, cudaStream_t stream);
 
+struct TopkWorkspace;
+// Merge tree for a scan whose CTAs only published their per-CTA lists (ws.defer_merge): groups of
+// lists are merged by independent CTAs, level by level, and the last level writes ws.out_* (and
+// snapshots / re-arms the error word and the grid threshold). `scratch` holds the intermediate lists.
+struct DeviceBuf;
+Status run_merge_tree(const TopkWorkspace& ws, uint32_t nq, uint32_t lists, DeviceBuf& scratch, cudaStream_t stream);
+// True when the per-CTA lists of a scan are better merged by the tree than by the last CTA.
+inline bool merge_tree_wanted(size_t lists, size_t k) { return lists * k > 16384; }
+
 }  // namespace vb

@@ -173,6 +173,7 @@ struct TopkWorkspace {
     uint32_t* err_row;      // [nq] optional: first overflowing row (atomicMin by any CTA)
     uint32_t* out_err;      // [nq] optional: err_row snapshot taken by the last CTA (err_row re-armed)
     uint32_t k;
+    uint32_t defer_merge;   // 1: CTAs only publish their lists; the host runs the merge tree (large grid * k)
 };
 
 // Block-wide, called at a CTA-uniform cadence: adopts the grid-wide threshold, and when
@@ -205,6 +206,7 @@ __device__ __forceinline__ void collector_publish_and_merge(Collector& col, cons
         ws.cand_pays[slot * ws.k + i] = col.pays[i];
     }
     if (threadIdx.x == 0) ws.cand_counts[slot] = kept;
+    if (ws.defer_merge) return;   // merged by topk_tree_merge_kernel launches (select.cu)
     __threadfence();
     col.sync();
     if (threadIdx.x == 0) {
