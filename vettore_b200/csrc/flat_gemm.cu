@@ -1,0 +1,574 @@
+// flat_gemm.cu — K2: batched exact flat scan on the tensor cores. For a batch of queries the
+// scan is a dense contraction S[row][query] = rows . queries^T (reference flat.rs:104-118 run
+// once per query), so it goes to tcgen05 as 3xTF32 (fp32-accurate, tc.cuh) with the per-query
+// top-k fused into the epilogue: the N x Q score matrix never exists in memory.
+//
+// Geometry: UMMA M = 128 rows x N = 256 queries x K = 8, fp32 accumulator in TMEM (256 columns).
+// CTA c serves query block (c mod QB) over a contiguous range of row tiles. Per 32-dim K chunk:
+//   producer warp   TMA: A chunk [128 rows x 32] (16 KB) + B chunk hi/lo [256 queries x 32] (2 x 32 KB)
+//   split warps     A chunk -> (hi, lo) -> TMEM (tcgen05.st), double buffered
+//   MMA warp        12 tcgen05.mma kind::tf32 (hi.hi, hi.lo, lo.hi x 4 k-steps), B from shared memory
+//   epilogue warps  per finished tile: tcgen05.ld 8 x 32 columns, score -> (rank key, id rank) ->
+//                   compare with the query's running threshold (shared memory) -> append to the
+//                   query's candidate list; lists are compacted to their best k by a warp when they
+//                   could overflow, which also tightens the threshold.
+// A final kernel merges, per query, the lists of the CTAs that shared its query block.
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+#include "flat_gemm.h"
+#include "flat_scan.cuh"
+#include "tc.cuh"
+
+namespace vb {
+
+constexpr int kGmThreads = 320;          // warps 0-3 epilogue, 4-7 split, 8 producer, 9 MMA
+constexpr int kGmTile = 128;             // rows per tile (UMMA M)
+constexpr int kGmN = 256;                // queries per block (UMMA N)
+constexpr int kGmStages = 2;
+constexpr uint32_t kGmStageBytes = 16384 + 2 * 32768;   // A chunk + B hi + B lo
+constexpr uint32_t kGmList = 256;        // candidate list capacity per (CTA, query)
+constexpr uint32_t kGmACol = 256;        // TMEM: D at [0,256), A buffer u at 256 + 64 u: hi [0,32) lo [32,64)
+
+struct GemmParams {
+    uint32_t n, dims, nq, k;
+    int metric;                    // kCosine / kInnerProduct / kNegativeInnerProduct
+    uint32_t qblocks, ranges;      // query blocks, row ranges (qblocks * ranges CTAs do work)
+    const uint32_t* id_rank;       // [n] or null
+    u64* list_keys;                // [cta][256][kGmList]
+    u64* list_pays;
+    uint32_t* list_counts;         // [cta][256]
+    uint32_t* bad;                 // set when a non-finite score shows up (caller falls back)
+};
+
+// Best k of one list (<= 256 entries, 8 per lane) by k rounds of warp arg-min; rewrites the
+// list front in ascending order. Returns the k-th key (or kKeyMax when fewer than k entries).
+__device__ u64 warp_compact_list(u64* keys, u64* pays, uint32_t count, uint32_t k, int lane) {
+    u64 lk[8], lp[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t e = lane + 32u * i;
+        lk[i] = e < count ? keys[e] : kKeyMax;
+        lp[i] = e < count ? pays[e] : 0ull;
+    }
+    __syncwarp();
+    const uint32_t keep = min(count, k);
+    u64 kth = kKeyMax;
+    for (uint32_t r = 0; r < keep; ++r) {
+        u64 best = lk[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) best = lk[i] < best ? lk[i] : best;
+        u64 wmin = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const u64 other = __shfl_xor_sync(0xffffffffu, wmin, o);
+            wmin = other < wmin ? other : wmin;
+        }
+        u64 pay = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (lk[i] == wmin) { pay = lp[i]; lk[i] = kKeyMax; }
+        const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best == wmin)) - 1;
+        pay = __shfl_sync(0xffffffffu, pay, owner);
+        if (lane == 0) { keys[r] = wmin; pays[r] = pay; }
+        kth = wmin;
+    }
+    __syncwarp();
+    return count >= k ? kth : kKeyMax;
+}
+
+__global__ void __launch_bounds__(kGmThreads, 1)
+flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bhi,
+                      const __grid_constant__ CUtensorMap tmap_blo, const GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char gsmem[];
+    __shared__ __align__(8) uint64_t full_bar[kGmStages], empty_bar[kGmStages], a_ready[2], a_free[2], d_full, d_free;
+    __shared__ uint32_t tmem_slot;
+    __shared__ u64 s_thr[kGmN];
+    __shared__ uint32_t s_cnt[kGmN];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t qb = blockIdx.x % p.qblocks, rr = blockIdx.x / p.qblocks;
+    const bool active = rr < p.ranges;
+    const uint32_t tiles_total = (p.n + kGmTile - 1) / kGmTile;
+    const uint32_t tile0 = active ? (uint32_t)((uint64_t)tiles_total * rr / p.ranges) : 0;
+    const uint32_t tile1 = active ? (uint32_t)((uint64_t)tiles_total * (rr + 1) / p.ranges) : 0;
+    const uint32_t chunks = p.dims / 32;
+
+    for (int q = tid; q < kGmN; q += kGmThreads) { s_thr[q] = kKeyMax; s_cnt[q] = 0; }
+    if (tid == 0) {
+        for (int s = 0; s < kGmStages; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 5);      // 4 split warps (A consumed) + MMA commit (B consumed)
+            tc::mbar_init(&a_ready[s], 4);
+            tc::mbar_init(&a_free[s], 1);
+        }
+        tc::mbar_init(&d_full, 1);
+        tc::mbar_init(&d_free, 4);
+        tc::mbar_fence_init();
+    }
+    if (warp == 9) tc::tmem_alloc(&tmem_slot, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+
+    if (warp == 8) {
+        // ===== producer =====
+        if (lane == 0) {
+            uint32_t cc = 0;
+            for (uint32_t tile = tile0; tile < tile1; ++tile) {
+                for (uint32_t kc = 0; kc < chunks; ++kc, ++cc) {
+                    const uint32_t s = cc % kGmStages, ph = (cc / kGmStages) & 1u;
+                    unsigned char* st = gsmem + (size_t)s * kGmStageBytes;
+                    tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+                    tc::mbar_arrive_expect_tx(&full_bar[s], kGmStageBytes);
+                    tc::tma_load_2d(st, &tmap_a, kc * 32, tile * kGmTile, &full_bar[s]);
+                    tc::tma_load_2d(st + 16384, &tmap_bhi, kc * 32, qb * kGmN, &full_bar[s]);
+                    tc::tma_load_2d(st + 16384 + 32768, &tmap_blo, kc * 32, qb * kGmN, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer (warp-uniform control flow, one elected lane issues) =====
+        const uint32_t idesc = tc::umma_idesc_tf32(kGmTile, kGmN);
+        uint32_t cc = 0, it = 0;
+        for (uint32_t tile = tile0; tile < tile1; ++tile, ++it) {
+            for (uint32_t kc = 0; kc < chunks; ++kc, ++cc) {
+                const uint32_t s = cc % kGmStages, ph = (cc / kGmStages) & 1u;
+                tc::mbar_wait(&full_bar[s], ph);          // B chunk landed
+                tc::mbar_wait(&a_ready[s], ph);           // A chunk split into TMEM
+                if (kc == 0) tc::mbar_wait(&d_free, (it & 1u) ^ 1u);   // epilogue drained the accumulator
+                tc::fence_after_sync();
+                const uint32_t st_addr = tc::smem_addr(gsmem + (size_t)s * kGmStageBytes);
+                const uint64_t bh0 = tc::umma_smem_desc_sw128(st_addr + 16384);
+                const uint64_t bl0 = tc::umma_smem_desc_sw128(st_addr + 16384 + 32768);
+                const uint32_t a0 = tbase + kGmACol + s * 64u;
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                        for (uint32_t term = 0; term < 3; ++term) {
+                            const uint64_t bdesc = (term == 1 ? bl0 : bh0) + (uint64_t)(ks * 2u);
+                            const uint32_t a_addr = a0 + ks * 8u + (term == 2 ? 32u : 0u);
+                            tc::umma_tf32_ts(tbase, a_addr, bdesc, idesc, (kc | ks | term) != 0u);
+                        }
+                    }
+                    tc::umma_commit(&a_free[s]);
+                    tc::umma_commit(&empty_bar[s]);
+                    if (kc + 1 == chunks) tc::umma_commit(&d_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== split warps: A chunk -> (hi, lo) -> TMEM =====
+        const uint32_t quarter = warp & 3u;
+        const uint32_t row = quarter * 32u + lane;
+        const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
+        uint32_t cc = 0;
+        for (uint32_t tile = tile0; tile < tile1; ++tile) {
+            for (uint32_t kc = 0; kc < chunks; ++kc, ++cc) {
+                const uint32_t s = cc % kGmStages, ph = (cc / kGmStages) & 1u;
+                tc::mbar_wait(&full_bar[s], ph);
+                tc::mbar_wait(&a_free[s], ph ^ 1u);
+                tc::fence_after_sync();
+                const unsigned char* blk = gsmem + (size_t)s * kGmStageBytes + row * 128u;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) {
+                    const float4 v = *reinterpret_cast<const float4*>(blk + ((c ^ (row & 7u)) << 4));
+                    const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t hbits = __float_as_uint(xs[e]) & 0xFFFFE000u;
+                        hi[c * 4 + e] = hbits;
+                        lo[c * 4 + e] = __float_as_uint(xs[e] - __uint_as_float(hbits));
+                    }
+                }
+                tc::tmem_st32(lane_addr + kGmACol + s * 64u, hi);
+                tc::tmem_st32(lane_addr + kGmACol + s * 64u + 32u, lo);
+                tc::tmem_st_wait();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    tc::mbar_arrive(&a_ready[s]);
+                    tc::mbar_arrive(&empty_bar[s]);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps 0-3 =====
+        const uint32_t quarter = warp;
+        const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
+        const size_t list_base = (size_t)blockIdx.x * kGmN;
+        uint32_t it = 0;
+        for (uint32_t tile = tile0; tile < tile1; ++tile, ++it) {
+            const uint32_t row = tile * kGmTile + quarter * 32u + lane;
+            const bool valid = row < p.n;
+            const uint32_t idr = valid ? (p.id_rank ? __ldg(p.id_rank + row) : row) : 0u;
+            tc::mbar_wait(&d_full, it & 1u);
+            tc::fence_after_sync();
+            for (uint32_t cg = 0; cg < kGmN / 32; ++cg) {
+                if (qb * kGmN + cg * 32u >= p.nq) break;       // padded query columns (uniform)
+                uint32_t r[32];
+                tc::tmem_ld32(lane_addr + cg * 32u, r);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t q = cg * 32u + j;
+                    float raw = __uint_as_float(r[j]);
+                    if (p.metric == kNegativeInnerProduct) raw = -raw;
+                    if (valid && !isfinite(raw)) *p.bad = 1u;
+                    const uint32_t rk = order_key(p.metric == kCosine ? __fsub_rn(1.0f, raw)
+                                                  : p.metric == kInnerProduct ? -raw : raw);   // distances.rs:113-119
+                    const u64 key = ((u64)rk << 32) | idr;
+                    if (valid && qb * kGmN + q < p.nq && key < s_thr[q]) {
+                        const uint32_t slot = atomicAdd(&s_cnt[q], 1u);
+                        if (slot < kGmList) {
+                            p.list_keys[(list_base + q) * kGmList + slot] = key;
+                            p.list_pays[(list_base + q) * kGmList + slot] = ((u64)__float_as_uint(raw) << 32) | row;
+                        }
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&d_free);
+            // lists that could overflow during the next tile are cut back to their best k
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            __threadfence_block();
+            for (uint32_t q = warp; q < kGmN; q += 4) {
+                const uint32_t cnt = min(s_cnt[q], kGmList);
+                if (cnt + kGmTile > kGmList) {
+                    const u64 kth = warp_compact_list(p.list_keys + (list_base + q) * kGmList,
+                                                      p.list_pays + (list_base + q) * kGmList, cnt, p.k, lane);
+                    if (lane == 0) { s_cnt[q] = min(cnt, p.k); s_thr[q] = kth; }
+                }
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        // final cut of every list of this CTA
+        for (uint32_t q = warp; q < kGmN; q += 4) {
+            const uint32_t cnt = min(s_cnt[q], kGmList);
+            if (cnt > 0) warp_compact_list(p.list_keys + (list_base + q) * kGmList, p.list_pays + (list_base + q) * kGmList,
+                                           cnt, p.k, lane);
+            if (lane == 0) p.list_counts[list_base + q] = min(cnt, p.k);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 9) tc::tmem_dealloc(tbase, 512);
+}
+
+// Per query: merge the sorted lists of the CTAs that served its query block.
+__global__ void __launch_bounds__(128)
+flat_gemm_merge_kernel(const GemmParams p, uint32_t cap, u64* out_keys, u64* out_pays, uint32_t* out_counts) {
+    extern __shared__ __align__(1024) unsigned char gsmem[];
+    __shared__ u64 s_thresh;
+    __shared__ uint32_t s_count;
+    const uint32_t q = blockIdx.x, qb = q / kGmN, ql = q % kGmN;
+    Collector col;
+    col.init(gsmem, &s_thresh, &s_count, cap, p.k);
+    __syncthreads();
+    const GemmParams pp = p;
+    auto list_of = [pp, qb, ql](uint32_t l) { return ((size_t)(l * pp.qblocks + qb) * kGmN + ql); };
+    collector_merge_lists(
+        col, p.ranges, p.k, [&](uint32_t l) { return pp.list_counts[list_of(l)]; },
+        [&](uint32_t l, uint32_t i) { return pp.list_keys[list_of(l) * kGmList + i]; },
+        [&](uint32_t l, uint32_t i) { return pp.list_pays[list_of(l) * kGmList + i]; });
+    const uint32_t total = *col.count;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        out_keys[(size_t)q * p.k + i] = col.keys[i];
+        out_pays[(size_t)q * p.k + i] = col.pays[i];
+    }
+    if (threadIdx.x == 0) out_counts[q] = total;
+}
+
+// The tensor-core scores are a FILTER: fp32 accumulation inside the MMA datapath truncates, so a
+// score can be off by ~5e-8 * (3 * dims / 8) * |row| * |query| (measured 1.4e-5 at dims = 768 for an
+// all-positive dot). Every query therefore keeps k' > k approximate candidates, which are re-scored
+// here exactly like the single-query kernel does (same lane mapping and summation order as
+// flat_scan_kernel, f64 recovery included) and re-ranked. The kept set provably contains the true
+// top-k when the worst kept approximate rank, minus the error bound, is still beyond the exact
+// k-th rank; otherwise the query is flagged and redone on the single-query path.
+struct RescoreParams {
+    const float* rows;
+    size_t stride;
+    uint32_t dims, n, k, kprime;
+    const uint32_t* id_rank;
+    const float* queries;        // [nq, dims]
+    const u64* cand_keys;        // [nq][kprime] approximate keys, ascending
+    const u64* cand_pays;        // [nq][kprime]
+    const uint32_t* cand_counts; // [nq]
+    float err_coeff;             // bound = err_coeff * |query| * max |row|
+    float max_row_norm;
+    u64* out_pays;               // [nq][k]
+    uint32_t* out_counts;        // [nq]
+    uint32_t* flags;             // [nq]: 1 = redo on the single-query path, 2 = metric overflow
+};
+
+__device__ __forceinline__ float rank_from_key(u64 key) {
+    const uint32_t kbits = (uint32_t)(key >> 32);
+    const uint32_t bits = (kbits & 0x80000000u) ? (kbits ^ 0x80000000u) : ~kbits;
+    return __uint_as_float(bits);
+}
+
+template <int M>
+__global__ void __launch_bounds__(128) flat_gemm_rescore_kernel(const RescoreParams p) {
+    __shared__ __align__(16) unsigned char col_mem[256 * 16];
+    __shared__ u64 s_thresh;
+    __shared__ uint32_t s_count;
+    __shared__ float s_qn2[4];
+    const uint32_t q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Collector col;
+    col.init(col_mem, &s_thresh, &s_count, 256, p.k);
+    __syncthreads();
+    const uint32_t cnt = min(p.cand_counts[q], p.kprime);
+    const uint32_t nvec = p.dims >> 2;
+    const float4* q4 = reinterpret_cast<const float4*>(p.queries + (size_t)q * p.dims);
+    float qn2 = 0.0f;
+    for (uint32_t idx = lane; idx < nvec; idx += 32) {
+        const float4 v = __ldg(q4 + idx);
+        qn2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    qn2 = warp_sum(qn2);
+    bool fatal_any = false;
+    for (uint32_t c = warp; c < cnt; c += 4) {
+        const uint32_t row = (uint32_t)p.cand_pays[(size_t)q * p.kprime + c];
+        const float4* rp = reinterpret_cast<const float4*>(p.rows + (size_t)row * p.stride);
+        Scorer<M> sc;
+        sc.init();
+        for (uint32_t idx = lane; idx < nvec; idx += 32) sc.accum(__ldg(q4 + idx), ldg_stream(rp + idx));
+        bool bad, fatal;
+        float raw = sc.finish(0.0, bad, fatal);
+        if (bad) {
+            Recover<M> rc;
+            rc.init();
+            for (uint32_t idx = lane; idx < nvec; idx += 32) rc.accum(__ldg(q4 + idx), ldg_stream(rp + idx));
+            raw = rc.finish(fatal);
+        }
+        fatal_any |= fatal;
+        if (lane == 0) {
+            const uint32_t idr = p.id_rank ? __ldg(p.id_rank + row) : row;
+            col.push(((u64)order_key(rank_value(M, raw)) << 32) | idr, ((u64)__float_as_uint(raw) << 32) | row);
+        }
+    }
+    if (fatal_any && lane == 0) p.flags[q] = 2u;
+    const uint32_t kept = col.compact();
+    for (uint32_t i = threadIdx.x; i < kept; i += blockDim.x) p.out_pays[(size_t)q * p.k + i] = col.pays[i];
+    if (threadIdx.x == 0) {
+        p.out_counts[q] = kept;
+        // completeness check (see above); only needed when candidates were actually dropped
+        if (cnt == p.kprime && p.kprime < p.n && kept == p.k) {
+            const float bound = p.err_coeff * sqrtf(qn2) * p.max_row_norm;
+            const float worst_kept_approx = rank_from_key(p.cand_keys[(size_t)q * p.kprime + cnt - 1]);
+            const float exact_kth = rank_from_key(col.keys[p.k - 1]);
+            if (!(worst_kept_approx - bound > exact_kth) && p.flags[q] == 0u) p.flags[q] = 1u;
+        }
+    }
+    (void)s_qn2;
+}
+
+
+// queries [nq, dims] -> zero-padded hi / lo matrices [nq_pad, dims]
+__global__ void split_queries_kernel(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dims, float* hi, float* lo) {
+    const size_t total = (size_t)nq_pad * dims;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = i < (size_t)nq * dims ? q[i] : 0.0f;
+        const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        hi[i] = h;
+        lo[i] = x - h;
+    }
+}
+
+bool flat_gemm_eligible(int metric, size_t dims, size_t stride, size_t nq, size_t k, size_t n) {
+    if (std::getenv("VB_FLAT_NO_GEMM")) return false;
+    if (metric != kCosine && metric != kInnerProduct && metric != kNegativeInnerProduct) return false;
+    if (dims % 32 != 0 || stride != dims) return false;
+    const char* min_env = std::getenv("VB_FLAT_GEMM_MIN_BATCH");
+    const size_t min_batch = min_env ? (size_t)std::atoi(min_env) : 16;
+    if (nq < min_batch) return false;
+    if (k == 0 || 2 * k + 16 > 128 || n < 1024) return false;   // k' = 2k + 16 candidates kept per query
+    return true;
+}
+
+// max over rows of |row| (f32 from an f64 sum), one warp per row; non-negative floats order like uints
+__global__ void row_norm_max_kernel(const float* rows, size_t stride, uint32_t dims, uint32_t n, uint32_t* out_bits) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    float best = 0.0f;
+    for (size_t r = warp; r < n; r += warps) {
+        double s = 0.0;
+        for (uint32_t c = lane; c < dims; c += 32) {
+            const double v = rows[r * stride + c];
+            s = fma(v, v, s);
+        }
+        s = warp_sum(s);
+        best = fmaxf(best, (float)sqrt(s) * 1.0000002f);
+    }
+    if (lane == 0) atomicMax(out_bits, __float_as_uint(best));
+}
+
+Status flat_gemm_max_row_norm(SearchCtx& ctx, const float* d_rows, size_t stride, size_t n, size_t dims, float* out) {
+    VB_TRY(ctx.q_norms.reserve(16));
+    uint32_t* d_bits = ctx.q_norms.as<uint32_t>() + 2;
+    VB_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t), ctx.stream));
+    row_norm_max_kernel<<<148 * 8, 256, 0, ctx.stream>>>(d_rows, stride, (uint32_t)dims, (uint32_t)n, d_bits);
+    uint32_t bits = 0;
+    VB_CUDA(cudaMemcpyAsync(&bits, d_bits, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
+    VB_CUDA(cudaStreamSynchronize(ctx.stream));
+    std::memcpy(out, &bits, 4);
+    return Status::Ok();
+}
+
+typedef void (*RescoreKernel)(const RescoreParams);
+static RescoreKernel rescore_lookup(int metric) {
+    switch (metric) {
+        case kCosine: return flat_gemm_rescore_kernel<kCosine>;
+        case kInnerProduct: return flat_gemm_rescore_kernel<kInnerProduct>;
+        case kNegativeInnerProduct: return flat_gemm_rescore_kernel<kNegativeInnerProduct>;
+    }
+    return nullptr;
+}
+
+Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t stride, const uint32_t* d_id_rank,
+                        size_t n, size_t dims, float max_row_norm, const float* h_queries, size_t nq, size_t k,
+                        GemmResult* out) {
+    int dev = 0, sms = 0;
+    VB_CUDA(cudaGetDevice(&dev));
+    VB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const uint32_t qblocks_total = (uint32_t)((nq + kGmN - 1) / kGmN);
+    const uint32_t group = std::min<uint32_t>(qblocks_total, (uint32_t)sms);   // query blocks per launch
+    const size_t nq_pad = (size_t)qblocks_total * kGmN;
+    const size_t kprime = std::min<size_t>(std::min<size_t>(2 * k + 16, 128), n);   // approximate candidates kept
+    RescoreKernel rescore = rescore_lookup(metric);
+    if (!rescore) return Status::Cuda("metric not served by the batched kernel");
+
+    // stage queries, split into hi / lo on the device
+    const size_t qbytes = nq * dims * sizeof(float);
+    VB_TRY(ctx.h_queries.reserve(qbytes));
+    VB_TRY(ctx.queries.reserve(qbytes));
+    std::memcpy(ctx.h_queries.p, h_queries, qbytes);
+    VB_CUDA(cudaMemcpyAsync(ctx.queries.p, ctx.h_queries.p, qbytes, cudaMemcpyHostToDevice, ctx.stream));
+    VB_TRY(ctx.staging.reserve(2 * nq_pad * dims * sizeof(float)));
+    float* q_hi = ctx.staging.as<float>();
+    float* q_lo = q_hi + nq_pad * dims;
+    split_queries_kernel<<<148 * 4, 256, 0, ctx.stream>>>(ctx.queries.as<float>(), (uint32_t)nq, (uint32_t)nq_pad,
+                                                         (uint32_t)dims, q_hi, q_lo);
+    VB_CUDA(cudaGetLastError());
+
+    const size_t max_ctas = (size_t)sms;
+    VB_TRY(ctx.cand_keys.reserve(max_ctas * kGmN * kGmList * sizeof(u64)));
+    VB_TRY(ctx.cand_pays.reserve(max_ctas * kGmN * kGmList * sizeof(u64)));
+    VB_TRY(ctx.cand_counts.reserve(max_ctas * kGmN * sizeof(uint32_t) + 16));
+    // approximate stage output: keys | pays [nq_pad][k'] and counts [nq_pad]
+    VB_TRY(ctx.dump_keys.reserve(nq_pad * kprime * sizeof(u64)));
+    VB_TRY(ctx.dump_pays.reserve(nq_pad * kprime * sizeof(u64)));
+    VB_TRY(ctx.staging_rank.reserve(nq_pad * sizeof(uint32_t)));
+    // final output: pays [nq_pad][k] | counts [nq_pad] | flags [nq_pad]
+    VB_TRY(ctx.result.reserve(nq_pad * k * sizeof(u64) + 2 * nq_pad * sizeof(uint32_t)));
+
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    const size_t gsmem = (size_t)kGmStages * kGmStageBytes + 1024;
+    std::call_once(attr_once, [&] {
+        attr_err = cudaFuncSetAttribute(flat_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+    });
+    if (attr_err != cudaSuccess) return Status::Cuda(cudaGetErrorString(attr_err));
+
+    CUtensorMap tmap_a;
+    VB_TRY(make_tmap_rows_sw128(d_rows, n, stride, kGmTile, &tmap_a));
+    uint32_t cap = 256;
+    while (cap < 2 * kprime + 64) cap <<= 1;
+    u64* apx_keys = ctx.dump_keys.as<u64>();
+    u64* apx_pays = ctx.dump_pays.as<u64>();
+    uint32_t* apx_counts = ctx.staging_rank.as<uint32_t>();
+    u64* out_pays = ctx.result.as<u64>();
+    uint32_t* out_counts = reinterpret_cast<uint32_t*>(out_pays + nq_pad * k);
+    uint32_t* out_flags = out_counts + nq_pad;
+    VB_CUDA(cudaMemsetAsync(out_flags, 0, nq_pad * sizeof(uint32_t), ctx.stream));
+    VB_TRY(ctx.q_norms.reserve(16));
+    uint32_t* d_bad = ctx.q_norms.as<uint32_t>();   // scratch flag word, zero == fine
+    VB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), ctx.stream));
+
+    for (uint32_t qb0 = 0; qb0 < qblocks_total; qb0 += group) {
+        const uint32_t qblocks = std::min(group, qblocks_total - qb0);
+        const size_t q0 = (size_t)qb0 * kGmN;
+        const uint32_t nq_here = (uint32_t)std::min<size_t>(nq - q0, (size_t)qblocks * kGmN);
+        CUtensorMap tmap_bhi, tmap_blo;
+        VB_TRY(make_tmap_rows_sw128(q_hi + q0 * dims, (uint64_t)qblocks * kGmN, dims, kGmN, &tmap_bhi));
+        VB_TRY(make_tmap_rows_sw128(q_lo + q0 * dims, (uint64_t)qblocks * kGmN, dims, kGmN, &tmap_blo));
+        GemmParams p{};
+        p.n = (uint32_t)n;
+        p.dims = (uint32_t)dims;
+        p.nq = nq_here;
+        p.k = (uint32_t)kprime;
+        p.metric = metric;
+        p.qblocks = qblocks;
+        p.ranges = std::max<uint32_t>(1, (uint32_t)sms / qblocks);
+        p.id_rank = d_id_rank;
+        p.list_keys = ctx.cand_keys.as<u64>();
+        p.list_pays = ctx.cand_pays.as<u64>();
+        p.list_counts = ctx.cand_counts.as<uint32_t>();
+        p.bad = d_bad;
+        const uint32_t grid = p.qblocks * p.ranges;
+        flat_gemm_topk_kernel<<<grid, kGmThreads, gsmem, ctx.stream>>>(tmap_a, tmap_bhi, tmap_blo, p);
+        VB_CUDA(cudaGetLastError());
+        flat_gemm_merge_kernel<<<nq_here, 128, (size_t)cap * 16, ctx.stream>>>(p, cap, apx_keys + q0 * kprime,
+                                                                              apx_pays + q0 * kprime, apx_counts + q0);
+        VB_CUDA(cudaGetLastError());
+    }
+    RescoreParams rp{};
+    rp.rows = d_rows;
+    rp.stride = stride;
+    rp.dims = (uint32_t)dims;
+    rp.n = (uint32_t)n;
+    rp.k = (uint32_t)k;
+    rp.kprime = (uint32_t)kprime;
+    rp.id_rank = d_id_rank;
+    rp.queries = ctx.queries.as<float>();
+    rp.cand_keys = apx_keys;
+    rp.cand_pays = apx_pays;
+    rp.cand_counts = apx_counts;
+    rp.err_coeff = 1.0e-7f * (float)(3 * dims / 8);
+    rp.max_row_norm = max_row_norm;
+    rp.out_pays = out_pays;
+    rp.out_counts = out_counts;
+    rp.flags = out_flags;
+    rescore<<<(unsigned)nq, 128, 0, ctx.stream>>>(rp);
+    VB_CUDA(cudaGetLastError());
+
+    const size_t res_bytes = nq_pad * k * sizeof(u64) + 2 * nq_pad * sizeof(uint32_t);
+    VB_TRY(ctx.h_result.reserve(res_bytes + 16));
+    uint32_t* h_bad = reinterpret_cast<uint32_t*>(ctx.h_result.as<unsigned char>() + res_bytes);
+    cudaError_t e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, res_bytes, cudaMemcpyDeviceToHost, ctx.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx.stream);
+    if (e != cudaSuccess) {
+        ctx.poison();
+        return Status::Cuda(cudaGetErrorString(e));
+    }
+    out->non_finite = *h_bad != 0;
+    out->k = k;
+    out->counts.resize(nq);
+    out->flags.resize(nq);
+    out->rows.resize(nq * k);
+    out->raws.resize(nq * k);
+    const u64* pays = ctx.h_result.as<u64>();
+    const uint32_t* counts = reinterpret_cast<const uint32_t*>(pays + nq_pad * k);
+    const uint32_t* flags = counts + nq_pad;
+    for (size_t q = 0; q < nq; ++q) {
+        out->counts[q] = counts[q];
+        out->flags[q] = (uint8_t)flags[q];
+        for (size_t i = 0; i < k; ++i) {
+            const u64 pay = pays[q * k + i];
+            uint32_t bits = (uint32_t)(pay >> 32);
+            std::memcpy(&out->raws[q * k + i], &bits, 4);
+            out->rows[q * k + i] = (uint32_t)pay;
+        }
+    }
+    return Status::Ok();
+}
+
+}  // namespace vb

@@ -1,0 +1,29 @@
+// flat_gemm.h — K2: batched exact flat scan on tcgen05 (3xTF32) with fused per-query top-k.
+#pragma once
+#include <vector>
+
+#include "runtime.h"
+
+namespace vb {
+
+struct GemmResult {
+    size_t k = 0;
+    bool non_finite = false;          // a tensor-core score overflowed: redo the whole batch on the K1 path
+    std::vector<uint8_t> flags;       // [nq] 0 ok, 1 redo this query on the K1 path, 2 metric overflow
+    std::vector<uint32_t> counts;     // [nq]
+    std::vector<uint32_t> rows;       // [nq][k] device rows
+    std::vector<float> raws;          // [nq][k]
+};
+
+// Dot-product family (flat cosine == dot of stored vectors, inner product, negative inner product),
+// dims a multiple of 32 with no row padding, k <= 128, batches of >= 16 queries (VB_FLAT_GEMM_MIN_BATCH).
+bool flat_gemm_eligible(int metric, size_t dims, size_t stride, size_t nq, size_t k, size_t n);
+
+// max_row_norm: upper bound of |row| over the index (flat_gemm_max_row_norm), used by the
+// completeness check of the exact re-scoring stage.
+Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t stride, const uint32_t* d_id_rank,
+                        size_t n, size_t dims, float max_row_norm, const float* h_queries, size_t nq, size_t k,
+                        GemmResult* out);
+Status flat_gemm_max_row_norm(SearchCtx& ctx, const float* d_rows, size_t stride, size_t n, size_t dims, float* out);
+
+}  // namespace vb

@@ -2,6 +2,7 @@
 // (flat.rs:59-144, search.rs:38-73) so errors are indistinguishable at the NIF boundary.
 #include "flat_index.h"
 
+#include "flat_gemm.h"
 #include "hamming.h"
 
 #include <algorithm>
@@ -143,6 +144,7 @@ Status FlatIndex::insert_many(size_t n, const char* ids, const uint64_t* id_off,
     }
     if (n == 0) return Status::Ok();
     if (n_ + n >= kRankSpace - 1) return Status::Cuda("index row limit (2^32) exceeded");
+    max_norm_ = -1.0f;   // recomputed on the next batched search
     if (dev_ctx_) VB_CUDA(cudaDeviceSynchronize());
 
     if (dim_ == 0) {
@@ -274,6 +276,51 @@ Status FlatIndex::search(const float* queries, size_t nq, size_t len, size_t lim
     VB_CUDA(cudaSetDevice(device_));
     CtxLease ctx;
     VB_TRY(ctx.get());
+    const size_t kk = std::min(limit, n_);
+    if (flat_gemm_eligible(metric_, dim_, stride_, nq, kk, n_)) {
+        // K2: the batch is one dense contraction on the tensor cores (+ exact re-scoring)
+        {
+            std::lock_guard<std::mutex> ng(norm_mu_);
+            if (max_norm_ < 0.0f) VB_TRY(flat_gemm_max_row_norm(*ctx.ctx, d_rows_, stride_, n_, dim_, &max_norm_));
+        }
+        GemmResult gr;
+        VB_TRY(flat_gemm_search(*ctx.ctx, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, queries, nq, kk, &gr));
+        if (!gr.non_finite) {
+            std::vector<size_t> redo;
+            for (size_t q = 0; q < nq; ++q) {
+                if (gr.flags[q] == 2) return Status::Ref("metric overflow");
+                if (gr.flags[q] == 1) { redo.push_back(q); continue; }
+                Hits& h = (*out)[q];
+                for (uint32_t i = 0; i < gr.counts[q]; ++i) {
+                    const uint32_t row = gr.rows[q * gr.k + i];
+                    h.add(row_id_[row].data(), row_id_[row].size(), gr.raws[q * gr.k + i], row);
+                }
+            }
+            // queries whose candidate set could not be proven complete: single-query kernel
+            for (size_t q : redo) {
+                ScanJob one;
+                one.metric = metric_;
+                one.d_rows = d_rows_;
+                one.row_stride = stride_;
+                one.d_id_rank = d_rank_;
+                one.n = (uint32_t)n_;
+                one.dims = (uint32_t)dim_;
+                one.whole_rows = true;
+                one.h_queries = queries + q * len;
+                one.nq = 1;
+                one.q_len = len;
+                one.k = kk;
+                ScanResult r1;
+                VB_TRY(run_scan(*ctx.ctx, one, &r1));
+                if (r1.err_rows[0] != kNoError) return Status::Ref("metric overflow");
+                Hits& h = (*out)[q];
+                for (uint32_t i = 0; i < r1.counts[0]; ++i)
+                    h.add(row_id_[r1.rows[i]].data(), row_id_[r1.rows[i]].size(), r1.raws[i], r1.rows[i]);
+            }
+            return Status::Ok();
+        }
+        // an overflowing score needs the f64 recovery of the per-query kernel: fall through
+    }
     ScanJob job;
     job.metric = metric_;
     job.d_rows = d_rows_;
@@ -285,7 +332,7 @@ Status FlatIndex::search(const float* queries, size_t nq, size_t len, size_t lim
     job.h_queries = queries;
     job.nq = (uint32_t)nq;
     job.q_len = len;
-    job.k = std::min(limit, n_);
+    job.k = kk;
     ScanResult res;
     VB_TRY(run_scan(*ctx.ctx, job, &res));
     for (size_t q = 0; q < nq; ++q)

@@ -11,6 +11,7 @@
 // fall back to an even relabel when a gap is exhausted.
 #pragma once
 #include <map>
+#include <mutex>
 #include <shared_mutex>
 #include <string>
 #include <vector>
@@ -74,6 +75,8 @@ class FlatIndex {
     std::vector<uint32_t> h_rank_;
     std::map<std::string, uint32_t> id_row_;
     bool external_ranks_ = false;
+    std::mutex norm_mu_;
+    float max_norm_ = -1.0f;   // max |row| (device reduction, lazily), < 0 = unknown
     SearchCtx* dev_ctx_ = nullptr;  // workspace of the stream-ordered device-level entry
 };
 
