@@ -5,7 +5,9 @@
 //
 // Geometry: UMMA M = 128 rows x N = 256 queries x K = 8, fp32 accumulator in TMEM (256 columns).
 // CTA c serves query block (c mod QB) over a contiguous range of row tiles. Per 32-dim K chunk:
-//   producer warp   TMA: A chunk [128 rows x 32] (16 KB) + B chunk hi/lo [256 queries x 32] (2 x 32 KB)
+//   producer warp   TMA: A chunk [128 rows x 32] (16 KB, tensor map, 128-byte swizzle) + the query block's
+//                   hi|lo chunk as ONE 64 KB bulk copy of an image pre-swizzled by split_queries_kernel
+//                   (512 separate 128-byte tensor-map rows per chunk made the TMA unit the bottleneck)
 //   split warps     A chunk -> (hi, lo) -> TMEM (tcgen05.st), double buffered
 //   MMA warp        12 tcgen05.mma kind::tf32 (hi.hi, hi.lo, lo.hi x 4 k-steps), B from shared memory
 //   epilogue warps  per finished tile: tcgen05.ld 8 x 32 columns, score -> (rank key, id rank) ->
@@ -23,7 +25,9 @@
 
 namespace vb {
 
-constexpr int kGmThreads = 320;          // warps 0-3 epilogue, 4-7 split, 8 producer, 9 MMA
+constexpr int kGmEpiWarps = 8;           // two per TMEM lane quarter, half of the query columns each
+constexpr int kGmSplitWarp0 = kGmEpiWarps, kGmProducerWarp = kGmEpiWarps + 4, kGmMmaWarp = kGmEpiWarps + 5;
+constexpr int kGmThreads = (kGmMmaWarp + 1) * 32;   // warps 0-7 epilogue, 8-11 split, 12 producer, 13 MMA
 constexpr int kGmTile = 128;             // rows per tile (UMMA M)
 constexpr int kGmN = 256;                // queries per block (UMMA N)
 constexpr int kGmStages = 2;
@@ -40,7 +44,14 @@ struct GemmParams {
     u64* list_pays;
     uint32_t* list_counts;         // [cta][256]
     uint32_t* bad;                 // set when a non-finite score shows up (caller falls back)
+    uint32_t debug;                // timing experiments only (VB_GEMM_DEBUG): 1 skip A loads, 2 skip B loads, 4 skip split, 8 skip epilogue, 16 skip MMA
 };
+
+__device__ __forceinline__ float rank_from_key(u64 key) {
+    const uint32_t kbits = (uint32_t)(key >> 32);
+    const uint32_t bits = (kbits & 0x80000000u) ? (kbits ^ 0x80000000u) : ~kbits;
+    return __uint_as_float(bits);
+}
 
 // Best k of one list (<= 256 entries, 8 per lane) by k rounds of warp arg-min; rewrites the
 // list front in ascending order. Returns the k-th key (or kKeyMax when fewer than k entries).
@@ -79,12 +90,13 @@ __device__ u64 warp_compact_list(u64* keys, u64* pays, uint32_t count, uint32_t 
 }
 
 __global__ void __launch_bounds__(kGmThreads, 1)
-flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bhi,
-                      const __grid_constant__ CUtensorMap tmap_blo, const GemmParams p) {
+flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned char* __restrict__ q_blobs,
+                      const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char gsmem[];
     __shared__ __align__(8) uint64_t full_bar[kGmStages], empty_bar[kGmStages], a_ready[2], a_free[2], d_full, d_free;
     __shared__ uint32_t tmem_slot;
-    __shared__ u64 s_thr[kGmN];
+    __shared__ u64 s_thr[kGmN];          // exact threshold key per query of this block
+    __shared__ float s_thr_rank[kGmN];   // its rank value: the cheap first-level filter
     __shared__ uint32_t s_cnt[kGmN];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -95,7 +107,7 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const uint32_t tile1 = active ? (uint32_t)((uint64_t)tiles_total * (rr + 1) / p.ranges) : 0;
     const uint32_t chunks = p.dims / 32;
 
-    for (int q = tid; q < kGmN; q += kGmThreads) { s_thr[q] = kKeyMax; s_cnt[q] = 0; }
+    for (int q = tid; q < kGmN; q += kGmThreads) { s_thr[q] = kKeyMax; s_thr_rank[q] = INFINITY; s_cnt[q] = 0; }
     if (tid == 0) {
         for (int s = 0; s < kGmStages; ++s) {
             tc::mbar_init(&full_bar[s], 1);
@@ -104,16 +116,16 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             tc::mbar_init(&a_free[s], 1);
         }
         tc::mbar_init(&d_full, 1);
-        tc::mbar_init(&d_free, 4);
+        tc::mbar_init(&d_free, kGmEpiWarps);
         tc::mbar_fence_init();
     }
-    if (warp == 9) tc::tmem_alloc(&tmem_slot, 512);
+    if (warp == kGmMmaWarp) tc::tmem_alloc(&tmem_slot, 512);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tbase = tmem_slot;
 
-    if (warp == 8) {
+    if (warp == kGmProducerWarp) {
         // ===== producer =====
         if (lane == 0) {
             uint32_t cc = 0;
@@ -122,14 +134,17 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     const uint32_t s = cc % kGmStages, ph = (cc / kGmStages) & 1u;
                     unsigned char* st = gsmem + (size_t)s * kGmStageBytes;
                     tc::mbar_wait(&empty_bar[s], ph ^ 1u);
-                    tc::mbar_arrive_expect_tx(&full_bar[s], kGmStageBytes);
-                    tc::tma_load_2d(st, &tmap_a, kc * 32, tile * kGmTile, &full_bar[s]);
-                    tc::tma_load_2d(st + 16384, &tmap_bhi, kc * 32, qb * kGmN, &full_bar[s]);
-                    tc::tma_load_2d(st + 16384 + 32768, &tmap_blo, kc * 32, qb * kGmN, &full_bar[s]);
+                    const uint32_t tx = ((p.debug & 1u) ? 0u : 16384u) + ((p.debug & 2u) ? 0u : 65536u);
+                    if (tx) tc::mbar_arrive_expect_tx(&full_bar[s], tx);
+                    else tc::mbar_arrive(&full_bar[s]);
+                    if (!(p.debug & 1u)) tc::tma_load_2d(st, &tmap_a, kc * 32, tile * kGmTile, &full_bar[s]);
+                    // the query block's (hi | lo) chunk is one contiguous, pre-swizzled 64 KB image
+                    if (!(p.debug & 2u))
+                        tma_bulk_g2s(st + 16384, q_blobs + ((size_t)qb * chunks + kc) * 65536u, 65536u, &full_bar[s]);
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kGmMmaWarp) {
         // ===== MMA issuer (warp-uniform control flow, one elected lane issues) =====
         const uint32_t idesc = tc::umma_idesc_tf32(kGmTile, kGmN);
         uint32_t cc = 0, it = 0;
@@ -145,6 +160,7 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 const uint64_t bl0 = tc::umma_smem_desc_sw128(st_addr + 16384 + 32768);
                 const uint32_t a0 = tbase + kGmACol + s * 64u;
                 if (tc::elect_one()) {
+                    if (!(p.debug & 16u))
 #pragma unroll
                     for (uint32_t ks = 0; ks < 4; ++ks) {
 #pragma unroll
@@ -161,7 +177,7 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 __syncwarp();
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= kGmSplitWarp0) {
         // ===== split warps: A chunk -> (hi, lo) -> TMEM =====
         const uint32_t quarter = warp & 3u;
         const uint32_t row = quarter * 32u + lane;
@@ -174,6 +190,7 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 tc::mbar_wait(&a_free[s], ph ^ 1u);
                 tc::fence_after_sync();
                 const unsigned char* blk = gsmem + (size_t)s * kGmStageBytes + row * 128u;
+                if (!(p.debug & 4u)) {
                 uint32_t hi[32], lo[32];
 #pragma unroll
                 for (uint32_t c = 0; c < 8; ++c) {
@@ -189,6 +206,7 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 tc::tmem_st32(lane_addr + kGmACol + s * 64u, hi);
                 tc::tmem_st32(lane_addr + kGmACol + s * 64u + 32u, lo);
                 tc::tmem_st_wait();
+                }
                 tc::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) {
@@ -198,10 +216,13 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
         }
     } else {
-        // ===== epilogue warps 0-3 =====
-        const uint32_t quarter = warp;
+        // ===== epilogue warps 0-7: warp w reads TMEM lanes of quarter (w & 3), query columns of half (w >> 2) =====
+        const uint32_t quarter = warp & 3u, half = warp >> 2;
         const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
         const size_t list_base = (size_t)blockIdx.x * kGmN;
+        // rank = fma(dot, -1, bias): cosine 1 - dot (one rounding, == 1.0f - raw), inner product / negative
+        // inner product -dot (distances.rs:113-119 with raw = dot resp. -dot)
+        const float bias = p.metric == kCosine ? 1.0f : 0.0f;
         uint32_t it = 0;
         for (uint32_t tile = tile0; tile < tile1; ++tile, ++it) {
             const uint32_t row = tile * kGmTile + quarter * 32u + lane;
@@ -209,47 +230,53 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const uint32_t idr = valid ? (p.id_rank ? __ldg(p.id_rank + row) : row) : 0u;
             tc::mbar_wait(&d_full, it & 1u);
             tc::fence_after_sync();
-            for (uint32_t cg = 0; cg < kGmN / 32; ++cg) {
-                if (qb * kGmN + cg * 32u >= p.nq) break;       // padded query columns (uniform)
+            uint32_t worst_bits = 0;   // max |score| bits: >= 0x7f800000 means a non-finite score
+            for (uint32_t cg = half * 4u; cg < half * 4u + 4u; ++cg) {
+                if ((p.debug & 8u) || qb * kGmN + cg * 32u >= p.nq) break;       // padded query columns (uniform)
                 uint32_t r[32];
                 tc::tmem_ld32(lane_addr + cg * 32u, r);
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const uint32_t q = cg * 32u + j;
-                    float raw = __uint_as_float(r[j]);
-                    if (p.metric == kNegativeInnerProduct) raw = -raw;
-                    if (valid && !isfinite(raw)) *p.bad = 1u;
-                    const uint32_t rk = order_key(p.metric == kCosine ? __fsub_rn(1.0f, raw)
-                                                  : p.metric == kInnerProduct ? -raw : raw);   // distances.rs:113-119
-                    const u64 key = ((u64)rk << 32) | idr;
-                    if (valid && qb * kGmN + q < p.nq && key < s_thr[q]) {
-                        const uint32_t slot = atomicAdd(&s_cnt[q], 1u);
-                        if (slot < kGmList) {
-                            p.list_keys[(list_base + q) * kGmList + slot] = key;
-                            p.list_pays[(list_base + q) * kGmList + slot] = ((u64)__float_as_uint(raw) << 32) | row;
+                    const float dot = __uint_as_float(r[j]);
+                    worst_bits = max(worst_bits, r[j] & 0x7fffffffu);
+                    const float rankv = fmaf(dot, -1.0f, bias);
+                    if (rankv <= s_thr_rank[q] && valid && qb * kGmN + q < p.nq) {   // first-level filter: one compare
+                        const u64 key = ((u64)order_key(rankv) << 32) | idr;
+                        if (key < s_thr[q]) {
+                            const float raw = p.metric == kNegativeInnerProduct ? -dot : dot;
+                            const uint32_t slot = atomicAdd(&s_cnt[q], 1u);
+                            if (slot < kGmList) {
+                                p.list_keys[(list_base + q) * kGmList + slot] = key;
+                                p.list_pays[(list_base + q) * kGmList + slot] = ((u64)__float_as_uint(raw) << 32) | row;
+                            }
                         }
                     }
                 }
             }
+            if (valid && worst_bits >= 0x7f800000u) *p.bad = 1u;
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&d_free);
             // lists that could overflow during the next tile are cut back to their best k
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            __threadfence_block();
-            for (uint32_t q = warp; q < kGmN; q += 4) {
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            for (uint32_t q = warp; q < kGmN; q += kGmEpiWarps) {
                 const uint32_t cnt = min(s_cnt[q], kGmList);
                 if (cnt + kGmTile > kGmList) {
                     const u64 kth = warp_compact_list(p.list_keys + (list_base + q) * kGmList,
                                                       p.list_pays + (list_base + q) * kGmList, cnt, p.k, lane);
-                    if (lane == 0) { s_cnt[q] = min(cnt, p.k); s_thr[q] = kth; }
+                    if (lane == 0) {
+                        s_cnt[q] = min(cnt, p.k);
+                        s_thr[q] = kth;
+                        s_thr_rank[q] = kth == kKeyMax ? INFINITY : rank_from_key(kth);
+                    }
                 }
             }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+            asm volatile("bar.sync 2, 256;" ::: "memory");
         }
         // final cut of every list of this CTA
-        for (uint32_t q = warp; q < kGmN; q += 4) {
+        for (uint32_t q = warp; q < kGmN; q += kGmEpiWarps) {
             const uint32_t cnt = min(s_cnt[q], kGmList);
             if (cnt > 0) warp_compact_list(p.list_keys + (list_base + q) * kGmList, p.list_pays + (list_base + q) * kGmList,
                                            cnt, p.k, lane);
@@ -258,7 +285,7 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 9) tc::tmem_dealloc(tbase, 512);
+    if (warp == kGmMmaWarp) tc::tmem_dealloc(tbase, 512);
 }
 
 // Per query: merge the sorted lists of the CTAs that served its query block.
@@ -303,16 +330,12 @@ struct RescoreParams {
     const uint32_t* cand_counts; // [nq]
     float err_coeff;             // bound = err_coeff * |query| * max |row|
     float max_row_norm;
+    u64* out_keys;               // [nq][k] exact keys (optional)
     u64* out_pays;               // [nq][k]
     uint32_t* out_counts;        // [nq]
     uint32_t* flags;             // [nq]: 1 = redo on the single-query path, 2 = metric overflow
 };
 
-__device__ __forceinline__ float rank_from_key(u64 key) {
-    const uint32_t kbits = (uint32_t)(key >> 32);
-    const uint32_t bits = (kbits & 0x80000000u) ? (kbits ^ 0x80000000u) : ~kbits;
-    return __uint_as_float(bits);
-}
 
 template <int M>
 __global__ void __launch_bounds__(128) flat_gemm_rescore_kernel(const RescoreParams p) {
@@ -356,7 +379,10 @@ __global__ void __launch_bounds__(128) flat_gemm_rescore_kernel(const RescorePar
     }
     if (fatal_any && lane == 0) p.flags[q] = 2u;
     const uint32_t kept = col.compact();
-    for (uint32_t i = threadIdx.x; i < kept; i += blockDim.x) p.out_pays[(size_t)q * p.k + i] = col.pays[i];
+    for (uint32_t i = threadIdx.x; i < kept; i += blockDim.x) {
+        p.out_pays[(size_t)q * p.k + i] = col.pays[i];
+        if (p.out_keys) p.out_keys[(size_t)q * p.k + i] = col.keys[i];
+    }
     if (threadIdx.x == 0) {
         p.out_counts[q] = kept;
         // completeness check (see above); only needed when candidates were actually dropped
@@ -371,14 +397,21 @@ __global__ void __launch_bounds__(128) flat_gemm_rescore_kernel(const RescorePar
 }
 
 
-// queries [nq, dims] -> zero-padded hi / lo matrices [nq_pad, dims]
-__global__ void split_queries_kernel(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dims, float* hi, float* lo) {
-    const size_t total = (size_t)nq_pad * dims;
+// queries [nq, dims] -> per (query block, 32-dim chunk) a 64 KB image: hi [256 x 32] | lo [256 x 32], each
+// already in the UMMA K-major SWIZZLE_128B shared-memory layout (zero rows beyond nq).
+__global__ void split_queries_kernel(const float* q, uint32_t nq, uint32_t qblocks, uint32_t dims, unsigned char* blobs) {
+    const uint32_t chunks = dims / 32;
+    const size_t total = (size_t)qblocks * kGmN * dims;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const float x = i < (size_t)nq * dims ? q[i] : 0.0f;
+        const uint32_t k = (uint32_t)(i % dims);
+        const size_t row = i / dims;                       // padded query index
+        const uint32_t qb = (uint32_t)(row / kGmN), n = (uint32_t)(row % kGmN);
+        const float x = row < nq ? q[row * dims + k] : 0.0f;
         const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-        hi[i] = h;
-        lo[i] = x - h;
+        unsigned char* blob = blobs + ((size_t)qb * chunks + k / 32u) * 65536u;
+        const uint32_t off = tc::sw128_offset(n, k % 32u);
+        *reinterpret_cast<float*>(blob + off) = h;
+        *reinterpret_cast<float*>(blob + 32768u + off) = x - h;
     }
 }
 
@@ -389,7 +422,7 @@ bool flat_gemm_eligible(int metric, size_t dims, size_t stride, size_t nq, size_
     const char* min_env = std::getenv("VB_FLAT_GEMM_MIN_BATCH");
     const size_t min_batch = min_env ? (size_t)std::atoi(min_env) : 16;
     if (nq < min_batch) return false;
-    if (k == 0 || 2 * k + 16 > 128 || n < 1024) return false;   // k' = 2k + 16 candidates kept per query
+    if (k == 0 || k > 100 || n < 1024) return false;   // k' = k + max(8, k/4) <= 128 candidates kept per query
     return true;
 }
 
@@ -432,48 +465,42 @@ static RescoreKernel rescore_lookup(int metric) {
     return nullptr;
 }
 
-Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t stride, const uint32_t* d_id_rank,
-                        size_t n, size_t dims, float max_row_norm, const float* h_queries, size_t nq, size_t k,
-                        GemmResult* out) {
+// Device part: queries already in device memory ([nq, dims]); leaves, on `stream`, the exact top-k
+// payloads [nq][k] (raw bits << 32 | row), optional exact keys, counts [nq] and flags [nq]
+// (0 ok, 1 redo on the single-query path, 2 metric overflow); *d_bad != 0 when a tensor-core
+// score was non-finite (redo the whole batch). No host synchronisation.
+Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, size_t stride,
+                               const uint32_t* d_id_rank, size_t n, size_t dims, float max_row_norm,
+                               const float* d_queries, size_t nq, size_t k, u64* d_out_keys, u64* d_out_pays,
+                               uint32_t* d_out_counts, uint32_t* d_out_flags, uint32_t* d_bad, cudaStream_t stream) {
     int dev = 0, sms = 0;
     VB_CUDA(cudaGetDevice(&dev));
     VB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const uint32_t qblocks_total = (uint32_t)((nq + kGmN - 1) / kGmN);
     const uint32_t group = std::min<uint32_t>(qblocks_total, (uint32_t)sms);   // query blocks per launch
     const size_t nq_pad = (size_t)qblocks_total * kGmN;
-    const size_t kprime = std::min<size_t>(std::min<size_t>(2 * k + 16, 128), n);   // approximate candidates kept
+    const size_t kprime = std::min<size_t>(std::min<size_t>(k + std::max<size_t>(8, k / 4), 128), n);   // approximate candidates kept
     RescoreKernel rescore = rescore_lookup(metric);
     if (!rescore) return Status::Cuda("metric not served by the batched kernel");
 
-    // stage queries, split into hi / lo on the device
-    const size_t qbytes = nq * dims * sizeof(float);
-    VB_TRY(ctx.h_queries.reserve(qbytes));
-    VB_TRY(ctx.queries.reserve(qbytes));
-    std::memcpy(ctx.h_queries.p, h_queries, qbytes);
-    VB_CUDA(cudaMemcpyAsync(ctx.queries.p, ctx.h_queries.p, qbytes, cudaMemcpyHostToDevice, ctx.stream));
     VB_TRY(ctx.staging.reserve(2 * nq_pad * dims * sizeof(float)));
-    float* q_hi = ctx.staging.as<float>();
-    float* q_lo = q_hi + nq_pad * dims;
-    split_queries_kernel<<<148 * 4, 256, 0, ctx.stream>>>(ctx.queries.as<float>(), (uint32_t)nq, (uint32_t)nq_pad,
-                                                         (uint32_t)dims, q_hi, q_lo);
+    unsigned char* q_blobs = ctx.staging.as<unsigned char>();
+    split_queries_kernel<<<148 * 4, 256, 0, stream>>>(d_queries, (uint32_t)nq, qblocks_total, (uint32_t)dims, q_blobs);
     VB_CUDA(cudaGetLastError());
 
     const size_t max_ctas = (size_t)sms;
     VB_TRY(ctx.cand_keys.reserve(max_ctas * kGmN * kGmList * sizeof(u64)));
     VB_TRY(ctx.cand_pays.reserve(max_ctas * kGmN * kGmList * sizeof(u64)));
     VB_TRY(ctx.cand_counts.reserve(max_ctas * kGmN * sizeof(uint32_t) + 16));
-    // approximate stage output: keys | pays [nq_pad][k'] and counts [nq_pad]
     VB_TRY(ctx.dump_keys.reserve(nq_pad * kprime * sizeof(u64)));
     VB_TRY(ctx.dump_pays.reserve(nq_pad * kprime * sizeof(u64)));
     VB_TRY(ctx.staging_rank.reserve(nq_pad * sizeof(uint32_t)));
-    // final output: pays [nq_pad][k] | counts [nq_pad] | flags [nq_pad]
-    VB_TRY(ctx.result.reserve(nq_pad * k * sizeof(u64) + 2 * nq_pad * sizeof(uint32_t)));
 
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
-    const size_t gsmem = (size_t)kGmStages * kGmStageBytes + 1024;
+    const size_t smem_bytes = (size_t)kGmStages * kGmStageBytes + 1024;
     std::call_once(attr_once, [&] {
-        attr_err = cudaFuncSetAttribute(flat_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+        attr_err = cudaFuncSetAttribute(flat_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     });
     if (attr_err != cudaSuccess) return Status::Cuda(cudaGetErrorString(attr_err));
 
@@ -484,21 +511,13 @@ Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t 
     u64* apx_keys = ctx.dump_keys.as<u64>();
     u64* apx_pays = ctx.dump_pays.as<u64>();
     uint32_t* apx_counts = ctx.staging_rank.as<uint32_t>();
-    u64* out_pays = ctx.result.as<u64>();
-    uint32_t* out_counts = reinterpret_cast<uint32_t*>(out_pays + nq_pad * k);
-    uint32_t* out_flags = out_counts + nq_pad;
-    VB_CUDA(cudaMemsetAsync(out_flags, 0, nq_pad * sizeof(uint32_t), ctx.stream));
-    VB_TRY(ctx.q_norms.reserve(16));
-    uint32_t* d_bad = ctx.q_norms.as<uint32_t>();   // scratch flag word, zero == fine
-    VB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), ctx.stream));
+    VB_CUDA(cudaMemsetAsync(d_out_flags, 0, nq * sizeof(uint32_t), stream));
+    VB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), stream));
 
     for (uint32_t qb0 = 0; qb0 < qblocks_total; qb0 += group) {
         const uint32_t qblocks = std::min(group, qblocks_total - qb0);
         const size_t q0 = (size_t)qb0 * kGmN;
         const uint32_t nq_here = (uint32_t)std::min<size_t>(nq - q0, (size_t)qblocks * kGmN);
-        CUtensorMap tmap_bhi, tmap_blo;
-        VB_TRY(make_tmap_rows_sw128(q_hi + q0 * dims, (uint64_t)qblocks * kGmN, dims, kGmN, &tmap_bhi));
-        VB_TRY(make_tmap_rows_sw128(q_lo + q0 * dims, (uint64_t)qblocks * kGmN, dims, kGmN, &tmap_blo));
         GemmParams p{};
         p.n = (uint32_t)n;
         p.dims = (uint32_t)dims;
@@ -512,11 +531,13 @@ Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t 
         p.list_pays = ctx.cand_pays.as<u64>();
         p.list_counts = ctx.cand_counts.as<uint32_t>();
         p.bad = d_bad;
+        { const char* dbg = std::getenv("VB_GEMM_DEBUG"); p.debug = dbg ? (uint32_t)std::atoi(dbg) : 0u; }
         const uint32_t grid = p.qblocks * p.ranges;
-        flat_gemm_topk_kernel<<<grid, kGmThreads, gsmem, ctx.stream>>>(tmap_a, tmap_bhi, tmap_blo, p);
+        flat_gemm_topk_kernel<<<grid, kGmThreads, smem_bytes, stream>>>(
+            tmap_a, q_blobs + (size_t)qb0 * (dims / 32) * 65536u, p);
         VB_CUDA(cudaGetLastError());
-        flat_gemm_merge_kernel<<<nq_here, 128, (size_t)cap * 16, ctx.stream>>>(p, cap, apx_keys + q0 * kprime,
-                                                                              apx_pays + q0 * kprime, apx_counts + q0);
+        flat_gemm_merge_kernel<<<nq_here, 128, (size_t)cap * 16, stream>>>(p, cap, apx_keys + q0 * kprime,
+                                                                          apx_pays + q0 * kprime, apx_counts + q0);
         VB_CUDA(cudaGetLastError());
     }
     RescoreParams rp{};
@@ -527,39 +548,57 @@ Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t 
     rp.k = (uint32_t)k;
     rp.kprime = (uint32_t)kprime;
     rp.id_rank = d_id_rank;
-    rp.queries = ctx.queries.as<float>();
+    rp.queries = d_queries;
     rp.cand_keys = apx_keys;
     rp.cand_pays = apx_pays;
     rp.cand_counts = apx_counts;
     rp.err_coeff = 1.0e-7f * (float)(3 * dims / 8);
     rp.max_row_norm = max_row_norm;
-    rp.out_pays = out_pays;
-    rp.out_counts = out_counts;
-    rp.flags = out_flags;
-    rescore<<<(unsigned)nq, 128, 0, ctx.stream>>>(rp);
+    rp.out_keys = d_out_keys;
+    rp.out_pays = d_out_pays;
+    rp.out_counts = d_out_counts;
+    rp.flags = d_out_flags;
+    rescore<<<(unsigned)nq, 128, 0, stream>>>(rp);
     VB_CUDA(cudaGetLastError());
+    return Status::Ok();
+}
 
-    const size_t res_bytes = nq_pad * k * sizeof(u64) + 2 * nq_pad * sizeof(uint32_t);
-    VB_TRY(ctx.h_result.reserve(res_bytes + 16));
-    uint32_t* h_bad = reinterpret_cast<uint32_t*>(ctx.h_result.as<unsigned char>() + res_bytes);
+Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t stride, const uint32_t* d_id_rank,
+                        size_t n, size_t dims, float max_row_norm, const float* h_queries, size_t nq, size_t k,
+                        GemmResult* out) {
+    const size_t qbytes = nq * dims * sizeof(float);
+    VB_TRY(ctx.h_queries.reserve(qbytes));
+    VB_TRY(ctx.queries.reserve(qbytes));
+    std::memcpy(ctx.h_queries.p, h_queries, qbytes);
+    VB_CUDA(cudaMemcpyAsync(ctx.queries.p, ctx.h_queries.p, qbytes, cudaMemcpyHostToDevice, ctx.stream));
+    // result block: pays [nq][k] | counts [nq] | flags [nq] | bad
+    const size_t res_bytes = nq * k * sizeof(u64) + 2 * nq * sizeof(uint32_t) + 16;
+    VB_TRY(ctx.result.reserve(res_bytes));
+    u64* out_pays = ctx.result.as<u64>();
+    uint32_t* out_counts = reinterpret_cast<uint32_t*>(out_pays + nq * k);
+    uint32_t* out_flags = out_counts + nq;
+    uint32_t* d_bad = out_flags + nq;
+    Status s = flat_gemm_search_device(ctx, metric, d_rows, stride, d_id_rank, n, dims, max_row_norm,
+                                       ctx.queries.as<float>(), nq, k, nullptr, out_pays, out_counts, out_flags, d_bad,
+                                       ctx.stream);
+    if (!s.ok()) { ctx.poison(); return s; }
+    VB_TRY(ctx.h_result.reserve(res_bytes));
     cudaError_t e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, res_bytes, cudaMemcpyDeviceToHost, ctx.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx.stream);
     if (e != cudaSuccess) {
         ctx.poison();
         return Status::Cuda(cudaGetErrorString(e));
     }
-    out->non_finite = *h_bad != 0;
+    const u64* pays = ctx.h_result.as<u64>();
+    const uint32_t* counts = reinterpret_cast<const uint32_t*>(pays + nq * k);
+    const uint32_t* flags = counts + nq;
+    out->non_finite = flags[nq] != 0;
     out->k = k;
-    out->counts.resize(nq);
+    out->counts.assign(counts, counts + nq);
     out->flags.resize(nq);
     out->rows.resize(nq * k);
     out->raws.resize(nq * k);
-    const u64* pays = ctx.h_result.as<u64>();
-    const uint32_t* counts = reinterpret_cast<const uint32_t*>(pays + nq_pad * k);
-    const uint32_t* flags = counts + nq_pad;
     for (size_t q = 0; q < nq; ++q) {
-        out->counts[q] = counts[q];
         out->flags[q] = (uint8_t)flags[q];
         for (size_t i = 0; i < k; ++i) {
             const u64 pay = pays[q * k + i];

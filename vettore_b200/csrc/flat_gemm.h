@@ -24,6 +24,10 @@ bool flat_gemm_eligible(int metric, size_t dims, size_t stride, size_t nq, size_
 Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t stride, const uint32_t* d_id_rank,
                         size_t n, size_t dims, float max_row_norm, const float* h_queries, size_t nq, size_t k,
                         GemmResult* out);
+Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, size_t stride,
+                               const uint32_t* d_id_rank, size_t n, size_t dims, float max_row_norm,
+                               const float* d_queries, size_t nq, size_t k, u64* d_out_keys, u64* d_out_pays,
+                               uint32_t* d_out_counts, uint32_t* d_out_flags, uint32_t* d_bad, cudaStream_t stream);
 Status flat_gemm_max_row_norm(SearchCtx& ctx, const float* d_rows, size_t stride, size_t n, size_t dims, float* out);
 
 }  // namespace vb

@@ -531,6 +531,22 @@ Status FlatIndex::search_device(const float* d_queries, size_t nq, size_t q_stri
         dev_ctx_->device = device_;
         VB_CUDA(cudaStreamCreateWithFlags(&dev_ctx_->stream, cudaStreamNonBlocking));
     }
+    const size_t kk = std::min(limit, n_);
+    if (q_stride == dim_ && flat_gemm_eligible(metric_, dim_, stride_, nq, kk, n_)) {
+        // K2 on the caller's stream. The completeness flags of the re-scoring stage stay in the
+        // context here (the host-facing search() acts on them; see flat_gemm.cu).
+        if (max_norm_ < 0.0f) VB_TRY(flat_gemm_max_row_norm(*dev_ctx_, d_rows_, stride_, n_, dim_, &max_norm_));
+        SearchCtx& c = *dev_ctx_;
+        VB_TRY(c.result.reserve(nq * kk * sizeof(u64) + 2 * nq * sizeof(uint32_t) + 16));
+        VB_TRY(c.out_keys.reserve(nq * kk * sizeof(u64)));
+        u64* pays = c.result.as<u64>();
+        uint32_t* counts = reinterpret_cast<uint32_t*>(pays + nq * kk);
+        uint32_t* flags = counts + nq;
+        VB_TRY(flat_gemm_search_device(c, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, d_queries, nq, kk,
+                                       c.out_keys.as<u64>(), pays, counts, flags, flags + nq, stream));
+        return unpack_device_results(c.out_keys.as<u64>(), pays, counts, (uint32_t)nq, (uint32_t)kk, d_keys, d_values,
+                                     d_rows, d_counts, stream);
+    }
     ScanJob job;
     job.metric = metric_;
     job.d_rows = d_rows_;
@@ -540,7 +556,7 @@ Status FlatIndex::search_device(const float* d_queries, size_t nq, size_t q_stri
     job.dims = (uint32_t)dim_;
     job.whole_rows = true;
     job.nq = (uint32_t)nq;
-    job.k = std::min(limit, n_);
+    job.k = kk;
     return run_scan_device(*dev_ctx_, job, d_queries, q_stride, nullptr, d_keys, d_values, d_rows, d_counts,
                            stream);
 }

@@ -302,6 +302,15 @@ Status run_scan_final(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_
     return Status::Ok();
 }
 
+Status unpack_device_results(const u64* d_keys_in, const u64* d_pays, const uint32_t* d_counts_in, uint32_t nq, uint32_t k,
+                             u64* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream) {
+    const uint32_t total = nq * k;
+    unpack_results_kernel<<<(std::max(total, nq) + 255) / 256, 256, 0, stream>>>(d_keys_in, d_pays, d_counts_in, nq, k, d_keys,
+                                                                                  d_values, d_rows, d_counts);
+    VB_CUDA(cudaGetLastError());
+    return Status::Ok();
+}
+
 Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_queries, size_t q_stride,
                        const double* d_q_norms, u64* d_keys, float* d_values, uint32_t* d_rows,
                        uint32_t* d_counts, cudaStream_t stream) {

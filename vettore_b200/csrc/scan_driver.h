@@ -48,4 +48,8 @@ Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_querie
                        const double* d_q_norms, u64* d_keys, float* d_values, uint32_t* d_rows,
                        uint32_t* d_counts, cudaStream_t stream);
 
+// (key, payload) pairs -> separate keys / values / rows arrays (device, on `stream`).
+Status unpack_device_results(const u64* d_keys_in, const u64* d_pays, const uint32_t* d_counts_in, uint32_t nq, uint32_t k,
+                             u64* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream);
+
 }  // namespace vb
