@@ -185,8 +185,11 @@ def test_binary_top_k_validates_empty_batches_limits_and_word_boundaries():  # s
     assert err(nifs.binary_top_k([("bad", [0])], q, 65, 1)) == "dimension mismatch"
 
 
-@pytest.mark.parametrize("dims", [1, 63, 64, 65, 127, 128, 129, 384, 768, 1024, 2100])
-def test_binary_top_k_random_codes_bit_exact(dims):  # distances.rs:675-707 + search.rs:76-92
+@pytest.mark.parametrize("dims", [1, 63, 64, 65, 127, 128, 129, 256, 300, 384, 576, 768, 1024, 2048, 2100, 4096, 4500, 8192])
+@pytest.mark.parametrize("no_stream", [False, True])
+def test_binary_top_k_random_codes_bit_exact(dims, no_stream, monkeypatch):  # distances.rs:675-707 + search.rs:76-92
+    if no_stream:   # K3's register-staged kernel also for the shapes the TMA ring would take
+        monkeypatch.setenv("VB_HAMMING_NO_STREAM", "1")
     rng = np.random.default_rng(dims)
     nw = (dims + 63) // 64
     n = 777

@@ -123,3 +123,30 @@ def test_collection_mirror_shapes_results_like_the_reference():
     c.delete("e042")
     assert ok(c.search(q, limit=5))[0].id != "e042"
     assert c.search(q, limit=0) == ("error", "invalid_limit")
+
+
+@pytest.mark.parametrize("n,dims,k,narrow", [(300_000, 256, 1000, False), (250_000, 192, 500, False),
+                                             (200_000, 64, 300, True), (150_000, 100, 1000, False)])
+@pytest.mark.parametrize("no_stream", [False, True])
+def test_hamming_large_k_over_many_rows(n, dims, k, narrow, no_stream, monkeypatch):
+    """K3 with k > 64 (histogram thresholds) over enough rows that every CTA prunes many times; the expected order is
+    (distance, id bytes) as binary_top_k's (search.rs:186-203). `narrow` packs the distances into few values so the
+    k-th distance is a large tie. The grid is capped so each CTA meets many collector checkpoints."""
+    monkeypatch.setenv("VB_HAMMING_MAX_GRID", "3")
+    if no_stream:   # the register-staged kernel instead of the TMA ring
+        monkeypatch.setenv("VB_HAMMING_NO_STREAM", "1")
+    rng = np.random.default_rng(n + dims)
+    nw = (dims + 63) // 64
+    codes = rng.integers(0, 2 ** 63, size=(n, nw), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, nw), dtype=np.uint64)
+    if narrow:
+        codes &= np.uint64(0xFF)
+    q = codes[17].copy()
+    ids = [f"{(i * 7919) % n:07d}" for i in range(n)]
+    mask = np.full(nw, np.uint64(0xFFFFFFFFFFFFFFFF))
+    if dims % 64:
+        mask[-1] = np.uint64((1 << (dims % 64)) - 1)
+    dist = np.bitwise_count((codes ^ q) & mask).sum(axis=1).astype(np.int64)
+    order = sorted(range(n), key=lambda i: (dist[i], ids[i]))[:k]
+    got = ok(nifs.binary_top_k([(ids[i], codes[i]) for i in range(n)], q, dims, k))
+    assert [h[0] for h in got] == [ids[i] for i in order]
+    assert [h[1] for h in got] == [float(dist[i]) for i in order]

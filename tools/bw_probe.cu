@@ -109,8 +109,9 @@ float time_it(F f, int iters = 20) {
     return ms / iters;
 }
 
-int main() {
-    const size_t bytes = (size_t)3072 * 1000 * 1000;  // the 1M x 768 fp32 corpus
+int main(int argc, char** argv) {
+    // default: the 1M x 768 fp32 corpus; argv[1] = size in MB (e.g. 12800 for the 100M x 1024-bit codes)
+    const size_t bytes = (argc > 1 ? (size_t)atoll(argv[1]) : (size_t)3072) * 1000 * 1000;
     unsigned char* d; float* out;
     CK(cudaMalloc(&d, bytes)); CK(cudaMalloc(&out, 4));
     CK(cudaMemset(d, 1, bytes));
