@@ -122,6 +122,24 @@ int vb_flat_quantized_search(vb_flat* index, const float* query, size_t len, int
 int vb_flat_search_device(vb_flat* index, const float* d_queries, size_t nq, size_t q_stride,
                           size_t limit, uint64_t* d_keys, float* d_values, uint32_t* d_rows,
                           uint32_t* d_counts, void* stream);
+/* Row-sharded quantized_search (collection.ex:699-713 over a corpus split by rows), stage 1:
+ * sign-packs the device queries (distances.rs:413-423) and scans THIS shard's code mirror for
+ * its best `candidates` by (Hamming distance, id rank) — binary_top_k, search.rs:76-92. Output
+ * convention of vb_flat_search_device. The shards' lists are all-gathered and merged with
+ * vb_topk_merge_device into the global candidate set. candidates <= 1024. */
+int vb_flat_hamming_device(vb_flat* index, const float* d_queries, size_t nq, size_t q_stride,
+                           size_t candidates, uint64_t* d_keys, float* d_values, uint32_t* d_rows,
+                           uint32_t* d_counts, void* stream);
+/* Stage 2: exact rerank (vector_top_k at full length, search.rs:38-73; cosine = the f64 true
+ * cosine, distances.rs:160-177) of those global candidates that live on `shard`.
+ * d_global_rows: the merged candidate rows (`shard << 32 | row`, vb_topk_merge_device's rows
+ * output), *d_global_count of them, at most max_candidates. Writes this shard's best
+ * min(limit, owned) (possibly 0) in the vb_flat_search_device convention. One query.
+ * Synchronises `stream` once (the owned-candidate count sizes the scan). */
+int vb_flat_rerank_owned_device(vb_flat* index, const float* d_query, size_t q_stride, int metric_code,
+                                const uint64_t* d_global_rows, const uint32_t* d_global_count,
+                                size_t max_candidates, uint32_t shard, size_t limit, uint64_t* d_keys,
+                                float* d_values, uint32_t* d_rows, uint32_t* d_counts, void* stream);
 /* Overrides the id tie-break ranks of the resident rows (row-sharded corpora: ranks must
  * be comparable across shards). ranks[row] for row < rows, in insertion (device row) order. */
 int vb_flat_set_id_ranks(vb_flat* index, const uint32_t* ranks, size_t n);
@@ -173,6 +191,17 @@ int vb_mv_insert_many_device(vb_mv* index, size_t ndocs, const char* ids, const 
 int vb_mv_delete(vb_mv* index, const char* id, size_t id_len);
 int vb_mv_search(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit,
                  vb_hits** out);
+/* Document-sharded MaxSim (multi_vector.rs:90-132 over a corpus split by documents): same
+ * search, and the shard's sorted top-k is ALSO left in device memory in the
+ * vb_flat_search_device convention (keys = score-order key << 32 | id rank, scores, document
+ * slots, count) so the shards' lists can be all-gathered and merged with
+ * vb_topk_merge_device. An empty shard writes count 0. limit >= 1, tq >= 1. */
+int vb_mv_search_packed_device(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_t tq,
+                               size_t limit, uint64_t* d_keys, float* d_values, uint32_t* d_rows,
+                               uint32_t* d_counts, vb_hits** out);
+/* Overrides the id tie-break ranks, one per document slot in insertion order (sharded corpora:
+ * ranks must compare across shards). Valid until the next insert/delete relabels. */
+int vb_mv_set_id_ranks(vb_mv* index, const uint32_t* ranks, size_t n);
 int vb_mv_info(vb_mv* index, size_t* docs, size_t* tokens, size_t* dimension);
 
 /* compress_sign_bits/1, nifs.rs:125-129 -> distances.rs:413-423. words[ceil(len/64)]. */

@@ -80,3 +80,156 @@ def test_single_shard_wrapper_roundtrip():
     hits = sh.search(q)[0]
     got = [(ids[h.row], h.value) for h in hits]
     assert_hits_match(got, oracle.flat_search_dense("cosine", rows, ids, q[0].numpy(), k)[1])
+
+
+# ---------------------------------------------------------------------------------------------
+# Row-sharded quantized_search and document-sharded MaxSim:
+# the shards live on one device here and the "all-gather" is the layout NCCL would produce.
+from test_pipelines_gpu import ref_quantized  # noqa: E402  (oracle composition of collection.ex:699-713)
+from vettore_b200.sharded import ShardedMv, ShardedQuantized, set_global_mv_ranks  # noqa: E402
+
+
+def _merge(gathered, lay, lists, k_in, k_out, dev, stream):
+    out_keys = torch.zeros(k_out, dtype=torch.int64, device=dev)
+    out_vals = torch.zeros(k_out, dtype=torch.float32, device=dev)
+    out_rows = torch.zeros(k_out, dtype=torch.int64, device=dev)
+    out_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    g = gathered.data_ptr()
+    rc = _lib.lib().vb_topk_merge_device(C.c_void_p(g + lay["keys"]), C.c_void_p(g + lay["values"]),
+                                         C.c_void_p(g + lay["rows"]), C.c_void_p(g + lay["counts"]), lay["bytes"],
+                                         1, lists, k_in, k_out, C.c_void_p(out_keys.data_ptr()),
+                                         C.c_void_p(out_vals.data_ptr()), C.c_void_p(out_rows.data_ptr()),
+                                         C.c_void_p(out_cnt.data_ptr()), stream)
+    assert rc == 0, _lib.last_error()
+    return out_vals, out_rows, out_cnt
+
+
+@pytest.mark.parametrize("metric", ["cosine", "l2", "inner_product"])
+@pytest.mark.parametrize("shards,n_per,d,cand,k", [(2, 2000, 256, 100, 10), (4, 900, 128, 300, 10), (3, 50, 96, 1000, 7)])
+def test_sharded_quantized_equals_single_index_and_oracle(shards, n_per, d, cand, k, metric):
+    dev = torch.device("cuda", 0)
+    n = shards * n_per
+    rows = _rows(n, d, seed=shards * 77 + d)
+    q = _rows(1, d, seed=11)
+    ids = [f"{i:09d}" for i in range(n)]
+    code = nifs.METRIC_CODE[metric]
+    cand_eff, k_eff = min(cand, 1024), k
+    lay_c, lay_k = packed_layout(1, cand_eff), packed_layout(1, k_eff)
+    gath_c = torch.zeros(shards * lay_c["bytes"], dtype=torch.uint8, device=dev)
+    gath_k = torch.zeros(shards * lay_k["bytes"], dtype=torch.uint8, device=dev)
+    dq = torch.from_numpy(q).to(dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    shard_idx = []
+    for s in range(shards):
+        idx = getattr(nifs, f"flat_new_{metric}")()
+        assert nifs.flat_insert_matrix(idx, ids[s * n_per:(s + 1) * n_per], rows[s * n_per:(s + 1) * n_per]) == ("ok", ())
+        set_global_ranks(idx, s * n_per, n_per)
+        shard_idx.append(idx)
+        b = gath_c.data_ptr() + s * lay_c["bytes"]
+        rc = _lib.lib().vb_flat_hamming_device(idx.handle, C.c_void_p(dq.data_ptr()), 1, d, cand_eff,
+                                               C.c_void_p(b + lay_c["keys"]), C.c_void_p(b + lay_c["values"]),
+                                               C.c_void_p(b + lay_c["rows"]), C.c_void_p(b + lay_c["counts"]), stream)
+        assert rc == 0, _lib.last_error()
+    _, c_rows, c_cnt = _merge(gath_c, lay_c, shards, cand_eff, cand_eff, dev, stream)
+    torch.cuda.synchronize()
+    assert int(c_cnt.item()) == min(cand_eff, n)
+    for s, idx in enumerate(shard_idx):
+        b = gath_k.data_ptr() + s * lay_k["bytes"]
+        rc = _lib.lib().vb_flat_rerank_owned_device(idx.handle, C.c_void_p(dq.data_ptr()), d, code,
+                                                    C.c_void_p(c_rows.data_ptr()), C.c_void_p(c_cnt.data_ptr()), cand_eff, s,
+                                                    k_eff, C.c_void_p(b + lay_k["keys"]), C.c_void_p(b + lay_k["values"]),
+                                                    C.c_void_p(b + lay_k["rows"]), C.c_void_p(b + lay_k["counts"]), stream)
+        assert rc == 0, _lib.last_error()
+    vals, rws, cnt = _merge(gath_k, lay_k, shards, k_eff, k_eff, dev, stream)
+    torch.cuda.synchronize()
+    vals, rws = vals.cpu().numpy(), rws.cpu().numpy().astype(np.uint64)
+    got = [(ids[int(rws[i] >> np.uint64(32)) * n_per + int(rws[i] & np.uint64(0xFFFFFFFF))], float(vals[i]))
+           for i in range(int(cnt.item()))]
+    vectors = [(ids[i], rows[i]) for i in range(n)]
+    assert_hits_match(got, ref_quantized(vectors, q[0], code, cand_eff, k_eff))
+    whole = getattr(nifs, f"flat_new_{metric}")()
+    assert nifs.flat_insert_matrix(whole, ids, rows) == ("ok", ())
+    st, single = nifs.flat_quantized_search(whole, q[0], code, cand_eff, k_eff)
+    assert st == "ok"
+    assert_hits_match(got, single)
+
+
+def test_sharded_quantized_wrapper_single_rank():
+    n, d = 6000, 192
+    rows, q = _rows(n, d, 21), _rows(1, d, 22)
+    ids = [f"{i:09d}" for i in range(n)]
+    idx = nifs.flat_new_cosine()
+    assert nifs.flat_insert_matrix(idx, ids, rows) == ("ok", ())
+    sh = ShardedQuantized(idx, candidates=200, limit=10, metric_code=nifs.METRIC_CODE["cosine"])
+    hits = sh.search(torch.from_numpy(q).pin_memory())
+    got = [(ids[h.row], h.value) for h in hits]
+    st, exp = nifs.flat_quantized_search(idx, q[0], nifs.METRIC_CODE["cosine"], 200, 10)
+    assert st == "ok"
+    assert_hits_match(got, exp)
+
+
+def _docs(ndocs, td, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((ndocs, td, d)).astype(np.float32)
+    return (x / np.linalg.norm(x.astype(np.float64), axis=2, keepdims=True)).astype(np.float32)
+
+
+@pytest.mark.parametrize("metric", ["inner_product", "cosine", "l2"])
+@pytest.mark.parametrize("shards,docs_per,td,d,tq,k", [(2, 300, 32, 64, 8, 10), (4, 100, 128, 128, 32, 10), (3, 40, 5, 48, 3, 50)])
+def test_sharded_maxsim_equals_single_index_and_oracle(shards, docs_per, td, d, tq, k, metric):
+    dev = torch.device("cuda", 0)
+    ndocs = shards * docs_per
+    docs = _docs(ndocs, td, d, seed=shards * 31 + td)
+    query = _docs(1, tq, d, seed=5)[0]
+    ids = [f"{i:09d}" for i in range(ndocs)]
+    lay = packed_layout(1, k)
+    gathered = torch.zeros(shards * lay["bytes"], dtype=torch.uint8, device=dev)
+    keep = []
+    for s in range(shards):
+        mv = nifs.mv_new(metric)
+        lo, hi = s * docs_per, (s + 1) * docs_per
+        assert nifs.mv_insert_tensor(mv, ids[lo:hi], docs[lo:hi])[0] == "ok"
+        set_global_mv_ranks(mv, lo, docs_per)
+        keep.append(mv)
+        b = gathered.data_ptr() + s * lay["bytes"]
+        res = nifs.mv_search_packed_device(mv, query, k, C.c_void_p(b + lay["keys"]), C.c_void_p(b + lay["values"]),
+                                           C.c_void_p(b + lay["rows"]), C.c_void_p(b + lay["counts"]))
+        assert res[0] == "ok", res
+    torch.cuda.synchronize()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vals, rws, cnt = _merge(gathered, lay, shards, k, k, dev, stream)
+    torch.cuda.synchronize()
+    vals, rws = vals.cpu().numpy(), rws.cpu().numpy().astype(np.uint64)
+    got = [(ids[int(rws[i] >> np.uint64(32)) * docs_per + int(rws[i] & np.uint64(0xFFFFFFFF))], float(vals[i]))
+           for i in range(int(cnt.item()))]
+    whole = nifs.mv_new(metric)
+    assert nifs.mv_insert_tensor(whole, ids, docs)[0] == "ok"
+    st, single = nifs.mv_search(whole, query, k)
+    assert st == "ok"
+    assert_hits_match(got, single)
+    st, exp = oracle.multi_vector_top_k([(ids[i], docs[i]) for i in range(ndocs)], query, nifs.METRIC_CODE[metric], k)
+    assert st == "ok"
+    assert_hits_match(got, exp)
+
+
+def test_sharded_maxsim_wrapper_single_rank():
+    docs, query = _docs(500, 32, 64, 9), _docs(1, 16, 64, 10)[0]
+    ids = [f"{i:09d}" for i in range(500)]
+    mv = nifs.mv_new("inner_product")
+    assert nifs.mv_insert_tensor(mv, ids, docs)[0] == "ok"
+    hits = ShardedMv(mv, k=10).search(query)
+    st, exp = nifs.mv_search(mv, query, 10)
+    assert st == "ok"
+    assert_hits_match([(ids[h.row], h.value) for h in hits], exp)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL exchange between real ranks)")
+def test_nccl_two_rank_sharded_paths_match_single_index():
+    """tools/sharded_check.py under torchrun: flat (K1 and K2 batch), quantized and MaxSim over 2 ranks."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "sharded_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "sharded paths match the single-index results" in res.stdout

@@ -39,6 +39,8 @@ SIGNATURES = {
     "vb_flat_funnel_search": (C.c_int, [_vp, _f32p, _sz, C.c_int, C.POINTER(_sz), _sz, _sz, _sz, _vpp]),
     "vb_flat_quantized_search": (C.c_int, [_vp, _f32p, _sz, C.c_int, _sz, _sz, _vpp]),
     "vb_flat_search_device": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "vb_flat_hamming_device": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "vb_flat_rerank_owned_device": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp, _vp, _sz, C.c_uint32, _sz, _vp, _vp, _vp, _vp, _vp]),
     "vb_flat_set_id_ranks": (C.c_int, [_vp, _u32p, _sz]),
     "vb_topk_merge_device": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "vb_vector_top_k": (C.c_int, [_sz, C.c_char_p, _u64p, _f32p, _u64p, _f32p, _sz, C.c_int, _sz, _sz, _vpp]),
@@ -53,6 +55,8 @@ SIGNATURES = {
     "vb_mv_insert_many_device": (C.c_int, [_vp, _sz, C.c_char_p, _u64p, _vp, _sz, _sz]),
     "vb_mv_delete": (C.c_int, [_vp, C.c_char_p, _sz]),
     "vb_mv_search": (C.c_int, [_vp, _f32p, _u64p, _sz, _sz, _vpp]),
+    "vb_mv_search_packed_device": (C.c_int, [_vp, _f32p, _u64p, _sz, _sz, _vp, _vp, _vp, _vp, _vpp]),
+    "vb_mv_set_id_ranks": (C.c_int, [_vp, _u32p, _sz]),
     "vb_mv_info": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
 }
 

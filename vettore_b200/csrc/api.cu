@@ -184,6 +184,20 @@ int vb_flat_search_device(vb_flat* index, const float* d_queries, size_t nq, siz
                                              static_cast<cudaStream_t>(stream)));
 }
 
+int vb_flat_hamming_device(vb_flat* index, const float* d_queries, size_t nq, size_t q_stride, size_t candidates,
+                           uint64_t* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, void* stream) {
+    return finish(index->impl->hamming_device(d_queries, nq, q_stride, candidates, reinterpret_cast<vb::u64*>(d_keys),
+                                              d_values, d_rows, d_counts, static_cast<cudaStream_t>(stream)));
+}
+int vb_flat_rerank_owned_device(vb_flat* index, const float* d_query, size_t q_stride, int metric_code,
+                                const uint64_t* d_global_rows, const uint32_t* d_global_count, size_t max_candidates,
+                                uint32_t shard, size_t limit, uint64_t* d_keys, float* d_values, uint32_t* d_rows,
+                                uint32_t* d_counts, void* stream) {
+    return finish(index->impl->rerank_owned_device(d_query, q_stride, metric_code,
+                                                   reinterpret_cast<const vb::u64*>(d_global_rows), d_global_count,
+                                                   max_candidates, shard, limit, reinterpret_cast<vb::u64*>(d_keys),
+                                                   d_values, d_rows, d_counts, static_cast<cudaStream_t>(stream)));
+}
 int vb_flat_set_id_ranks(vb_flat* index, const uint32_t* ranks, size_t n) {
     return finish(index->impl->set_id_ranks(ranks, n));
 }
@@ -472,6 +486,19 @@ int vb_mv_search(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_
     if (!s.ok()) return finish(s);
     *out = new vb_hits{std::move(hits)};
     return VB_OK;
+}
+int vb_mv_search_packed_device(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit,
+                               uint64_t* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, vb_hits** out) {
+    *out = nullptr;
+    vb::Hits hits;
+    vb::Status s = index->impl->search_packed_device(q_vals, q_off, tq, limit, reinterpret_cast<vb::u64*>(d_keys), d_values,
+                                                     d_rows, d_counts, &hits);
+    if (!s.ok()) return finish(s);
+    *out = new vb_hits{std::move(hits)};
+    return VB_OK;
+}
+int vb_mv_set_id_ranks(vb_mv* index, const uint32_t* ranks, size_t n) {
+    return finish(index->impl->set_id_ranks(ranks, n));
 }
 int vb_mv_info(vb_mv* index, size_t* docs, size_t* tokens, size_t* dimension) {
     index->impl->info(docs, tokens, dimension);

@@ -561,6 +561,106 @@ Status FlatIndex::search_device(const float* d_queries, size_t nq, size_t q_stri
                            stream);
 }
 
+// ---- row-sharded quantized_search pieces (all-gather of the local candidates,
+// global select, every owner reranks its own survivors) ------------------------------------------
+__global__ void select_owned_rows_kernel(const u64* global_rows, const uint32_t* global_count, uint32_t max_candidates,
+                                         uint32_t shard, uint32_t* row_sel, uint32_t* owned) {
+    const uint32_t n = min(*global_count, max_candidates);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const u64 r = global_rows[i];
+        if ((uint32_t)(r >> 32) == shard) row_sel[atomicAdd(owned, 1u)] = (uint32_t)r;
+    }
+}
+
+// f64 norm of the query, accumulated in index order like distances.rs:160-177 does.
+__global__ void query_norm_f64_kernel(const float* q, uint32_t dims, double* out) {
+    double s = 0.0;
+    for (uint32_t i = 0; i < dims; ++i) s += (double)q[i] * (double)q[i];
+    *out = sqrt(s);
+}
+
+Status FlatIndex::hamming_device(const float* d_queries, size_t nq, size_t q_stride, size_t candidates, u64* d_keys,
+                                 float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream) {
+    if (candidates == 0 || nq == 0) return Status::Cuda("device candidate pass needs candidates >= 1 and nq >= 1");
+    std::unique_lock<std::shared_mutex> g(mu_);  // owns dev_ctx_; may build the code mirror
+    if (n_ == 0) return Status::Cuda("device candidate pass on an empty index");
+    if (q_stride < dim_) return Status::Ref("dimension mismatch");
+    VB_CUDA(cudaSetDevice(device_));
+    if (!d_codes_) VB_TRY(ensure_codes());
+    if (!dev_ctx_) {
+        dev_ctx_ = new SearchCtx();
+        dev_ctx_->device = device_;
+        VB_CUDA(cudaStreamCreateWithFlags(&dev_ctx_->stream, cudaStreamNonBlocking));
+    }
+    SearchCtx& c = *dev_ctx_;
+    const size_t cand = std::min(candidates, n_);
+    if (cand > (size_t)kMaxFusedK) return Status::Cuda("quantized candidates must be in 1..1024 for the resident pipeline");
+    const size_t nw = code_words_;
+    VB_TRY(c.staging.reserve(nq * nw * sizeof(u64)));
+    VB_TRY(sign_pack_device(d_queries, q_stride, (uint32_t)nq, (uint32_t)dim_, c.staging.as<u64>(), stream));
+    cudaStream_t saved = c.stream;
+    c.stream = stream;   // workspace arming must be ordered on the caller's stream
+    Status s = hamming_scan_device(c, d_codes_, (uint32_t)n_, (uint32_t)nw, (uint32_t)dim_, d_rank_, c.staging.as<u64>(),
+                                   (uint32_t)nq, (uint32_t)cand, stream);
+    c.stream = saved;
+    VB_TRY(s);
+    const u64* pays = c.result.as<u64>();
+    return unpack_device_results(c.out_keys.as<u64>(), pays, reinterpret_cast<const uint32_t*>(pays + nq * cand),
+                                 (uint32_t)nq, (uint32_t)cand, d_keys, d_values, d_rows, d_counts, stream);
+}
+
+Status FlatIndex::rerank_owned_device(const float* d_query, size_t q_stride, int metric_code, const u64* d_global_rows,
+                                      const uint32_t* d_global_count, size_t max_candidates, uint32_t shard,
+                                      size_t limit, u64* d_keys, float* d_values, uint32_t* d_rows,
+                                      uint32_t* d_counts, cudaStream_t stream) {
+    if (metric_code < 0 || metric_code > 8) return Status::Ref("unknown metric");
+    if (limit == 0 || max_candidates == 0) return Status::Cuda("device rerank needs limit >= 1 and candidates >= 1");
+    std::unique_lock<std::shared_mutex> g(mu_);
+    if (q_stride < stride_ || (q_stride & 3)) return Status::Ref("dimension mismatch");
+    VB_CUDA(cudaSetDevice(device_));
+    if (!dev_ctx_) {
+        dev_ctx_ = new SearchCtx();
+        dev_ctx_->device = device_;
+        VB_CUDA(cudaStreamCreateWithFlags(&dev_ctx_->stream, cudaStreamNonBlocking));
+    }
+    SearchCtx& c = *dev_ctx_;
+    VB_TRY(c.row_sel.reserve(max_candidates * sizeof(uint32_t)));
+    VB_TRY(c.row_sel2.reserve(16));
+    VB_TRY(c.h_misc.reserve(16));
+    VB_TRY(c.q_norms.reserve(sizeof(double)));
+    uint32_t* d_owned = c.row_sel2.as<uint32_t>();
+    uint32_t* h_owned = c.h_misc.as<uint32_t>();
+    VB_CUDA(cudaMemsetAsync(d_owned, 0, sizeof(uint32_t), stream));
+    select_owned_rows_kernel<<<1, 256, 0, stream>>>(d_global_rows, d_global_count, (uint32_t)max_candidates, shard,
+                                                    c.row_sel.as<uint32_t>(), d_owned);
+    VB_CUDA(cudaGetLastError());
+    VB_CUDA(cudaMemcpyAsync(h_owned, d_owned, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    VB_CUDA(cudaStreamSynchronize(stream));
+    const uint32_t owned = *h_owned;
+    if (owned == 0 || n_ == 0) {   // nothing of the global candidate set lives here: an empty list
+        VB_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t), stream));
+        return Status::Ok();
+    }
+    ScanJob job;
+    job.metric = metric_code == kCosine ? kCosineTrue : metric_code;   // exact_rerank -> vector_top_k
+    job.d_rows = d_rows_;
+    job.row_stride = stride_;
+    job.d_id_rank = d_rank_;
+    job.d_row_sel = c.row_sel.as<uint32_t>();
+    job.n = owned;
+    job.dims = (uint32_t)dim_;
+    job.whole_rows = true;
+    job.nq = 1;
+    job.k = std::min<size_t>(limit, owned);
+    const double* d_norm = nullptr;
+    if (job.metric == kCosineTrue) {
+        query_norm_f64_kernel<<<1, 1, 0, stream>>>(d_query, (uint32_t)dim_, c.q_norms.as<double>());
+        VB_CUDA(cudaGetLastError());
+        d_norm = c.q_norms.as<double>();
+    }
+    return run_scan_device(c, job, d_query, q_stride, d_norm, d_keys, d_values, d_rows, d_counts, stream);
+}
+
 Status FlatIndex::set_id_ranks(const uint32_t* ranks, size_t n) {
     std::unique_lock<std::shared_mutex> g(mu_);
     if (n != n_) return Status::Ref("dimension mismatch");

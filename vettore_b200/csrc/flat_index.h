@@ -46,6 +46,17 @@ class FlatIndex {
                             Hits* out);
     Status search_device(const float* d_queries, size_t nq, size_t q_stride, size_t limit, u64* d_keys,
                          float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream);
+    // Row-sharded quantized_search, stage 1: sign-packs the device queries and scans this shard's
+    // code mirror for the best `candidates` (same output convention as search_device).
+    Status hamming_device(const float* d_queries, size_t nq, size_t q_stride, size_t candidates, u64* d_keys,
+                          float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream);
+    // Stage 2: exact rerank (vector_top_k semantics at full length) of those of the globally selected
+    // candidates (`shard << 32 | row`, *d_global_count of them) that live on `shard`. One stream
+    // synchronisation (the number of owned candidates sizes the launch).
+    Status rerank_owned_device(const float* d_query, size_t q_stride, int metric_code, const u64* d_global_rows,
+                               const uint32_t* d_global_count, size_t max_candidates, uint32_t shard, size_t limit,
+                               u64* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts,
+                               cudaStream_t stream);
     Status set_id_ranks(const uint32_t* ranks, size_t n);
     void info(size_t* rows, size_t* dim);
 

@@ -9,6 +9,7 @@
 // sum turns non-finite. One CTA owns one document at a time; S is produced in 32 x 128
 // register-tiled blocks (each thread a 4 x 4 patch) from shared-memory chunks of 32 dims.
 #include "maxsim.h"
+#include "scan_driver.h"
 
 #include <cstdlib>
 
@@ -299,6 +300,11 @@ Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out) {
     p.ws.out_err = p.ws.out_counts + 1;
     kernel<<<grid, kMsThreads, smem, ctx.stream>>>(p);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && job.d_keys_out) {
+        Status u = unpack_device_results(p.ws.out_keys, p.ws.out_pays, p.ws.out_counts, 1, k, job.d_keys_out, job.d_values_out,
+                                         job.d_rows_out, job.d_counts_out, ctx.stream);
+        if (!u.ok()) { ctx.poison(); return u; }
+    }
     const size_t bytes = (size_t)k * sizeof(u64) + 8;
     if (e == cudaSuccess) e = ctx.h_result.reserve(bytes).ok() ? cudaSuccess : cudaErrorMemoryAllocation;
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, bytes, cudaMemcpyDeviceToHost, ctx.stream);

@@ -23,6 +23,12 @@ struct MaxSimJob {
     size_t k = 0;
     uint32_t uniform_td = 0;               // every document slot has exactly this many tokens (0 = ragged)
     const float* d_inv_dnorm = nullptr;    // [ntok] 1/|token| (device), enables the tensor-core cosine path
+    // optional: the sorted list is ALSO left on the device in the vb_flat_search_device convention
+    // (keys = order key << 32 | doc rank, scores, doc slots, count) for the sharded merge
+    u64* d_keys_out = nullptr;
+    float* d_values_out = nullptr;
+    uint32_t* d_rows_out = nullptr;
+    uint32_t* d_counts_out = nullptr;
 };
 
 struct MaxSimResult {
@@ -55,6 +61,11 @@ class MvIndex {
     Status insert_many_device(size_t ndocs, const char* ids, const uint64_t* id_off, const float* d_tokens,
                               size_t td, size_t dim);
     Status search(const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, Hits* out);
+    // Document-sharded search: the shard's sorted top-k also stays on the device (see MaxSimJob).
+    Status search_packed_device(const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, u64* d_keys,
+                                float* d_values, uint32_t* d_rows, uint32_t* d_counts, Hits* out);
+    // Overrides the id tie-break ranks (per document slot) so they compare across shards.
+    Status set_id_ranks(const uint32_t* ranks, size_t n);
     void info(size_t* docs, size_t* tokens, size_t* dim);
 
   private:
@@ -62,6 +73,8 @@ class MvIndex {
     Status reserve_docs(size_t need);
     Status relabel();
     Status compact();
+    Status search_impl(const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, u64* d_keys,
+                       float* d_values, uint32_t* d_rows, uint32_t* d_counts, Hits* out);
 
     const int metric_;
     const int device_;

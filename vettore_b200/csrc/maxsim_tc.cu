@@ -17,6 +17,7 @@
 //               over each document's tokens (31-shuffle transpose butterfly + shared memory
 //               across warps), f32 sum in query order, collector push (topk.cuh)
 #include "maxsim.h"
+#include "scan_driver.h"
 #include "tc.cuh"
 #include "topk.cuh"
 
@@ -392,6 +393,11 @@ Status maxsim_tc_top_k(SearchCtx& ctx, const MaxSimJob& job, uint32_t td, const 
     p.ws.out_err = p.ws.out_counts + 1;
     maxsim_tc_kernel<<<grid, kTcThreads, smem, ctx.stream>>>(tmap, p);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && job.d_keys_out) {
+        Status u = unpack_device_results(p.ws.out_keys, p.ws.out_pays, p.ws.out_counts, 1, k, job.d_keys_out, job.d_values_out,
+                                         job.d_rows_out, job.d_counts_out, ctx.stream);
+        if (!u.ok()) { ctx.poison(); return u; }
+    }
     const size_t bytes = (size_t)k * sizeof(u64) + 8;
     if (e == cudaSuccess && !ctx.h_result.reserve(bytes).ok()) e = cudaErrorMemoryAllocation;
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, bytes, cudaMemcpyDeviceToHost, ctx.stream);

@@ -332,6 +332,30 @@ Status MvIndex::remove(const char* id, size_t id_len) {
 }
 
 Status MvIndex::search(const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, Hits* out) {
+    return search_impl(q_vals, q_off, tq, limit, nullptr, nullptr, nullptr, nullptr, out);
+}
+
+Status MvIndex::search_packed_device(const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, u64* d_keys,
+                                     float* d_values, uint32_t* d_rows, uint32_t* d_counts, Hits* out) {
+    if (!d_keys || !d_values || !d_rows || !d_counts) return Status::Cuda("device outputs required");
+    if (limit == 0 || tq == 0) return Status::Cuda("sharded multi-vector search needs limit >= 1 and a non-empty query");
+    VB_CUDA(cudaSetDevice(device_));
+    VB_CUDA(cudaMemset(d_counts, 0, sizeof(uint32_t)));   // an empty shard contributes an empty list
+    return search_impl(q_vals, q_off, tq, limit, d_keys, d_values, d_rows, d_counts, out);
+}
+
+Status MvIndex::set_id_ranks(const uint32_t* ranks, size_t n) {
+    std::unique_lock<std::shared_mutex> g(mu_);
+    if (n != ndocs_) return Status::Ref("dimension mismatch");
+    VB_CUDA(cudaSetDevice(device_));
+    for (size_t d = 0; d < n; ++d)
+        if (h_rank_[d] != kDead) h_rank_[d] = ranks[d];
+    if (n > 0) VB_CUDA(cudaMemcpy(d_doc_rank_, h_rank_.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return Status::Ok();
+}
+
+Status MvIndex::search_impl(const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, u64* d_keys,
+                            float* d_values, uint32_t* d_rows, uint32_t* d_counts, Hits* out) {
     *out = Hits{};
     // multi_vector.rs:96-97: the query is validated on its own first.
     size_t qdim = 0;
@@ -375,6 +399,10 @@ Status MvIndex::search(const float* q_vals, const uint64_t* q_off, size_t tq, si
     job.k = k;
     job.uniform_td = uniform_known_ ? uniform_td_ : 0;
     job.d_inv_dnorm = d_inv_norm_;
+    job.d_keys_out = d_keys;
+    job.d_values_out = d_values;
+    job.d_rows_out = d_rows;
+    job.d_counts_out = d_counts;
     MaxSimResult res;
     VB_TRY(maxsim_top_k(*ctx.ctx, job, &res));
     if (res.err != kNoError) return Status::Ref((res.err & 1u) ? "score overflow" : "metric overflow");

@@ -360,6 +360,15 @@ def mv_search(index: MvRef, query_vectors, limit: int):
     return _err() if rc else ("ok", _take_hits(h))
 
 
+def mv_search_packed_device(index: MvRef, query_vectors, limit: int, d_keys, d_values, d_rows, d_counts):
+    """Additive (document-sharded MaxSim): `mv_search` whose sorted top-k also stays on the device."""
+    qv, qoff = _ragged(list(query_vectors) if not isinstance(query_vectors, np.ndarray) else query_vectors, np.float32)
+    h = C.c_void_p()
+    rc = lib().vb_mv_search_packed_device(index.handle, _ptr(qv, _f32p), _ptr(qoff, _u64p), len(qoff) - 1,
+                                          min(int(limit), SIZE_MAX), d_keys, d_values, d_rows, d_counts, C.byref(h))
+    return _err() if rc else ("ok", _take_hits(h))
+
+
 def mv_info(index: MvRef):
     docs, toks, dim = C.c_size_t(), C.c_size_t(), C.c_size_t()
     lib().vb_mv_info(index.handle, C.byref(docs), C.byref(toks), C.byref(dim))

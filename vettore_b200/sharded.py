@@ -124,6 +124,127 @@ class ShardedFlat:
         return self.decode(host.numpy(), dq.shape[0])
 
 
+def _merge_gathered(gathered: torch.Tensor, lay: dict, nq: int, lists: int, k_in: int, k_out: int, out: torch.Tensor,
+                    stream: C.c_void_p) -> tuple[int, int, int, int]:
+    """K7 over `lists` all-gathered records of layout `lay`; returns the byte offsets (keys, values, rows u64,
+    counts) of the merged record inside `out`."""
+    o_keys = 0
+    o_vals = o_keys + nq * k_out * 8
+    o_rows = (o_vals + nq * k_out * 4 + 7) // 8 * 8
+    o_counts = o_rows + nq * k_out * 8
+    base = gathered.data_ptr()
+    rc = lib().vb_topk_merge_device(C.c_void_p(base + lay["keys"]), C.c_void_p(base + lay["values"]),
+                                    C.c_void_p(base + lay["rows"]), C.c_void_p(base + lay["counts"]), lay["bytes"],
+                                    nq, lists, k_in, k_out, C.c_void_p(out.data_ptr() + o_keys),
+                                    C.c_void_p(out.data_ptr() + o_vals), C.c_void_p(out.data_ptr() + o_rows),
+                                    C.c_void_p(out.data_ptr() + o_counts), stream)
+    if rc:
+        raise RuntimeError(_lib.last_error())
+    return o_keys, o_vals, o_rows, o_counts
+
+
+def _decode_merged(host: np.ndarray, offs: tuple[int, int, int, int], k: int) -> list[ShardHit]:
+    _, o_vals, o_rows, o_counts = offs
+    vals = host[o_vals:o_vals + k * 4].view(np.float32)
+    rows = host[o_rows:o_rows + k * 8].view(np.uint64)
+    count = int(host[o_counts:o_counts + 4].view(np.uint32)[0])
+    return [ShardHit(int(rows[i]) >> 32, int(rows[i]) & 0xFFFFFFFF, float(vals[i])) for i in range(count)]
+
+
+class ShardedQuantized:
+    """Row-sharded ``quantized_search`` (collection.ex:699-713): every rank scans
+    the sign codes of ITS rows for its best ``candidates`` (K3), the lists are all-gathered and merged into
+    the global candidate set (K7), every rank reranks exactly the survivors it owns (K4, vector_top_k
+    semantics), and a second, tiny all-gather + merge yields the global top-``limit``."""
+
+    def __init__(self, index: nifs.FlatRef, candidates: int, limit: int, metric_code: int, group=None,
+                 device: torch.device | None = None):
+        self.index, self.cand, self.k, self.metric_code = index, int(candidates), int(limit), int(metric_code)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.lay_c, self.lay_k = packed_layout(1, self.cand), packed_layout(1, self.k)
+        z = lambda n: torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self.local_c, self.gath_c = z(self.lay_c["bytes"]), z(self.world * self.lay_c["bytes"])
+        self.local_k, self.gath_k = z(self.lay_k["bytes"]), z(self.world * self.lay_k["bytes"])
+        self.out_c, self.out_k = z(self.cand * 20 + 64), z(self.k * 20 + 64)
+
+    def search_device(self, d_query: torch.Tensor) -> tuple[torch.Tensor, tuple[int, int, int, int]]:
+        """``d_query``: ``[1, q_stride]`` float32 on the device. Returns the merged record and its offsets."""
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+        _, stride = d_query.shape
+        lc, lk = self.lay_c, self.lay_k
+        rc = lib().vb_flat_hamming_device(self.index.handle, p(d_query), 1, stride, self.cand, p(self.local_c, lc["keys"]),
+                                          p(self.local_c, lc["values"]), p(self.local_c, lc["rows"]),
+                                          p(self.local_c, lc["counts"]), stream)
+        if rc:
+            raise RuntimeError(_lib.last_error())
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gath_c, self.local_c, group=self.group)
+        else:
+            self.gath_c.copy_(self.local_c)
+        offs_c = _merge_gathered(self.gath_c, lc, 1, self.world, self.cand, self.cand, self.out_c, stream)
+        rc = lib().vb_flat_rerank_owned_device(self.index.handle, p(d_query), stride, self.metric_code,
+                                               p(self.out_c, offs_c[2]), p(self.out_c, offs_c[3]), self.cand, self.rank,
+                                               self.k, p(self.local_k, lk["keys"]), p(self.local_k, lk["values"]),
+                                               p(self.local_k, lk["rows"]), p(self.local_k, lk["counts"]), stream)
+        if rc:
+            raise RuntimeError(_lib.last_error())
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gath_k, self.local_k, group=self.group)
+        else:
+            self.gath_k.copy_(self.local_k)
+        offs_k = _merge_gathered(self.gath_k, lk, 1, self.world, self.k, self.k, self.out_k, stream)
+        return self.out_k, offs_k
+
+    def search(self, query_host: torch.Tensor) -> list[ShardHit]:
+        out, offs = self.search_device(query_host.to(self.device, non_blocking=True))
+        return _decode_merged(out.cpu().numpy(), offs, self.k)
+
+
+class ShardedMv:
+    """Document-sharded MaxSim (multi_vector.rs:90-132): every rank scores the
+    documents it owns (K5) and keeps its sorted top-k on the device; one all-gather + K7 merge."""
+
+    def __init__(self, index: "nifs.MvRef", k: int, group=None, device: torch.device | None = None):
+        self.index, self.k, self.group = index, int(k), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.lay = packed_layout(1, self.k)
+        self.local = torch.zeros(self.lay["bytes"], dtype=torch.uint8, device=self.device)
+        self.gathered = torch.zeros(self.world * self.lay["bytes"], dtype=torch.uint8, device=self.device)
+        self.out = torch.zeros(self.k * 20 + 64, dtype=torch.uint8, device=self.device)
+
+    def search(self, query_tokens: np.ndarray) -> list[ShardHit]:
+        """``query_tokens``: host ``[tq, dim]`` float32 (the reference API takes the query by value)."""
+        lay = self.lay
+        p = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+        res = nifs.mv_search_packed_device(self.index, query_tokens, self.k, p(self.local, lay["keys"]),
+                                           p(self.local, lay["values"]), p(self.local, lay["rows"]),
+                                           p(self.local, lay["counts"]))
+        if res[0] != "ok":
+            raise RuntimeError(res[1])
+        torch.cuda.synchronize(self.device)   # the library scored on its own stream
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
+        else:
+            self.gathered.copy_(self.local)
+        offs = _merge_gathered(self.gathered, lay, 1, self.world, self.k, self.k, self.out, stream)
+        return _decode_merged(self.out.cpu().numpy(), offs, self.k)
+
+
+def set_global_mv_ranks(index: "nifs.MvRef", base: int, docs: int) -> None:
+    """Id ranks for document ids that sort like the global document number."""
+    ranks = (np.arange(docs, dtype=np.uint64) + np.uint64(base)).astype(np.uint32)
+    rc = lib().vb_mv_set_id_ranks(index.handle, ranks.ctypes.data_as(C.POINTER(C.c_uint32)), docs)
+    if rc:
+        raise RuntimeError(_lib.last_error())
+
+
 def set_global_ranks(index: nifs.FlatRef, base: int, rows: int) -> None:
     """Id ranks for ids that sort like the global row number (zero-padded decimals)."""
     ranks = (np.arange(rows, dtype=np.uint64) + np.uint64(base)).astype(np.uint32)
