@@ -81,3 +81,49 @@ def test_packed_layout_is_aligned_and_disjoint():
         assert lay["keys"] % 8 == 0 and lay["values"] % 4 == 0 and lay["rows"] % 4 == 0 and lay["counts"] % 4 == 0
         assert lay["values"] - lay["keys"] == nq * k * 8 and lay["rows"] - lay["values"] == nq * k * 4
         assert lay["bytes"] % 16 == 0 and lay["bytes"] >= lay["counts"] + 4 * nq
+
+
+def _quantized_worker(rank, world, port, n_per, d, cand, k, out_path):
+    """Two-stage exchange of the row-sharded quantized_search (ShardedQuantized's host logic): local Hamming
+    candidates -> all-gather -> global candidate set -> every owner reranks its survivors -> all-gather -> top-k.
+    Must equal the reference composition (collection.ex:699-713) over the whole corpus."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(99)
+    rows = rng.integers(-3, 4, size=(world * n_per, d)).astype(np.float32)   # coarse values: many Hamming ties
+    rows[rows == 0] = 1.0
+    q = rng.integers(-3, 4, size=d).astype(np.float32)
+    q[q == 0] = -1.0
+    code = 2  # cosine: exact rerank uses the true cosine (search.rs:56-60)
+    ids = [f"{i:09d}" for i in range(world * n_per)]
+    base = rank * n_per
+    qcode = oracle.compress_sign_bits(q)
+    local_codes = [(ids[base + i], oracle.compress_sign_bits(rows[base + i])) for i in range(n_per)]
+    st, local_cands = oracle.binary_top_k(local_codes, qcode, d, cand)
+    assert st == "ok"
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local_cands)
+    merged = sorted((h for lst in gathered for h in lst), key=lambda h: (h[1], h[0]))[:cand]
+    mine = [(i, rows[int(i)]) for i, _ in merged if base <= int(i) < base + n_per]
+    st, local_top = oracle.vector_top_k(mine, q, code, d, k) if mine else ("ok", [])
+    assert st == "ok"
+    gathered2 = [None] * world
+    dist.all_gather_object(gathered2, local_top)
+    final = sorted((h for lst in gathered2 for h in lst),
+                   key=lambda h: (total_order_key(oracle.rank_value("cosine", h[1])), h[0]))[:k]
+    # reference composition over the whole corpus
+    codes = [(ids[i], oracle.compress_sign_bits(rows[i])) for i in range(world * n_per)]
+    keep = {h[0] for h in oracle.binary_top_k(codes, qcode, d, cand)[1]}
+    st, expect = oracle.vector_top_k([(ids[i], rows[i]) for i in range(world * n_per) if ids[i] in keep], q, code, d, k)
+    assert st == "ok" and final == expect, (final, expect)
+    if rank == 0:
+        open(out_path, "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cand,k", [(20, 5), (150, 10)])
+def test_two_rank_gloo_quantized_two_stage_exchange_equals_reference_composition(tmp_path, cand, k):
+    out = tmp_path / "ok.txt"
+    mp.spawn(_quantized_worker, args=(2, _free_port(), 120, 96, cand, k, str(out)), nprocs=2, join=True)
+    assert out.read_text() == "ok"
