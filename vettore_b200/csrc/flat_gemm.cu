@@ -32,7 +32,8 @@ constexpr int kGmTile = 128;             // rows per tile (UMMA M)
 constexpr int kGmN = 256;                // queries per block (UMMA N)
 constexpr int kGmStages = 2;
 constexpr uint32_t kGmStageBytes = 16384 + 2 * 32768;   // A chunk + B hi + B lo
-constexpr uint32_t kGmList = 256;        // candidate list capacity per (CTA, query)
+constexpr uint32_t kGmListSmall = 256;   // candidate list capacity per (CTA, query), k' <= 64
+constexpr uint32_t kGmListLarge = 512;   // ... larger k': a cut back to k' must leave room for many tiles
 constexpr uint32_t kGmACol = 256;        // TMEM: D at [0,256), A buffer u at 256 + 64 u: hi [0,32) lo [32,64)
 
 struct GemmParams {
@@ -40,7 +41,8 @@ struct GemmParams {
     int metric;                    // kCosine / kInnerProduct / kNegativeInnerProduct
     uint32_t qblocks, ranges;      // query blocks, row ranges (qblocks * ranges CTAs do work)
     const uint32_t* id_rank;       // [n] or null
-    u64* list_keys;                // [cta][256][kGmList]
+    uint32_t list_cap;             // kGmListSmall / kGmListLarge
+    u64* list_keys;                // [cta][256][list_cap]
     u64* list_pays;
     uint32_t* list_counts;         // [cta][256]
     uint32_t* bad;                 // set when a non-finite score shows up (caller falls back)
@@ -53,40 +55,79 @@ __device__ __forceinline__ float rank_from_key(u64 key) {
     return __uint_as_float(bits);
 }
 
-// Best k of one list (<= 256 entries, 8 per lane) by k rounds of warp arg-min; rewrites the
-// list front in ascending order. Returns the k-th key (or kKeyMax when fewer than k entries).
-__device__ u64 warp_compact_list(u64* keys, u64* pays, uint32_t count, uint32_t k, int lane) {
-    u64 lk[8], lp[8];
+// Cuts one list (<= 32 * PL entries, PL per lane in registers) back to its best k WITHOUT sorting:
+// the k-th smallest key is found by bisection on the key VALUE (32-bit rank word first, then the id
+// word among rank ties; one predicated compare per entry and one REDUX per step), then the entries
+// up to it are stream-compacted to the front of the list. Returns the k-th key (kKeyMax when the
+// list holds fewer than k entries). The merge that consumes the lists does not need them sorted.
+template <int PL>
+__device__ __noinline__ u64 warp_select_list(u64* keys, u64* pays, uint32_t count, uint32_t k, int lane) {
+    constexpr unsigned kFull = 0xffffffffu;
+    if (count < k) return kKeyMax;
+    u64 lk[PL], lp[PL];
+    uint32_t hmin = 0xffffffffu, hmax = 0u;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < PL; ++i) {
         const uint32_t e = lane + 32u * i;
-        lk[i] = e < count ? keys[e] : kKeyMax;
-        lp[i] = e < count ? pays[e] : 0ull;
-    }
-    __syncwarp();
-    const uint32_t keep = min(count, k);
-    u64 kth = kKeyMax;
-    for (uint32_t r = 0; r < keep; ++r) {
-        u64 best = lk[0];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) best = lk[i] < best ? lk[i] : best;
-        u64 wmin = best;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const u64 other = __shfl_xor_sync(0xffffffffu, wmin, o);
-            wmin = other < wmin ? other : wmin;
+        const bool valid = e < count;
+        lk[i] = valid ? keys[e] : kKeyMax;
+        lp[i] = valid ? pays[e] : 0ull;
+        if (valid) {
+            hmin = min(hmin, (uint32_t)(lk[i] >> 32));
+            hmax = max(hmax, (uint32_t)(lk[i] >> 32));
         }
-        u64 pay = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (lk[i] == wmin) { pay = lp[i]; lk[i] = kKeyMax; }
-        const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best == wmin)) - 1;
-        pay = __shfl_sync(0xffffffffu, pay, owner);
-        if (lane == 0) { keys[r] = wmin; pays[r] = pay; }
-        kth = wmin;
     }
     __syncwarp();
-    return count >= k ? kth : kKeyMax;
+    uint32_t lo = __reduce_min_sync(kFull, hmin), hi = __reduce_max_sync(kFull, hmax);
+    while (lo < hi) {                 // smallest rank word H with #(word <= H) >= k
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        uint32_t c = 0;
+#pragma unroll
+        for (int i = 0; i < PL; ++i) c += ((uint32_t)(lk[i] >> 32) <= mid && lane + 32u * i < count) ? 1u : 0u;
+        c = __reduce_add_sync(kFull, c);
+        if (c >= k) hi = mid; else lo = mid + 1u;
+    }
+    const uint32_t H = lo;
+    uint32_t c_less = 0, c_eq = 0;
+#pragma unroll
+    for (int i = 0; i < PL; ++i) {
+        const bool valid = lane + 32u * i < count;
+        c_less += (valid && (uint32_t)(lk[i] >> 32) < H) ? 1u : 0u;
+        c_eq += (valid && (uint32_t)(lk[i] >> 32) == H) ? 1u : 0u;
+    }
+    c_less = __reduce_add_sync(kFull, c_less);
+    c_eq = __reduce_add_sync(kFull, c_eq);
+    const uint32_t need = k - c_less;          // 1 <= need <= c_eq entries of the tie group survive
+    uint32_t lcut = 0xffffffffu;
+    if (c_eq > need) {                         // rank ties at the cut: the id word decides
+        uint32_t l0 = 0u, l1 = 0xffffffffu;
+        while (l0 < l1) {
+            const uint32_t mid = l0 + ((l1 - l0) >> 1);
+            uint32_t c = 0;
+#pragma unroll
+            for (int i = 0; i < PL; ++i)
+                c += (lane + 32u * i < count && (uint32_t)(lk[i] >> 32) == H && (uint32_t)lk[i] <= mid) ? 1u : 0u;
+            c = __reduce_add_sync(kFull, c);
+            if (c >= need) l1 = mid; else l0 = mid + 1u;
+        }
+        lcut = l0;
+    }
+    const u64 T = ((u64)H << 32) | lcut;
+    uint32_t base = 0, kth_lo = 0;
+#pragma unroll
+    for (int i = 0; i < PL; ++i) {
+        const bool keep = lane + 32u * i < count && lk[i] <= T;
+        const uint32_t m = __ballot_sync(kFull, keep);
+        if (keep) {
+            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+            keys[pos] = lk[i];
+            pays[pos] = lp[i];
+            if ((uint32_t)(lk[i] >> 32) == H) kth_lo = max(kth_lo, (uint32_t)lk[i]);
+        }
+        base += __popc(m);
+    }
+    __syncwarp();
+    return ((u64)H << 32) | __reduce_max_sync(kFull, kth_lo);
 }
 
 __global__ void __launch_bounds__(kGmThreads, 1)
@@ -247,9 +288,9 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned
                         if (key < s_thr[q]) {
                             const float raw = p.metric == kNegativeInnerProduct ? -dot : dot;
                             const uint32_t slot = atomicAdd(&s_cnt[q], 1u);
-                            if (slot < kGmList) {
-                                p.list_keys[(list_base + q) * kGmList + slot] = key;
-                                p.list_pays[(list_base + q) * kGmList + slot] = ((u64)__float_as_uint(raw) << 32) | row;
+                            if (slot < p.list_cap) {
+                                p.list_keys[(list_base + q) * p.list_cap + slot] = key;
+                                p.list_pays[(list_base + q) * p.list_cap + slot] = ((u64)__float_as_uint(raw) << 32) | row;
                             }
                         }
                     }
@@ -262,10 +303,12 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned
             // lists that could overflow during the next tile are cut back to their best k
             asm volatile("bar.sync 2, 256;" ::: "memory");
             for (uint32_t q = warp; q < kGmN; q += kGmEpiWarps) {
-                const uint32_t cnt = min(s_cnt[q], kGmList);
-                if (cnt + kGmTile > kGmList) {
-                    const u64 kth = warp_compact_list(p.list_keys + (list_base + q) * kGmList,
-                                                      p.list_pays + (list_base + q) * kGmList, cnt, p.k, lane);
+                const uint32_t cnt = min(s_cnt[q], p.list_cap);
+                if (cnt + kGmTile > p.list_cap) {
+                    u64* lkeys = p.list_keys + (list_base + q) * p.list_cap;
+                    u64* lpays = p.list_pays + (list_base + q) * p.list_cap;
+                    const u64 kth = p.list_cap == kGmListSmall ? warp_select_list<8>(lkeys, lpays, cnt, p.k, lane)
+                                                               : warp_select_list<16>(lkeys, lpays, cnt, p.k, lane);
                     if (lane == 0) {
                         s_cnt[q] = min(cnt, p.k);
                         s_thr[q] = kth;
@@ -277,9 +320,13 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned
         }
         // final cut of every list of this CTA
         for (uint32_t q = warp; q < kGmN; q += kGmEpiWarps) {
-            const uint32_t cnt = min(s_cnt[q], kGmList);
-            if (cnt > 0) warp_compact_list(p.list_keys + (list_base + q) * kGmList, p.list_pays + (list_base + q) * kGmList,
-                                           cnt, p.k, lane);
+            const uint32_t cnt = min(s_cnt[q], p.list_cap);
+            u64* lkeys = p.list_keys + (list_base + q) * p.list_cap;
+            u64* lpays = p.list_pays + (list_base + q) * p.list_cap;
+            if (cnt > 0) {
+                if (p.list_cap == kGmListSmall) warp_select_list<8>(lkeys, lpays, cnt, p.k, lane);
+                else warp_select_list<16>(lkeys, lpays, cnt, p.k, lane);
+            }
             if (lane == 0) p.list_counts[list_base + q] = min(cnt, p.k);
         }
     }
@@ -302,8 +349,8 @@ flat_gemm_merge_kernel(const GemmParams p, uint32_t cap, u64* out_keys, u64* out
     auto list_of = [pp, qb, ql](uint32_t l) { return ((size_t)(l * pp.qblocks + qb) * kGmN + ql); };
     collector_merge_lists(
         col, p.ranges, p.k, [&](uint32_t l) { return pp.list_counts[list_of(l)]; },
-        [&](uint32_t l, uint32_t i) { return pp.list_keys[list_of(l) * kGmList + i]; },
-        [&](uint32_t l, uint32_t i) { return pp.list_pays[list_of(l) * kGmList + i]; });
+        [&](uint32_t l, uint32_t i) { return pp.list_keys[list_of(l) * pp.list_cap + i]; },
+        [&](uint32_t l, uint32_t i) { return pp.list_pays[list_of(l) * pp.list_cap + i]; });
     const uint32_t total = *col.count;
     for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
         out_keys[(size_t)q * p.k + i] = col.keys[i];
@@ -489,8 +536,9 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     VB_CUDA(cudaGetLastError());
 
     const size_t max_ctas = (size_t)sms;
-    VB_TRY(ctx.cand_keys.reserve(max_ctas * kGmN * kGmList * sizeof(u64)));
-    VB_TRY(ctx.cand_pays.reserve(max_ctas * kGmN * kGmList * sizeof(u64)));
+    const uint32_t list_cap = kprime <= 64 ? kGmListSmall : kGmListLarge;
+    VB_TRY(ctx.cand_keys.reserve(max_ctas * kGmN * list_cap * sizeof(u64)));
+    VB_TRY(ctx.cand_pays.reserve(max_ctas * kGmN * list_cap * sizeof(u64)));
     VB_TRY(ctx.cand_counts.reserve(max_ctas * kGmN * sizeof(uint32_t) + 16));
     VB_TRY(ctx.dump_keys.reserve(nq_pad * kprime * sizeof(u64)));
     VB_TRY(ctx.dump_pays.reserve(nq_pad * kprime * sizeof(u64)));
@@ -527,6 +575,7 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
         p.qblocks = qblocks;
         p.ranges = std::max<uint32_t>(1, (uint32_t)sms / qblocks);
         p.id_rank = d_id_rank;
+        p.list_cap = list_cap;
         p.list_keys = ctx.cand_keys.as<u64>();
         p.list_pays = ctx.cand_pays.as<u64>();
         p.list_counts = ctx.cand_counts.as<uint32_t>();
