@@ -62,3 +62,33 @@ def test_batched_search_ties_resolve_by_id():
     got = ok(nifs.flat_search_batch(idx, queries, k))
     for qi in range(nq):
         assert got[qi] == ok(oracle.flat_search_dense("inner_product", rows, ids, queries[qi], k))
+
+
+@pytest.mark.parametrize("k", [40, 100])
+def test_batched_search_large_k_many_tiles_per_cta(k):
+    """Enough rows per CTA that the per-(CTA, query) candidate lists are cut back several times
+    (value-bisection select), with a continuous score distribution."""
+    n, d, nq = 250_000, 64, 16
+    rows, queries = _rows(n, d, 77), _rows(nq, d, 78)
+    ids = [f"{(i * 7919) % n:06d}" for i in range(n)]
+    idx = nifs.flat_new_cosine()
+    ok(nifs.flat_insert_matrix(idx, ids, rows))
+    got = ok(nifs.flat_search_batch(idx, queries, k))
+    for qi in range(nq):
+        assert_hits_match(got[qi], ok(oracle.flat_search_dense("cosine", rows, ids, queries[qi], k)))
+
+
+@pytest.mark.parametrize("k", [25, 100])
+def test_batched_search_large_k_ties_at_the_cut(k):
+    """Small-integer rows over many tiles: the cut of a candidate list falls inside large groups of equal
+    scores, so the id word decides which of them survive (second bisection)."""
+    rng = np.random.default_rng(6)
+    n, d, nq = 120_000, 32, 16
+    rows = rng.integers(-1, 2, size=(n, d)).astype(np.float32)
+    queries = rng.integers(-1, 2, size=(nq, d)).astype(np.float32)
+    ids = [f"{(i * 31) % n:06d}" for i in range(n)]
+    idx = nifs.flat_new_inner_product()
+    ok(nifs.flat_insert_matrix(idx, ids, rows))
+    got = ok(nifs.flat_search_batch(idx, queries, k))
+    for qi in range(nq):
+        assert got[qi] == ok(oracle.flat_search_dense("inner_product", rows, ids, queries[qi], k))
