@@ -81,6 +81,15 @@ int vb_flat_insert(vb_flat* index, const char* id, size_t id_len, const float* v
  * All-or-nothing validation; duplicate ids in a batch: last wins. */
 int vb_flat_insert_many(vb_flat* index, size_t n, const char* ids, const uint64_t* id_off,
                         const float* values, const uint64_t* value_off);
+/* Additive: capacity hint for a bulk load (rebuild_index, collection.ex:426-433) — the HBM matrix is
+ * allocated once for `rows` rows instead of growing by doubling. Does not change the contents. */
+int vb_flat_reserve(vb_flat* index, size_t rows);
+/* Additive (the ingest step before the scan: Index.put_many /
+ * rebuild_index, index/flat.ex:35-39, collection.ex:426-433): same insert_many, rows already in
+ * device memory as one contiguous [n, dimension] fp32 matrix. Same validation (finite check
+ * runs on the device), all-or-nothing, duplicate ids: last wins. */
+int vb_flat_insert_many_device(vb_flat* index, size_t n, const char* ids, const uint64_t* id_off,
+                               const float* d_values, size_t dimension);
 /* flat_delete/2, nifs.rs:286-295 -> FlatIndex::delete, flat.rs:88-93. */
 int vb_flat_delete(vb_flat* index, const char* id, size_t id_len);
 /* flat_search/3, nifs.rs:297-309 -> FlatIndex::search, flat.rs:96-124.

@@ -286,3 +286,40 @@ def test_resident_prefix_top_k_matches_by_value_semantics():
     assert_hits_match(ok(nifs.flat_prefix_top_k(idx, subset, q, 2, 128, 10)), ok(oracle.vector_top_k(sub_vectors, q, 2, 128, 10)))
     assert err(nifs.flat_prefix_top_k(idx, None, q, 2, 0, 10)) == "invalid prefix dimensions"
     assert err(nifs.flat_prefix_top_k(idx, None, q, 9, 8, 10)) == "unknown metric"
+
+
+@pytest.mark.parametrize("dim", [96, 127, 768])
+def test_device_bulk_ingest_equals_host_ingest(dim):
+    """vb_flat_insert_many_device (rows already in HBM) must leave the index exactly as insert_many would:
+    same validation, upserts in place, duplicate ids in a batch -> last wins, sign codes follow."""
+    import torch
+    rng = np.random.default_rng(dim)
+    n = 3000
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    ids = [f"r{i:05d}" for i in range(n)]
+    ids[17] = ids[5]                       # duplicate id inside the batch: row 17 wins
+    ids[2999] = ids[2998]
+    host, devi = nifs.flat_new_l2(), nifs.flat_new_l2()
+    assert nifs.flat_insert_matrix(host, ids, rows) == ("ok", ())
+    d_rows = torch.from_numpy(rows).cuda()
+    assert nifs.flat_insert_device(devi, ids, d_rows.data_ptr(), dim) == ("ok", ())
+    assert nifs.flat_info(host) == nifs.flat_info(devi)
+    # second batch: upserts of existing ids mixed with new ones
+    rows2 = rng.standard_normal((200, dim)).astype(np.float32)
+    ids2 = [ids[i * 3] if i % 2 else f"n{i:04d}" for i in range(200)]
+    assert nifs.flat_insert_matrix(host, ids2, rows2) == ("ok", ())
+    d_rows2 = torch.from_numpy(rows2).cuda()
+    assert nifs.flat_insert_device(devi, ids2, d_rows2.data_ptr(), dim) == ("ok", ())
+    for q in (rows[5], rows[17], rows2[1], rng.standard_normal(dim).astype(np.float32)):
+        assert nifs.flat_search(devi, q, 20) == nifs.flat_search(host, q, 20)
+        assert nifs.flat_quantized_search(devi, q, nifs.METRIC_CODE["l2"], 50, 10) == \
+            nifs.flat_quantized_search(host, q, nifs.METRIC_CODE["l2"], 50, 10)
+    # all-or-nothing validation on the device copy
+    bad = rows2.copy()
+    bad[150, dim // 2] = np.inf
+    before = nifs.flat_info(devi)
+    assert nifs.flat_insert_device(devi, [f"x{i}" for i in range(200)], torch.from_numpy(bad).cuda().data_ptr(), dim) == \
+        ("error", "vector contains a non-finite value")
+    assert nifs.flat_insert_device(devi, ["y"], d_rows2.data_ptr(), dim + 1) == ("error", "dimension mismatch")
+    assert nifs.flat_insert_device(nifs.flat_new_l2(), ["y"], d_rows2.data_ptr(), 0) == ("error", "vector must not be empty")
+    assert nifs.flat_info(devi) == before

@@ -31,6 +31,8 @@ SIGNATURES = {
     "vb_flat_free": (None, [_vp]),
     "vb_flat_insert": (C.c_int, [_vp, C.c_char_p, _sz, _f32p, _sz]),
     "vb_flat_insert_many": (C.c_int, [_vp, _sz, C.c_char_p, _u64p, _f32p, _u64p]),
+    "vb_flat_reserve": (C.c_int, [_vp, _sz]),
+    "vb_flat_insert_many_device": (C.c_int, [_vp, _sz, C.c_char_p, _u64p, _vp, _sz]),
     "vb_flat_delete": (C.c_int, [_vp, C.c_char_p, _sz]),
     "vb_flat_search": (C.c_int, [_vp, _f32p, _sz, _sz, _vpp]),
     "vb_flat_search_batch": (C.c_int, [_vp, _f32p, _sz, _sz, _sz, _vpp]),

@@ -117,6 +117,11 @@ int vb_flat_insert_many(vb_flat* index, size_t n, const char* ids, const uint64_
     return finish(index->impl->insert_many(n, ids, id_off, values, value_off, false));
 }
 
+int vb_flat_reserve(vb_flat* index, size_t rows) { return finish(index->impl->reserve(rows)); }
+int vb_flat_insert_many_device(vb_flat* index, size_t n, const char* ids, const uint64_t* id_off,
+                               const float* d_values, size_t dimension) {
+    return finish(index->impl->insert_many_device(n, ids, id_off, d_values, dimension));
+}
 int vb_flat_delete(vb_flat* index, const char* id, size_t id_len) {
     return finish(index->impl->remove(id, id_len));
 }

@@ -54,6 +54,7 @@ void FlatIndex::info(size_t* rows, size_t* dim) {
 Status FlatIndex::grow(size_t need_rows) {
     if (need_rows <= cap_) return Status::Ok();
     size_t new_cap = std::max<size_t>(need_rows, std::max<size_t>(cap_ * 2, 1024));
+    if (reserve_hint_ >= need_rows) new_cap = reserve_hint_;   // sized by the caller: no head-room guess
     float* rows = nullptr;
     uint32_t* rank = nullptr;
     cudaError_t e = cudaMalloc(&rows, new_cap * stride_ * sizeof(float));
@@ -84,6 +85,18 @@ Status FlatIndex::grow(size_t need_rows) {
     d_rows_ = rows;
     d_rank_ = rank;
     cap_ = new_cap;
+    return Status::Ok();
+}
+
+Status FlatIndex::reserve(size_t rows) {
+    std::unique_lock<std::shared_mutex> g(mu_);
+    if (rows >= kRankSpace - 1) return Status::Cuda("index row limit (2^32) exceeded");
+    reserve_hint_ = rows;
+    if (dim_ != 0 && rows > cap_) {
+        VB_CUDA(cudaSetDevice(device_));
+        if (dev_ctx_) VB_CUDA(cudaDeviceSynchronize());
+        VB_TRY(grow(rows));
+    }
     return Status::Ok();
 }
 
@@ -219,6 +232,86 @@ Status FlatIndex::insert_many(size_t n, const char* ids, const uint64_t* id_off,
         }
     }
     stage.release();
+    return st;
+}
+
+// Sets *bad when any of the n * dim values is NaN or infinite.
+__global__ void any_non_finite_kernel(const float* v, size_t total, uint32_t* bad) {
+    bool b = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        b |= (__float_as_uint(v[i]) & 0x7f800000u) == 0x7f800000u;
+    if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31) == 0) *bad = 1u;
+}
+
+Status FlatIndex::insert_many_device(size_t n, const char* ids, const uint64_t* id_off, const float* d_values,
+                                     size_t dim) {
+    std::unique_lock<std::shared_mutex> g(mu_);
+    VB_CUDA(cudaSetDevice(device_));
+    if (n == 0) return Status::Ok();
+    // flat.rs:70-76 / 136-144 on the device copy: all-or-nothing
+    if (dim == 0) return Status::Ref("vector must not be empty");
+    if (dim_ != 0 && dim != dim_) return Status::Ref("dimension mismatch");
+    if (n_ + n >= kRankSpace - 1) return Status::Cuda("index row limit (2^32) exceeded");
+    {
+        uint32_t* d_bad = nullptr;
+        uint32_t h_bad = 0;
+        VB_CUDA(cudaMalloc(&d_bad, sizeof(uint32_t)));
+        cudaMemset(d_bad, 0, sizeof(uint32_t));
+        any_non_finite_kernel<<<1184, 256>>>(d_values, n * dim, d_bad);
+        cudaError_t e = cudaMemcpy(&h_bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        cudaFree(d_bad);
+        if (e != cudaSuccess) return Status::Cuda(cudaGetErrorString(e));
+        if (h_bad) return Status::Ref("vector contains a non-finite value");
+    }
+    max_norm_ = -1.0f;
+    if (dev_ctx_) VB_CUDA(cudaDeviceSynchronize());
+    if (dim_ == 0) {
+        dim_ = dim;
+        stride_ = (dim_ + 3) & ~(size_t)3;
+    }
+    VB_TRY(grow(n_ + n));
+    const size_t n_before = n_;
+    bool relabel_needed = false;
+    Status st = Status::Ok();
+    // rows [run0, i) of the batch are new ids in a row: they land at device rows [run_dst, ...)
+    size_t run0 = 0, run_dst = n_;
+    auto copy_rows = [&](size_t dst_row, size_t src_row, size_t rows) -> Status {
+        if (rows == 0) return Status::Ok();
+        float* dst = d_rows_ + dst_row * stride_;
+        if (stride_ != dim_) VB_CUDA(cudaMemset(dst, 0, rows * stride_ * sizeof(float)));
+        VB_CUDA(cudaMemcpy2D(dst, stride_ * sizeof(float), d_values + src_row * dim_, dim_ * sizeof(float),
+                             dim_ * sizeof(float), rows, cudaMemcpyDeviceToDevice));
+        return Status::Ok();
+    };
+    for (size_t i = 0; i < n && st.ok(); ++i) {
+        std::string id(ids + id_off[i], ids + id_off[i + 1]);
+        auto hint = id_row_.end();
+        if (!(!id_row_.empty() && std::prev(hint)->first < id)) hint = id_row_.lower_bound(id);
+        if (hint != id_row_.end() && hint->first == id) {   // upsert: replace in place (after pending appends)
+            st = copy_rows(run_dst, run0, i - run0);
+            run_dst += i - run0;
+            run0 = i + 1;
+            if (st.ok()) st = copy_rows(hint->second, i, 1);
+            if (st.ok() && hint->second < n_before) st = pack_rows(hint->second, 1);
+            continue;
+        }
+        const uint32_t row = (uint32_t)n_;
+        auto it = id_row_.emplace_hint(hint, id, row);
+        row_id_.push_back(std::move(id));
+        h_rank_.push_back(0);
+        ++n_;
+        st = assign_rank(it, row, &relabel_needed);
+    }
+    if (st.ok()) st = copy_rows(run_dst, run0, n - run0);
+    if (st.ok()) st = pack_rows(n_before, n_ - n_before);
+    if (st.ok()) {
+        if (relabel_needed) st = relabel_all();
+        else if (n_ > n_before) {
+            cudaError_t e = cudaMemcpy(d_rank_ + n_before, h_rank_.data() + n_before,
+                                       (n_ - n_before) * sizeof(uint32_t), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) st = Status::Cuda(cudaGetErrorString(e));
+        }
+    }
     return st;
 }
 

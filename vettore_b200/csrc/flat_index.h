@@ -30,6 +30,12 @@ class FlatIndex {
     // values[value_off[i] .. value_off[i+1]).
     Status insert_many(size_t n, const char* ids, const uint64_t* id_off, const float* values,
                        const uint64_t* value_off, bool single);
+    // Capacity hint: the next growth allocates room for `rows` rows at once (no realloc + copy while a
+    // large corpus streams in; doubling would need old + new matrix resident together).
+    Status reserve(size_t rows);
+    // Bulk ingest of rows that already sit in device memory: [n, dim] fp32, contiguous (rebuild_index
+    // from a device-side snapshot, device-generated corpora). Same validation and upsert rules.
+    Status insert_many_device(size_t n, const char* ids, const uint64_t* id_off, const float* d_values, size_t dim);
     Status remove(const char* id, size_t id_len);                                    // flat.rs:88-93
     Status search(const float* queries, size_t nq, size_t len, size_t limit, std::vector<Hits>* out);  // flat.rs:96-124
     // search.rs:38-73 over resident rows (all rows, or the listed ids).
@@ -77,7 +83,7 @@ class FlatIndex {
     std::shared_mutex mu_;
     size_t dim_ = 0;        // 0 == None (flat.rs:16)
     size_t stride_ = 0;     // floats per device row
-    size_t n_ = 0, cap_ = 0;
+    size_t n_ = 0, cap_ = 0, reserve_hint_ = 0;
     float* d_rows_ = nullptr;
     uint32_t* d_rank_ = nullptr;
     u64* d_codes_ = nullptr;   // [cap, code_words_] sign codes of the rows, kept in sync once built

@@ -151,6 +151,20 @@ def flat_insert_matrix(index: FlatRef, ids: Sequence, matrix: np.ndarray):
     return _err() if rc else ("ok", ())
 
 
+def flat_reserve(index: FlatRef, rows: int):
+    """Additive: pre-size the HBM matrix for a bulk load."""
+    rc = lib().vb_flat_reserve(index.handle, int(rows))
+    return _err() if rc else ("ok", ())
+
+
+def flat_insert_device(index: FlatRef, ids: Sequence, device_ptr: int, dimension: int):
+    """Additive bulk ingest: `len(ids)` rows of `dimension` float32 at `device_ptr` (device memory, contiguous)."""
+    blob, ioff = _ids_blob(ids)
+    rc = lib().vb_flat_insert_many_device(index.handle, len(ids), blob, _ptr(ioff, _u64p), C.c_void_p(int(device_ptr)),
+                                          int(dimension))
+    return _err() if rc else ("ok", ())
+
+
 def flat_delete(index: FlatRef, id):
     """nifs.rs:286-295."""
     b = _enc(id)
