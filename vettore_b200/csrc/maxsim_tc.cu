@@ -5,25 +5,31 @@
 //
 // Shape of the work (C5: 1M docs x 128 tokens x 128 dims, 32 query tokens): the token matrix
 // is streamed once (tokens * D * 4 bytes, HBM-bound at 16 flop/B), every 128-token tile is a
-// [128 x D] . [D x 32] product. Per SM, one persistent CTA of 14 warps:
-//   warp 12     producer: TMA 2D tiled loads (128-byte swizzle) of token chunks into a 4-stage ring
-//   warps 4-11  split: each thread owns one token row (= one TMEM lane), reads it from the
+// [128 x D] . [D x 32] product. Per SM, one persistent CTA of 18 warps:
+//   warp 16     producer: TMA 2D tiled loads (128-byte swizzle) of token chunks into a 4-stage ring
+//   warps 8-15  split: each thread owns one token row (= one TMEM lane), reads it from the
 //               swizzled tile (conflict-free 128-bit LDS), splits x = hi + lo and writes both
 //               halves into TMEM with tcgen05.st (A operand from TMEM: no second smem round trip)
-//   warp 13     MMA issuer: per tile 3 * D/8 tcgen05.mma kind::tf32 (A in TMEM, B = query
+//   warp 17     MMA issuer: per tile 3 * D/8 tcgen05.mma kind::tf32 (A in TMEM, B = query
 //               tokens resident in shared memory in the UMMA K-major SWIZZLE_128B layout),
 //               fp32 accumulators in TMEM (2 buffers x 4 independent partial accumulators)
-//   warps 0-3   epilogue: tcgen05.ld the [128 x 32] tile, similarity transform, per-query max
-//               over each document's tokens (31-shuffle transpose butterfly + shared memory
-//               across warps), f32 sum in query order, collector push (topk.cuh)
+//   warps 0-7   epilogue, two groups of 4 warps that take alternate tiles (group g owns accumulator
+//               buffer g): tcgen05.ld the [128 x 32] tile, similarity transform, per-query max over
+//               each document's tokens (31-shuffle transpose butterfly + shared memory across the
+//               group's warps), f32 sum in query order, collector push (topk.cuh). One tile's
+//               epilogue is a ~2100-cycle dependent chain (tcgen05.ld, 5 shuffle levels, a barrier,
+//               the 32-step ordered sum); a single group capped the kernel at one tile per chain.
 #include "maxsim.h"
+
+#include <cstdlib>
 #include "scan_driver.h"
 #include "tc.cuh"
 #include "topk.cuh"
 
 namespace vb {
 
-constexpr int kTcEpiWarps = 4, kTcSplitWarps = 8;
+constexpr int kTcEpiWarps = 8, kTcSplitWarps = 8;   // epilogue: two groups of 4 warps, alternating tiles
+constexpr int kTcEpiGroupWarps = 4;
 constexpr int kTcProducerWarp = kTcEpiWarps + kTcSplitWarps, kTcMmaWarp = kTcProducerWarp + 1;
 constexpr int kTcThreads = (kTcMmaWarp + 1) * 32;
 constexpr int kTcStages = 4;     // ring stages of one chunk (<= 2 K blocks = 32 KB) each
@@ -45,6 +51,7 @@ struct MaxSimTcParams {
     const float* inv_qnorm;       // [tq], cosine only
     uint32_t cap;
     uint32_t* err;
+    uint32_t debug;               // timing experiments only (VB_MAXSIM_DEBUG): 1 skip MMAs, 2 skip the split work, 4 skip the TMA loads, 8 skip the epilogue math
     TopkWorkspace ws;
 };
 
@@ -62,6 +69,21 @@ __device__ __forceinline__ float warp_transpose_max(float (&v)[32], int lane) {
         }
     }
     return v[0];
+}
+
+// Same for 16 per-lane values: 8 + 4 + 2 + 1 exchanges, then one plain step; lanes 2c and 2c + 1 hold column c.
+__device__ __forceinline__ float warp_transpose_max16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+        const bool hi = (lane & (half * 2)) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = hi ? v[i] : v[i + half];
+            const float keep = hi ? v[i + half] : v[i];
+            v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, half * 2));
+        }
+    }
+    return fmaxf(v[0], __shfl_xor_sync(0xffffffffu, v[0], 1));
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -97,7 +119,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
         }
         for (int b = 0; b < kTcAccBufs; ++b) {
             tc::mbar_init(&d_full[b], 1);
-            tc::mbar_init(&d_free[b], kTcEpiWarps);
+            tc::mbar_init(&d_free[b], kTcEpiGroupWarps);
         }
         tc::mbar_fence_init();
     }
@@ -132,8 +154,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
                     const uint32_t s = cc % kTcStages, ph = (cc / kTcStages) & 1u;
                     const uint32_t blocks = min(2u, KB - 2u * j);
                     tc::mbar_wait(&empty_bar[s], ph ^ 1u);
-                    tc::mbar_arrive_expect_tx(&full_bar[s], blocks * 16384u);
-                    for (uint32_t h = 0; h < blocks; ++h)
+                    tc::mbar_arrive_expect_tx(&full_bar[s], (p.debug & 4u) ? 0u : blocks * 16384u);
+                    for (uint32_t h = 0; h < blocks && !(p.debug & 4u); ++h)
                         tc::tma_load_2d(ring + (size_t)s * kTcChunkBytes + (size_t)h * 16384, &tmap, (2u * j + h) * 32u,
                                         tile * kTcTile, &full_bar[s]);
                 }
@@ -162,7 +184,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
                 if (tc::elect_one()) {
 #pragma unroll
                     for (uint32_t h = 0; h < 2; ++h) {
-                        if (h < blocks) {
+                        if (h < blocks && !(p.debug & 1u)) {
                             const uint32_t first = (j | h) == 0u ? 0u : 1u;
 #pragma unroll
                             for (uint32_t term = 0; term < 3; ++term) {
@@ -196,7 +218,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
                 tc::mbar_wait(&full_bar[s], ph);
                 tc::mbar_wait(&a_free[u], ((cc >> 1) & 1u) ^ 1u);   // MMAs that read this A buffer are done
                 tc::fence_after_sync();
-                if (h < blocks) {
+                if (h < blocks && !(p.debug & 2u)) {
                     const unsigned char* blk = ring + (size_t)s * kTcChunkBytes + (size_t)h * 16384 + row * 128u;
                     uint32_t hi[32], lo[32];
 #pragma unroll
@@ -223,14 +245,15 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
             }
         }
     } else {
-        // ===== epilogue warps 0-3 =====
-        const uint32_t quarter = warp;                        // TMEM lanes [32 * warp, +32)
+        // ===== epilogue warps 0-7: group (warp >> 2) handles tiles it = group, group + 2, ... =====
+        const uint32_t quarter = warp & 3u, group = warp >> 2;   // TMEM lanes [32 * quarter, +32)
         const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
-        const uint32_t warps_per_doc = p.td / 32u;            // 1, 2 or 4
+        const uint32_t warps_per_doc = p.td / 32u;               // 1, 2 or 4
+        const uint32_t my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
+        const uint32_t b = group;                                // accumulator buffer of this group (kTcAccBufs == 2)
         u64 g_prefetch = kKeyMax;
-        uint32_t it = 0;
-        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const uint32_t b = it % kTcAccBufs;
+        for (uint32_t it = group; it < my_tiles; it += 2u) {
+            const uint32_t tile = blockIdx.x + it * gridDim.x;
             const uint32_t token = tile * kTcTile + quarter * 32u + lane;
             float inv_dn = 1.0f;
             if (p.metric == kCosineTrue) inv_dn = token < ntok ? __ldg(p.inv_dnorm + token) : 0.0f;
@@ -238,18 +261,20 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
             tc::fence_after_sync();
             float v[32];
             {
-                uint32_t r0[32], r1[32];
                 const uint32_t acc = lane_addr + kTcAccCol + b * (kTcChains * kTcN);
-                tc::tmem_ld32(acc, r0);
-                tc::tmem_ld32(acc + kTcN, r1);
-                tc::tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r0[q]) + __uint_as_float(r1[q]);
-                tc::tmem_ld32(acc + 2 * kTcN, r0);
-                tc::tmem_ld32(acc + 3 * kTcN, r1);
-                tc::tmem_ld_wait();
+                for (int hcol = 0; hcol < 2; ++hcol) {
+                    uint32_t r0[16], r1[16], r2[16], r3[16];
+                    tc::tmem_ld16(acc + hcol * 16, r0);
+                    tc::tmem_ld16(acc + kTcN + hcol * 16, r1);
+                    tc::tmem_ld16(acc + 2 * kTcN + hcol * 16, r2);
+                    tc::tmem_ld16(acc + 3 * kTcN + hcol * 16, r3);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] += __uint_as_float(r0[q]) + __uint_as_float(r1[q]);
+                    for (int q = 0; q < 16; ++q)
+                        v[hcol * 16 + q] = (__uint_as_float(r0[q]) + __uint_as_float(r1[q])) +
+                                           (__uint_as_float(r2[q]) + __uint_as_float(r3[q]));
+                }
             }
             tc::fence_before_sync();
             __syncwarp();
@@ -266,7 +291,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
             float wmax = warp_transpose_max(v, lane);                      // lane q: max over this warp's tokens
             if (p.metric == kCosineTrue) wmax = fminf(1.0f, fmaxf(-1.0f, wmax * s_invq[lane]));
             s_part[b][quarter][lane] = wmax;
-            col.sync();                                                      // the 4 epilogue warps
+            asm volatile("bar.sync %0, 128;" ::"r"(3u + group) : "memory");   // the 4 warps of this group
             // document leaders: the first warp of each document combines its warps; one lane then adds
             // the per-query maxima in query order (multi_vector.rs:81-84) straight from shared memory
             // (32 pipelined loads + 32 dependent adds instead of a 32-deep shuffle chain).
@@ -297,7 +322,10 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
                     }
                 }
             }
-            if ((it & 15u) == 15u) collector_checkpoint(col, p.ws, 0, 16 * 4, g_prefetch);
+            // Both groups meet (all 8 warps) each time the CTA has finished another 16 tiles; a window only
+            // counts when it lies inside this CTA's tiles, so both groups pass the same number of checkpoints.
+            if ((it + 2u) / 16u != it / 16u && (it / 16u + 1u) * 16u <= my_tiles)
+                collector_checkpoint(col, p.ws, 0, 16 * 4, g_prefetch);
         }
         collector_publish_and_merge(col, p.ws, 0, &s_last);
     }
@@ -379,6 +407,7 @@ Status maxsim_tc_top_k(SearchCtx& ctx, const MaxSimJob& job, uint32_t td, const 
     p.query = ctx.queries.as<float>();
     p.inv_qnorm = ctx.queries.as<float>() + (size_t)job.tq * job.dims;
     p.cap = cap;
+    { const char* dbg = std::getenv("VB_MAXSIM_DEBUG"); p.debug = dbg ? (uint32_t)std::atoi(dbg) : 0u; }
     p.err = ctx.err_row();
     p.ws.k = k;
     p.ws.cand_keys = ctx.cand_keys.as<u64>();
