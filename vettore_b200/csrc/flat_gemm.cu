@@ -544,13 +544,8 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     VB_TRY(ctx.dump_pays.reserve(nq_pad * kprime * sizeof(u64)));
     VB_TRY(ctx.staging_rank.reserve(nq_pad * sizeof(uint32_t)));
 
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
     const size_t smem_bytes = (size_t)kGmStages * kGmStageBytes + 1024;
-    std::call_once(attr_once, [&] {
-        attr_err = cudaFuncSetAttribute(flat_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    });
-    if (attr_err != cudaSuccess) return Status::Cuda(cudaGetErrorString(attr_err));
+    VB_TRY(ensure_dynamic_smem_for(flat_gemm_topk_kernel, smem_bytes));
 
     CUtensorMap tmap_a;
     VB_TRY(make_tmap_rows_sw128(d_rows, n, stride, kGmTile, &tmap_a));

@@ -1,6 +1,7 @@
 // flat_scan.cu — variant selection and launch of the K1/K4 scan kernels.
 #include "flat_scan.cuh"
 #include "flat_scan.h"
+#include "runtime.h"
 
 #include <cstdlib>
 #include <map>
@@ -95,16 +96,7 @@ static Status plan_stream(int metric, int nv, size_t row_stride, uint32_t n, uin
     const int stages_env = env_int("VB_STREAM_STAGES", 0);
     if (stages_env >= 2 && (uint32_t)stages_env < stages) stages = stages_env;
     const size_t smem = (size_t)stages * tile_bytes + (size_t)cap * 16;
-    static std::mutex mu;
-    static std::map<const void*, size_t> attr_cache;
-    {
-        std::lock_guard<std::mutex> g(mu);
-        auto it = attr_cache.find((const void*)kernel);
-        if (it == attr_cache.end() || it->second < smem) {
-            VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-            attr_cache[(const void*)kernel] = budget;
-        }
-    }
+    VB_TRY(ensure_dynamic_smem_for(kernel, budget));   // cached per (device, kernel)
     const int sms = device_sm_count();
     if (sms <= 0) return Status::Cuda("no CUDA device");
     const uint32_t tiles = (n + tile_rows - 1) / tile_rows;
@@ -153,6 +145,7 @@ Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, bool contigu
     const uint32_t cap = next_pow2(2 * kk + slack);
     const size_t smem = (size_t)cap * 16;
 
+    VB_TRY(ensure_dynamic_smem_for(kernel, smem));      // cached per (device, kernel); occupancy is device independent here
     static std::mutex mu;
     static std::map<std::pair<const void*, size_t>, int> occ_cache;
     int per_sm = 0;
@@ -161,8 +154,6 @@ Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, bool contigu
         auto key = std::make_pair((const void*)kernel, smem);
         auto it = occ_cache.find(key);
         if (it == occ_cache.end()) {
-            if (smem > 48 * 1024)
-                VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kScanThreads, smem));
             if (per_sm < 1) return Status::Cuda("scan kernel does not fit on an SM");
             occ_cache[key] = per_sm;

@@ -591,7 +591,7 @@ static Status launch_hamming(SearchCtx& ctx, HammingParams p, uint32_t nq, uint3
             uint32_t logg = 0;
             while ((1u << logg) < p.g) ++logg;
             HammingStreamKernel kernel = hamming_stream_kernel_for(logg);
-            VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+            VB_TRY(ensure_dynamic_smem_for(kernel, budget));
             const uint32_t tiles = (p.n + geom.tile_rows - 1) / geom.tile_rows;
             uint32_t grid_x = std::min<uint32_t>(tiles, (uint32_t)sms);
             if (const char* e = std::getenv("VB_HAMMING_MAX_GRID"))
@@ -617,7 +617,7 @@ static Status launch_hamming(SearchCtx& ctx, HammingParams p, uint32_t nq, uint3
     if (const char* e = std::getenv("VB_HAM_CTAS")) cps = std::atoi(e);
     HammingKernel kernel = cps == 3 ? (wide ? hamming_kernel_for<true, 3>(logg) : hamming_kernel_for<false, 3>(logg))
                                     : (wide ? hamming_kernel_for<true, 2>(logg) : hamming_kernel_for<false, 2>(logg));
-    if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VB_TRY(ensure_dynamic_smem_for(kernel, smem));
     int per_sm = 0;
     VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kHamThreads, smem));
     if (per_sm < 1) return Status::Cuda("hamming kernel does not fit on an SM");

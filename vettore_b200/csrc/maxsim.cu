@@ -260,7 +260,7 @@ Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out) {
     while (cap < 2 * k || cap < k + 64) cap <<= 1;
     const size_t smem = (size_t)cap * 16 + (size_t)job.tq * sizeof(float);
     if (smem > 160 * 1024) return Status::Cuda("too many query tokens for the multi-vector kernel");
-    if (smem > 16 * 1024) VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VB_TRY(ensure_dynamic_smem_for(kernel, smem));
     int per_sm = 0, dev = 0, sms = 0;
     VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kMsThreads, smem));
     VB_CUDA(cudaGetDevice(&dev));

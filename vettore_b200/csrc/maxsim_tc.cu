@@ -376,12 +376,7 @@ Status maxsim_tc_top_k(SearchCtx& ctx, const MaxSimJob& job, uint32_t td, const 
     uint32_t cap = 256;
     while (cap < 2 * k || cap < k + 64) cap <<= 1;
     const size_t smem = (size_t)kTcStages * kTcChunkBytes + 2 * (size_t)KB * 4096 + (size_t)cap * 16 + 1024;
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(maxsim_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    });
-    if (attr_err != cudaSuccess) return Status::Cuda(cudaGetErrorString(attr_err));
+    VB_TRY(ensure_dynamic_smem_for(maxsim_tc_kernel, 220 * 1024));
     if (smem > 220 * 1024) return Status::Cuda("maxsim tensor-core kernel: shared memory budget exceeded");
     int dev = 0, sms = 0;
     VB_CUDA(cudaGetDevice(&dev));

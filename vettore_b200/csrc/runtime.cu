@@ -1,6 +1,9 @@
 // runtime.cu — buffers, search contexts and the context pool (see runtime.h).
 #include "runtime.h"
 
+#include <map>
+#include <utility>
+
 namespace vb {
 
 Status DeviceBuf::reserve(size_t bytes) {
@@ -95,6 +98,20 @@ void CtxPool::release(SearchCtx* ctx) {
 CtxPool& ctx_pool() {
     static CtxPool* pool = new CtxPool();  // intentionally leaked (see ~CtxPool)
     return *pool;
+}
+
+Status ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> granted;
+    if (bytes <= 48 * 1024) return Status::Ok();
+    int dev = 0;
+    VB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(mu);
+    size_t& have = granted[{dev, kernel}];
+    if (have >= bytes) return Status::Ok();
+    VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+    return Status::Ok();
 }
 
 }  // namespace vb

@@ -59,6 +59,12 @@ class CtxPool {
 
 CtxPool& ctx_pool();
 
+// Raises a kernel's dynamic shared-memory limit once per (device, kernel, size): function attributes are
+// per device, so a process-wide `static bool` would leave the second GPU of a process unconfigured.
+Status ensure_dynamic_smem(const void* kernel, size_t bytes);
+template <typename K>
+inline Status ensure_dynamic_smem_for(K kernel, size_t bytes) { return ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), bytes); }
+
 struct CtxLease {
     SearchCtx* ctx = nullptr;
     ~CtxLease() { if (ctx) ctx_pool().release(ctx); }

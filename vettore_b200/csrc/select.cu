@@ -63,11 +63,7 @@ Status topk_merge_device(const u64* d_keys, const float* d_values, const uint32_
     uint32_t cap = 256;
     while (cap < 2 * k_out || cap < k_out + k_in) cap <<= 1;
     const size_t smem = (size_t)cap * 16;
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-        VB_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
-    }
+    VB_TRY(ensure_dynamic_smem_for(topk_merge_kernel, smem));
     topk_merge_kernel<<<(unsigned)nq, 256, smem, stream>>>(d_keys, d_values, d_rows, d_counts, list_stride, (uint32_t)lists,
                                                           (uint32_t)k_in, (uint32_t)k_out, cap, d_keys_out,
                                                           d_values_out, d_rows_out, d_counts_out);
@@ -124,11 +120,7 @@ Status run_merge_tree(const TopkWorkspace& ws, uint32_t nq, uint32_t lists, Devi
     uint32_t cap = 256;
     while (cap < 2 * k + 64) cap <<= 1;
     const size_t smem = (size_t)cap * 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VB_CUDA(cudaFuncSetAttribute(topk_tree_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-    }
+    VB_TRY(ensure_dynamic_smem_for(topk_tree_merge_kernel, smem));
     // scratch: two ping-pong levels of at most ceil(lists / group) lists each
     const uint32_t l1 = (lists + kTreeGroup - 1) / kTreeGroup;
     const size_t level_entries = (size_t)nq * l1 * k;
