@@ -120,7 +120,7 @@ Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, bool contigu
     const uint32_t nvec = (dims + 3) / 4;
     const uint32_t need = (nvec + 31) / 32;
     int nv, r;
-    if (need <= 1) { nv = 1; r = 4; }
+    if (need <= 1) { nv = 1; r = 8; }
     else if (need <= 2) { nv = 2; r = 4; }
     else if (need <= 3) { nv = 3; r = 4; }
     else if (need <= 4) { nv = 4; r = 4; }

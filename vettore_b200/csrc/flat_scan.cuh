@@ -225,6 +225,104 @@ __device__ __forceinline__ void emit_row(const ScanParams& p, Collector& col, ui
     }
 }
 
+// Per-lane partial state of one row, reduced across the warp only once per group of rows.
+template <int M>
+struct PartialTraits {
+    static constexpr bool kIsDouble = (M == kCosineTrue);
+    static constexpr bool kIsCount = (M == kHamming || M == kJaccard);
+    static constexpr bool kIsMax = (M == kChebyshev);
+    static constexpr int kComps = (M == kJaccard || M == kCosineTrue) ? 2 : 1;
+    using T = typename std::conditional<kIsDouble, double,
+                                        typename std::conditional<kIsCount, uint32_t, float>::type>::type;
+    __device__ static __forceinline__ T zero() { return T(0); }
+    __device__ static __forceinline__ T op(T a, T b) {
+        if constexpr (kIsMax) return fmaxf(a, b);
+        else return a + b;
+    }
+    // lane-local partial of one row from the Scorer accumulators
+    __device__ static __forceinline__ void from_scorer(const Scorer<M>& sc, T (&out)[kComps]) {
+        if constexpr (kIsDouble) { out[0] = sc.d0; out[1] = sc.d1; }
+        else if constexpr (M == kJaccard) { out[0] = sc.c0; out[1] = sc.c1; }
+        else if constexpr (M == kHamming) { out[0] = sc.c0; }
+        else if constexpr (kIsMax) { out[0] = fmaxf(fmaxf(sc.s0, sc.s1), fmaxf(sc.s2, sc.s3)); }
+        else { out[0] = (sc.s0 + sc.s1) + (sc.s2 + sc.s3); }
+    }
+    // warp-reduced partial -> raw metric value (the tail of Scorer::finish)
+    __device__ static __forceinline__ float finalize(const T (&v)[kComps], double q_norm, bool& bad, bool& fatal) {
+        bad = false;
+        fatal = false;
+        float r;
+        if constexpr (M == kCosine || M == kInnerProduct || M == kL2Squared || M == kManhattan || M == kChebyshev) {
+            r = v[0];
+            bad = !isfinite(r);
+        } else if constexpr (M == kNegativeInnerProduct) {
+            r = -v[0];
+            bad = !isfinite(r);
+        } else if constexpr (M == kL2) {
+            bad = !isfinite(v[0]);
+            r = sqrtf(v[0]);
+        } else if constexpr (M == kHamming) {
+            r = (float)v[0];
+        } else if constexpr (M == kJaccard) {
+            r = v[1] == 0u ? 0.0f : __fsub_rn(1.0f, __fdiv_rn((float)v[0], (float)v[1]));
+        } else {
+            const double rn = sqrt(v[1]);
+            if (q_norm == 0.0 || rn == 0.0) {
+                r = 0.0f;
+            } else {
+                double s = v[0] / (q_norm * rn);
+                if (!isfinite(s)) { fatal = true; s = 0.0; }
+                s = s < -1.0 ? -1.0 : (s > 1.0 ? 1.0 : s);
+                r = (float)s;
+            }
+        }
+        return r;
+    }
+};
+
+// Reduces R (1, 2, 4 or 8) per-lane partial rows across the warp, transposing as it goes: each of the first
+// log2(R) stages halves the rows a lane still carries, the remaining stages are plain xor steps. The xor
+// offsets run 16, 8, 4, 2, 1 for every row, i.e. the same summation tree as warp_sum. Afterwards v[0] of
+// lane L holds the total of row row_slot_of_lane<R>(L).
+template <typename Tr, typename T, int C, int R>
+__device__ __forceinline__ void butterfly_rows(T (&v)[R][C], int lane) {
+    int live = R;
+#pragma unroll
+    for (int bit = 16; bit >= 1; bit >>= 1) {
+        if (live > 1) {
+            const bool hi = (lane & bit) != 0;
+            const int half = live / 2;
+#pragma unroll
+            for (int i = 0; i < R / 2; ++i)
+                if (i < half) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const T send = hi ? v[i][c] : v[i + half][c], keep = hi ? v[i + half][c] : v[i][c];
+                        v[i][c] = Tr::op(keep, __shfl_xor_sync(0xffffffffu, send, bit));
+                    }
+                }
+            live = half;
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[0][c] = Tr::op(v[0][c], __shfl_xor_sync(0xffffffffu, v[0][c], bit));
+        }
+    }
+}
+// First lane of the group that ends up with row slot r (inverse of row_slot_of_lane).
+template <int R>
+__device__ __forceinline__ constexpr uint32_t lead_lane_of_slot(int r) {
+    return R == 8 ? (uint32_t)((((r >> 2) & 1) << 4) | (((r >> 1) & 1) << 3) | ((r & 1) << 2))
+         : R == 4 ? (uint32_t)((((r >> 1) & 1) << 4) | ((r & 1) << 3))
+         : R == 2 ? (uint32_t)((r & 1) << 4) : 0u;
+}
+template <int R>
+__device__ __forceinline__ int row_slot_of_lane(int lane) {
+    if constexpr (R == 8) return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    else if constexpr (R == 4) return ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    else if constexpr (R == 2) return (lane >> 4) & 1;
+    else return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // Kernel A. NV > 0: query and R rows in registers (dims <= 128 * NV). NV == 0: generic loop.
 template <int M, int NV, int R>
@@ -291,6 +389,12 @@ flat_scan_kernel(const ScanParams p) {
                     b[r][j] = (valid && idx < nvec) ? ldg_stream(rp[r] + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
+            // Lane-local partials of the R rows, ONE transposing butterfly for all of them, and the metric's
+            // tail (for the true cosine an f64 sqrt and divide) evaluated once for R rows, one row per lane group.
+            using Tr = PartialTraits<M>;
+            using PT = typename Tr::T;
+            constexpr int C = Tr::kComps;
+            PT part[R][C];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (need_mask) {
@@ -298,9 +402,41 @@ flat_scan_kernel(const ScanParams p) {
                     for (int j = 0; j < NV; ++j)
                         if (lane + 32u * j == tail_idx) mask_tail(b[r][j], tail_rem);
                 }
-                bool fatal;
-                raw[r] = score_row_regs<M, NV>(q, b[r], q_norm, fatal);
-                if (fatal && (r0 + r) < p.n && lane == 0) atomicMin(p.err_row + qi, r0 + r);
+                Scorer<M> sc;
+                sc.init();
+#pragma unroll
+                for (int j = 0; j < NV; ++j) sc.accum(q[j], b[r][j]);
+                Tr::from_scorer(sc, part[r]);
+            }
+            butterfly_rows<Tr, PT, C, R>(part, lane);
+            const int slot = row_slot_of_lane<R>(lane);
+            const bool owner = (lane & (32 / R - 1)) == 0 && (r0 + slot) < p.n;
+            bool bad, fatal;
+            float rawv = Tr::finalize(part[0], q_norm, bad, fatal);
+            if constexpr (kCanOverflow<M>) {
+                uint32_t todo = __ballot_sync(0xffffffffu, owner && bad);
+                if (todo) {   // cold path: redo the overflowed rows in f64 from the registers, warp-wide, one row at a time
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (todo & (1u << lead_lane_of_slot<R>(r))) {
+                            Recover<M> rc;
+                            rc.init();
+#pragma unroll
+                            for (int j = 0; j < NV; ++j) rc.accum(q[j], b[r][j]);
+                            bool f2;
+                            const float rec = rc.finish(f2);
+                            if (slot == r) { rawv = rec; fatal = f2; }
+                        }
+                    }
+                }
+            }
+            uint32_t drow_s = drow[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r)
+                if (slot == r) drow_s = drow[r];
+            if (owner) {
+                if (fatal) atomicMin(p.err_row + qi, r0 + slot);
+                emit_row<M>(p, col, qi, dump, dump ? kKeyMax : col.threshold(), rawv, r0 + slot, drow_s);
             }
         } else {
 #pragma unroll
@@ -333,7 +469,7 @@ flat_scan_kernel(const ScanParams p) {
             }
         }
 
-        if (lane == 0) {
+        if (NV == 0 && lane == 0) {
             const u64 T = dump ? kKeyMax : col.threshold();
 #pragma unroll
             for (int r = 0; r < R; ++r)
@@ -387,61 +523,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 struct StreamGeom {
     uint32_t stages;      // ring depth
     uint32_t tile_bytes;  // bytes per stage (tile_rows * row_stride * 4), multiple of 128
-};
-
-// Per-lane partial state of one row, reduced across the warp only once per group of rows.
-template <int M>
-struct PartialTraits {
-    static constexpr bool kIsDouble = (M == kCosineTrue);
-    static constexpr bool kIsCount = (M == kHamming || M == kJaccard);
-    static constexpr bool kIsMax = (M == kChebyshev);
-    static constexpr int kComps = (M == kJaccard || M == kCosineTrue) ? 2 : 1;
-    using T = typename std::conditional<kIsDouble, double,
-                                        typename std::conditional<kIsCount, uint32_t, float>::type>::type;
-    __device__ static __forceinline__ T zero() { return T(0); }
-    __device__ static __forceinline__ T op(T a, T b) {
-        if constexpr (kIsMax) return fmaxf(a, b);
-        else return a + b;
-    }
-    // lane-local partial of one row from the Scorer accumulators
-    __device__ static __forceinline__ void from_scorer(const Scorer<M>& sc, T (&out)[kComps]) {
-        if constexpr (kIsDouble) { out[0] = sc.d0; out[1] = sc.d1; }
-        else if constexpr (M == kJaccard) { out[0] = sc.c0; out[1] = sc.c1; }
-        else if constexpr (M == kHamming) { out[0] = sc.c0; }
-        else if constexpr (kIsMax) { out[0] = fmaxf(fmaxf(sc.s0, sc.s1), fmaxf(sc.s2, sc.s3)); }
-        else { out[0] = (sc.s0 + sc.s1) + (sc.s2 + sc.s3); }
-    }
-    // warp-reduced partial -> raw metric value (the tail of Scorer::finish)
-    __device__ static __forceinline__ float finalize(const T (&v)[kComps], double q_norm, bool& bad, bool& fatal) {
-        bad = false;
-        fatal = false;
-        float r;
-        if constexpr (M == kCosine || M == kInnerProduct || M == kL2Squared || M == kManhattan || M == kChebyshev) {
-            r = v[0];
-            bad = !isfinite(r);
-        } else if constexpr (M == kNegativeInnerProduct) {
-            r = -v[0];
-            bad = !isfinite(r);
-        } else if constexpr (M == kL2) {
-            bad = !isfinite(v[0]);
-            r = sqrtf(v[0]);
-        } else if constexpr (M == kHamming) {
-            r = (float)v[0];
-        } else if constexpr (M == kJaccard) {
-            r = v[1] == 0u ? 0.0f : __fsub_rn(1.0f, __fdiv_rn((float)v[0], (float)v[1]));
-        } else {
-            const double rn = sqrt(v[1]);
-            if (q_norm == 0.0 || rn == 0.0) {
-                r = 0.0f;
-            } else {
-                double s = v[0] / (q_norm * rn);
-                if (!isfinite(s)) { fatal = true; s = 0.0; }
-                s = s < -1.0 ? -1.0 : (s > 1.0 ? 1.0 : s);
-                r = (float)s;
-            }
-        }
-        return r;
-    }
 };
 
 constexpr int kGroupRows = 8;  // rows whose partials one warp reduces with a single butterfly

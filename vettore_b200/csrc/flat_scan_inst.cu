@@ -15,7 +15,7 @@ namespace vb {
     if (nv == NV && r == R) return flat_scan_kernel<VB_METRIC, NV, R>;
 
 ScanKernel VB_CAT(flat_scan_kernel_metric_, VB_METRIC)(int nv, int r) {
-    VB_VARIANT(1, 4)
+    VB_VARIANT(1, 4) VB_VARIANT(1, 8)
     VB_VARIANT(2, 4)
     VB_VARIANT(3, 4) VB_VARIANT(3, 2)
     VB_VARIANT(4, 4) VB_VARIANT(4, 2)
