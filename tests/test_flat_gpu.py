@@ -323,3 +323,36 @@ def test_device_bulk_ingest_equals_host_ingest(dim):
     assert nifs.flat_insert_device(devi, ["y"], d_rows2.data_ptr(), dim + 1) == ("error", "dimension mismatch")
     assert nifs.flat_insert_device(nifs.flat_new_l2(), ["y"], d_rows2.data_ptr(), 0) == ("error", "vector must not be empty")
     assert nifs.flat_info(devi) == before
+
+
+@pytest.mark.parametrize("ints", [False, True])
+@pytest.mark.parametrize("metric,n,d,k", [("cosine", 400_000, 64, 100), ("l2", 300_000, 96, 1000), ("inner_product", 250_000, 128, 333)])
+def test_large_k_flat_search_many_rows(metric, n, d, k, ints):
+    """k >= 32 takes the launch-wide pivot ladder (topk.cuh): every CTA prunes with a bound proven over the
+    whole launch. Small-integer rows make the bound fall into huge groups of tied ranks."""
+    rng = np.random.default_rng(n + k)
+    if ints:
+        rows = rng.integers(-2, 3, size=(n, d)).astype(np.float32)
+        q = rng.integers(-2, 3, size=d).astype(np.float32)
+    else:
+        rows = rng.standard_normal((n, d)).astype(np.float32)
+        q = rng.standard_normal(d).astype(np.float32)
+    ids = [f"{(i * 7919) % n:07d}" for i in range(n)]
+    idx = getattr(nifs, f"flat_new_{metric}")()
+    assert nifs.flat_insert_matrix(idx, ids, rows) == ("ok", ())
+    got = ok(nifs.flat_search(idx, q, k))
+    exp = ok(oracle.flat_search_dense(metric, rows, ids, q, k))
+    assert_hits_match(got, exp, exact_ids=ints)
+    # prefix scoring over all rows (K4, register-staged kernel) with the same ladder; for metrics other than
+    # cosine vector_top_k on a prefix is the flat search over the truncated rows (search.rs:56-60)
+    h = d // 2
+    got = ok(nifs.flat_prefix_top_k(idx, None, q, nifs.METRIC_CODE[metric], h, k))
+    if metric != "cosine":
+        exp = ok(oracle.flat_search_dense(metric, np.ascontiguousarray(rows[:, :h]), ids, q[:h].copy(), k))
+        assert_hits_match(got, exp, exact_ids=ints)
+    else:
+        r64, q64 = rows[:, :h].astype(np.float64), q[:h].astype(np.float64)
+        den = np.linalg.norm(r64, axis=1) * np.linalg.norm(q64)
+        cos = np.where(den > 0, (r64 @ q64) / np.where(den > 0, den, 1.0), 0.0).clip(-1.0, 1.0).astype(np.float32)
+        order = sorted(range(n), key=lambda i: (float(np.float32(1.0) - cos[i]), ids[i]))[:k]
+        assert_hits_match(got, [(ids[i], float(cos[i])) for i in order], exact_ids=False)

@@ -339,6 +339,7 @@ flat_scan_kernel(const ScanParams p) {
 
     Collector col;
     col.init(smem, &s_thresh, &s_count, p.cap, p.ws.k);
+    collector_attach_pivots(col, p.ws);
     __syncthreads();
 
     const uint32_t nvec = (p.dims + 3u) >> 2;           // float4 slots in the prefix
@@ -587,6 +588,7 @@ flat_stream_kernel(const ScanParams p, const StreamGeom geom) {
 
     Collector col;
     col.init(col_mem, &s_thresh, &s_count, p.cap, p.ws.k, W * 32, 1);
+    collector_attach_pivots(col, p.ws);
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < geom.stages; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -709,7 +711,11 @@ flat_stream_kernel(const ScanParams p, const StreamGeom geom) {
         if (!(p.debug & 4u) && (grp & (kGroupsPerSync - 1)) == kGroupsPerSync - 1)
             collector_checkpoint(col, p.ws, qi, kGroupsPerSync * kGroupRows * W, g_prefetch);
     }
-    collector_publish_and_merge(col, p.ws, qi, &s_last);
+    // every tile was consumed, so the ring is idle: the last CTA merges in ring + collector memory
+    const uint32_t total_smem = geom.stages * geom.tile_bytes + p.cap * 16u;
+    uint32_t big_cap = p.cap;
+    while ((size_t)big_cap * 2u * 16u <= total_smem) big_cap *= 2u;
+    collector_publish_and_merge(col, p.ws, qi, &s_last, smem, big_cap);
 }
 
 }  // namespace vb

@@ -49,8 +49,30 @@ static void fill_params(const SearchCtx& ctx, const ScanJob& job, const float* d
     p->ws.err_row = ctx.err_row();
     p->ws.out_err = p->ws.out_counts + job.nq;
     p->ws.defer_merge = 0;
+    p->ws.piv_keys = nullptr;
+    p->ws.piv_counts = nullptr;
+    p->ws.piv_state = nullptr;
     p->dump_keys = nullptr;
     p->dump_pays = nullptr;
+}
+
+// Launch-wide pivot ladder for large k (topk.cuh, collector_pivot_step): per query slot 16 keys, 16 counters
+// and a state word, zeroed on the launch stream before every scan that uses it.
+constexpr uint32_t kPivotMinK = 32;
+static Status arm_pivots(SearchCtx& ctx, ScanParams* p, uint32_t nq, size_t k, cudaStream_t stream) {
+    p->ws.piv_keys = nullptr;
+    p->ws.piv_counts = nullptr;
+    p->ws.piv_state = nullptr;
+    if (k < kPivotMinK || std::getenv("VB_NO_PIVOTS")) return Status::Ok();
+    const size_t keys_b = (size_t)nq * kPivots * sizeof(u64), cnt_b = (size_t)nq * kPivots * sizeof(uint32_t);
+    const size_t bytes = keys_b + cnt_b + (size_t)nq * sizeof(uint32_t);
+    VB_TRY(ctx.hist.reserve(bytes));
+    VB_CUDA(cudaMemsetAsync(ctx.hist.p, 0, bytes, stream));
+    unsigned char* base = ctx.hist.as<unsigned char>();
+    p->ws.piv_keys = reinterpret_cast<u64*>(base);
+    p->ws.piv_counts = reinterpret_cast<uint32_t*>(base + keys_b);
+    p->ws.piv_state = reinterpret_cast<uint32_t*>(base + keys_b + cnt_b);
+    return Status::Ok();
 }
 
 // Copies err_row into the result block and re-arms it (one thread per query).
@@ -177,6 +199,7 @@ Status run_scan(SearchCtx& ctx, const ScanJob& job, ScanResult* out) {
     fill_params(ctx, job, ctx.queries.as<float>(), q_stride,
                 job.metric == kCosineTrue ? ctx.q_norms.as<double>() : nullptr, k, &p);
     p.ws.defer_merge = merge_tree_wanted(plan.grid_x, k) ? 1u : 0u;
+    VB_TRY(arm_pivots(ctx, &p, job.nq, k, ctx.stream));
     Status s = run_flat_scan(plan, p, job.nq, ctx.stream);
     if (s.ok() && p.ws.defer_merge) s = run_merge_tree(p.ws, job.nq, plan.grid_x, ctx.sort_tmp, ctx.stream);
     if (!s.ok()) { ctx.poison(); return s; }
@@ -256,6 +279,7 @@ Status run_scan_to_rows(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint3
     ScanParams p;
     fill_params(ctx, job, d_q, q_stride, d_norm, k, &p);
     p.ws.defer_merge = merge_tree_wanted(plan.grid_x, k) ? 1u : 0u;
+    VB_TRY(arm_pivots(ctx, &p, 1, k, ctx.stream));
     Status s = run_flat_scan(plan, p, 1, ctx.stream);
     if (s.ok() && p.ws.defer_merge) s = run_merge_tree(p.ws, 1, plan.grid_x, ctx.sort_tmp, ctx.stream);
     if (!s.ok()) { ctx.poison(); return s; }
@@ -279,6 +303,7 @@ Status run_scan_final(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_
     ScanParams p;
     fill_params(ctx, job, d_q, q_stride, d_norm, k, &p);
     p.ws.defer_merge = merge_tree_wanted(plan.grid_x, k) ? 1u : 0u;
+    VB_TRY(arm_pivots(ctx, &p, 1, k, ctx.stream));
     Status s = run_flat_scan(plan, p, 1, ctx.stream);
     if (s.ok() && p.ws.defer_merge) s = run_merge_tree(p.ws, 1, plan.grid_x, ctx.sort_tmp, ctx.stream);
     if (!s.ok()) { ctx.poison(); return s; }
@@ -327,6 +352,7 @@ Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_querie
     ScanParams p;
     fill_params(ctx, job, d_queries, q_stride, d_q_norms, k, &p);
     p.ws.defer_merge = merge_tree_wanted(plan.grid_x, k) ? 1u : 0u;
+    VB_TRY(arm_pivots(ctx, &p, job.nq, k, stream));
     s = run_flat_scan(plan, p, job.nq, stream);
     if (s.ok() && p.ws.defer_merge) s = run_merge_tree(p.ws, job.nq, plan.grid_x, ctx.sort_tmp, stream);
     if (!s.ok()) { ctx.poison(); return s; }

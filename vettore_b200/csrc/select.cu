@@ -77,7 +77,7 @@ constexpr uint32_t kTreeGroup = 16;
 __global__ void __launch_bounds__(256)
 topk_tree_merge_kernel(const u64* keys_in, const u64* pays_in, const uint32_t* counts_in, uint32_t lists_in,
                        uint32_t k, uint32_t cap, u64* keys_out, u64* pays_out, uint32_t* counts_out,
-                       uint32_t lists_out, uint32_t* err_row, uint32_t* out_err, u64* g_thresh) {
+                       uint32_t lists_out, uint32_t* err_row, uint32_t* out_err, u64* g_thresh, const u64* g_bound) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ u64 s_thresh;
     __shared__ uint32_t s_count;
@@ -86,6 +86,11 @@ topk_tree_merge_kernel(const u64* keys_in, const u64* pays_in, const uint32_t* c
     Collector col;
     col.init(smem, &s_thresh, &s_count, cap, k);
     __syncthreads();
+    // the scan's launch-wide bound (k-th key some CTA proved, or a pivot below which k rows were counted)
+    if (threadIdx.x == 0 && g_bound != nullptr) {
+        const u64 g = g_bound[qi];
+        if (g != kKeyMax) atomicMin(col.thresh, g + 1);
+    }
     const u64* qk = keys_in + ((size_t)qi * lists_in + l0) * k;
     const u64* qp = pays_in + ((size_t)qi * lists_in + l0) * k;
     const uint32_t* qc = counts_in + (size_t)qi * lists_in + l0;
@@ -119,6 +124,7 @@ Status run_merge_tree(const TopkWorkspace& ws, uint32_t nq, uint32_t lists, Devi
     const uint32_t k = ws.k;
     uint32_t cap = 256;
     while (cap < 2 * k + 64) cap <<= 1;
+    if (k > 64) cap = std::max<uint32_t>(cap, 4096);   // sparse lists under a tight bound: one pass, one sort
     const size_t smem = (size_t)cap * 16;
     VB_TRY(ensure_dynamic_smem_for(topk_tree_merge_kernel, smem));
     // scratch: two ping-pong levels of at most ceil(lists / group) lists each
@@ -149,7 +155,7 @@ Status run_merge_tree(const TopkWorkspace& ws, uint32_t nq, uint32_t lists, Devi
         }
         topk_tree_merge_kernel<<<dim3(lout, nq), 256, smem, stream>>>(kin, pin, cin, lin, k, cap, kout, pout, cout, lout,
                                                                       ws.err_row, lout == 1 ? ws.out_err : nullptr,
-                                                                      lout == 1 ? ws.g_thresh : nullptr);
+                                                                      lout == 1 ? ws.g_thresh : nullptr, ws.g_thresh);
         VB_CUDA(cudaGetLastError());
         if (lout == 1) break;
         kin = kout;

@@ -14,6 +14,8 @@
 
 namespace vb {
 
+constexpr uint32_t kPivots = 16;   // rungs of the launch-wide pivot ladder
+
 struct Collector {
     u64* keys;          // smem [cap]
     u64* pays;          // smem [cap]
@@ -23,6 +25,10 @@ struct Collector {
     uint32_t k;
     uint32_t nthreads;  // threads taking part (threadIdx.x < nthreads), multiple of 32
     uint32_t bar_id;    // hardware barrier they synchronise on (0 == __syncthreads when all do)
+    // launch-wide pivot ladder (large k, see collector_pivot_step): shared-memory copies, null when unused
+    u64* piv;           // [kPivots] ascending pivot keys
+    uint32_t* piv_bins; // [kPivots] pushes since the last flush, by first pivot >= key
+    uint32_t* piv_on;   // 1 once the ladder was adopted
 
     __device__ __forceinline__ void init(unsigned char* smem, u64* s_thresh, uint32_t* s_count,
                                          uint32_t cap_, uint32_t k_, uint32_t nthreads_ = 0,
@@ -35,6 +41,9 @@ struct Collector {
         k = k_;
         nthreads = nthreads_ ? nthreads_ : blockDim.x;
         bar_id = bar_id_;
+        piv = nullptr;
+        piv_bins = nullptr;
+        piv_on = nullptr;
         if (threadIdx.x == 0) { *thresh = kKeyMax; *count = 0; }
     }
 
@@ -53,10 +62,20 @@ struct Collector {
 
     __device__ __forceinline__ u64 threshold() const { return *reinterpret_cast<volatile u64*>(thresh); }
 
+    // Counts `key` into the bin of the first pivot that is >= key (nothing if it is beyond the ladder).
+    __device__ __forceinline__ void count_pivot(u64 key) {
+        uint32_t j = 0;
+#pragma unroll
+        for (uint32_t step = kPivots / 2; step > 0; step >>= 1)
+            if (piv[j + step - 1] < key) j += step;
+        if (piv[j] >= key) atomicAdd(&piv_bins[j], 1u);
+    }
+
     // Any thread. The caller guarantees (by its sync cadence) that cap is not exceeded.
     __device__ __forceinline__ void push(u64 key, u64 pay) {
         uint32_t slot = atomicAdd(count, 1u);
         if (slot < cap) { keys[slot] = key; pays[slot] = pay; }
+        if (piv_on != nullptr && *reinterpret_cast<volatile uint32_t*>(piv_on)) count_pivot(key);
     }
 
     // Block-wide (every thread of the CTA must call). Sorts the buffer ascending, keeps the
@@ -174,6 +193,11 @@ struct TopkWorkspace {
     uint32_t* out_err;      // [nq] optional: err_row snapshot taken by the last CTA (err_row re-armed)
     uint32_t k;
     uint32_t defer_merge;   // 1: CTAs only publish their lists; the host runs the merge tree (large grid * k)
+    // launch-wide pivot ladder (optional, large k; zeroed before every launch): per query slot
+    // kPivots ascending keys, kPivots counters and a state word (0 none, 1 being written, 2 published)
+    u64* piv_keys;
+    uint32_t* piv_counts;
+    uint32_t* piv_state;
 };
 
 // Block-wide, called at a CTA-uniform cadence: adopts the grid-wide threshold, and when
@@ -181,6 +205,84 @@ struct TopkWorkspace {
 // CTA's own k-th key. `g_prefetch` (meaningful in thread 0) carries the grid-wide threshold
 // loaded one cadence earlier, so the global-memory round trip overlaps the scan instead of
 // stalling the CTA at the barrier; it is re-issued here for the next call.
+// Gives the collector its shared-memory copy of the pivot ladder (call right after init, before the CTA's
+// first barrier, by every thread of the CTA; kernels whose workspace carries no ladder skip it).
+__device__ __forceinline__ void collector_attach_pivots(Collector& col, const TopkWorkspace& ws) {
+    __shared__ u64 s_piv[kPivots];
+    __shared__ uint32_t s_piv_bins[kPivots];
+    __shared__ uint32_t s_piv_on;
+    if (ws.piv_state == nullptr) return;
+    col.piv = s_piv;
+    col.piv_bins = s_piv_bins;
+    col.piv_on = &s_piv_on;
+    if (threadIdx.x < kPivots) { s_piv[threadIdx.x] = kKeyMax; s_piv_bins[threadIdx.x] = 0u; }
+    if (threadIdx.x == 0) s_piv_on = 0u;
+}
+
+// Launch-wide pivot ladder (float keys, large k): a CTA's own k-th key only bounds the top-k of ITS rows
+// (with 148 CTAs and k = 100 that lets ~1.5 % of all rows through). The first CTA that has sorted its buffer
+// publishes kPivots of its keys (ranks cnt-1, (cnt-1)/2, (cnt-1)/4, ...) as a ladder; from then on every CTA
+// counts the rows it pushes into the ladder's bins, folds the counts into launch-wide counters at its
+// checkpoints, and adopts as threshold the smallest pivot below which the WHOLE launch has already seen k
+// rows. Every row is counted at most once and late counts only loosen the bound, so it is always valid.
+// Block-wide, CTA-uniform. `sorted` = the buffer was just compacted (sorted, *count entries).
+__device__ __forceinline__ void collector_pivot_step(Collector& col, const TopkWorkspace& ws, uint32_t qi, bool sorted) {
+    __shared__ uint32_t s_state;
+    u64* g_piv = ws.piv_keys + (size_t)qi * kPivots;
+    uint32_t* g_cnt = ws.piv_counts + (size_t)qi * kPivots;
+    uint32_t* g_state = ws.piv_state + qi;
+    if (*reinterpret_cast<volatile uint32_t*>(col.piv_on) == 0u) {
+        if (threadIdx.x == 0) s_state = *reinterpret_cast<volatile uint32_t*>(g_state);
+        col.sync();
+        const uint32_t state = s_state;
+        if (state == 2u) {            // adopt the published ladder and count what the buffer already holds
+            if (threadIdx.x < kPivots) col.piv[threadIdx.x] = __ldcg(g_piv + threadIdx.x);
+            col.sync();
+            const uint32_t n = min(*col.count, col.cap);
+            for (uint32_t i = threadIdx.x; i < n; i += col.nthreads) col.count_pivot(col.keys[i]);
+            if (threadIdx.x == 0) *col.piv_on = 1u;
+            col.sync();
+        } else {
+            if (state == 0u && sorted && threadIdx.x == 0) {
+                const uint32_t cnt = *col.count;
+                if (cnt >= 2u && atomicCAS(g_state, 0u, 1u) == 0u) {
+                    for (uint32_t j = 0; j < kPivots; ++j) g_piv[j] = col.keys[(cnt - 1u) >> (kPivots - 1u - j)];
+                    __threadfence();
+                    atomicExch(g_state, 2u);
+                }
+            }
+            return;                   // adopted at the next checkpoint
+        }
+    }
+    // fold this CTA's bins into the launch-wide counters, then read them back
+    if (threadIdx.x < kPivots) {
+        const uint32_t v = col.piv_bins[threadIdx.x];
+        if (v) {
+            atomicAdd(g_cnt + threadIdx.x, v);
+            col.piv_bins[threadIdx.x] = 0u;
+        }
+    }
+    col.sync();
+    if (threadIdx.x < 32) {
+        const uint32_t lane = threadIdx.x;
+        uint32_t c = lane < kPivots ? __ldcg(g_cnt + lane) : 0u;
+#pragma unroll
+        for (int o = 1; o < (int)kPivots; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, c, o);
+            if ((int)lane >= o) c += v;
+        }
+        const uint32_t ok = __ballot_sync(0xffffffffu, lane < kPivots && c >= ws.k);
+        if (ok != 0u && lane == (uint32_t)(__ffs(ok) - 1)) {
+            const u64 bound = col.piv[lane] + 1ull;      // k rows with key <= this pivot exist
+            if (bound < *col.thresh) {
+                atomicMin(col.thresh, bound);
+                atomicMin(ws.g_thresh + qi, bound);
+            }
+        }
+    }
+    col.sync();
+}
+
 __device__ __forceinline__ void collector_checkpoint(Collector& col, const TopkWorkspace& ws, uint32_t qi,
                                                      uint32_t slack, u64& g_prefetch) {
     if (threadIdx.x == 0 && g_prefetch < col.threshold()) atomicMin(col.thresh, g_prefetch);
@@ -190,6 +292,7 @@ __device__ __forceinline__ void collector_checkpoint(Collector& col, const TopkW
         col.compact();
         if (threadIdx.x == 0 && *col.thresh != kKeyMax) atomicMin(ws.g_thresh + qi, *col.thresh);
     }
+    if (col.piv_on != nullptr) collector_pivot_step(col, ws, qi, need);
     if (threadIdx.x == 0) g_prefetch = ld_volatile_u64(ws.g_thresh + qi);
 }
 
@@ -197,9 +300,25 @@ __device__ __forceinline__ void collector_checkpoint(Collector& col, const TopkW
 // grid (per query slot) merges every list and writes the sorted result. `s_last` is a
 // shared-memory flag owned by the caller.
 __device__ __forceinline__ void collector_publish_and_merge(Collector& col, const TopkWorkspace& ws, uint32_t qi,
-                                                            int* s_last) {
-    const uint32_t kept = col.compact();
-    if (threadIdx.x == 0 && *col.thresh != kKeyMax) atomicMin(ws.g_thresh + qi, *col.thresh);
+                                                            int* s_last, unsigned char* big_mem = nullptr,
+                                                            uint32_t big_cap = 0) {
+    __shared__ uint32_t s_publish;
+    const uint32_t kept0 = col.compact();
+    // Adopt the launch-wide bound once more and publish only what it still admits (the buffer is sorted):
+    // with a tight bound a CTA hands over a few entries instead of k, which is what keeps the merge short.
+    if (threadIdx.x == 0) {
+        if (*col.thresh != kKeyMax) atomicMin(ws.g_thresh + qi, *col.thresh);
+        const u64 g = ld_volatile_u64(ws.g_thresh + qi);
+        const u64 T = g == kKeyMax ? kKeyMax : g + 1;      // keys are unique: "<= g" is "< g + 1"
+        uint32_t lo = 0, hi = kept0;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (col.keys[mid] < T) lo = mid + 1; else hi = mid;
+        }
+        s_publish = lo;
+    }
+    col.sync();
+    const uint32_t kept = s_publish;
     const size_t slot = (size_t)qi * gridDim.x + blockIdx.x;
     for (uint32_t i = threadIdx.x; i < kept; i += col.nthreads) {
         ws.cand_keys[slot * ws.k + i] = col.keys[i];
@@ -219,6 +338,13 @@ __device__ __forceinline__ void collector_publish_and_merge(Collector& col, cons
 
     // Every list's k-th key was folded into g_thresh: nothing above the smallest of them can be
     // in the global top-k. Keys are unique, so "<= g" is "< g + 1".
+    // The last CTA may merge in a larger buffer (e.g. the drained TMA ring): with up to big_cap candidates
+    // below the bound, one pass and one sort finish the merge instead of many small windows.
+    if (big_mem != nullptr && big_cap > col.cap) {
+        col.keys = reinterpret_cast<u64*>(big_mem);
+        col.pays = col.keys + big_cap;
+        col.cap = big_cap;
+    }
     if (threadIdx.x == 0) {
         const u64 g = ld_volatile_u64(ws.g_thresh + qi);
         *col.thresh = g == kKeyMax ? kKeyMax : g + 1;
