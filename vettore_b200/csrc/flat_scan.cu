@@ -89,7 +89,9 @@ static Status plan_stream(int metric, int nv, size_t row_stride, uint32_t n, uin
     const uint32_t tile_bytes = (uint32_t)(((size_t)tile_rows * row_stride * 4 + 127) & ~(size_t)127);
     const uint32_t groups_per_sync = std::max(1, kStreamSyncEvery / (kGroupRows / rpw));
     const uint32_t slack = groups_per_sync * kGroupRows * warps;
-    const uint32_t cap = next_pow2(2 * k + slack);
+    // room for k kept entries plus the pushes between two compactions; beyond k = 256 the launch-wide bound
+    // (pivot ladder) keeps pushes rare, so half of k again is plenty and the ring keeps its stages
+    const uint32_t cap = next_pow2(k <= 256 ? 2 * k + slack : k + k / 2 + slack);
     const size_t budget = 200 * 1024;
     if ((size_t)cap * 16 + 2 * (size_t)tile_bytes > budget) return Status::Ok();
     uint32_t stages = (uint32_t)std::min<size_t>(kStreamMaxStages, (budget - (size_t)cap * 16) / tile_bytes);
@@ -142,7 +144,7 @@ Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, bool contigu
     }
     const uint32_t slack = kSyncEvery * kScanWarps * r;
     const uint32_t kk = dump ? 1 : k;
-    const uint32_t cap = next_pow2(2 * kk + slack);
+    const uint32_t cap = next_pow2(kk <= 256 ? 2 * kk + slack : kk + kk / 2 + slack);   // as in plan_stream
     const size_t smem = (size_t)cap * 16;
 
     VB_TRY(ensure_dynamic_smem_for(kernel, smem));      // cached per (device, kernel); occupancy is device independent here

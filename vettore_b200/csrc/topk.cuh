@@ -29,6 +29,7 @@ struct Collector {
     u64* piv;           // [kPivots] ascending pivot keys
     uint32_t* piv_bins; // [kPivots] pushes since the last flush, by first pivot >= key
     uint32_t* piv_on;   // 1 once the ladder was adopted
+    uint32_t* piv_early;// CTA 0 only: 1 once it has sorted its first rows to publish the ladder
 
     __device__ __forceinline__ void init(unsigned char* smem, u64* s_thresh, uint32_t* s_count,
                                          uint32_t cap_, uint32_t k_, uint32_t nthreads_ = 0,
@@ -44,6 +45,7 @@ struct Collector {
         piv = nullptr;
         piv_bins = nullptr;
         piv_on = nullptr;
+        piv_early = nullptr;
         if (threadIdx.x == 0) { *thresh = kKeyMax; *count = 0; }
     }
 
@@ -210,13 +212,14 @@ struct TopkWorkspace {
 __device__ __forceinline__ void collector_attach_pivots(Collector& col, const TopkWorkspace& ws) {
     __shared__ u64 s_piv[kPivots];
     __shared__ uint32_t s_piv_bins[kPivots];
-    __shared__ uint32_t s_piv_on;
+    __shared__ uint32_t s_piv_on, s_piv_early;
     if (ws.piv_state == nullptr) return;
     col.piv = s_piv;
     col.piv_bins = s_piv_bins;
     col.piv_on = &s_piv_on;
+    col.piv_early = &s_piv_early;
     if (threadIdx.x < kPivots) { s_piv[threadIdx.x] = kKeyMax; s_piv_bins[threadIdx.x] = 0u; }
-    if (threadIdx.x == 0) s_piv_on = 0u;
+    if (threadIdx.x == 0) { s_piv_on = 0u; s_piv_early = 0u; }
 }
 
 // Launch-wide pivot ladder (float keys, large k): a CTA's own k-th key only bounds the top-k of ITS rows
@@ -286,11 +289,19 @@ __device__ __forceinline__ void collector_pivot_step(Collector& col, const TopkW
 __device__ __forceinline__ void collector_checkpoint(Collector& col, const TopkWorkspace& ws, uint32_t qi,
                                                      uint32_t slack, u64& g_prefetch) {
     if (threadIdx.x == 0 && g_prefetch < col.threshold()) atomicMin(col.thresh, g_prefetch);
+    // CTA 0 of a query sorts its first rows early (once) so the pivot ladder exists long before any buffer fills:
+    // with k large against the rows a CTA sees, no CTA would otherwise compact before the end of the scan.
+    const bool early = col.piv_early != nullptr && blockIdx.x == 0 &&
+                       *reinterpret_cast<volatile uint32_t*>(col.piv_early) == 0u;
     const bool need = col.sync_or(
-        (threadIdx.x & 31) == 0 && *reinterpret_cast<volatile uint32_t*>(col.count) + slack > col.cap);
+        (threadIdx.x & 31) == 0 && (*reinterpret_cast<volatile uint32_t*>(col.count) + slack > col.cap ||
+                                    (early && *reinterpret_cast<volatile uint32_t*>(col.count) >= 64u)));
     if (need) {
         col.compact();
-        if (threadIdx.x == 0 && *col.thresh != kKeyMax) atomicMin(ws.g_thresh + qi, *col.thresh);
+        if (threadIdx.x == 0) {
+            if (*col.thresh != kKeyMax) atomicMin(ws.g_thresh + qi, *col.thresh);
+            if (col.piv_early != nullptr) *col.piv_early = 1u;
+        }
     }
     if (col.piv_on != nullptr) collector_pivot_step(col, ws, qi, need);
     if (threadIdx.x == 0) g_prefetch = ld_volatile_u64(ws.g_thresh + qi);
