@@ -356,3 +356,19 @@ def test_large_k_flat_search_many_rows(metric, n, d, k, ints):
         cos = np.where(den > 0, (r64 @ q64) / np.where(den > 0, den, 1.0), 0.0).clip(-1.0, 1.0).astype(np.float32)
         order = sorted(range(n), key=lambda i: (float(np.float32(1.0) - cos[i]), ids[i]))[:k]
         assert_hits_match(got, [(ids[i], float(cos[i])) for i in order], exact_ids=False)
+
+
+def test_small_batch_large_k_uses_one_ladder_per_query(monkeypatch):
+    """A batch below the K2 threshold runs K1 with one grid row per query: every query slot owns its pivot
+    ladder, counters and bound."""
+    rng = np.random.default_rng(11)
+    n, d, nq, k = 200_000, 64, 5, 64
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    queries = rng.standard_normal((nq, d)).astype(np.float32)
+    queries[2] = -queries[1]          # opposite rankings in neighbouring slots
+    ids = [f"{i:06d}" for i in range(n)]
+    idx = nifs.flat_new_inner_product()
+    assert nifs.flat_insert_matrix(idx, ids, rows) == ("ok", ())
+    got = ok(nifs.flat_search_batch(idx, queries, k))
+    for qi in range(nq):
+        assert_hits_match(got[qi], ok(oracle.flat_search_dense("inner_product", rows, ids, queries[qi], k)))
