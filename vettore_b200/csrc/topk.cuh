@@ -235,7 +235,10 @@ __device__ __forceinline__ void collector_pivot_step(Collector& col, const TopkW
     uint32_t* g_cnt = ws.piv_counts + (size_t)qi * kPivots;
     uint32_t* g_state = ws.piv_state + qi;
     if (*reinterpret_cast<volatile uint32_t*>(col.piv_on) == 0u) {
-        if (threadIdx.x == 0) s_state = *reinterpret_cast<volatile uint32_t*>(g_state);
+        if (threadIdx.x == 0) {
+            s_state = *reinterpret_cast<volatile uint32_t*>(g_state);
+            __threadfence();          // the ladder is read only after the flag that publishes it
+        }
         col.sync();
         const uint32_t state = s_state;
         if (state == 2u) {            // adopt the published ladder and count what the buffer already holds
