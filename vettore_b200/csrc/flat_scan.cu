@@ -4,6 +4,7 @@
 #include "runtime.h"
 
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 
@@ -72,8 +73,9 @@ static uint32_t next_pow2(uint32_t v) {
 }
 
 // Kernel B: whole contiguous rows streamed through a shared-memory ring by TMA bulk copies.
-static Status plan_stream(int metric, int nv, size_t row_stride, uint32_t n, uint32_t k, ScanPlan* plan,
-                          bool* taken) {
+static Status plan_stream(int metric, int nv, size_t row_stride, uint32_t row_floats, uint32_t tail_rem, bool use_tmap,
+                          uint32_t n, uint32_t k, ScanPlan* plan, bool* taken) {
+    (void)row_stride;
     *taken = false;
     int rpw = nv <= 2 ? 4 : (nv <= 4 ? 2 : 1);
     int warps = nv >= 12 ? 8 : 16;
@@ -86,7 +88,7 @@ static Status plan_stream(int metric, int nv, size_t row_stride, uint32_t n, uin
     StreamKernel kernel = lookup_stream(metric, nv, rpw, warps);
     if (!kernel) return Status::Ok();
     const uint32_t tile_rows = warps * rpw;
-    const uint32_t tile_bytes = (uint32_t)(((size_t)tile_rows * row_stride * 4 + 127) & ~(size_t)127);
+    const uint32_t tile_bytes = (uint32_t)(((size_t)tile_rows * row_floats * 4 + 127) & ~(size_t)127);
     const uint32_t groups_per_sync = std::max(1, kStreamSyncEvery / (kGroupRows / rpw));
     const uint32_t slack = groups_per_sync * kGroupRows * warps;
     // room for k kept entries plus the pushes between two compactions; beyond k = 256 the launch-wide bound
@@ -111,11 +113,15 @@ static Status plan_stream(int metric, int nv, size_t row_stride, uint32_t n, uin
     plan->smem = smem;
     plan->stages = stages;
     plan->tile_bytes = tile_bytes;
+    plan->row_floats = row_floats;
+    plan->tail_rem = tail_rem;
+    plan->tile_rows = tile_rows;
+    plan->use_tmap = use_tmap;
     *taken = true;
     return Status::Ok();
 }
 
-Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, bool contiguous, uint32_t n, uint32_t k,
+Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, int layout, uint32_t n, uint32_t k,
                       bool dump, ScanPlan* plan) {
     if (metric < 0 || metric > 9) return Status::Ref("unknown metric");
     if (dims == 0 || n == 0) return Status::Cuda("empty scan");
@@ -137,9 +143,14 @@ Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, bool contigu
 
     if (!dump && k > (uint32_t)kMaxFusedK) return Status::Cuda("k beyond fused collector");
     *plan = ScanPlan{};
-    if (!dump && contiguous && nv > 0 && (size_t)nvec * 4 == row_stride && !env_int("VB_SCAN_NO_STREAM", 0)) {
+    if (!dump && nv > 0 && !env_int("VB_SCAN_NO_STREAM", 0)) {
         bool taken = false;
-        VB_TRY(plan_stream(metric, nv, row_stride, n, k, plan, &taken));
+        if (layout == kScanWholeRows && (size_t)nvec * 4 == row_stride) {
+            VB_TRY(plan_stream(metric, nv, row_stride, /*row_floats=*/(uint32_t)row_stride, 4, false, n, k, plan, &taken));
+        } else if (layout != kScanRowList && nvec * 4 <= 256 && (row_stride & 3) == 0 && !env_int("VB_SCAN_NO_PREFIX_STREAM", 0)) {
+            // every row, only its first columns: a 2D tensor map moves just those columns (box <= 256 floats wide)
+            VB_TRY(plan_stream(metric, nv, row_stride, nvec * 4, dims - 4 * (nvec - 1), true, n, k, plan, &taken));
+        }
         if (taken) return Status::Ok();
     }
     const uint32_t slack = kSyncEvery * kScanWarps * r;
@@ -182,8 +193,12 @@ Status run_flat_scan(const ScanPlan& plan, ScanParams params, uint32_t nq, cudaS
     params.cap = plan.cap;
     dim3 grid(plan.grid_x, nq);
     if (plan.stream_kernel) {
-        StreamGeom geom{plan.stages, plan.tile_bytes};
-        plan.stream_kernel<<<grid, plan.stream_threads, plan.smem, stream>>>(params, geom);
+        StreamGeom geom{plan.stages, plan.tile_bytes, plan.row_floats, plan.tail_rem, plan.use_tmap ? 1u : 0u};
+        CUtensorMap tmap;
+        std::memset(&tmap, 0, sizeof(tmap));
+        if (plan.use_tmap)
+            VB_TRY(make_tmap_rows_prefix(params.rows, params.n, params.row_stride, plan.row_floats, plan.tile_rows, &tmap));
+        plan.stream_kernel<<<grid, plan.stream_threads, plan.smem, stream>>>(params, geom, tmap);
     } else {
         plan.kernel<<<grid, kScanThreads, plan.smem, stream>>>(params);
     }

@@ -24,6 +24,7 @@
 #pragma once
 #include <type_traits>
 
+#include "tc.cuh"
 #include "topk.cuh"
 
 namespace vb {
@@ -523,7 +524,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 
 struct StreamGeom {
     uint32_t stages;      // ring depth
-    uint32_t tile_bytes;  // bytes per stage (tile_rows * row_stride * 4), multiple of 128
+    uint32_t tile_bytes;  // bytes per stage (tile_rows * row_floats * 4), multiple of 128
+    uint32_t row_floats;  // floats per row IN SHARED MEMORY: the row stride (whole rows) or the padded prefix
+    uint32_t tail_rem;    // valid components of the last float4 of a row (4 = nothing to mask)
+    uint32_t use_tmap;    // 1: prefix scan, tiles arrive through the 2D tensor map (only the scored columns)
 };
 
 constexpr int kGroupRows = 8;  // rows whose partials one warp reduces with a single butterfly
@@ -564,7 +568,7 @@ __device__ __forceinline__ int slot_of_lane(int lane) { return ((lane >> 4) & 1)
 // defers the cross-lane reduction until it has kGroupRows row partials.
 template <int M, int NV, int RPW, int W>
 __global__ void __launch_bounds__(W * 32 + 32, 1)
-flat_stream_kernel(const ScanParams p, const StreamGeom geom) {
+flat_stream_kernel(const ScanParams p, const StreamGeom geom, const __grid_constant__ CUtensorMap tmap) {
     using Tr = PartialTraits<M>;
     using T = typename Tr::T;
     constexpr int C = Tr::kComps;
@@ -582,7 +586,7 @@ flat_stream_kernel(const ScanParams p, const StreamGeom geom) {
     const uint32_t qi = blockIdx.y;
     constexpr uint32_t kTileRows = W * RPW;
     const uint32_t num_tiles = (p.n + kTileRows - 1u) / kTileRows;
-    const uint32_t row_bytes = (uint32_t)p.row_stride * 4u;
+    const uint32_t row_bytes = geom.row_floats * 4u;
     unsigned char* ring = smem;
     unsigned char* col_mem = smem + (size_t)geom.stages * geom.tile_bytes;
 
@@ -606,18 +610,26 @@ flat_stream_kernel(const ScanParams p, const StreamGeom geom) {
                 const uint32_t s = it % geom.stages, ph = (it / geom.stages) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 const uint32_t row0 = tile * kTileRows;
-                const uint32_t rows = min(kTileRows, p.n - row0);
-                const uint32_t bytes = rows * row_bytes;
-                mbar_arrive_expect_tx(&full_bar[s], bytes);
-                tma_bulk_g2s(ring + (size_t)s * geom.tile_bytes, p.rows + (size_t)row0 * p.row_stride, bytes,
-                             &full_bar[s]);
+                if (geom.use_tmap) {
+                    // box = [kTileRows rows x row_floats columns]; rows past the matrix are zero-filled and still count
+                    mbar_arrive_expect_tx(&full_bar[s], kTileRows * row_bytes);
+                    tc::tma_load_2d(ring + (size_t)s * geom.tile_bytes, &tmap, 0u, row0, &full_bar[s]);
+                } else {
+                    const uint32_t rows = min(kTileRows, p.n - row0);
+                    const uint32_t bytes = rows * row_bytes;
+                    mbar_arrive_expect_tx(&full_bar[s], bytes);
+                    tma_bulk_g2s(ring + (size_t)s * geom.tile_bytes, p.rows + (size_t)row0 * p.row_stride, bytes,
+                                 &full_bar[s]);
+                }
             }
         }
         return;
     }
 
     // ===== consumers =====
-    const uint32_t nvec = (uint32_t)p.row_stride >> 2;
+    const uint32_t nvec = geom.row_floats >> 2;
+    const uint32_t tail_idx = nvec - 1u;
+    const bool need_mask = geom.tail_rem != 4u;         // prefix not a multiple of 4: the box carries columns beyond it
     const float4* q4 = reinterpret_cast<const float4*>(p.queries + (size_t)qi * p.q_stride);
     const double q_norm = (M == kCosineTrue) ? p.q_norms[qi] : 0.0;
     float4 q[NV];
@@ -651,7 +663,11 @@ flat_stream_kernel(const ScanParams p, const StreamGeom geom) {
 #pragma unroll
                 for (int j = 0; j < NV; ++j) {
                     const uint32_t idx = lane + 32u * j;
-                    if (idx < nvec) rc.accum(q[j], ldg_stream(rp + idx));
+                    if (idx < nvec) {
+                        float4 bv = ldg_stream(rp + idx);
+                        if (need_mask && idx == tail_idx) mask_tail(bv, geom.tail_rem);
+                        rc.accum(q[j], bv);
+                    }
                 }
                 bool f2;
                 const float rec = rc.finish(f2);
@@ -691,6 +707,7 @@ flat_stream_kernel(const ScanParams p, const StreamGeom geom) {
                 for (int j = 0; j < NV; ++j) {
                     const uint32_t idx = lane + 32u * j;
                     b[r][j] = (valid && idx < nvec) ? rp[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (need_mask && idx == tail_idx) mask_tail(b[r][j], geom.tail_rem);
                 }
             }
 #pragma unroll

@@ -11,6 +11,11 @@
 
 namespace vb {
 
+static int scan_layout(const ScanJob& job) {
+    if (job.d_row_sel != nullptr) return kScanRowList;
+    return job.whole_rows ? kScanWholeRows : kScanPrefixAllRows;
+}
+
 static Status prepare_workspace(SearchCtx& ctx, const ScanPlan& plan, uint32_t nq, size_t k) {
     VB_TRY(ctx.arm_ctrl(nq));
     const size_t lists = (size_t)nq * plan.grid_x;
@@ -127,7 +132,7 @@ static Status stage_queries(SearchCtx& ctx, const ScanJob& job, size_t* q_stride
 // k beyond the fused collector: every key/payload to HBM, then a device radix sort.
 static Status run_scan_dump(SearchCtx& ctx, const ScanJob& job, size_t q_stride, ScanResult* out) {
     ScanPlan plan;
-    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, job.d_row_sel == nullptr && job.whole_rows, job.n, 1, /*dump=*/true, &plan));
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, scan_layout(job), job.n, 1, /*dump=*/true, &plan));
     VB_TRY(prepare_workspace(ctx, plan, 1, 1));
     const size_t n = job.n, k = job.k;
     VB_TRY(ctx.dump_keys.reserve(n * sizeof(u64)));
@@ -193,7 +198,7 @@ Status run_scan(SearchCtx& ctx, const ScanJob& job, ScanResult* out) {
     }
 
     ScanPlan plan;
-    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, job.d_row_sel == nullptr && job.whole_rows, job.n, (uint32_t)k, false, &plan));
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, scan_layout(job), job.n, (uint32_t)k, false, &plan));
     VB_TRY(prepare_workspace(ctx, plan, job.nq, k));
     ScanParams p;
     fill_params(ctx, job, ctx.queries.as<float>(), q_stride,
@@ -273,7 +278,7 @@ Status run_scan_to_rows(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint3
     const double* d_norm = nullptr;
     VB_TRY(stage_query_slot(ctx, job, slot, nslots, &d_q, &q_stride, &d_norm));
     ScanPlan plan;
-    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, job.d_row_sel == nullptr && job.whole_rows, job.n,
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, scan_layout(job), job.n,
                           (uint32_t)k, false, &plan));
     VB_TRY(prepare_workspace(ctx, plan, 1, k));
     ScanParams p;
@@ -297,7 +302,7 @@ Status run_scan_final(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_
     const double* d_norm = nullptr;
     VB_TRY(stage_query_slot(ctx, job, slot, nslots, &d_q, &q_stride, &d_norm));
     ScanPlan plan;
-    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, job.d_row_sel == nullptr && job.whole_rows, job.n,
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, scan_layout(job), job.n,
                           (uint32_t)k, false, &plan));
     VB_TRY(prepare_workspace(ctx, plan, 1, k));
     ScanParams p;
@@ -343,7 +348,7 @@ Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_querie
     const size_t k = std::min<size_t>(job.k, job.n);
     if (k > (size_t)kMaxFusedK) return Status::Cuda("limit beyond the fused collector (1024)");
     ScanPlan plan;
-    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, job.d_row_sel == nullptr && job.whole_rows, job.n, (uint32_t)k, false, &plan));
+    VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, scan_layout(job), job.n, (uint32_t)k, false, &plan));
     cudaStream_t saved = ctx.stream;
     ctx.stream = stream;  // workspace arming must be ordered on the caller's stream
     Status s = prepare_workspace(ctx, plan, job.nq, k);

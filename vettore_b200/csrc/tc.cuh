@@ -170,5 +170,9 @@ __device__ __forceinline__ float tf32_lo(float x) {
 // runtime so the library does not link libcuda directly.
 Status make_tmap_rows_sw128(const float* base, uint64_t rows, uint64_t row_stride_floats, uint32_t box_rows,
                             CUtensorMap* out);
+// Same matrix, no swizzle: box = the first `box_cols` floats (<= 256, multiple of 4) x box_rows (<= 256) rows,
+// landing densely packed in shared memory. Feeds the prefix scans (only the scored columns leave HBM).
+Status make_tmap_rows_prefix(const float* base, uint64_t rows, uint64_t row_stride_floats, uint32_t box_cols,
+                             uint32_t box_rows, CUtensorMap* out);
 
 }  // namespace vb

@@ -10,30 +10,47 @@
 
 namespace vb {
 
-Status make_tmap_rows_sw128(const float* base, uint64_t rows, uint64_t row_stride_floats, uint32_t box_rows,
-                            CUtensorMap* out) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
+static TmapEncodeFn tmap_encode_fn() {
+    static TmapEncodeFn encode = nullptr;
     static std::once_flag once;
     std::call_once(once, [] {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            encode = reinterpret_cast<EncodeFn>(fn);
+            encode = reinterpret_cast<TmapEncodeFn>(fn);
     });
+    return encode;
+}
+
+static Status make_tmap_rows(const float* base, uint64_t rows, uint64_t row_stride_floats, uint32_t box_cols,
+                             uint32_t box_rows, CUtensorMapSwizzle swizzle, CUtensorMap* out) {
+    TmapEncodeFn encode = tmap_encode_fn();
     if (!encode) return Status::Cuda("cuTensorMapEncodeTiled unavailable");
     const cuuint64_t gdim[2] = {row_stride_floats, rows};
     const cuuint64_t gstride[1] = {row_stride_floats * sizeof(float)};
-    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estride[2] = {1, 1};
     CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return Status::Cuda("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return Status::Ok();
+}
+
+Status make_tmap_rows_sw128(const float* base, uint64_t rows, uint64_t row_stride_floats, uint32_t box_rows,
+                            CUtensorMap* out) {
+    return make_tmap_rows(base, rows, row_stride_floats, 32, box_rows, CU_TENSOR_MAP_SWIZZLE_128B, out);
+}
+
+Status make_tmap_rows_prefix(const float* base, uint64_t rows, uint64_t row_stride_floats, uint32_t box_cols,
+                             uint32_t box_rows, CUtensorMap* out) {
+    if (box_cols == 0 || box_cols > 256 || (box_cols & 3) || box_rows == 0 || box_rows > 256)
+        return Status::Cuda("prefix tensor map: box out of range");
+    return make_tmap_rows(base, rows, row_stride_floats, box_cols, box_rows, CU_TENSOR_MAP_SWIZZLE_NONE, out);
 }
 
 __global__ void __launch_bounds__(128) tc_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* B,
