@@ -707,8 +707,14 @@ flat_stream_kernel(const ScanParams p, const StreamGeom geom, const __grid_const
                 for (int j = 0; j < NV; ++j) {
                     const uint32_t idx = lane + 32u * j;
                     b[r][j] = (valid && idx < nvec) ? rp[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (need_mask && idx == tail_idx) mask_tail(b[r][j], geom.tail_rem);
                 }
+            }
+            if (need_mask) {   // CTA-uniform and AFTER every load was issued: a select between loads serialises them
+#pragma unroll
+                for (int r = 0; r < RPW; ++r)
+#pragma unroll
+                    for (int j = 0; j < NV; ++j)
+                        if (lane + 32u * j == tail_idx) mask_tail(b[r][j], geom.tail_rem);
             }
 #pragma unroll
             for (int r = 0; r < RPW; ++r) {
