@@ -359,7 +359,9 @@ def run_b200(args):
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed
                          # ncu --set full capture (profiles/r1_flat_stream_ncu_summary.txt); default shape only
-                         "traffic": 3.0802e9 if (n, d, k) == (1_000_000, 768, 10) else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                         # (profiles/r1_flat_stream_ncu_summary.txt: 3.073186 GB + 6.35 MB)
+                         "traffic": 3.0795e9 if (n, d, k) == (1_000_000, 768, 10) else None,
                          "peak_source": peak_src,
                          "kernel": "vb::flat_stream_kernel<cosine, NV=6, RPW=1, W=16> (TMA-staged ring; the timed "
                                    "launch pair also holds the ~3 us unpack kernel)",
