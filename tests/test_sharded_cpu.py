@@ -127,3 +127,32 @@ def test_two_rank_gloo_quantized_two_stage_exchange_equals_reference_composition
     out = tmp_path / "ok.txt"
     mp.spawn(_quantized_worker, args=(2, _free_port(), 120, 96, cand, k, str(out)), nprocs=2, join=True)
     assert out.read_text() == "ok"
+
+
+def _maxsim_worker(rank, world, port, docs_per, k, out_path):
+    """Document-sharded MaxSim (ShardedMv's host logic): per-shard top-k -> all-gather -> merge by
+    (score descending, id ascending) must equal multi_vector_top_k over the whole corpus (multi_vector.rs:90-132)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)
+    docs = rng.integers(-2, 3, size=(world * docs_per, 4, 8)).astype(np.float32)   # coarse values: many score ties
+    query = rng.integers(-2, 3, size=(3, 8)).astype(np.float32)
+    ids = [f"{i:06d}" for i in range(world * docs_per)]
+    lo = rank * docs_per
+    st, local = oracle.multi_vector_top_k([(ids[i], docs[i]) for i in range(lo, lo + docs_per)], query, 3, k)
+    assert st == "ok"
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    merged = sorted((h for lst in gathered for h in lst), key=lambda h: (-total_order_key(h[1]), h[0]))[:k]
+    st, expect = oracle.multi_vector_top_k([(ids[i], docs[i]) for i in range(world * docs_per)], query, 3, k)
+    assert st == "ok" and merged == expect, (merged, expect)
+    if rank == 0:
+        open(out_path, "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_maxsim_merge_equals_global_top_k(tmp_path):
+    out = tmp_path / "ok.txt"
+    mp.spawn(_maxsim_worker, args=(2, _free_port(), 150, 10, str(out)), nprocs=2, join=True)
+    assert out.read_text() == "ok"
