@@ -111,7 +111,9 @@ int vb_flat_prefix_top_k(vb_flat* index, size_t n_ids, const char* ids, const ui
 /* Additive: funnel_search (collection.ex:244-260, 674-691) run entirely on the resident
  * matrix. Stage s keeps the best `candidates` rows of the previous stage's survivors under
  * vector_top_k semantics at prefix stages[s]; the last step is the exact rerank at the full
- * query length with `limit`. One host synchronisation in total. candidates <= 1024. */
+ * query length with `limit`. One host synchronisation in total. Any `candidates` / `limit`
+ * (collection.ex:509-510 defaults candidates to 10 x limit): up to 1024 survivors per stage stay in
+ * the fused collector, beyond that the stage scores every row and radix-sorts on the device. */
 int vb_flat_funnel_search(vb_flat* index, const float* query, size_t len, int metric_code,
                           const size_t* stages, size_t n_stages, size_t candidates, size_t limit,
                           vb_hits** out);
@@ -126,8 +128,13 @@ int vb_flat_quantized_search(vb_flat* index, const float* query, size_t len, int
 /* Device-level entry (inputs already in HBM; used for kernel-only timing and by the
  * row-sharded multi-GPU path). Queries: nq rows of `q_stride` floats (q_stride % 4 == 0,
  * zero padded) in device memory. Writes, per query, k = min(limit, rows) sorted entries:
- * keys (rank-order key << 32 | id rank), raw values and device rows. No host sync;
- * `stream` is a cudaStream_t. limit must be <= 1024 here. */
+ * keys (rank-order key << 32 | id rank), raw values and device rows. `stream` is a cudaStream_t.
+ * Single queries and small batches are stream-ordered with no host synchronisation; an unrecoverable
+ * overflow ("metric overflow", flat.rs:105) cannot be returned from there and raises a sticky bit read by
+ * vb_flat_device_status. Batches that take the tensor-core path (>= 16 queries, dot-product metrics)
+ * synchronise `stream` once: queries whose candidate set the exact re-scoring stage could not prove
+ * complete are redone by the single-query kernel before the call returns, and "metric overflow" is
+ * returned as VB_ERR. Any limit (beyond 1024: dump + radix sort per query). */
 int vb_flat_search_device(vb_flat* index, const float* d_queries, size_t nq, size_t q_stride,
                           size_t limit, uint64_t* d_keys, float* d_values, uint32_t* d_rows,
                           uint32_t* d_counts, void* stream);
@@ -135,7 +142,7 @@ int vb_flat_search_device(vb_flat* index, const float* d_queries, size_t nq, siz
  * sign-packs the device queries (distances.rs:413-423) and scans THIS shard's code mirror for
  * its best `candidates` by (Hamming distance, id rank) — binary_top_k, search.rs:76-92. Output
  * convention of vb_flat_search_device. The shards' lists are all-gathered and merged with
- * vb_topk_merge_device into the global candidate set. candidates <= 1024. */
+ * vb_topk_merge_device into the global candidate set (which takes lists of up to 1024 entries). */
 int vb_flat_hamming_device(vb_flat* index, const float* d_queries, size_t nq, size_t q_stride,
                            size_t candidates, uint64_t* d_keys, float* d_values, uint32_t* d_rows,
                            uint32_t* d_counts, void* stream);
@@ -149,6 +156,9 @@ int vb_flat_rerank_owned_device(vb_flat* index, const float* d_query, size_t q_s
                                 const uint64_t* d_global_rows, const uint32_t* d_global_count,
                                 size_t max_candidates, uint32_t shard, size_t limit, uint64_t* d_keys,
                                 float* d_values, uint32_t* d_rows, uint32_t* d_counts, void* stream);
+/* Sticky status of the device-level entries above since the last call: bit 0 = a scan met an
+ * unrecoverable overflow (the reference's "metric overflow"). Synchronises the device, clears the word. */
+int vb_flat_device_status(vb_flat* index, uint32_t* status);
 /* Overrides the id tie-break ranks of the resident rows (row-sharded corpora: ranks must
  * be comparable across shards). ranks[row] for row < rows, in insertion (device row) order. */
 int vb_flat_set_id_ranks(vb_flat* index, const uint32_t* ranks, size_t n);

@@ -150,3 +150,52 @@ def test_hamming_large_k_over_many_rows(n, dims, k, narrow, no_stream, monkeypat
     got = ok(nifs.binary_top_k([(ids[i], codes[i]) for i in range(n)], q, dims, k))
     assert [h[0] for h in got] == [ids[i] for i in order]
     assert [h[1] for h in got] == [float(dist[i]) for i in order]
+
+
+# ---- candidates / limit beyond the fused collector (1024): the reference has no such bound
+# (collection.ex:509-510: candidates default to 10 x limit; limits up to 2^32 - 1) ------------------
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+@pytest.mark.parametrize("n,d,cand,limit", [(6000, 96, 1025, 10), (6000, 96, 5000, 200), (3000, 64, 3000, 1500)])
+def test_quantized_pipeline_beyond_1024_candidates(metric, n, d, cand, limit):
+    rows = _rows(n, d, n + 11 * d)
+    if metric == "cosine":
+        rows = np.stack([normalize_l2(r) for r in rows])
+    ids = [f"{(i * 7919) % n:06d}" for i in range(n)]
+    q = normalize_l2(_rows(1, d, 9)[0])
+    idx = getattr(nifs, f"flat_new_{metric}")()
+    ok(nifs.flat_insert_matrix(idx, ids, rows))
+    code = nifs.METRIC_CODE[metric]
+    vectors = [(ids[i], rows[i]) for i in range(n)]
+    assert_hits_match(ok(nifs.flat_quantized_search(idx, q, code, cand, limit)), ref_quantized(vectors, q, code, cand, limit))
+
+
+@pytest.mark.parametrize("metric", ["cosine", "inner_product"])
+@pytest.mark.parametrize("n,d,stages,cand,limit", [(6000, 128, [32, 64], 1025, 10), (6000, 128, [64], 5000, 200),
+                                                   (2500, 64, [16, 32], 2500, 1100)])
+def test_funnel_pipeline_beyond_1024_candidates(metric, n, d, stages, cand, limit):
+    rows = _rows(n, d, n + 13 * d)
+    if metric == "cosine":
+        rows = np.stack([normalize_l2(r) for r in rows])
+    ids = [f"{(i * 104729) % n:06d}" for i in range(n)]
+    q = normalize_l2(_rows(1, d, 4)[0])
+    idx = getattr(nifs, f"flat_new_{metric}")()
+    ok(nifs.flat_insert_matrix(idx, ids, rows))
+    code = nifs.METRIC_CODE[metric]
+    vectors = [(ids[i], rows[i]) for i in range(n)]
+    assert_hits_match(ok(nifs.flat_funnel_search(idx, q, code, stages, cand, limit)),
+                      ref_funnel(vectors, q, code, stages, cand, limit))
+
+
+def test_collection_default_candidates_with_limit_200():
+    """`limit: 200` with the default candidates (10 x limit = 2000) used to hit the 1024 wall."""
+    n, d = 5000, 64
+    rows = _rows(n, d, 77)
+    c = Collection("cosine")
+    ok(c.put_many([Embedding(f"e{i:05d}", rows[i]) for i in range(n)]))
+    q = rows[5] + 0.05
+    vectors = [(f"e{i:05d}", normalize_l2(rows[i])) for i in range(n)]
+    qn = normalize_l2(q)
+    got = ok(c.quantized_search(q, limit=200))
+    assert_hits_match([(r.id, r.score) for r in got], ref_quantized(vectors, qn, 2, 2000, 200))
+    got = ok(c.funnel_search(q, limit=200, stages=[32]))
+    assert_hits_match([(r.id, r.score) for r in got], ref_funnel(vectors, qn, 2, [32], 2000, 200))

@@ -43,6 +43,7 @@ SIGNATURES = {
     "vb_flat_search_device": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "vb_flat_hamming_device": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "vb_flat_rerank_owned_device": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp, _vp, _sz, C.c_uint32, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "vb_flat_device_status": (C.c_int, [_vp, _u32p]),
     "vb_flat_set_id_ranks": (C.c_int, [_vp, _u32p, _sz]),
     "vb_topk_merge_device": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "vb_vector_top_k": (C.c_int, [_sz, C.c_char_p, _u64p, _f32p, _u64p, _f32p, _sz, C.c_int, _sz, _sz, _vpp]),

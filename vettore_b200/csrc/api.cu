@@ -203,6 +203,7 @@ int vb_flat_rerank_owned_device(vb_flat* index, const float* d_query, size_t q_s
                                                    max_candidates, shard, limit, reinterpret_cast<vb::u64*>(d_keys),
                                                    d_values, d_rows, d_counts, static_cast<cudaStream_t>(stream)));
 }
+int vb_flat_device_status(vb_flat* index, uint32_t* status) { return finish(index->impl->device_status(status)); }
 int vb_flat_set_id_ranks(vb_flat* index, const uint32_t* ranks, size_t n) {
     return finish(index->impl->set_id_ranks(ranks, n));
 }

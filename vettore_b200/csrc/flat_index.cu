@@ -43,6 +43,84 @@ FlatIndex::~FlatIndex() {
     if (d_rows_) cudaFree(d_rows_);
     if (d_rank_) cudaFree(d_rank_);
     if (d_codes_) cudaFree(d_codes_);
+    if (d_status_) cudaFreeHost(d_status_);
+}
+
+// Index mutators work on the legacy default stream; searches run on non-blocking streams that do
+// not order against it, and D2D copies / memsets return before they complete. Every mutator ends
+// here, still holding the write lock, so a search that starts next sees the finished state.
+Status FlatIndex::finish_mutation() {
+    VB_CUDA(cudaStreamSynchronize(nullptr));
+    return Status::Ok();
+}
+
+Status FlatIndex::ensure_dev_ctx() {
+    if (!dev_ctx_) {
+        dev_ctx_ = new SearchCtx();
+        dev_ctx_->device = device_;
+        VB_CUDA(cudaStreamCreateWithFlags(&dev_ctx_->stream, cudaStreamNonBlocking));
+    }
+    if (!d_status_) {   // pinned host word (UVA: the kernels store to the same address): reading it costs no copy
+        VB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&d_status_), 16, cudaHostAllocPortable));
+        d_status_[0] = 0u;
+    }
+    return Status::Ok();
+}
+
+Status FlatIndex::device_status(uint32_t* out) {
+    std::unique_lock<std::shared_mutex> g(mu_);
+    *out = 0;
+    if (!d_status_) return Status::Ok();
+    VB_CUDA(cudaSetDevice(device_));
+    VB_CUDA(cudaDeviceSynchronize());
+    *out = *reinterpret_cast<volatile uint32_t*>(d_status_);
+    d_status_[0] = 0u;
+    return Status::Ok();
+}
+
+int64_t FlatIndex::find_row(const std::string& id) const {
+    if (sorted_) {
+        auto pos = std::lower_bound(row_id_.begin(), row_id_.end(), id);
+        return (pos != row_id_.end() && *pos == id) ? (int64_t)(pos - row_id_.begin()) : -1;
+    }
+    auto it = id_row_.find(id);
+    return it == id_row_.end() ? -1 : (int64_t)it->second;
+}
+
+void FlatIndex::leave_sorted_mode() {
+    if (!sorted_) return;
+    id_row_.clear();
+    for (size_t r = 0; r < row_id_.size(); ++r) id_row_.emplace_hint(id_row_.end(), row_id_[r], (uint32_t)r);
+    sorted_ = false;
+}
+
+bool FlatIndex::add_id(std::string&& id, uint32_t* existing, bool* relabel_needed) {
+    const uint32_t row = (uint32_t)n_;
+    if (sorted_) {
+        if (n_ == 0 || row_id_.back() < id) {   // ascending append: O(1), no map
+            uint64_t r = row;
+            if (!external_ranks_ && !*relabel_needed) {
+                r = (n_ == 0 ? 0 : (uint64_t)h_rank_.back()) + kAppendStep;
+                if (r >= kRankSpace - 1) { *relabel_needed = true; r = row; }
+            }
+            row_id_.push_back(std::move(id));
+            h_rank_.push_back((uint32_t)r);
+            ++n_;
+            return true;
+        }
+        const int64_t found = find_row(id);
+        if (found >= 0) { *existing = (uint32_t)found; return false; }
+        leave_sorted_mode();
+    }
+    auto hint = id_row_.end();
+    if (!(!id_row_.empty() && std::prev(hint)->first < id)) hint = id_row_.lower_bound(id);
+    if (hint != id_row_.end() && hint->first == id) { *existing = hint->second; return false; }
+    auto it = id_row_.emplace_hint(hint, id, row);
+    row_id_.push_back(std::move(id));
+    h_rank_.push_back(0);
+    ++n_;
+    assign_rank(it, row, relabel_needed);
+    return true;
 }
 
 void FlatIndex::info(size_t* rows, size_t* dim) {
@@ -118,9 +196,16 @@ Status FlatIndex::ensure_codes() {
 Status FlatIndex::relabel_all() {
     const uint64_t spacing = std::max<uint64_t>(1, std::min<uint64_t>(kRankSpace / (n_ + 1), 1u << 20));
     uint64_t r = 0;
-    for (auto& kv : id_row_) {
-        r += spacing;
-        h_rank_[kv.second] = (uint32_t)std::min<uint64_t>(r, kRankSpace - 1);
+    if (sorted_) {
+        for (size_t row = 0; row < n_; ++row) {
+            r += spacing;
+            h_rank_[row] = (uint32_t)std::min<uint64_t>(r, kRankSpace - 1);
+        }
+    } else {
+        for (auto& kv : id_row_) {
+            r += spacing;
+            h_rank_[kv.second] = (uint32_t)std::min<uint64_t>(r, kRankSpace - 1);
+        }
     }
     if (n_ > 0) VB_CUDA(cudaMemcpy(d_rank_, h_rank_.data(), n_ * sizeof(uint32_t), cudaMemcpyHostToDevice));
     return Status::Ok();
@@ -192,15 +277,9 @@ Status FlatIndex::insert_many(size_t n, const char* ids, const uint64_t* id_off,
 
     for (size_t i = 0; i < n && st.ok(); ++i) {
         std::string id(ids + id_off[i], ids + id_off[i + 1]);
-        auto hint = id_row_.end();
-        if (!id_row_.empty() && std::prev(hint)->first < id) {
-            // ascending append (rebuild_index feeds ids sorted, collection.ex:426-433): O(1) insert
-        } else {
-            hint = id_row_.lower_bound(id);
-        }
-        if (hint != id_row_.end() && hint->first == id) {
+        uint32_t row = 0;
+        if (!add_id(std::move(id), &row, &relabel_needed)) {
             // upsert of an existing id (flat.rs:64 / :79): replace the row in place
-            const uint32_t row = hint->second;
             if (row >= flushed_to) {
                 fill_row(sbuf + (row - flushed_to) * stride_, i);  // still staged (duplicate id in this batch)
             } else {
@@ -211,13 +290,7 @@ Status FlatIndex::insert_many(size_t n, const char* ids, const uint64_t* id_off,
             }
             continue;
         }
-        const uint32_t row = (uint32_t)n_;
-        auto it = id_row_.emplace_hint(hint, id, row);
-        row_id_.push_back(std::move(id));
-        h_rank_.push_back(0);
-        ++n_;
-        st = assign_rank(it, row, &relabel_needed);
-        if (staged == stage_rows && st.ok()) st = flush();
+        if (staged == stage_rows) st = flush();
         fill_row(sbuf + staged * stride_, i);
         ++staged;
     }
@@ -232,6 +305,7 @@ Status FlatIndex::insert_many(size_t n, const char* ids, const uint64_t* id_off,
         }
     }
     stage.release();
+    if (st.ok()) st = finish_mutation();
     return st;
 }
 
@@ -285,22 +359,15 @@ Status FlatIndex::insert_many_device(size_t n, const char* ids, const uint64_t* 
     };
     for (size_t i = 0; i < n && st.ok(); ++i) {
         std::string id(ids + id_off[i], ids + id_off[i + 1]);
-        auto hint = id_row_.end();
-        if (!(!id_row_.empty() && std::prev(hint)->first < id)) hint = id_row_.lower_bound(id);
-        if (hint != id_row_.end() && hint->first == id) {   // upsert: replace in place (after pending appends)
+        uint32_t row = 0;
+        if (!add_id(std::move(id), &row, &relabel_needed)) {   // upsert: replace in place (after pending appends)
             st = copy_rows(run_dst, run0, i - run0);
             run_dst += i - run0;
             run0 = i + 1;
-            if (st.ok()) st = copy_rows(hint->second, i, 1);
-            if (st.ok() && hint->second < n_before) st = pack_rows(hint->second, 1);
+            if (st.ok()) st = copy_rows(row, i, 1);
+            if (st.ok() && row < n_before) st = pack_rows(row, 1);
             continue;
         }
-        const uint32_t row = (uint32_t)n_;
-        auto it = id_row_.emplace_hint(hint, id, row);
-        row_id_.push_back(std::move(id));
-        h_rank_.push_back(0);
-        ++n_;
-        st = assign_rank(it, row, &relabel_needed);
     }
     if (st.ok()) st = copy_rows(run_dst, run0, n - run0);
     if (st.ok()) st = pack_rows(n_before, n_ - n_before);
@@ -312,6 +379,7 @@ Status FlatIndex::insert_many_device(size_t n, const char* ids, const uint64_t* 
             if (e != cudaSuccess) st = Status::Cuda(cudaGetErrorString(e));
         }
     }
+    if (st.ok()) st = finish_mutation();
     return st;
 }
 
@@ -328,17 +396,21 @@ void FlatIndex::reset_if_empty() {
     d_codes_ = nullptr;
     code_words_ = 0;
     external_ranks_ = false;
+    sorted_ = true;
+    id_row_.clear();
 }
 
 Status FlatIndex::remove(const char* id, size_t id_len) {
     std::unique_lock<std::shared_mutex> g(mu_);
-    auto it = id_row_.find(std::string(id, id + id_len));
-    if (it == id_row_.end()) return Status::Ok();
+    const std::string key(id, id + id_len);
+    const int64_t found = find_row(key);
+    if (found < 0) return Status::Ok();
     VB_CUDA(cudaSetDevice(device_));
     if (dev_ctx_) VB_CUDA(cudaDeviceSynchronize());
-    const uint32_t row = it->second;
+    const uint32_t row = (uint32_t)found;
     const uint32_t last = (uint32_t)(n_ - 1);
-    id_row_.erase(it);
+    if (row != last) leave_sorted_mode();   // the hole is filled by the last row: rows leave id order
+    if (!sorted_) id_row_.erase(key);
     if (row != last) {  // move the last row into the hole; its rank label travels with it
         VB_CUDA(cudaMemcpy(d_rows_ + (size_t)row * stride_, d_rows_ + (size_t)last * stride_,
                            stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
@@ -354,7 +426,7 @@ Status FlatIndex::remove(const char* id, size_t id_len) {
     h_rank_.pop_back();
     --n_;
     reset_if_empty();
-    return Status::Ok();
+    return finish_mutation();
 }
 
 Status FlatIndex::search(const float* queries, size_t nq, size_t len, size_t limit, std::vector<Hits>* out) {
@@ -453,8 +525,8 @@ Status FlatIndex::prefix_top_k(bool all_rows, size_t n_ids, const char* ids, con
     if (!all_rows) {
         sel.reserve(n_ids);
         for (size_t i = 0; i < n_ids; ++i) {
-            auto it = id_row_.find(std::string(ids + id_off[i], ids + id_off[i + 1]));
-            if (it != id_row_.end()) sel.push_back(it->second);
+            const int64_t row = find_row(std::string(ids + id_off[i], ids + id_off[i + 1]));
+            if (row >= 0) sel.push_back((uint32_t)row);
         }
     }
     const size_t cand = all_rows ? n_ : sel.size();
@@ -508,8 +580,7 @@ Status FlatIndex::funnel_search(const float* query, size_t len, int metric_code,
     if (n_ == 0) return Status::Ok();
     for (size_t s = 0; s <= nstages; ++s)
         if ((s < nstages ? stages[s] : len) > dim_) return Status::Ref("dimension mismatch");
-    if (candidates == 0 || std::min(candidates, n_) > (size_t)kMaxFusedK)
-        return Status::Cuda("funnel candidates must be in 1..1024 for the resident pipeline");
+    if (candidates == 0) return Status::Ok();   // vector_top_k(limit 0) -> [] at the first stage (search.rs:48)
     VB_CUDA(cudaSetDevice(device_));
     CtxLease ctx;
     VB_TRY(ctx.get());
@@ -540,7 +611,6 @@ Status FlatIndex::funnel_search(const float* query, size_t len, int metric_code,
     job.whole_rows = len == dim_;
     job.d_row_sel = nstages == 0 ? nullptr : ctx->row_sel.as<uint32_t>();
     job.k = std::max<size_t>(1, std::min(limit, survivors));
-    if (job.k > (size_t)kMaxFusedK) return Status::Cuda("limit beyond the fused collector (1024)");
     ScanResult res;
     VB_TRY(run_scan_final(*ctx.ctx, job, (uint32_t)nstages, nslots, &res));
     for (size_t s = 0; s < nstages; ++s)
@@ -560,19 +630,25 @@ Status FlatIndex::quantized_search(const float* query, size_t len, int metric_co
     if (metric_code < 0 || metric_code > 8) return Status::Ref("unknown metric");
     if (len == 0) return Status::Ref("vector must not be empty");
     if (!all_finite(query, len)) return Status::Ref("vector contains a non-finite value");
-    {
-        std::unique_lock<std::shared_mutex> g(mu_);   // first use builds the code mirror
-        if (n_ > 0 && !d_codes_) {
-            VB_CUDA(cudaSetDevice(device_));
-            VB_TRY(ensure_codes());
-        }
-    }
     std::shared_lock<std::shared_mutex> g(mu_);
+    while (n_ > 0 && !d_codes_) {
+        // first use builds the code mirror under the write lock; re-check after re-acquiring the read
+        // lock (a delete-to-empty in the window frees the mirror again, reset_if_empty)
+        g.unlock();
+        {
+            std::unique_lock<std::shared_mutex> w(mu_);
+            if (n_ > 0 && !d_codes_) {
+                VB_CUDA(cudaSetDevice(device_));
+                VB_TRY(ensure_codes());
+                VB_TRY(finish_mutation());
+            }
+        }
+        g.lock();
+    }
     if (n_ == 0) return Status::Ok();
     if (len != dim_) return Status::Ref("dimension mismatch");
     const size_t cand = std::min(candidates, n_);
-    if (cand == 0 || cand > (size_t)kMaxFusedK)
-        return Status::Cuda("quantized candidates must be in 1..1024 for the resident pipeline");
+    if (cand == 0) return Status::Ok();   // binary_top_k(limit 0) -> [] (search.rs:95-97)
     VB_CUDA(cudaSetDevice(device_));
     CtxLease ctx;
     VB_TRY(ctx.get());
@@ -585,9 +661,16 @@ Status FlatIndex::quantized_search(const float* query, size_t len, int metric_co
         if (query[i] >= 0.0f) hq[i / 64] |= 1ull << (i % 64);
     VB_TRY(ctx->staging.reserve(nw * sizeof(u64)));
     VB_CUDA(cudaMemcpyAsync(ctx->staging.p, hq, nw * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    VB_TRY(hamming_scan_device(*ctx.ctx, d_codes_, (uint32_t)n_, (uint32_t)nw, (uint32_t)dim_, d_rank_,
-                               ctx->staging.as<u64>(), 1, (uint32_t)cand, ctx->stream));
-    VB_TRY(extract_rows(*ctx.ctx, ctx->result.as<u64>(), (uint32_t)cand));
+    if (cand <= (size_t)kMaxFusedK) {
+        VB_TRY(hamming_scan_device(*ctx.ctx, d_codes_, (uint32_t)n_, (uint32_t)nw, (uint32_t)dim_, d_rank_,
+                                   ctx->staging.as<u64>(), 1, (uint32_t)cand, ctx->stream));
+        VB_TRY(extract_rows(*ctx.ctx, ctx->result.as<u64>(), (uint32_t)cand));
+    } else {
+        // more candidates than the fused collector holds (collection.ex:509-510: 10 x limit by default)
+        VB_TRY(hamming_dump_sorted(*ctx.ctx, d_codes_, (uint32_t)n_, (uint32_t)nw, (uint32_t)dim_, d_rank_,
+                                   ctx->staging.as<u64>(), ctx->stream));
+        VB_TRY(extract_rows(*ctx.ctx, ctx->dump_pays2.as<u64>(), (uint32_t)cand));
+    }
     ScanJob job;
     job.metric = metric_code == kCosine ? kCosineTrue : metric_code;   // exact_rerank -> vector_top_k
     job.d_rows = d_rows_;
@@ -619,27 +702,8 @@ Status FlatIndex::search_device(const float* d_queries, size_t nq, size_t q_stri
     if (n_ == 0) return Status::Cuda("device search on an empty index");
     if (q_stride < stride_ || (q_stride & 3)) return Status::Ref("dimension mismatch");
     VB_CUDA(cudaSetDevice(device_));
-    if (!dev_ctx_) {
-        dev_ctx_ = new SearchCtx();
-        dev_ctx_->device = device_;
-        VB_CUDA(cudaStreamCreateWithFlags(&dev_ctx_->stream, cudaStreamNonBlocking));
-    }
+    VB_TRY(ensure_dev_ctx());
     const size_t kk = std::min(limit, n_);
-    if (q_stride == dim_ && flat_gemm_eligible(metric_, dim_, stride_, nq, kk, n_)) {
-        // K2 on the caller's stream. The completeness flags of the re-scoring stage stay in the
-        // context here (the host-facing search() acts on them; see flat_gemm.cu).
-        if (max_norm_ < 0.0f) VB_TRY(flat_gemm_max_row_norm(*dev_ctx_, d_rows_, stride_, n_, dim_, &max_norm_));
-        SearchCtx& c = *dev_ctx_;
-        VB_TRY(c.result.reserve(nq * kk * sizeof(u64) + 2 * nq * sizeof(uint32_t) + 16));
-        VB_TRY(c.out_keys.reserve(nq * kk * sizeof(u64)));
-        u64* pays = c.result.as<u64>();
-        uint32_t* counts = reinterpret_cast<uint32_t*>(pays + nq * kk);
-        uint32_t* flags = counts + nq;
-        VB_TRY(flat_gemm_search_device(c, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, d_queries, nq, kk,
-                                       c.out_keys.as<u64>(), pays, counts, flags, flags + nq, stream));
-        return unpack_device_results(c.out_keys.as<u64>(), pays, counts, (uint32_t)nq, (uint32_t)kk, d_keys, d_values,
-                                     d_rows, d_counts, stream);
-    }
     ScanJob job;
     job.metric = metric_;
     job.d_rows = d_rows_;
@@ -650,7 +714,45 @@ Status FlatIndex::search_device(const float* d_queries, size_t nq, size_t q_stri
     job.whole_rows = true;
     job.nq = (uint32_t)nq;
     job.k = kk;
-    return run_scan_device(*dev_ctx_, job, d_queries, q_stride, nullptr, d_keys, d_values, d_rows, d_counts,
+    if (q_stride == dim_ && flat_gemm_eligible(metric_, dim_, stride_, nq, kk, n_)) {
+        // K2 on the caller's stream. The tensor-core scores are a filter: the exact re-scoring stage
+        // flags every query whose kept set could not be proven to hold the true top-k (1), or whose
+        // exact score overflowed (2), and raises `bad` when a tensor-core score was non-finite. Those
+        // are resolved HERE, like FlatIndex::search does: one small D2H read of the flag words, then
+        // the flagged queries are redone by the single-query kernel into the same output slots — so a
+        // batch through this entry (the row-sharded path) is exactly as complete as the host-facing one.
+        if (max_norm_ < 0.0f) VB_TRY(flat_gemm_max_row_norm(*dev_ctx_, d_rows_, stride_, n_, dim_, &max_norm_));
+        SearchCtx& c = *dev_ctx_;
+        VB_TRY(c.result.reserve(nq * kk * sizeof(u64) + 2 * nq * sizeof(uint32_t) + 16));
+        VB_TRY(c.out_keys.reserve(nq * kk * sizeof(u64)));
+        VB_TRY(c.h_misc.reserve((nq + 1) * sizeof(uint32_t)));
+        u64* pays = c.result.as<u64>();
+        uint32_t* counts = reinterpret_cast<uint32_t*>(pays + nq * kk);
+        uint32_t* flags = counts + nq;
+        VB_TRY(flat_gemm_search_device(c, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, d_queries, nq, kk,
+                                       c.out_keys.as<u64>(), pays, counts, flags, flags + nq, stream));
+        VB_TRY(unpack_device_results(c.out_keys.as<u64>(), pays, counts, (uint32_t)nq, (uint32_t)kk, d_keys, d_values,
+                                     d_rows, d_counts, stream));
+        uint32_t* h_flags = c.h_misc.as<uint32_t>();
+        VB_CUDA(cudaMemcpyAsync(h_flags, flags, (nq + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        VB_CUDA(cudaStreamSynchronize(stream));
+        if (h_flags[nq] != 0) {
+            // a non-finite tensor-core score: the f64 recovery lives in the per-query kernel, redo all
+            return run_scan_device(c, job, d_queries, q_stride, nullptr, d_keys, d_values, d_rows, d_counts, d_status_,
+                                   stream);
+        }
+        for (size_t q = 0; q < nq; ++q) {
+            if (h_flags[q] == 2) return Status::Ref("metric overflow");
+            if (h_flags[q] != 1) continue;
+            ScanJob one = job;
+            one.nq = 1;
+            VB_TRY(run_scan_device(c, one, d_queries + q * q_stride, q_stride, nullptr, d_keys ? d_keys + q * kk : nullptr,
+                                   d_values ? d_values + q * kk : nullptr, d_rows ? d_rows + q * kk : nullptr,
+                                   d_counts ? d_counts + q : nullptr, d_status_, stream));
+        }
+        return Status::Ok();
+    }
+    return run_scan_device(*dev_ctx_, job, d_queries, q_stride, nullptr, d_keys, d_values, d_rows, d_counts, d_status_,
                            stream);
 }
 
@@ -679,18 +781,23 @@ Status FlatIndex::hamming_device(const float* d_queries, size_t nq, size_t q_str
     if (n_ == 0) return Status::Cuda("device candidate pass on an empty index");
     if (q_stride < dim_) return Status::Ref("dimension mismatch");
     VB_CUDA(cudaSetDevice(device_));
-    if (!d_codes_) VB_TRY(ensure_codes());
-    if (!dev_ctx_) {
-        dev_ctx_ = new SearchCtx();
-        dev_ctx_->device = device_;
-        VB_CUDA(cudaStreamCreateWithFlags(&dev_ctx_->stream, cudaStreamNonBlocking));
-    }
+    if (!d_codes_) { VB_TRY(ensure_codes()); VB_TRY(finish_mutation()); }
+    VB_TRY(ensure_dev_ctx());
     SearchCtx& c = *dev_ctx_;
     const size_t cand = std::min(candidates, n_);
-    if (cand > (size_t)kMaxFusedK) return Status::Cuda("quantized candidates must be in 1..1024 for the resident pipeline");
     const size_t nw = code_words_;
     VB_TRY(c.staging.reserve(nq * nw * sizeof(u64)));
     VB_TRY(sign_pack_device(d_queries, q_stride, (uint32_t)nq, (uint32_t)dim_, c.staging.as<u64>(), stream));
+    if (cand > (size_t)kMaxFusedK) {   // beyond the fused collector: dump + radix sort per query
+        for (size_t q = 0; q < nq; ++q) {
+            VB_TRY(hamming_dump_sorted(c, d_codes_, (uint32_t)n_, (uint32_t)nw, (uint32_t)dim_, d_rank_,
+                                       c.staging.as<u64>() + q * nw, stream));
+            VB_TRY(unpack_sorted_device(c.dump_keys2.as<u64>(), c.dump_pays2.as<u64>(), (uint32_t)cand,
+                                        d_keys ? d_keys + q * cand : nullptr, d_values ? d_values + q * cand : nullptr,
+                                        d_rows ? d_rows + q * cand : nullptr, d_counts ? d_counts + q : nullptr, stream));
+        }
+        return Status::Ok();
+    }
     cudaStream_t saved = c.stream;
     c.stream = stream;   // workspace arming must be ordered on the caller's stream
     Status s = hamming_scan_device(c, d_codes_, (uint32_t)n_, (uint32_t)nw, (uint32_t)dim_, d_rank_, c.staging.as<u64>(),
@@ -711,11 +818,7 @@ Status FlatIndex::rerank_owned_device(const float* d_query, size_t q_stride, int
     std::unique_lock<std::shared_mutex> g(mu_);
     if (q_stride < stride_ || (q_stride & 3)) return Status::Ref("dimension mismatch");
     VB_CUDA(cudaSetDevice(device_));
-    if (!dev_ctx_) {
-        dev_ctx_ = new SearchCtx();
-        dev_ctx_->device = device_;
-        VB_CUDA(cudaStreamCreateWithFlags(&dev_ctx_->stream, cudaStreamNonBlocking));
-    }
+    VB_TRY(ensure_dev_ctx());
     SearchCtx& c = *dev_ctx_;
     VB_TRY(c.row_sel.reserve(max_candidates * sizeof(uint32_t)));
     VB_TRY(c.row_sel2.reserve(16));
@@ -751,7 +854,7 @@ Status FlatIndex::rerank_owned_device(const float* d_query, size_t q_stride, int
         VB_CUDA(cudaGetLastError());
         d_norm = c.q_norms.as<double>();
     }
-    return run_scan_device(c, job, d_query, q_stride, d_norm, d_keys, d_values, d_rows, d_counts, stream);
+    return run_scan_device(c, job, d_query, q_stride, d_norm, d_keys, d_values, d_rows, d_counts, d_status_, stream);
 }
 
 Status FlatIndex::set_id_ranks(const uint32_t* ranks, size_t n) {
@@ -762,7 +865,7 @@ Status FlatIndex::set_id_ranks(const uint32_t* ranks, size_t n) {
     std::copy(ranks, ranks + n, h_rank_.begin());
     if (n > 0) VB_CUDA(cudaMemcpy(d_rank_, h_rank_.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     external_ranks_ = true;
-    return Status::Ok();
+    return finish_mutation();
 }
 
 }  // namespace vb

@@ -65,6 +65,10 @@ class FlatIndex {
                                cudaStream_t stream);
     Status set_id_ranks(const uint32_t* ranks, size_t n);
     void info(size_t* rows, size_t* dim);
+    // Sticky status of the stream-ordered device-level entries since the last call (they cannot return
+    // the reference's error strings): bit 0 = a scan met an unrecoverable overflow ("metric overflow").
+    // Synchronises the device; clears the word.
+    Status device_status(uint32_t* out);
 
     // Resident matrix view for sibling indexes (valid under the caller's own lock discipline).
     const float* device_rows() const { return d_rows_; }
@@ -77,6 +81,16 @@ class FlatIndex {
     Status relabel_all();
     Status assign_rank(std::map<std::string, uint32_t>::iterator it, uint32_t row, bool* relabel_needed);
     void reset_if_empty();
+    // Id table. While every insert so far was an ascending append (rebuild_index feeds ids sorted,
+    // collection.ex:426-433) the rows themselves are in id order: lookups are a binary search over
+    // row_id_ and no ordered map exists (`sorted_`). The first out-of-order insert or hole-filling
+    // delete materialises id_row_ once (O(n)) and the general path takes over.
+    int64_t find_row(const std::string& id) const;
+    void leave_sorted_mode();
+    // Registers a new id at row n_ (bookkeeping only); false = the id exists (row in *existing).
+    bool add_id(std::string&& id, uint32_t* existing, bool* relabel_needed);
+    Status ensure_dev_ctx();
+    Status finish_mutation();   // orders the mutation's default-stream work before the lock is released
 
     const int metric_;
     const int device_;
@@ -90,11 +104,13 @@ class FlatIndex {
     size_t code_words_ = 0;
     std::vector<std::string> row_id_;
     std::vector<uint32_t> h_rank_;
-    std::map<std::string, uint32_t> id_row_;
+    std::map<std::string, uint32_t> id_row_;   // general mode only (see sorted_)
+    bool sorted_ = true;
     bool external_ranks_ = false;
     std::mutex norm_mu_;
     float max_norm_ = -1.0f;   // max |row| (device reduction, lazily), < 0 = unknown
     SearchCtx* dev_ctx_ = nullptr;  // workspace of the stream-ordered device-level entry
+    uint32_t* d_status_ = nullptr;  // sticky status word of the device-level entries
 };
 
 }  // namespace vb

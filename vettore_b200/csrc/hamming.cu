@@ -657,6 +657,34 @@ Status hamming_scan_device(SearchCtx& ctx, const u64* d_codes, uint32_t n, uint3
     return s;
 }
 
+Status hamming_dump_sorted(SearchCtx& ctx, const u64* d_codes, uint32_t n, uint32_t nw, uint32_t dims,
+                           const uint32_t* d_rank, const u64* d_query, cudaStream_t stream) {
+    VB_TRY(ctx.dump_keys.reserve((size_t)n * sizeof(u64)));
+    VB_TRY(ctx.dump_pays.reserve((size_t)n * sizeof(u64)));
+    VB_TRY(ctx.dump_keys2.reserve((size_t)n * sizeof(u64)));
+    VB_TRY(ctx.dump_pays2.reserve((size_t)n * sizeof(u64)));
+    HammingParams p{};
+    p.codes = d_codes;
+    p.n = n;
+    p.nw = nw;
+    p.dims = dims;
+    p.id_rank = d_rank;
+    p.queries = d_query;
+    p.dump_keys = ctx.dump_keys.as<u64>();
+    p.dump_pays = ctx.dump_pays.as<u64>();
+    size_t tmp_bytes = 0;
+    VB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx.dump_keys.as<u64>(), ctx.dump_keys2.as<u64>(),
+                                            ctx.dump_pays.as<u64>(), ctx.dump_pays2.as<u64>(), (int64_t)n, 0, 64,
+                                            stream));
+    VB_TRY(ctx.sort_tmp.reserve(tmp_bytes));
+    VB_TRY(launch_hamming(ctx, p, 1, 1, true, stream));
+    // keys are distance << 32 | id rank: distances need at most 32 bits, so the sort covers bits 0..63
+    VB_CUDA(cub::DeviceRadixSort::SortPairs(ctx.sort_tmp.p, tmp_bytes, ctx.dump_keys.as<u64>(),
+                                            ctx.dump_keys2.as<u64>(), ctx.dump_pays.as<u64>(),
+                                            ctx.dump_pays2.as<u64>(), (int64_t)n, 0, 64, stream));
+    return Status::Ok();
+}
+
 Status hamming_top_k_resident(SearchCtx& ctx, const u64* d_codes, size_t n, size_t nw, size_t dims,
                               const uint32_t* d_rank, const uint64_t* h_query, size_t k,
                               std::vector<uint32_t>* rows, std::vector<float>* values) {
@@ -679,28 +707,8 @@ Status hamming_top_k_resident(SearchCtx& ctx, const u64* d_codes, size_t n, size
         VB_CUDA(cudaStreamSynchronize(ctx.stream));
         count = *reinterpret_cast<const uint32_t*>(h_pays + k);
     } else {
-        VB_TRY(ctx.dump_keys.reserve(n * sizeof(u64)));
-        VB_TRY(ctx.dump_pays.reserve(n * sizeof(u64)));
-        VB_TRY(ctx.dump_keys2.reserve(n * sizeof(u64)));
-        VB_TRY(ctx.dump_pays2.reserve(n * sizeof(u64)));
-        HammingParams p{};
-        p.codes = d_codes;
-        p.n = (uint32_t)n;
-        p.nw = (uint32_t)nw;
-        p.dims = (uint32_t)dims;
-        p.id_rank = d_rank;
-        p.queries = ctx.queries.as<u64>();
-        p.dump_keys = ctx.dump_keys.as<u64>();
-        p.dump_pays = ctx.dump_pays.as<u64>();
-        VB_TRY(launch_hamming(ctx, p, 1, 1, true, ctx.stream));
-        size_t tmp_bytes = 0;
-        VB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx.dump_keys.as<u64>(), ctx.dump_keys2.as<u64>(),
-                                                ctx.dump_pays.as<u64>(), ctx.dump_pays2.as<u64>(), (int64_t)n, 0, 64,
-                                                ctx.stream));
-        VB_TRY(ctx.sort_tmp.reserve(tmp_bytes));
-        VB_CUDA(cub::DeviceRadixSort::SortPairs(ctx.sort_tmp.p, tmp_bytes, ctx.dump_keys.as<u64>(),
-                                                ctx.dump_keys2.as<u64>(), ctx.dump_pays.as<u64>(),
-                                                ctx.dump_pays2.as<u64>(), (int64_t)n, 0, 64, ctx.stream));
+        VB_TRY(hamming_dump_sorted(ctx, d_codes, (uint32_t)n, (uint32_t)nw, (uint32_t)dims, d_rank,
+                                   ctx.queries.as<u64>(), ctx.stream));
         VB_CUDA(cudaMemcpyAsync(ctx.h_result.p, ctx.dump_pays2.p, k * sizeof(u64), cudaMemcpyDeviceToHost,
                                 ctx.stream));
         VB_CUDA(cudaStreamSynchronize(ctx.stream));

@@ -14,6 +14,11 @@ Status hamming_scan_device(SearchCtx& ctx, const u64* d_codes, uint32_t n, uint3
                            const uint32_t* d_id_rank, const u64* d_queries, uint32_t nq, uint32_t k,
                            cudaStream_t stream);
 
+// Candidate counts beyond the fused collector: every row's key to HBM, one radix sort; the n sorted
+// (key, payload) pairs are left in ctx.dump_keys2 / ctx.dump_pays2. One query, stream-ordered, no host sync.
+Status hamming_dump_sorted(SearchCtx& ctx, const u64* d_codes, uint32_t n, uint32_t nw, uint32_t dims,
+                           const uint32_t* d_rank, const u64* d_query, cudaStream_t stream);
+
 // By-value helper: uploads host codes/ranks/query, scans, returns sorted (row, distance).
 // Any k (beyond the fused collector the scan dumps every key and radix-sorts).
 Status hamming_top_k_host(SearchCtx& ctx, const uint64_t* h_codes, size_t n, size_t nw, size_t dims,

@@ -53,7 +53,7 @@ void SearchCtx::destroy() {
     cudaSetDevice(device);
     DeviceBuf* dbufs[] = {&queries, &q_norms, &cand_keys, &cand_pays, &cand_counts, &ctrl, &out_keys, &result,
                           &row_sel, &row_sel2, &staging, &staging_rank, &dump_keys, &dump_pays, &dump_keys2, &dump_pays2,
-                          &sort_tmp, &hist};
+                          &sort_tmp, &hist, &misc};
     for (DeviceBuf* b : dbufs) b->release();
     h_queries.release();
     h_result.release();

@@ -34,6 +34,7 @@ struct SearchCtx {
     cudaStream_t stream = nullptr;
     DeviceBuf queries, q_norms, cand_keys, cand_pays, cand_counts, ctrl, out_keys, result, row_sel, row_sel2;
     DeviceBuf staging, staging_rank, dump_keys, dump_pays, dump_keys2, dump_pays2, sort_tmp, hist;
+    DeviceBuf misc;                 // a few scratch words (overflow flag of a dump scan, owned-candidate count)
     PinnedBuf h_queries, h_result, h_misc;
     uint32_t ctrl_queries = 0;      // query slots armed in `ctrl`
 

@@ -86,10 +86,13 @@ __global__ void collect_err_kernel(uint32_t* err_row, uint32_t* out_err, uint32_
     if (i < nq) { out_err[i] = err_row[i]; err_row[i] = kNoError; }
 }
 
+// `err` (optional): per-query overflow words of the scan; any set word raises bit 0 of *status (sticky,
+// read by vb_flat_device_status: the device-level entries cannot return "metric overflow" themselves).
 __global__ void unpack_results_kernel(const u64* keys, const u64* pays, const uint32_t* counts, uint32_t nq,
                                       uint32_t k, u64* out_keys, float* out_values, uint32_t* out_rows,
-                                      uint32_t* out_counts) {
+                                      uint32_t* out_counts, const uint32_t* err, uint32_t* status) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq && err != nullptr && status != nullptr && err[i] != kNoError) *(volatile uint32_t*)status = 1u;
     if (i < nq * k) {
         uint32_t q = i / k, j = i - q * k;
         bool valid = j < counts[q];
@@ -129,12 +132,20 @@ static Status stage_queries(SearchCtx& ctx, const ScanJob& job, size_t* q_stride
     return Status::Ok();
 }
 
-// k beyond the fused collector: every key/payload to HBM, then a device radix sort.
-static Status run_scan_dump(SearchCtx& ctx, const ScanJob& job, size_t q_stride, ScanResult* out) {
+// k beyond the fused collector: every key/payload of ONE query to HBM, then a device radix sort.
+// Leaves the n sorted (key, payload) pairs in ctx.dump_keys2 / ctx.dump_pays2 and the query's
+// overflow word in *d_err_dst (device memory; the control word is re-armed). Stream-ordered, no
+// host synchronisation.
+static Status dump_and_sort(SearchCtx& ctx, const ScanJob& job, const float* d_q, size_t q_stride,
+                            const double* d_norm, uint32_t* d_err_dst, cudaStream_t stream) {
     ScanPlan plan;
     VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, scan_layout(job), job.n, 1, /*dump=*/true, &plan));
-    VB_TRY(prepare_workspace(ctx, plan, 1, 1));
-    const size_t n = job.n, k = job.k;
+    cudaStream_t saved = ctx.stream;
+    ctx.stream = stream;   // workspace arming must be ordered on the launch stream
+    Status ws = prepare_workspace(ctx, plan, 1, 1);
+    ctx.stream = saved;
+    VB_TRY(ws);
+    const size_t n = job.n;
     VB_TRY(ctx.dump_keys.reserve(n * sizeof(u64)));
     VB_TRY(ctx.dump_pays.reserve(n * sizeof(u64)));
     VB_TRY(ctx.dump_keys2.reserve(n * sizeof(u64)));
@@ -142,8 +153,34 @@ static Status run_scan_dump(SearchCtx& ctx, const ScanJob& job, size_t q_stride,
     size_t tmp_bytes = 0;
     VB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx.dump_keys.as<u64>(), ctx.dump_keys2.as<u64>(),
                                             ctx.dump_pays.as<u64>(), ctx.dump_pays2.as<u64>(), (int64_t)n, 0, 64,
-                                            ctx.stream));
+                                            stream));
     VB_TRY(ctx.sort_tmp.reserve(tmp_bytes));
+    ScanJob one = job;
+    one.nq = 1;
+    ScanParams p;
+    fill_params(ctx, one, d_q, q_stride, d_norm, 1, &p);
+    p.dump_keys = ctx.dump_keys.as<u64>();
+    p.dump_pays = ctx.dump_pays.as<u64>();
+    VB_TRY(run_flat_scan(plan, p, 1, stream));
+    VB_CUDA(cub::DeviceRadixSort::SortPairs(ctx.sort_tmp.p, tmp_bytes, ctx.dump_keys.as<u64>(),
+                                            ctx.dump_keys2.as<u64>(), ctx.dump_pays.as<u64>(),
+                                            ctx.dump_pays2.as<u64>(), (int64_t)n, 0, 64, stream));
+    collect_err_kernel<<<1, 32, 0, stream>>>(ctx.err_row(), d_err_dst, 1);
+    VB_CUDA(cudaGetLastError());
+    return Status::Ok();
+}
+
+// Scratch word receiving the overflow flag of a dump scan.
+static Status dump_err_word(SearchCtx& ctx, uint32_t** out, uint32_t nslots = 1) {
+    VB_TRY(ctx.misc.reserve(((size_t)nslots + 16) * sizeof(uint32_t)));   // same size for every stage of a pipeline
+    *out = ctx.misc.as<uint32_t>();
+    return Status::Ok();
+}
+
+static Status run_scan_dump(SearchCtx& ctx, const ScanJob& job, size_t q_stride, ScanResult* out) {
+    const size_t k = job.k;
+    uint32_t* d_err = nullptr;
+    VB_TRY(dump_err_word(ctx, &d_err));
     VB_TRY(ctx.h_result.reserve(k * sizeof(u64) + 8));
     out->k = k;
     out->counts.assign(job.nq, 0);
@@ -151,26 +188,12 @@ static Status run_scan_dump(SearchCtx& ctx, const ScanJob& job, size_t q_stride,
     out->raws.assign((size_t)job.nq * k, 0.0f);
     out->err_rows.assign(job.nq, kNoError);
     for (uint32_t q = 0; q < job.nq; ++q) {
-        ScanJob one = job;
-        one.nq = 1;
-        ScanParams p;
-        fill_params(ctx, one, ctx.queries.as<float>() + (size_t)q * q_stride, q_stride,
-                    job.metric == kCosineTrue ? ctx.q_norms.as<double>() + q : nullptr, 1, &p);
-        p.dump_keys = ctx.dump_keys.as<u64>();
-        p.dump_pays = ctx.dump_pays.as<u64>();
-        VB_TRY(run_flat_scan(plan, p, 1, ctx.stream));
-        VB_CUDA(cub::DeviceRadixSort::SortPairs(ctx.sort_tmp.p, tmp_bytes, ctx.dump_keys.as<u64>(),
-                                                ctx.dump_keys2.as<u64>(), ctx.dump_pays.as<u64>(),
-                                                ctx.dump_pays2.as<u64>(), (int64_t)n, 0, 64, ctx.stream));
+        VB_TRY(dump_and_sort(ctx, job, ctx.queries.as<float>() + (size_t)q * q_stride, q_stride,
+                             job.metric == kCosineTrue ? ctx.q_norms.as<double>() + q : nullptr, d_err, ctx.stream));
         uint32_t* h_err = reinterpret_cast<uint32_t*>(ctx.h_result.as<u64>() + k);
-        collect_err_kernel<<<1, 32, 0, ctx.stream>>>(ctx.err_row(), ctx.err_row() + 1, 1);  // slot 1 = scratch
         VB_CUDA(cudaMemcpyAsync(ctx.h_result.p, ctx.dump_pays2.p, k * sizeof(u64), cudaMemcpyDeviceToHost,
                                 ctx.stream));
-        VB_CUDA(cudaMemcpyAsync(h_err, ctx.err_row() + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
-        VB_CUDA(cudaStreamSynchronize(ctx.stream));
-        // slot 1 was used as scratch for the error word: re-arm it
-        const uint32_t no_err = kNoError;
-        VB_CUDA(cudaMemcpyAsync(ctx.err_row() + 1, &no_err, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx.stream));
+        VB_CUDA(cudaMemcpyAsync(h_err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
         VB_CUDA(cudaStreamSynchronize(ctx.stream));
         const u64* pays = ctx.h_result.as<u64>();
         out->counts[q] = (uint32_t)k;
@@ -272,11 +295,21 @@ static Status stage_query_slot(SearchCtx& ctx, const ScanJob& job, uint32_t slot
 Status run_scan_to_rows(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_t nslots, uint32_t* h_err) {
     if (job.n == 0 || job.k == 0 || job.nq != 1) return Status::Cuda("bad pipeline stage");
     const size_t k = std::min<size_t>(job.k, job.n);
-    if (k > (size_t)kMaxFusedK) return Status::Cuda("stage candidates beyond the fused collector (1024)");
     size_t q_stride = 0;
     const float* d_q = nullptr;
     const double* d_norm = nullptr;
     VB_TRY(stage_query_slot(ctx, job, slot, nslots, &d_q, &q_stride, &d_norm));
+    if (k > (size_t)kMaxFusedK) {
+        // more survivors than the fused collector holds (collection.ex:509-510: candidates default to
+        // 10 x limit, unbounded): score every row, radix-sort, keep the first k rows. Still no host sync.
+        uint32_t* d_err = nullptr;
+        VB_TRY(dump_err_word(ctx, &d_err, nslots));
+        Status s = dump_and_sort(ctx, job, d_q, q_stride, job.metric == kCosineTrue ? d_norm : nullptr, d_err + slot,
+                                 ctx.stream);
+        if (!s.ok()) { ctx.poison(); return s; }
+        VB_CUDA(cudaMemcpyAsync(h_err, d_err + slot, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
+        return extract_rows(ctx, ctx.dump_pays2.as<u64>(), (uint32_t)k);
+    }
     ScanPlan plan;
     VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, scan_layout(job), job.n,
                           (uint32_t)k, false, &plan));
@@ -296,11 +329,37 @@ Status run_scan_to_rows(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint3
 Status run_scan_final(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_t nslots, ScanResult* out) {
     if (job.n == 0 || job.k == 0 || job.nq != 1) return Status::Cuda("bad pipeline stage");
     const size_t k = std::min<size_t>(job.k, job.n);
-    if (k > (size_t)kMaxFusedK) return Status::Cuda("limit beyond the fused collector (1024)");
     size_t q_stride = 0;
     const float* d_q = nullptr;
     const double* d_norm = nullptr;
     VB_TRY(stage_query_slot(ctx, job, slot, nslots, &d_q, &q_stride, &d_norm));
+    if (k > (size_t)kMaxFusedK) {
+        uint32_t* d_err = nullptr;
+        VB_TRY(dump_err_word(ctx, &d_err, nslots));
+        Status s = dump_and_sort(ctx, job, d_q, q_stride, job.metric == kCosineTrue ? d_norm : nullptr, d_err + slot,
+                                 ctx.stream);
+        if (!s.ok()) { ctx.poison(); return s; }
+        VB_TRY(ctx.h_result.reserve(k * sizeof(u64) + 8));
+        uint32_t* h_tail = reinterpret_cast<uint32_t*>(ctx.h_result.as<u64>() + k);
+        cudaError_t e = cudaMemcpyAsync(ctx.h_result.p, ctx.dump_pays2.p, k * sizeof(u64), cudaMemcpyDeviceToHost,
+                                        ctx.stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(h_tail, d_err + slot, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx.stream);
+        if (e != cudaSuccess) { ctx.poison(); return Status::Cuda(cudaGetErrorString(e)); }
+        const u64* pays = ctx.h_result.as<u64>();
+        out->k = k;
+        out->counts.assign(1, (uint32_t)k);
+        out->err_rows.assign(1, h_tail[0]);
+        out->rows.resize(k);
+        out->raws.resize(k);
+        for (size_t i = 0; i < k; ++i) {
+            uint32_t bits = (uint32_t)(pays[i] >> 32);
+            std::memcpy(&out->raws[i], &bits, 4);
+            out->rows[i] = (uint32_t)pays[i];
+        }
+        return Status::Ok();
+    }
     ScanPlan plan;
     VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, scan_layout(job), job.n,
                           (uint32_t)k, false, &plan));
@@ -336,17 +395,56 @@ Status unpack_device_results(const u64* d_keys_in, const u64* d_pays, const uint
                              u64* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream) {
     const uint32_t total = nq * k;
     unpack_results_kernel<<<(std::max(total, nq) + 255) / 256, 256, 0, stream>>>(d_keys_in, d_pays, d_counts_in, nq, k, d_keys,
-                                                                                  d_values, d_rows, d_counts);
+                                                                                  d_values, d_rows, d_counts, nullptr, nullptr);
+    VB_CUDA(cudaGetLastError());
+    return Status::Ok();
+}
+
+// Sorted dump of one query -> the caller's output arrays (k entries, all valid).
+__global__ void unpack_sorted_kernel(const u64* keys, const u64* pays, uint32_t k, u64* out_keys, float* out_values,
+                                     uint32_t* out_rows, uint32_t* out_count, const uint32_t* err, uint32_t* status) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) {
+        const u64 pay = pays[i];
+        if (out_keys) out_keys[i] = keys[i];
+        if (out_values) out_values[i] = __uint_as_float((uint32_t)(pay >> 32));
+        if (out_rows) out_rows[i] = (uint32_t)pay;
+    }
+    if (i == 0) {
+        if (out_count) *out_count = k;
+        if (err != nullptr && status != nullptr && *err != kNoError) *(volatile uint32_t*)status = 1u;
+    }
+}
+
+Status unpack_sorted_device(const u64* d_keys_in, const u64* d_pays, uint32_t k, u64* d_keys, float* d_values,
+                            uint32_t* d_rows, uint32_t* d_count, cudaStream_t stream) {
+    unpack_sorted_kernel<<<(k + 255) / 256, 256, 0, stream>>>(d_keys_in, d_pays, k, d_keys, d_values, d_rows, d_count,
+                                                              nullptr, nullptr);
     VB_CUDA(cudaGetLastError());
     return Status::Ok();
 }
 
 Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_queries, size_t q_stride,
                        const double* d_q_norms, u64* d_keys, float* d_values, uint32_t* d_rows,
-                       uint32_t* d_counts, cudaStream_t stream) {
+                       uint32_t* d_counts, uint32_t* d_status, cudaStream_t stream) {
     if (job.n == 0 || job.k == 0 || job.nq == 0) return Status::Cuda("empty scan job");
     const size_t k = std::min<size_t>(job.k, job.n);
-    if (k > (size_t)kMaxFusedK) return Status::Cuda("limit beyond the fused collector (1024)");
+    if (k > (size_t)kMaxFusedK) {
+        // beyond the fused collector: one dump + radix sort per query, sorted prefix to the outputs
+        uint32_t* d_err = nullptr;
+        VB_TRY(dump_err_word(ctx, &d_err));
+        for (uint32_t q = 0; q < job.nq; ++q) {
+            Status s = dump_and_sort(ctx, job, d_queries + (size_t)q * q_stride, q_stride,
+                                     d_q_norms ? d_q_norms + q : nullptr, d_err, stream);
+            if (!s.ok()) { ctx.poison(); return s; }
+            unpack_sorted_kernel<<<((uint32_t)k + 255) / 256, 256, 0, stream>>>(
+                ctx.dump_keys2.as<u64>(), ctx.dump_pays2.as<u64>(), (uint32_t)k, d_keys ? d_keys + (size_t)q * k : nullptr,
+                d_values ? d_values + (size_t)q * k : nullptr, d_rows ? d_rows + (size_t)q * k : nullptr,
+                d_counts ? d_counts + q : nullptr, d_err, d_status);
+            VB_CUDA(cudaGetLastError());
+        }
+        return Status::Ok();
+    }
     ScanPlan plan;
     VB_TRY(plan_flat_scan(job.metric, job.dims, job.row_stride, scan_layout(job), job.n, (uint32_t)k, false, &plan));
     cudaStream_t saved = ctx.stream;
@@ -363,7 +461,8 @@ Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_querie
     if (!s.ok()) { ctx.poison(); return s; }
     const uint32_t total = job.nq * (uint32_t)k;
     unpack_results_kernel<<<(std::max(total, job.nq) + 255) / 256, 256, 0, stream>>>(
-        p.ws.out_keys, p.ws.out_pays, p.ws.out_counts, job.nq, (uint32_t)k, d_keys, d_values, d_rows, d_counts);
+        p.ws.out_keys, p.ws.out_pays, p.ws.out_counts, job.nq, (uint32_t)k, d_keys, d_values, d_rows, d_counts,
+        p.ws.out_err, d_status);
     VB_CUDA(cudaGetLastError());
     return Status::Ok();
 }

@@ -44,12 +44,18 @@ Status run_scan_final(SearchCtx& ctx, const ScanJob& job, uint32_t slot, uint32_
 Status extract_rows(SearchCtx& ctx, const u64* d_pays, uint32_t n);
 
 // Device-resident variant: queries already on the device, sorted results stay on the device.
+// `d_status` (optional device word): bit 0 is raised when a query's scan hit an unrecoverable overflow
+// (the reference's "metric overflow"), since nothing can be returned to the host from here.
 Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_queries, size_t q_stride,
                        const double* d_q_norms, u64* d_keys, float* d_values, uint32_t* d_rows,
-                       uint32_t* d_counts, cudaStream_t stream);
+                       uint32_t* d_counts, uint32_t* d_status, cudaStream_t stream);
 
 // (key, payload) pairs -> separate keys / values / rows arrays (device, on `stream`).
 Status unpack_device_results(const u64* d_keys_in, const u64* d_pays, const uint32_t* d_counts_in, uint32_t nq, uint32_t k,
                              u64* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream);
+
+// The first k entries of a sorted (key, payload) dump -> keys / values / rows (+ count = k).
+Status unpack_sorted_device(const u64* d_keys_in, const u64* d_pays, uint32_t k, u64* d_keys, float* d_values,
+                            uint32_t* d_rows, uint32_t* d_count, cudaStream_t stream);
 
 }  // namespace vb

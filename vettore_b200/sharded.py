@@ -121,7 +121,19 @@ class ShardedFlat:
         dq = queries_host.to(self.device, non_blocking=True)
         out = self.search_device(dq)
         host = out.cpu()
+        check_device_status(self.index)
         return self.decode(host.numpy(), dq.shape[0])
+
+
+def check_device_status(index: nifs.FlatRef) -> None:
+    """The stream-ordered device entries cannot return the reference's "metric overflow" (flat.rs:105): they
+    raise a sticky bit instead, surfaced here once the result is on the host."""
+    st = C.c_uint32(0)
+    rc = lib().vb_flat_device_status(index.handle, C.byref(st))
+    if rc:
+        raise RuntimeError(_lib.last_error())
+    if st.value & 1:
+        raise RuntimeError("metric overflow")
 
 
 def _merge_gathered(gathered: torch.Tensor, lay: dict, nq: int, lists: int, k_in: int, k_out: int, out: torch.Tensor,
@@ -201,7 +213,9 @@ class ShardedQuantized:
 
     def search(self, query_host: torch.Tensor) -> list[ShardHit]:
         out, offs = self.search_device(query_host.to(self.device, non_blocking=True))
-        return _decode_merged(out.cpu().numpy(), offs, self.k)
+        host = out.cpu().numpy()
+        check_device_status(self.index)
+        return _decode_merged(host, offs, self.k)
 
 
 class ShardedMv:
