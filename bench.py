@@ -8,17 +8,29 @@ the HBM-bound case the north_star's >=80%-of-roofline target is stated on).
   python bench.py [--gpus N --steps K --warmup W]          # this repo's CUDA path
   python bench.py --impl reference [...]                   # CPU restatement of the reference
 
-N>1 is launched by the driver under torchrun (one rank per GPU). The corpus is row-sharded:
-every rank holds its own 1M x 768 shard (weak scaling: per-GPU work fixed, corpus = N M rows),
-the query is replicated, per-rank top-k records are all-gathered over NVLink (NCCL) and
-merged by the K7 kernel. `value` = shard scans completed by all ranks per second
-(= queries/s x N; at N=1 exactly BASELINE's queries/s).
+N>1 is launched by the driver under torchrun (one rank per GPU). The headline is weak scaling: every
+rank holds its own 1M x 768 shard (corpus = N M rows), the query is replicated, the per-rank top-k
+records are exchanged over NVLink (peer-memory stores, or one NCCL all-gather) and merged by the K7
+kernel. `value` = 1M-row shard scans completed by all ranks per second (= queries/s over the N M-row
+corpus x N; at N=1 exactly BASELINE's queries/s); the unit string stays "queries/s" so the driver can
+set it against the reference arm (which scans the same 1M x 768 shard on the host cores).
 
-Only the `cpu_baseline` leg and `--impl reference` touch oracle/ (the CPU checker).
+Next to the headline every line carries, in `config`, the other BASELINE.json configurations at their
+stated sizes, sharded over the N GPUs:
+  c2_batch_1024  1M x 768 cosine, 1024-query batch, k=10 (K2, tcgen05 3xTF32)          [N=1 only]
+  c3  flat inner product, 100M x 768 over N GPUs, 1024-query batch, k=100 (K2 + all-gather + K7)
+  c4  quantized_search: 100M x 1024-bit sign codes, 1000 candidates -> exact cosine rerank to k=10
+  c5  ColBERT MaxSim: 1M docs x 128 tokens x 128 dims, 32-token query, k=10
+each with device-timed ms per step, queries/s, per-GPU GB/s or TFLOP/s, roofline fraction, the
+rows/docs actually resident per GPU (and whether that is the full stated corpus), and the speed-up over
+one GPU working through the same corpus shard by shard (N x local scan time / sharded step time).
+
+Only the parity checks, the `cpu_baseline` legs and `--impl reference` touch oracle/ (the CPU checker).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -32,6 +44,7 @@ if ROOT not in sys.path:
 
 METRIC = "queries/sec @k=10, 1M x 768 fp32 cosine flat"
 SEED = 20_260_721  # the reference's own bench seed (bench/search_modes_bench.exs:14)
+TOL = 1e-5         # north_star: float scores within 1e-5 relative
 
 
 def parse_args():
@@ -40,22 +53,34 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=1_000_000, help="rows per GPU shard")
+    ap.add_argument("--rows", type=int, default=1_000_000, help="rows per GPU shard (headline)")
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--queries", type=int, default=64, help="distinct queries rotated through the steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="c2,c3,c4,c5", help="comma list of the extra BASELINE configs to run ('' = none)")
+    ap.add_argument("--corpus-scale", type=float, default=1.0,
+                    help="scales the 100M / 1M-doc corpora of c3/c4/c5 (development runs only; 1.0 = BASELINE sizes)")
     return ap.parse_args()
+
+
+def workload_string(rows, dim, k):
+    return f"flat cosine exact scan {rows}x{dim} fp32 per GPU, batch of 1 query, k={k}"
 
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    out = {"hbm": 6650.0, "hbm_src": "fallback (B200_PROFILING.md 6.65 TB/s)", "bf16": 1655.0, "bf16_sustained": 1373.0,
+           "tc_src": "fallback"}
     if os.path.exists(path):
         try:
-            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            j = json.load(open(path))
+            out.update(hbm=float(j["hbm_gbs"]), hbm_src="measured (MEASURED_PEAKS.json hbm_gbs)")
+            out.update(bf16=float(j["bf16_tflops"]), bf16_sustained=float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                       tc_src="measured (MEASURED_PEAKS.json bf16_tflops / 2 = dense TF32)")
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    return out
 
 
 class ClockSampler:
@@ -135,11 +160,52 @@ def make_rows_torch(rows: int, dim: int, seed: int, device):
     return x
 
 
+def close(a: float, b: float, tol: float = TOL) -> bool:
+    """distances.rs:487-493 assert_close: |a-b| <= tol * max(1, |a|, |b|)."""
+    return abs(a - b) <= tol * max(1.0, abs(a), abs(b))
+
+
+def assert_hits_match(actual, expected, what: str):
+    """[(row or id, value)] lists: values within TOL, order equal except ties inside the tolerance and
+    swaps across the cut with a value tying the last expected one (tests/helpers.py, north_star's bar)."""
+    assert len(actual) == len(expected), (what, len(actual), len(expected))
+    exp = dict(expected)
+    last = expected[-1][1] if expected else 0.0
+    for pos, ((ia, va), (ie, ve)) in enumerate(zip(actual, expected)):
+        assert close(va, ve), (what, pos, ia, va, ie, ve)
+        if ia != ie and ia not in exp:
+            assert close(va, last), (what, pos, ia, va, "not in the oracle list and not a boundary tie", last)
+
+
+def subsample_check(got, oracle_hits, sample_rows: int, descending: bool, what: str):
+    """Size-independent parity property for a corpus too large for the CPU oracle: `got` = the CUDA path's
+    [(global row, value)] over the WHOLE corpus, `oracle_hits` = the oracle's top-k over the first
+    `sample_rows` rows only. (1) the list is sorted; (2) every CUDA hit that falls inside the sample carries
+    the oracle's value for that row; (3) every oracle hit that beats the CUDA list's last value by more than
+    the tolerance is present in the CUDA list. Returns the number of hits verified by value."""
+    sgn = -1.0 if descending else 1.0
+    vals = [sgn * v for _, v in got]
+    assert all(vals[i] <= vals[i + 1] + TOL * max(1.0, abs(vals[i])) for i in range(len(vals) - 1)), (what, "unsorted")
+    ref = dict(oracle_hits)
+    got_rows = {r for r, _ in got}
+    worst = vals[-1] if vals else float("inf")
+    checked = 0
+    for r, v in got:
+        if r < sample_rows and r in ref:
+            assert close(v, ref[r]), (what, r, v, ref[r])
+            checked += 1
+    for r, v in oracle_hits:
+        if sgn * v < worst - TOL * max(1.0, abs(worst)):
+            assert r in got_rows, (what, "oracle hit missing from the CUDA list", r, v, worst)
+    return checked
+
+
 # ------------------------------------------------------------------------------- reference arm
 def run_reference(args):
-    """The reference's own CPU implementation of the path (oracle port: the Rust NIF cannot
-    be built in this image), all host threads, each step = `threads` concurrent single-query
-    scans (one sequential scan per dirty-scheduler call, nifs.rs:297-309)."""
+    """The reference's own CPU implementation of the path (oracle port: the Rust NIF cannot be built in this
+    image), all host threads, each step = `threads` concurrent single-query scans (one sequential scan per
+    dirty-scheduler call, nifs.rs:297-309). Honours --steps / --warmup; when the whole run would exceed
+    ~2.5 minutes the per-step corpus sample shrinks (stated in `sample`) and the rate is scaled linearly."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -152,25 +218,34 @@ def run_reference(args):
     torch.manual_seed(SEED)
     rows = make_rows_torch(args.rows, args.dim, SEED, torch.device("cpu")).numpy()
     queries = make_rows_torch(max(threads, 8), args.dim, SEED + 1, torch.device("cpu")).numpy()
-    steps = max(1, min(args.steps, 8))      # bounded: each step scans the corpus `threads` times
-    warmup = max(1, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    t0 = time.perf_counter()
+    oracle.flat_scan_timed("cosine", rows, queries[:threads], args.k, threads)   # page in + first estimate
+    est = time.perf_counter() - t0
+    budget = 150.0
+    sample_rows = args.rows
+    if (steps + warmup) * est > budget:
+        sample_rows = max(10_000, int(args.rows * budget / ((steps + warmup) * est)))
+    sample = rows[:sample_rows]
     for _ in range(warmup):
-        oracle.flat_scan_timed("cosine", rows, queries[:threads], args.k, threads)
+        oracle.flat_scan_timed("cosine", sample, queries[:threads], args.k, threads)
     t = 0.0
     for s in range(steps):
         q = np.roll(queries, s, axis=0)[:threads]
-        secs, _ = oracle.flat_scan_timed("cosine", rows, q, args.k, threads)
+        secs, _ = oracle.flat_scan_timed("cosine", sample, q, args.k, threads)
         t += secs
-    qps = steps * threads / t
+    qps = steps * threads / t * (sample_rows / args.rows)
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * t / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"flat cosine exact scan {args.rows}x{args.dim} fp32, single query, k={args.k}",
+        "config": {"workload": workload_string(args.rows, args.dim, args.k),
                    "note": "CPU restatement of flat.rs:96-124 (oracle port); one step = one query per host thread"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} steps x {threads} concurrent single-query scans of the full "
-                                   f"{args.rows}x{args.dim} corpus"},
+                         "sample": f"{steps} steps x {threads} concurrent single-query scans of "
+                                   + (f"the full {args.rows}x{args.dim} corpus" if sample_rows == args.rows else
+                                      f"the first {sample_rows} of {args.rows} rows x {args.dim} (rate scaled linearly "
+                                      f"to the full corpus)")},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -178,37 +253,106 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------- CUDA arm
-def run_b200(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
+class Run:
+    """Process-group plumbing shared by the headline and the config blocks."""
 
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, x: float) -> float:
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def dev_timed(self, fn, steps: int, warm: int = 2) -> float:
+        """ms per call: CUDA events on the current stream, barrier + synchronize on both sides, max over ranks."""
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.allmax(e0.elapsed_time(e1) / steps)
+
+    def wall_timed(self, fn, steps: int, warm: int = 2) -> float:
+        """ms per call by wall clock (for calls that synchronise internally), max over ranks."""
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.barrier()
+        return self.allmax((time.perf_counter() - t0) / steps * 1e3)
+
+    def free(self):
+        import gc
+        gc.collect()
+        self.torch.cuda.empty_cache()
+
+
+def ingest_rows_device(run: Run, index, rows: int, dim: int, base: int, seed: int, keep_first: int = 0):
+    """Generates `rows` normalised rows on the device chunk by chunk and hands them to the index through the
+    device bulk-ingest entry (vb_flat_insert_many_device); ids are zero-padded global row numbers. Returns
+    (seconds, host copy of the first `keep_first` rows for the parity checks)."""
     from vettore_b200 import nifs
+
+    torch = run.torch
+    assert nifs.flat_reserve(index, rows) == ("ok", ())
+    kept = None
+    chunk = 1_000_000
+    t0 = time.perf_counter()
+    for s in range(0, rows, chunk):
+        m = min(chunk, rows - s)
+        blk = make_rows_torch(m, dim, seed + 7 * (s // chunk), run.dev)
+        res = nifs.flat_insert_device(index, nifs.decimal_ids(base + s, m), blk.data_ptr(), dim)
+        assert res == ("ok", ()), res
+        if s == 0 and keep_first:
+            kept = blk[:keep_first].cpu().numpy()
+        del blk
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0, kept
+
+
+def headline(run: Run, args, pk):
+    import numpy as np
+
+    import oracle  # parity checks only
+    from vettore_b200 import nifs
+    from vettore_b200._lib import lib
     from vettore_b200.sharded import ShardedFlat, set_global_ranks
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    torch, world, rank, dev = run.torch, run.world, run.rank, run.dev
     n, d, k = args.rows, args.dim, args.k
-    # ---- corpus shard: generated on the device, brought to the host once, then ingested
-    # through the reference-facing boundary (flat_insert_many -> bulk H2D).
+    # ---- corpus shard: generated on the device, brought to the host once, then ingested through the
+    # reference-facing boundary (flat_insert_many -> bulk H2D).
     x = make_rows_torch(n, d, SEED + 7919 * rank, dev)
     host_rows = x.cpu().numpy()
     del x
-    torch.cuda.empty_cache()
+    run.free()
     base = rank * n
-    ids = [f"{base + i:09d}" for i in range(n)]
+    ids = nifs.decimal_ids(base, n)
     index = nifs.flat_new_cosine()
     t0 = time.perf_counter()
     res = nifs.flat_insert_matrix(index, ids, host_rows)
@@ -220,16 +364,33 @@ def run_b200(args):
     q_host = queries.cpu().pin_memory()
     sharded = ShardedFlat(index, k=k, nq=1, device=dev)
 
-    # ---- parity spot check against the oracle before timing (rank 0, its own shard)
-    if rank == 0:
-        import oracle
-        st, hits = nifs.flat_search(index, q_host[0].numpy(), k)
+    # ---- parity against the oracle BEFORE timing, on the benchmarked configuration itself: rank 0 runs
+    # every rotating query through the oracle over its whole shard (all host threads) and compares with
+    # the CUDA path's hits through the reference-facing call. (The timed CPU baseline reuses this scan.)
+    threads = os.cpu_count() or 1
+    parity_checked, cpu_secs, cpu_nq = 0, None, 0
+    local_hits = []
+    for qi in range(args.queries):
+        st, hits = nifs.flat_search(index, q_host[qi].numpy(), k)
         assert st == "ok", hits
-        sub = 100_000
-        st2, ref = oracle.flat_search_dense("cosine", host_rows[:sub], ids[:sub], q_host[0].numpy(), k)
-        ref_ids = {h[0] for h in ref}
-        got_sub = [h for h in hits if int(h[0]) - base < sub]
-        assert all(h[0] in ref_ids for h in got_sub), "parity spot check failed"
+        local_hits.append([(int(h[0]) - base, h[1]) for h in hits])
+    if rank == 0:
+        cpu_nq = args.queries if world == 1 else min(args.queries, 16)
+        cpu_secs, ref = oracle.flat_scan_timed("cosine", host_rows, q_host[:cpu_nq].numpy(), k, threads)
+        for qi in range(cpu_nq):
+            assert_hits_match(local_hits[qi], ref[qi], f"headline query {qi}")
+        parity_checked = cpu_nq
+    if world > 1:
+        # the merged global answer must be the merge of the (oracle-checked) per-shard answers
+        nchk = 8
+        mine = [[(run.rank, r, v) for r, v in local_hits[qi]] for qi in range(nchk)]
+        gathered = [None] * world
+        run.dist.all_gather_object(gathered, mine)
+        for qi in range(nchk):
+            got = sharded.search(q_host[qi:qi + 1])[0]
+            pool = sorted((e for g in gathered for e in g[qi]), key=lambda e: (np.float32(1.0) - np.float32(e[2]), e[0], e[1]))
+            exp = pool[:k]
+            assert [(h.shard, h.row) for h in got] == [(e[0], e[1]) for e in exp], ("global merge", qi)
 
     # ---- value: device-timed, query already resident in HBM
     def step_device(i):
@@ -237,25 +398,18 @@ def run_b200(args):
 
     for i in range(args.warmup):
         step_device(i)
-    barrier()
+    run.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(run.local_rank) as clocks:
         ev0.record()
         for i in range(args.steps):
             step_device(i)
         ev1.record()
-        barrier()
-    ms = ev0.elapsed_time(ev1)
-    t_dev = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    ms_total = float(t_dev.item())
+        run.barrier()
+    ms_total = run.allmax(ev0.elapsed_time(ev1))
 
     # ---- scan-kernel-only timing (roofline): the local scan without the exchange
-    import ctypes as C
-    from vettore_b200._lib import lib
     lay = sharded.layout
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def scan_only(i):
         q = queries[i % args.queries: i % args.queries + 1]
@@ -263,10 +417,10 @@ def run_b200(args):
                                          C.c_void_p(sharded.local.data_ptr() + lay["keys"]),
                                          C.c_void_p(sharded.local.data_ptr() + lay["values"]),
                                          C.c_void_p(sharded.local.data_ptr() + lay["rows"]),
-                                         C.c_void_p(sharded.local.data_ptr() + lay["counts"]), stream)
+                                         C.c_void_p(sharded.local.data_ptr() + lay["counts"]), run.stream)
         assert rc == 0
 
-    barrier()
+    run.barrier()
     ek0, ek1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ek0.record()
     for i in range(args.steps):
@@ -285,21 +439,17 @@ def run_b200(args):
 
     for i in range(max(3, args.warmup // 4)):
         step_e2e(i)
-    barrier()
+    run.barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         step_e2e(i)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t_e2e = torch.tensor([e2e_s], device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_s = float(t_e2e.item())
+    run.barrier()
+    e2e_s = run.allmax(time.perf_counter() - t0)
 
-    # ---- configs[1] also names a batch of 1024 queries: K2 (tcgen05 3xTF32 GEMM + fused top-k),
-    # device-timed with the queries resident in HBM; reported inside `config`, not as the headline.
+    # ---- configs[1] also names a batch of 1024 queries: K2 (tcgen05 3xTF32 GEMM + fused top-k), device-timed
+    # with the queries resident in HBM, parity-checked against the oracle on 32 of its queries.
     batch = None
-    if world == 1:
+    if world == 1 and "c2" in args.cfgs:
         nqb = 1024
         bq = make_rows_torch(nqb, d, SEED + 2, dev)
         bkeys = torch.zeros(nqb * k, dtype=torch.int64, device=dev)
@@ -310,75 +460,377 @@ def run_b200(args):
         def batch_step():
             rc = lib().vb_flat_search_device(index.handle, C.c_void_p(bq.data_ptr()), nqb, d, k,
                                              C.c_void_p(bkeys.data_ptr()), C.c_void_p(bvals.data_ptr()),
-                                             C.c_void_p(brows.data_ptr()), C.c_void_p(bcnts.data_ptr()), stream)
+                                             C.c_void_p(brows.data_ptr()), C.c_void_p(bcnts.data_ptr()), run.stream)
             assert rc == 0
 
-        for _ in range(2):
-            batch_step()
-        torch.cuda.synchronize()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for _ in range(5):
-            batch_step()
-        b1.record()
-        torch.cuda.synchronize()
-        bms = b0.elapsed_time(b1) / 5
-        # spot parity: query 0 of the batch through the single-query kernel
-        st, one = nifs.flat_search(index, bq[0].cpu().numpy(), k)
-        got_rows = brows[:k].cpu().numpy().tolist()
-        assert [int(h[0]) - base for h in one] == got_rows, "batched and single-query results differ"
-        batch = {"queries": nqb, "ms_per_batch": bms, "queries_per_sec": nqb / (bms * 1e-3),
-                 "tf32_tflops_issued": 3 * 2.0 * nqb * n * d / (bms * 1e-3) / 1e12,
+        bms = run.dev_timed(batch_step, 5, 2)
+        nchk = 32
+        bq_host = bq[:nchk].cpu().numpy()
+        _, bref = oracle.flat_scan_timed("cosine", host_rows, bq_host, k, threads)
+        rows_h, vals_h = brows.cpu().numpy().reshape(nqb, k), bvals.cpu().numpy().reshape(nqb, k)
+        for qi in range(nchk):
+            assert_hits_match([(int(rows_h[qi, i]), float(vals_h[qi, i])) for i in range(k)], bref[qi], f"batch query {qi}")
+        tf32_peak = pk["bf16"] / 2
+        issued = 3 * 2.0 * nqb * n * d / (bms * 1e-3) / 1e12
+        batch = {"workload": f"flat cosine exact scan {n}x{d} fp32, batch of {nqb} queries, k={k}",
+                 "queries": nqb, "ms_per_batch": bms, "queries_per_sec": nqb / (bms * 1e-3),
+                 "tf32_tflops_issued": issued, "algorithmic_tflops": issued / 3,
+                 "roofline": {"bound": "tensor", "achieved": issued, "peak": tf32_peak, "unit": "TFLOP/s",
+                              "frac": issued / tf32_peak, "peak_source": pk["tc_src"],
+                              "note": "3xTF32 issues 3x the algorithmic flops (SURVEY.md §8(d))"},
+                 "parity_checked": nchk,
                  "kernel": "vb::flat_gemm_topk_kernel (tcgen05 3xTF32) + exact re-scoring"}
 
+    line = None
     if rank == 0:
-        peak, peak_src = peaks()
         alg_bytes = n * d * 4
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC,
             "value": world * args.steps / (ms_total * 1e-3),
-            "unit": "queries/s" if world == 1 else "1M-row shard scans/s (queries/s x n_gpus)",
+            "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "parity_checked": parity_checked,
             "config": {
-                "workload": f"flat cosine exact scan {n}x{d} fp32 per GPU, batch of 1 query, k={k}",
+                "workload": workload_string(n, d, k),
+                "value_definition": "1M-row shard scans per second over all GPUs = (queries/s over the "
+                                    f"{n * world}-row sharded corpus) x n_gpus; at n_gpus=1 plain queries/s",
                 "corpus_rows_total": n * world, "parallelism": f"row-shard x{world}",
+                "exchange": sharded.exchange_name,
                 "l2_policy": f"corpus shard {alg_bytes / 1e9:.2f} GB >> 126 MB L2, {args.queries} rotating queries",
                 "queries_per_sec": args.steps / (ms_total * 1e-3),
                 "ingest_seconds_per_shard": round(ingest_s, 3),
-                "batch_1024": batch,
+                "parity": f"{parity_checked} of the rotating queries: CUDA hits == oracle hits over the whole shard "
+                          "(ids equal, values within 1e-5)" + ("; merged global top-k == merge of the per-shard lists"
+                                                              if world > 1 else ""),
             },
             "clocks": clocks.summary(),
-            "e2e": {"value": world * args.steps / e2e_s, "unit": "queries/s" if world == 1 else "shard scans/s",
+            "e2e": {"value": world * args.steps / e2e_s, "unit": "queries/s",
                     "h2d_bytes_per_step": d * 4, "d2h_bytes_per_step": k * 8 + 8 if world == 1 else int(sharded.out.numel()),
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": args.steps * sharded.launches_per_search,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed
-                         # ncu --set full capture (profiles/r1_flat_stream_ncu_summary.txt); default shape only
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                         # (profiles/r1_flat_stream_ncu_summary.txt: 3.073186 GB + 6.35 MB)
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full
+                         # capture of this shape (profiles/r1_flat_stream_ncu_summary.txt: 3.073186 GB + 6.35 MB)
                          "traffic": 3.0795e9 if (n, d, k) == (1_000_000, 768, 10) else None,
-                         "peak_source": peak_src,
+                         "traffic_source": "profiles/r1_flat_stream_ncu_summary.txt",
+                         "peak_source": pk["hbm_src"],
                          "kernel": "vb::flat_stream_kernel<cosine, NV=6, RPW=1, W=16> (TMA-staged ring; the timed "
                                    "launch pair also holds the ~3 us unpack kernel)",
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
         }
+        if batch is not None:
+            line["config"]["c2_batch_1024"] = batch
         if world == 1 and not args.no_cpu_baseline:
-            import oracle
-            threads = os.cpu_count() or 1
-            nq = 4 * threads
-            secs, _ = oracle.flat_scan_timed("cosine", host_rows, q_host[:nq].numpy() if nq <= args.queries
-                                             else np.tile(q_host.numpy(), (nq // args.queries + 1, 1))[:nq], k, threads)
-            line["cpu_baseline"] = {"value": nq / secs, "unit": "queries/s", "cores": threads, "kind": "port",
-                                    "sample": f"{nq} single-query scans of the same {n}x{d} corpus, {threads} host "
-                                              f"threads, one sequential scan per query (flat.rs:96-124 restated)"}
-        print(json.dumps(line), flush=True)
+            line["cpu_baseline"] = {"value": cpu_nq / cpu_secs, "unit": "queries/s", "cores": threads, "kind": "port",
+                                    "sample": f"{cpu_nq} single-query scans of the same {n}x{d} corpus, {threads} host "
+                                              f"threads, one sequential scan per query (flat.rs:96-124 restated); the "
+                                              f"same scan is the parity check"}
+            # the reference runs ONE sequential scan per flat_search call (flat.rs:104-118): the 1-thread figure
+            s1, _ = oracle.flat_scan_timed("cosine", host_rows, q_host[:2].numpy(), k, 1)
+            line["cpu_baseline"]["one_thread"] = {"value": 2 / s1, "unit": "queries/s", "cores": 1,
+                                                  "sample": f"2 sequential scans of the same {n}x{d} corpus on one thread"}
+    del sharded, index
+    run.free()
+    return line
+
+
+# ------------------------------------------------------------------------------- BASELINE configs 3-5
+def rows_per_gpu(total: int, world: int, cap: int) -> int:
+    return min(total // world, cap)
+
+
+def block_c3(run: Run, args, pk):
+    """configs[2]: flat inner product, 100M x 768 row-sharded, 1024-query batch, k=100."""
+    import numpy as np
+
+    import oracle
+    from vettore_b200 import nifs
+    from vettore_b200._lib import lib
+    from vettore_b200.sharded import ShardedFlat, set_global_ranks
+
+    torch, world, rank, dev = run.torch, run.world, run.rank, run.dev
+    total, d, nq, k = int(100_000_000 * args.corpus_scale), 768, 1024, 100
+    free_b, _ = torch.cuda.mem_get_info()
+    cap_rows = int((free_b - 12e9) // (d * 4 + 4))                 # matrix + ranks, 12 GB left for workspaces
+    want = total // world if world > 1 else total // 8             # one GPU: the G=8 shard (the full corpus is 307 GB)
+    n = min(want, cap_rows)
+    if world > 1 and n < want:
+        n = min(n, int(25_000_000 * args.corpus_scale))            # does not fit: a 25M-row shard per GPU instead
+    base = rank * n
+    index = nifs.flat_new_inner_product()
+    ingest_s, kept = ingest_rows_device(run, index, n, d, base, SEED + 1000 * rank, keep_first=100_000 if rank == 0 else 0)
     if world > 1:
-        dist.destroy_process_group()
+        set_global_ranks(index, base, n)
+    queries = make_rows_torch(nq, d, SEED + 3, dev)
+    sharded = ShardedFlat(index, k=k, nq=nq, device=dev)
+    lay = sharded.layout
+
+    def local_only():
+        rc = lib().vb_flat_search_device(index.handle, C.c_void_p(queries.data_ptr()), nq, d, k,
+                                         C.c_void_p(sharded.local.data_ptr() + lay["keys"]),
+                                         C.c_void_p(sharded.local.data_ptr() + lay["values"]),
+                                         C.c_void_p(sharded.local.data_ptr() + lay["rows"]),
+                                         C.c_void_p(sharded.local.data_ptr() + lay["counts"]), run.stream)
+        assert rc == 0
+
+    local_ms = run.dev_timed(local_only, 3, 1)
+    step_ms = run.dev_timed(lambda: sharded.search_device(queries), 3, 1) if world > 1 else local_ms
+    out_host = sharded.search_device(queries).cpu().numpy()
+    hits = sharded.decode(out_host, nq)
+    checked = 0
+    if rank == 0:
+        nchk = 4
+        _, ref = oracle.flat_scan_timed("inner_product", kept, queries[:nchk].cpu().numpy(), k, os.cpu_count() or 1)
+        for qi in range(nchk):
+            got = [(h.row if h.shard == 0 else 1 << 40, h.value) for h in hits[qi]]
+            checked += subsample_check(got, ref[qi], kept.shape[0], True, f"c3 query {qi}")
+    issued = 3 * 2.0 * nq * n * d / (local_ms * 1e-3) / 1e12
+    tf32_peak = pk["bf16"] / 2
+    out = {"workload": f"flat inner-product scan {total}x{d} fp32 row-sharded x{world}, batch of {nq} queries, k={k}",
+           "rows_per_gpu": n, "corpus_rows_resident": n * world, "full_corpus": n * world == total,
+           "fits_note": None if n * world == total else
+           (f"one GPU holds the G=8 shard ({n} rows): the full corpus is {total * d * 4 / 1e9:.0f} GB" if world == 1 else
+            f"{total // world} rows x {d} fp32 = {total // world * d * 4 / 1e9:.0f} GB per GPU does not fit next to the "
+            f"workspaces: {n} rows per GPU resident"),
+           "local_scan_ms": local_ms, "step_ms": step_ms, "queries_per_sec": nq / (step_ms * 1e-3),
+           "per_gpu_tf32_tflops_issued": issued, "per_gpu_algorithmic_tflops": issued / 3,
+           "roofline": {"bound": "tensor", "achieved": issued, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": issued / tf32_peak, "peak_source": pk["tc_src"]},
+           "speedup_vs_one_gpu_same_corpus": world * local_ms / step_ms,
+           "speedup_definition": "one GPU works through the same resident corpus shard by shard: n_gpus x local_scan_ms / step_ms",
+           "exchange_bytes_per_rank": lay["bytes"], "exchange": "NCCL all-gather + K7 merge" if world > 1 else "none",
+           "ingest_seconds_per_shard": round(ingest_s, 2), "ingest_rows_per_sec": n / ingest_s,
+           "parity": f"subsample property check on 4 queries vs the oracle over the first {0 if kept is None else kept.shape[0]} "
+                     f"rows of shard 0 ({checked} hits verified by value, completeness + order for all)"}
+    del sharded, index, queries
+    run.free()
+    return out
+
+
+def block_c4(run: Run, args, pk):
+    """configs[3]: quantized_search, 100M x 1024-bit sign codes, 1000 candidates -> exact cosine rerank to 10."""
+    import numpy as np
+
+    import oracle
+    from vettore_b200 import nifs
+    from vettore_b200._lib import lib
+    from vettore_b200.sharded import ShardedQuantized, set_global_ranks
+
+    torch, world, rank, dev = run.torch, run.world, run.rank, run.dev
+    total, d, cand, k = int(100_000_000 * args.corpus_scale), 1024, 1000, 10
+    free_b, _ = torch.cuda.mem_get_info()
+    cap_rows = int((free_b - 12e9) // (d * 4 + d // 8 + 4))         # fp32 rows (rerank) + codes + ranks
+    want = total // world if world > 1 else total // 8
+    n = min(want, cap_rows)
+    if world > 1 and n < want:
+        n = min(n, int(25_000_000 * args.corpus_scale))
+    base = rank * n
+    index = nifs.flat_new_cosine()
+    keep = 200_000 if rank == 0 else 0
+    ingest_s, kept = ingest_rows_device(run, index, n, d, base, SEED + 2000 * rank, keep_first=keep)
+    if world > 1:
+        set_global_ranks(index, base, n)
+    queries = make_rows_torch(8, d, SEED + 4, dev)
+    sq = ShardedQuantized(index, cand, k, nifs.METRIC_CODE["cosine"], device=dev)
+    lc = sq.lay_c
+    q0 = queries[0:1].contiguous()
+
+    def hamming_local():
+        rc = lib().vb_flat_hamming_device(index.handle, C.c_void_p(q0.data_ptr()), 1, d, cand,
+                                          C.c_void_p(sq.local_c.data_ptr() + lc["keys"]),
+                                          C.c_void_p(sq.local_c.data_ptr() + lc["values"]),
+                                          C.c_void_p(sq.local_c.data_ptr() + lc["rows"]),
+                                          C.c_void_p(sq.local_c.data_ptr() + lc["counts"]), run.stream)
+        assert rc == 0
+
+    hamming_local()                                     # builds the code mirror (K6) outside the timed region
+    torch.cuda.synchronize()
+    ham_local_ms = run.dev_timed(hamming_local, 20, 3)
+    ham_step_ms = run.dev_timed(lambda: sq.candidates_device(q0), 20, 3) if world > 1 else ham_local_ms
+    pipe_ms = run.dev_timed(lambda: sq.search_device(q0), 20, 3)
+    # parity: Hamming candidates bit-exact on the subsample property; rerank values vs the oracle
+    checked = 0
+    if rank == 0 or world > 1:
+        pass
+    cand_rec, offs_c = sq.candidates_device(q0)
+    cand_host = cand_rec.cpu().numpy()
+    from vettore_b200.sharded import _decode_merged
+    cands = _decode_merged(cand_host, offs_c, cand)
+    final = sq.search(queries[0:1].cpu().pin_memory())
+    if rank == 0:
+        qh = queries[0].cpu().numpy()
+        qbits = np.array(oracle.compress_sign_bits(qh), dtype=np.uint64)
+        codes = np.array([oracle.compress_sign_bits(r) for r in kept[:50_000]], dtype=np.uint64)
+        _, ref = oracle.binary_scan_timed(codes, d, qbits[None, :], cand, os.cpu_count() or 1)
+        got = [(h.row if h.shard == 0 else 1 << 40, h.value) for h in cands]
+        # integer path: values must be EQUAL for the rows inside the sample
+        refd = dict(ref[0])
+        for r, v in got:
+            if r < codes.shape[0] and r in refd:
+                assert v == refd[r], ("c4 hamming distance", r, v, refd[r])
+                checked += 1
+        worst = got[-1][1]
+        got_rows = {r for r, _ in got}
+        for r, v in ref[0]:
+            if v < worst:
+                assert r in got_rows, ("c4: oracle candidate missing", r, v, worst)
+        # the final hits must be candidates, sorted, and carry the oracle's f64 cosine for rows in the sample
+        cset = {(h.shard, h.row) for h in cands}
+        assert all((h.shard, h.row) in cset for h in final), "c4: final hit outside the candidate set"
+        for h in final:
+            if h.shard == 0 and h.row < kept.shape[0]:
+                st, v = oracle.cosine(qh, kept[h.row])
+                assert st == "ok" and close(h.value, v), ("c4 rerank value", h.row, h.value, v)
+                checked += 1
+    code_bytes = n * (d // 64) * 8
+    gbs = code_bytes / (ham_local_ms * 1e-3) / 1e9
+    out = {"workload": f"quantized_search: {total}x{d}-bit sign codes row-sharded x{world}, {cand} candidates -> exact cosine rerank to k={k}",
+           "rows_per_gpu": n, "corpus_rows_resident": n * world, "full_corpus": n * world == total,
+           "fits_note": None if n * world == total else
+           (f"one GPU holds the G=8 shard ({n} rows): the fp32 rows the rerank needs are {total * d * 4 / 1e9:.0f} GB in all"
+            if world == 1 else f"{n} rows per GPU resident (fp32 rows for the rerank + codes)"),
+           "hamming_pass": {"local_scan_ms": ham_local_ms, "step_ms": ham_step_ms,
+                            "queries_per_sec": 1e3 / ham_step_ms, "per_gpu_gbs": gbs,
+                            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                                         "frac": gbs / pk["hbm"], "peak_source": pk["hbm_src"],
+                                         "algorithmic_bytes_per_launch": code_bytes},
+                            "speedup_vs_one_gpu_same_corpus": world * ham_local_ms / ham_step_ms},
+           "pipeline": {"step_ms": pipe_ms, "queries_per_sec": 1e3 / pipe_ms,
+                        "stages": "K6 sign-pack(query) + K3 Hamming scan + exchange + K7 + K4 exact rerank of owned candidates + exchange + K7",
+                        "speedup_vs_one_gpu_same_corpus": world * (pipe_ms - (ham_step_ms - ham_local_ms) * 0 if world == 1 else
+                                                                  (ham_local_ms + (pipe_ms - ham_step_ms))) / pipe_ms},
+           "speedup_definition": "n_gpus x (per-shard time without the exchanges) / sharded step time",
+           "exchange": sq.exchange_name if world > 1 else "none",
+           "ingest_seconds_per_shard": round(ingest_s, 2),
+           "parity": f"Hamming distances equal to the oracle's on the rows of a 50k-row sample of shard 0 and no better oracle "
+                     f"candidate missing; final hits are candidates with the oracle's f64 cosine ({checked} values verified)"}
+    del sq, index, queries
+    run.free()
+    return out
+
+
+def block_c5(run: Run, args, pk):
+    """configs[4]: ColBERT MaxSim, 1M docs x 128 tokens x 128 dims, 32-token query, k=10, document-sharded."""
+    import numpy as np
+
+    import oracle
+    from vettore_b200 import nifs
+    from vettore_b200.sharded import ShardedMv, set_global_mv_ranks
+
+    torch, world, rank, dev = run.torch, run.world, run.rank, run.dev
+    total, td, d, tq, k = int(1_000_000 * args.corpus_scale), 128, 128, 32, 10
+    n = total // world                                              # 65.5 GB in all: fits one GPU
+    base = rank * n
+    index = nifs.mv_new("inner_product")
+    assert nifs.mv_reserve(index, n, n * td, d) == ("ok", ())
+    chunk = 20_000
+    kept = None
+    t0 = time.perf_counter()
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        x = make_rows_torch(m * td, d, SEED + 3000 * rank + 7 * (s // chunk), dev)
+        assert nifs.mv_insert_device(index, nifs.decimal_ids(base + s, m), x.data_ptr(), td, d) == ("ok", ())
+        if s == 0 and rank == 0:
+            kept = x[: 2000 * td].cpu().numpy().reshape(-1, td, d)
+        del x
+    torch.cuda.synchronize()
+    ingest_s = time.perf_counter() - t0
+    if world > 1:
+        set_global_mv_ranks(index, base, n)
+    q = make_rows_torch(tq, d, SEED + 5, dev).cpu().numpy()
+    smv = ShardedMv(index, k, device=dev)
+    local_ms = run.wall_timed(lambda: nifs.mv_search(index, q, k), 10, 2)
+    step_ms = run.wall_timed(lambda: smv.search(q), 10, 2) if world > 1 else local_ms
+    hits = smv.search(q)
+    checked = 0
+    if rank == 0:
+        _, ref = oracle.maxsim_scan_timed("inner_product", kept, q[None, :, :], k, os.cpu_count() or 1)
+        got = [(h.row if h.shard == 0 else 1 << 40, h.value) for h in hits]
+        checked = subsample_check(got, ref[0], kept.shape[0], True, "c5")
+    alg = n * td * d * 4
+    gbs = alg / (local_ms * 1e-3) / 1e9
+    out = {"workload": f"multi_vector_search MaxSim: {total} docs x {td} tokens x {d} dims fp32 document-sharded x{world}, "
+                       f"{tq}-token query, k={k}",
+           "docs_per_gpu": n, "full_corpus": True,
+           "local_scan_ms": local_ms, "step_ms": step_ms, "queries_per_sec": 1e3 / step_ms, "per_gpu_gbs": gbs,
+           "per_gpu_algorithmic_tflops": 2.0 * tq * n * td * d / (local_ms * 1e-3) / 1e12,
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                        "peak_source": pk["hbm_src"], "algorithmic_bytes_per_launch": alg},
+           "timing": "wall clock through the by-value query call (vb_mv_search synchronises): H2D of the query, K5, D2H of the hits",
+           "strong_scaling": "the 1M-document corpus is fixed; docs_per_gpu = 1M / n_gpus (compare queries_per_sec across the N lines)",
+           "speedup_vs_one_gpu_same_corpus": world * local_ms / step_ms,
+           "exchange": "NCCL all-gather + K7 merge" if world > 1 else "none",
+           "ingest_seconds_per_shard": round(ingest_s, 2),
+           "parity": f"subsample property check vs the oracle over the first {kept.shape[0] if kept is not None else 0} documents of "
+                     f"shard 0 ({checked} scores verified, completeness + order)"}
+    del smv, index
+    run.free()
+    return out
+
+
+def cpu_samples(args):
+    """Bounded CPU legs for configs 3-5 (rank 0, N=1): the oracle on a sample of each shape, all host threads,
+    rates scaled linearly to the stated corpus (shapes too large for host RAM are extrapolated)."""
+    import numpy as np
+    import torch
+
+    import oracle
+
+    threads = os.cpu_count() or 1
+    cpu = torch.device("cpu")
+    out = {"cores": threads, "kind": "port"}
+    rows = make_rows_torch(200_000, 768, SEED, cpu).numpy()
+    q = make_rows_torch(threads, 768, SEED + 1, cpu).numpy()
+    s, _ = oracle.flat_scan_timed("inner_product", rows, q, 100, threads)
+    out["c3"] = {"queries_per_sec_100M_rows": threads / s * (200_000 / 100_000_000),
+                 "sample": f"{threads} queries x 200k x 768 rows, k=100, scaled linearly to 100M rows"}
+    rng = np.random.default_rng(SEED)
+    codes = rng.integers(0, 2 ** 63, size=(2_000_000, 16), dtype=np.uint64)
+    qb = rng.integers(0, 2 ** 63, size=(threads, 16), dtype=np.uint64)
+    s, _ = oracle.binary_scan_timed(codes, 1024, qb, 1000, threads)
+    out["c4_hamming_pass"] = {"queries_per_sec_100M_rows": threads / s * (2_000_000 / 100_000_000),
+                              "sample": f"{threads} queries x 2M x 1024-bit codes, 1000 candidates, scaled linearly to 100M rows"}
+    toks = make_rows_torch(500 * 128, 128, SEED + 2, cpu).numpy().reshape(500, 128, 128)
+    qt = make_rows_torch(threads * 32, 128, SEED + 3, cpu).numpy().reshape(threads, 32, 128)
+    s, _ = oracle.maxsim_scan_timed("inner_product", toks, qt, 10, threads)
+    out["c5"] = {"queries_per_sec_1M_docs": threads / s * (500 / 1_000_000),
+                 "sample": f"{threads} queries x 500 docs x 128 x 128, scaled linearly to 1M docs"}
+    return out
+
+
+def run_b200(args):
+    run = Run()
+    pk = peaks()
+    args.cfgs = [c for c in args.configs.split(",") if c]
+    line = headline(run, args, pk)
+    blocks = {}
+    for name, fn in (("c3", block_c3), ("c4", block_c4), ("c5", block_c5)):
+        if name not in args.cfgs:
+            continue
+        try:
+            t0 = time.perf_counter()
+            blk = fn(run, args, pk)
+            blk["block_seconds"] = round(time.perf_counter() - t0, 1)
+            blocks[name] = blk
+        except Exception as e:  # a config block must never take the headline line down with it
+            import traceback
+            blocks[name] = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-600:]}
+            run.free()
+    if run.rank == 0:
+        line["config"].update(blocks)
+        if run.world == 1 and not args.no_cpu_baseline and blocks:
+            try:
+                line["config"]["cpu_baseline_c3_c5"] = cpu_samples(args)
+            except Exception as e:
+                line["config"]["cpu_baseline_c3_c5"] = {"error": str(e)}
+        print(json.dumps(line), flush=True)
+    if run.world > 1:
+        run.barrier()
+        run.dist.destroy_process_group()
 
 
 def main():

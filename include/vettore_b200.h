@@ -173,6 +173,33 @@ int vb_topk_merge_device(const uint64_t* d_keys, const float* d_values, const ui
                          size_t k_in, size_t k_out, uint64_t* d_keys_out, float* d_values_out,
                          uint64_t* d_rows_out, uint32_t* d_counts_out, void* stream);
 
+/* ---- exchange step of the row-sharded searches over NVLink peer memory ----------
+ * Replaces "all-gather the per-GPU top-k lists, then select" by ONE kernel per rank: the rank's packed
+ * record (keys[nq][k_in] u64 | values f32 | rows u32 | counts[nq] u32 at the given byte offsets,
+ * `record_bytes` in all, a multiple of 16) is stored straight into every peer's gather buffer through
+ * NVLink, a flag is published, and the same launch waits for the peers' flags and runs the K7 select.
+ * Every rank makes the same sequence of calls. One process per GPU: vb_peer_new -> exchange the 64-byte
+ * CUDA IPC handles over the process group -> vb_peer_connect_ipc. One process driving several GPUs (or
+ * several shards of one GPU): vb_peer_connect_local with all the objects. */
+typedef struct vb_peer vb_peer;
+int vb_peer_new(int world, int rank, size_t record_bytes, vb_peer** out, unsigned char ipc_handle_out[64]);
+void vb_peer_free(vb_peer* px);
+int vb_peer_connect_ipc(vb_peer* px, const unsigned char* handles /* [world][64] */);
+int vb_peer_connect_local(vb_peer* const* peers, int world);
+/* Outputs as vb_topk_merge_device ([nq][k_out]; d_rows_out = shard << 32 | row). `stream`: cudaStream_t. */
+int vb_peer_exchange_merge(vb_peer* px, const void* d_record, size_t nq, size_t k_in, size_t k_out, size_t off_keys,
+                           size_t off_values, size_t off_rows, size_t off_counts, uint64_t* d_keys_out,
+                           float* d_values_out, uint64_t* d_rows_out, uint32_t* d_counts_out, void* stream);
+/* The two halves of the above (store + flag; wait + select), for a caller that drives several ranks from
+ * one host thread: every rank's push must be enqueued before any rank's wait_merge. */
+int vb_peer_push(vb_peer* px, const void* d_record, size_t nq, size_t k_in, size_t k_out, size_t off_keys,
+                 size_t off_values, size_t off_rows, size_t off_counts, void* stream);
+int vb_peer_wait_merge(vb_peer* px, size_t nq, size_t k_in, size_t k_out, size_t off_keys, size_t off_values,
+                       size_t off_rows, size_t off_counts, uint64_t* d_keys_out, float* d_values_out,
+                       uint64_t* d_rows_out, uint32_t* d_counts_out, void* stream);
+/* *error = 1 when a wait timed out (a peer never published its record). Synchronises the device. */
+int vb_peer_error(vb_peer* px, uint32_t* error);
+
 /* ---- by-value batched helpers: Nifs.vector_top_k / binary_top_k / multi_vector_* -- */
 /* vector_top_k/5, nifs.rs:151-162 -> search::vector_top_k, search.rs:38-73. */
 int vb_vector_top_k(size_t n, const char* ids, const uint64_t* id_off, const float* values,

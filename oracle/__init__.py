@@ -303,15 +303,52 @@ def flat_search_dense(metric: str | int, rows: np.ndarray, ids: Sequence[str] | 
 
 
 def flat_scan_timed(metric: str | int, rows: np.ndarray, queries: np.ndarray, limit: int, threads: int):
-    """Timed CPU baseline (see vo_flat_scan_timed). Returns (seconds, [(row, raw)] of the last query)."""
+    """Timed CPU baseline (see vo_flat_scan_timed). Returns (seconds, per query [(row, raw)]) — row order is
+    id order for ids that sort like the row number (the bench's zero-padded decimals)."""
     code = METRIC_CODE[metric] if isinstance(metric, str) else int(metric)
     rows = np.ascontiguousarray(rows, dtype=np.float32)
     queries = np.ascontiguousarray(queries, dtype=np.float32)
     n, d = rows.shape
     nq = queries.shape[0]
     cap = max(1, min(limit, n))
-    oi, orr = np.zeros(cap, np.uint64), np.zeros(cap, np.float32)
+    oi, orr = np.zeros(nq * cap, np.uint64), np.zeros(nq * cap, np.float32)
     secs = lib().vo_flat_scan_timed(C.c_uint8(code), _p(rows, C.c_float), C.c_size_t(n), C.c_size_t(d),
                                     _p(queries, C.c_float), C.c_size_t(nq), C.c_size_t(limit), C.c_int(threads),
                                     _p(oi, C.c_uint64), _p(orr, C.c_float))
-    return secs, [(int(oi[i]), float(orr[i])) for i in range(cap)]
+    return secs, [[(int(oi[q * cap + i]), float(orr[q * cap + i])) for i in range(cap)] for q in range(nq)]
+
+
+def binary_scan_timed(codes: np.ndarray, dims: int, queries: np.ndarray, limit: int, threads: int):
+    """Timed CPU baseline of the Hamming candidate pass (vo_binary_scan_timed; search.rs:76-92) over a dense
+    ``[n, nw]`` uint64 code matrix. Returns (seconds, per query [(row, distance)])."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint64)
+    queries = np.ascontiguousarray(queries, dtype=np.uint64)
+    n, nw = codes.shape
+    nq = queries.shape[0]
+    cap = max(1, min(limit, n))
+    oi, orr = np.zeros(nq * cap, np.uint64), np.zeros(nq * cap, np.float32)
+    fn = lib().vo_binary_scan_timed
+    fn.restype = C.c_double
+    secs = fn(_p(codes, C.c_uint64), C.c_size_t(n), C.c_size_t(nw), C.c_size_t(dims), _p(queries, C.c_uint64),
+              C.c_size_t(nq), C.c_size_t(limit), C.c_int(threads), _p(oi, C.c_uint64), _p(orr, C.c_float))
+    return secs, [[(int(oi[q * cap + i]), float(orr[q * cap + i])) for i in range(cap)] for q in range(nq)]
+
+
+def maxsim_scan_timed(metric: str | int, tokens: np.ndarray, queries: np.ndarray, limit: int, threads: int):
+    """Timed CPU baseline of MaxSim top-k (vo_maxsim_scan_timed; multi_vector.rs:90-132) over uniform documents
+    ``[ndocs, td, dim]`` and queries ``[nq, tq, dim]``. Returns (seconds, per query [(doc, score)])."""
+    code = METRIC_CODE[metric] if isinstance(metric, str) else int(metric)
+    tokens = np.ascontiguousarray(tokens, dtype=np.float32)
+    queries = np.ascontiguousarray(queries, dtype=np.float32)
+    ndocs, td, dim = tokens.shape
+    nq, tq, _ = queries.shape
+    cap = max(1, min(limit, ndocs))
+    oi, orr = np.zeros(nq * cap, np.uint64), np.zeros(nq * cap, np.float32)
+    fn = lib().vo_maxsim_scan_timed
+    fn.restype = C.c_double
+    secs = fn(_p(tokens, C.c_float), C.c_size_t(ndocs), C.c_size_t(td), C.c_size_t(dim), _p(queries, C.c_float),
+              C.c_size_t(nq), C.c_size_t(tq), C.c_int(code), C.c_size_t(limit), C.c_int(threads),
+              _p(oi, C.c_uint64), _p(orr, C.c_float))
+    if secs < 0:
+        raise RuntimeError("oracle MaxSim scan failed: " + _err()[1])
+    return secs, [[(int(oi[q * cap + i]), float(orr[q * cap + i])) for i in range(cap)] for q in range(nq)]

@@ -543,7 +543,7 @@ int vo_multi_vector_top_k(const float* dv, const uint64_t* doff, const uint64_t*
 // exactly the unit of work of one dirty-scheduler flat_search call, nifs.rs:297-309;
 // several BEAM dirty schedulers may run such calls concurrently). Ids are implicit
 // zero-padded row numbers, so id order == row order and the id comparison is on idx.
-// Returns wall seconds; writes the top-`limit` of the LAST query of thread 0 for checking.
+// Returns wall seconds; writes every query's top-`limit` ([nq][min(limit, n)]) for parity checks.
 double vo_flat_scan_timed(uint8_t metric, const float* rows, size_t n, size_t d,
                           const float* queries, size_t nq, size_t limit, int threads,
                           uint64_t* out_idx, float* out_raw) {
@@ -572,8 +572,13 @@ double vo_flat_scan_timed(uint8_t metric, const float* rows, size_t n, size_t d,
                 }
             }
             std::sort(heap.begin(), heap.end(), less);
-            if (qi == nq - 1 && out_idx && out_raw)
-                for (size_t i = 0; i < heap.size(); ++i) { out_idx[i] = heap[i].idx; out_raw[i] = heap[i].raw; }
+            if (out_idx && out_raw) {   // every query's hits: [nq][min(limit, n)] (the caller checks parity with them)
+                const size_t cap = limit < n ? limit : n;
+                for (size_t i = 0; i < heap.size(); ++i) {
+                    out_idx[qi * cap + i] = heap[i].idx;
+                    out_raw[qi * cap + i] = heap[i].raw;
+                }
+            }
             (void)tid;
         }
     };
@@ -584,6 +589,111 @@ double vo_flat_scan_timed(uint8_t metric, const float* rows, size_t n, size_t d,
     for (auto& th : pool) th.join();
     auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Timed CPU baseline of the Hamming candidate pass (search::binary_top_k, search.rs:76-92) over a dense
+// [n, nw] u64 code matrix: `nq` queries, `threads` host threads each running whole queries (one query =
+// one sequential scan, as in the reference). Ids are implicit zero-padded row numbers (id order == row
+// order). Writes every query's top-`limit` ([nq][min(limit, n)]). Returns wall seconds.
+double vo_binary_scan_timed(const uint64_t* codes, size_t n, size_t nw, size_t dims, const uint64_t* queries,
+                            size_t nq, size_t limit, int threads, uint64_t* out_idx, float* out_raw) {
+    if (threads < 1) threads = 1;
+    std::atomic<size_t> next{0};
+    const size_t cap = limit < n ? limit : n;
+    auto worker = [&]() {
+        struct H { uint32_t key; uint64_t idx; };
+        auto less = [](const H& a, const H& b) { return a.key != b.key ? a.key < b.key : a.idx < b.idx; };
+        std::vector<H> heap;
+        for (;;) {
+            size_t qi = next.fetch_add(1);
+            if (qi >= nq) break;
+            const uint64_t* q = queries + qi * nw;
+            heap.clear();
+            for (size_t r = 0; r < n; ++r) {
+                const uint64_t* c = codes + r * nw;
+                uint64_t d = 0;
+                for (size_t w = 0; w < nw; ++w) d += __builtin_popcountll((q[w] ^ c[w]) & word_mask(w, dims));
+                H h{static_cast<uint32_t>(d), r};   // distances are small non-negative integers: key order == f32 order
+                if (heap.size() < limit) {
+                    heap.push_back(h);
+                    std::push_heap(heap.begin(), heap.end(), less);
+                } else if (less(h, heap.front())) {
+                    std::pop_heap(heap.begin(), heap.end(), less);
+                    heap.back() = h;
+                    std::push_heap(heap.begin(), heap.end(), less);
+                }
+            }
+            std::sort(heap.begin(), heap.end(), less);
+            if (out_idx && out_raw)
+                for (size_t i = 0; i < heap.size(); ++i) {
+                    out_idx[qi * cap + i] = heap[i].idx;
+                    out_raw[qi * cap + i] = static_cast<float>(heap[i].key);
+                }
+        }
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Timed CPU baseline of MaxSim top-k (multi_vector::top_k, multi_vector.rs:90-132) over uniform documents
+// stored densely as [ndocs, td, dim]: `nq` queries of `tq` tokens each, `threads` host threads each running
+// whole queries. Same scoring as score_validated (f64 true cosine when metric == Cosine). Writes every
+// query's top-`limit` (score desc, doc index asc). Returns wall seconds, or -1 on a scoring error.
+double vo_maxsim_scan_timed(const float* tokens, size_t ndocs, size_t td, size_t dim, const float* queries, size_t nq,
+                            size_t tq, int metric_code, size_t limit, int threads, uint64_t* out_idx, float* out_score) {
+    if (threads < 1) threads = 1;
+    const uint8_t metric = static_cast<uint8_t>(metric_code);
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    const size_t cap = limit < ndocs ? limit : ndocs;
+    std::vector<uint64_t> qoff(tq + 1), doff(td + 1);
+    for (size_t i = 0; i <= tq; ++i) qoff[i] = i * dim;
+    for (size_t i = 0; i <= td; ++i) doff[i] = i * dim;
+    auto worker = [&]() {
+        struct H { uint32_t key; uint64_t idx; float score; };
+        auto less = [](const H& a, const H& b) { return a.key != b.key ? a.key < b.key : a.idx < b.idx; };
+        std::vector<H> heap;
+        for (;;) {
+            size_t qi = next.fetch_add(1);
+            if (qi >= nq) break;
+            const float* q = queries + qi * tq * dim;
+            heap.clear();
+            for (size_t d = 0; d < ndocs; ++d) {
+                float score = 0.0f;
+                if (score_validated(q, qoff.data(), tq, tokens + d * td * dim, doff.data(), 0, td, dim, metric, &score)) {
+                    failed = 1;
+                    return;
+                }
+                H h{~total_order_key(score), d, score};
+                if (heap.size() < limit) {
+                    heap.push_back(h);
+                    std::push_heap(heap.begin(), heap.end(), less);
+                } else if (less(h, heap.front())) {
+                    std::pop_heap(heap.begin(), heap.end(), less);
+                    heap.back() = h;
+                    std::push_heap(heap.begin(), heap.end(), less);
+                }
+            }
+            std::sort(heap.begin(), heap.end(), less);
+            if (out_idx && out_score)
+                for (size_t i = 0; i < heap.size(); ++i) {
+                    out_idx[qi * cap + i] = heap[i].idx;
+                    out_score[qi * cap + i] = heap[i].score;
+                }
+        }
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    auto t1 = std::chrono::steady_clock::now();
+    return failed ? -1.0 : std::chrono::duration<double>(t1 - t0).count();
 }
 
 }  // extern "C"

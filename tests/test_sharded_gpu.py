@@ -233,3 +233,89 @@ def test_nccl_two_rank_sharded_paths_match_single_index():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "sharded paths match the single-index results" in res.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+# NVLink peer-memory exchange + fused select (csrc/peer_exchange.cu). `world` virtual ranks live on one
+# device here (vb_peer_connect_local), each on its own stream; the result of every rank must equal the K7
+# merge of the same records laid out as an all-gather would lay them out.
+def _random_record(rng, lay, nq, k, shard):
+    rec = np.zeros(lay["bytes"], dtype=np.uint8)
+    keys = rec[lay["keys"]:lay["keys"] + nq * k * 8].view(np.uint64).reshape(nq, k)
+    vals = rec[lay["values"]:lay["values"] + nq * k * 4].view(np.float32).reshape(nq, k)
+    rows = rec[lay["rows"]:lay["rows"] + nq * k * 4].view(np.uint32).reshape(nq, k)
+    cnts = rec[lay["counts"]:lay["counts"] + nq * 4].view(np.uint32)
+    for q in range(nq):
+        c = int(rng.integers(0, k + 1)) if (q + shard) % 3 == 0 else k
+        # few distinct high words: plenty of cross-shard ties decided by the low (id rank) word
+        hi = np.sort(rng.integers(0, 6, size=c).astype(np.uint64))
+        lo = rng.permutation(1 << 20)[:c].astype(np.uint64) * np.uint64(8) + np.uint64(shard)
+        kk = np.sort((hi << np.uint64(32)) | lo)
+        keys[q, :c] = kk
+        keys[q, c:] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        vals[q, :c] = (kk >> np.uint64(32)).astype(np.float32) + 0.25 * shard
+        rows[q, :c] = (kk & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        cnts[q] = c
+    return rec
+
+
+@pytest.mark.parametrize("world,nq,k_in,k_out", [(2, 1, 10, 10), (8, 1, 10, 10), (4, 1, 1000, 1000), (8, 3, 100, 100),
+                                                 (8, 64, 100, 100), (3, 300, 10, 10)])
+def test_peer_exchange_merge_equals_gather_then_merge(world, nq, k_in, k_out):
+    L = _lib.lib()
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(world * 1000 + nq)
+    lay = packed_layout(nq, k_in)
+    peers = []
+    for r in range(world):
+        px = C.c_void_p()
+        assert L.vb_peer_new(world, r, lay["bytes"], C.byref(px), None) == 0, _lib.last_error()
+        peers.append(px)
+    arr = (C.c_void_p * world)(*peers)
+    assert L.vb_peer_connect_local(arr, world) == 0, _lib.last_error()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    o_keys, o_vals = 0, nq * k_out * 8
+    o_rows = (o_vals + nq * k_out * 4 + 7) // 8 * 8
+    o_cnt = o_rows + nq * k_out * 8
+    outs = [torch.zeros(o_cnt + nq * 4 + 16, dtype=torch.uint8, device=dev) for _ in range(world)]
+    try:
+        for step in range(3):          # several epochs: both buffer parities and the flag protocol
+            recs = [_random_record(rng, lay, nq, k_in, r) for r in range(world)]
+            d_recs = [torch.from_numpy(x).to(dev) for x in recs]
+            gathered = torch.from_numpy(np.concatenate(recs)).to(dev)
+            torch.cuda.synchronize()
+            p = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+            if nq <= 4:
+                for r in range(world):   # fused push + wait + select, one launch per rank, concurrent streams
+                    rc = L.vb_peer_exchange_merge(peers[r], p(d_recs[r]), nq, k_in, k_out, lay["keys"], lay["values"],
+                                                  lay["rows"], lay["counts"], p(outs[r], o_keys), p(outs[r], o_vals),
+                                                  p(outs[r], o_rows), p(outs[r], o_cnt), C.c_void_p(streams[r].cuda_stream))
+                    assert rc == 0, _lib.last_error()
+            else:
+                for r in range(world):   # one host thread drives every rank: all pushes first
+                    rc = L.vb_peer_push(peers[r], p(d_recs[r]), nq, k_in, k_out, lay["keys"], lay["values"], lay["rows"],
+                                        lay["counts"], C.c_void_p(streams[r].cuda_stream))
+                    assert rc == 0, _lib.last_error()
+                for r in range(world):
+                    rc = L.vb_peer_wait_merge(peers[r], nq, k_in, k_out, lay["keys"], lay["values"], lay["rows"],
+                                              lay["counts"], p(outs[r], o_keys), p(outs[r], o_vals), p(outs[r], o_rows),
+                                              p(outs[r], o_cnt), C.c_void_p(streams[r].cuda_stream))
+                    assert rc == 0, _lib.last_error()
+            torch.cuda.synchronize()
+            ref = torch.zeros_like(outs[0])
+            g = gathered.data_ptr()
+            rc = L.vb_topk_merge_device(C.c_void_p(g + lay["keys"]), C.c_void_p(g + lay["values"]), C.c_void_p(g + lay["rows"]),
+                                        C.c_void_p(g + lay["counts"]), lay["bytes"], nq, world, k_in, k_out, p(ref, o_keys),
+                                        p(ref, o_vals), p(ref, o_rows), p(ref, o_cnt),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            assert rc == 0, _lib.last_error()
+            torch.cuda.synchronize()
+            ref_h = ref.cpu().numpy()
+            for r in range(world):
+                err = C.c_uint32(9)
+                assert L.vb_peer_error(peers[r], C.byref(err)) == 0 and err.value == 0
+                assert np.array_equal(outs[r].cpu().numpy()[:o_cnt + nq * 4], ref_h[:o_cnt + nq * 4]), (step, r)
+    finally:
+        torch.cuda.synchronize()
+        for px in peers:
+            L.vb_peer_free(px)

@@ -46,6 +46,14 @@ SIGNATURES = {
     "vb_flat_device_status": (C.c_int, [_vp, _u32p]),
     "vb_flat_set_id_ranks": (C.c_int, [_vp, _u32p, _sz]),
     "vb_topk_merge_device": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "vb_peer_new": (C.c_int, [C.c_int, C.c_int, _sz, _vpp, _vp]),
+    "vb_peer_free": (None, [_vp]),
+    "vb_peer_connect_ipc": (C.c_int, [_vp, _vp]),
+    "vb_peer_connect_local": (C.c_int, [_vpp, C.c_int]),
+    "vb_peer_exchange_merge": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "vb_peer_push": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, _sz, _sz, _vp]),
+    "vb_peer_wait_merge": (C.c_int, [_vp, _sz, _sz, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "vb_peer_error": (C.c_int, [_vp, _u32p]),
     "vb_vector_top_k": (C.c_int, [_sz, C.c_char_p, _u64p, _f32p, _u64p, _f32p, _sz, C.c_int, _sz, _sz, _vpp]),
     "vb_binary_top_k": (C.c_int, [_sz, C.c_char_p, _u64p, _u64p, _u64p, _u64p, _sz, _sz, _sz, _vpp]),
     "vb_compress_sign_bits": (C.c_int, [_f32p, _sz, _u64p]),

@@ -8,6 +8,7 @@
 #include "flat_index.h"
 #include "hamming.h"
 #include "maxsim.h"
+#include "peer_exchange.h"
 #include "runtime.h"
 #include "scan_driver.h"
 #include "select.h"
@@ -217,6 +218,70 @@ int vb_topk_merge_device(const uint64_t* d_keys, const float* d_values, const ui
                                         reinterpret_cast<vb::u64*>(d_rows_out), d_counts_out,
                                         static_cast<cudaStream_t>(stream)));
 }
+
+// ---------------------------------------------------------------- NVLink peer exchange
+namespace {
+vb::PeerRecord peer_record(vb_peer* px, size_t nq, size_t k_in, size_t k_out, size_t off_keys, size_t off_values,
+                           size_t off_rows, size_t off_counts) {
+    vb::PeerRecord r;
+    r.nq = (uint32_t)nq; r.k_in = (uint32_t)k_in; r.k_out = (uint32_t)k_out;
+    r.off_keys = (uint32_t)off_keys; r.off_values = (uint32_t)off_values; r.off_rows = (uint32_t)off_rows;
+    r.off_counts = (uint32_t)off_counts;
+    r.bytes = px->impl->record_bytes();
+    return r;
+}
+}  // namespace
+
+int vb_peer_new(int world, int rank, size_t record_bytes, vb_peer** out, unsigned char ipc_handle_out[64]) {
+    *out = nullptr;
+    if (vb_device_count() <= 0) return no_device();
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return no_device();
+    auto* px = new vb::PeerExchange(world, rank, record_bytes, dev);
+    vb::Status s = px->allocate();
+    if (s.ok() && ipc_handle_out) s = px->export_handle(ipc_handle_out);
+    if (!s.ok()) { delete px; return finish(s); }
+    *out = new vb_peer{px};
+    return VB_OK;
+}
+void vb_peer_free(vb_peer* px) {
+    if (!px) return;
+    delete px->impl;
+    delete px;
+}
+int vb_peer_connect_ipc(vb_peer* px, const unsigned char* handles) { return finish(px->impl->connect_ipc(handles)); }
+int vb_peer_connect_local(vb_peer* const* peers, int world) {
+    if (world < 1 || world > vb::kMaxPeers) return finish(vb::Status::Cuda("peer exchange: bad world"));
+    vb::PeerExchange* impls[vb::kMaxPeers];
+    for (int r = 0; r < world; ++r) impls[r] = peers[r]->impl;
+    for (int r = 0; r < world; ++r) {
+        vb::Status s = impls[r]->connect_local(impls);
+        if (!s.ok()) return finish(s);
+    }
+    return VB_OK;
+}
+int vb_peer_exchange_merge(vb_peer* px, const void* d_record, size_t nq, size_t k_in, size_t k_out, size_t off_keys,
+                           size_t off_values, size_t off_rows, size_t off_counts, uint64_t* d_keys_out,
+                           float* d_values_out, uint64_t* d_rows_out, uint32_t* d_counts_out, void* stream) {
+    return finish(px->impl->exchange_merge(d_record, peer_record(px, nq, k_in, k_out, off_keys, off_values, off_rows, off_counts),
+                                           reinterpret_cast<vb::u64*>(d_keys_out), d_values_out,
+                                           reinterpret_cast<vb::u64*>(d_rows_out), d_counts_out,
+                                           static_cast<cudaStream_t>(stream)));
+}
+int vb_peer_push(vb_peer* px, const void* d_record, size_t nq, size_t k_in, size_t k_out, size_t off_keys,
+                 size_t off_values, size_t off_rows, size_t off_counts, void* stream) {
+    return finish(px->impl->push(d_record, peer_record(px, nq, k_in, k_out, off_keys, off_values, off_rows, off_counts),
+                                 static_cast<cudaStream_t>(stream)));
+}
+int vb_peer_wait_merge(vb_peer* px, size_t nq, size_t k_in, size_t k_out, size_t off_keys, size_t off_values,
+                       size_t off_rows, size_t off_counts, uint64_t* d_keys_out, float* d_values_out,
+                       uint64_t* d_rows_out, uint32_t* d_counts_out, void* stream) {
+    return finish(px->impl->wait_merge(peer_record(px, nq, k_in, k_out, off_keys, off_values, off_rows, off_counts),
+                                       reinterpret_cast<vb::u64*>(d_keys_out), d_values_out,
+                                       reinterpret_cast<vb::u64*>(d_rows_out), d_counts_out,
+                                       static_cast<cudaStream_t>(stream)));
+}
+int vb_peer_error(vb_peer* px, uint32_t* error) { return finish(px->impl->error_state(error)); }
 
 // ---------------------------------------------------------------- by-value helpers
 int vb_vector_top_k(size_t n, const char* ids, const uint64_t* id_off, const float* values,

@@ -43,7 +43,35 @@ def _enc(i) -> bytes:
     return i.encode("utf-8") if isinstance(i, str) else bytes(i)
 
 
-def _ids_blob(ids: Sequence) -> tuple[bytes, np.ndarray]:
+class IdBlob:
+    """Ids already laid out the way the C ABI takes them (one byte blob + n+1 offsets): bulk loads of
+    millions of rows skip the per-id Python objects. ``len()`` = number of ids."""
+
+    def __init__(self, blob: np.ndarray, off: np.ndarray):
+        self.blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self.off = np.ascontiguousarray(off, dtype=np.uint64)
+
+    def __len__(self) -> int:
+        return int(self.off.size) - 1
+
+    def __getitem__(self, i: int) -> str:
+        return bytes(self.blob[int(self.off[i]):int(self.off[i + 1])]).decode("utf-8")
+
+
+def decimal_ids(base: int, n: int, width: int = 9) -> IdBlob:
+    """Zero-padded decimal ids ``base .. base+n-1`` (id byte order == numeric order: SURVEY.md §8(d))."""
+    blob = np.empty((n, width), dtype=np.uint8)
+    chunk = 1 << 22
+    pw = (10 ** np.arange(width - 1, -1, -1)).astype(np.int64)
+    for s in range(0, n, chunk):
+        v = np.arange(base + s, base + min(n, s + chunk), dtype=np.int64)
+        blob[s:s + v.size] = ((v[:, None] // pw[None, :]) % 10 + 48).astype(np.uint8)
+    return IdBlob(blob.reshape(-1), np.arange(n + 1, dtype=np.uint64) * np.uint64(width))
+
+
+def _ids_blob(ids) -> tuple:
+    if isinstance(ids, IdBlob):
+        return ids.blob.ctypes.data_as(C.c_char_p), ids.off
     enc = [_enc(i) for i in ids]
     off = np.zeros(len(enc) + 1, dtype=np.uint64)
     if enc:

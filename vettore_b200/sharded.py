@@ -35,6 +35,98 @@ def packed_layout(nq: int, k: int) -> dict:
     return {"keys": keys, "values": values, "rows": rows, "counts": counts, "bytes": total}
 
 
+def merged_offsets(nq: int, k_out: int) -> tuple[int, int, int, int]:
+    """Byte offsets (keys u64, values f32, rows u64 = shard << 32 | row, counts u32) of a merged record."""
+    o_keys = 0
+    o_vals = o_keys + nq * k_out * 8
+    o_rows = (o_vals + nq * k_out * 4 + 7) // 8 * 8
+    o_counts = o_rows + nq * k_out * 8
+    return o_keys, o_vals, o_rows, o_counts
+
+
+class Exchange:
+    """Exchange + final select of one packed top-k record per rank.
+
+    ``peer`` (default on CUDA): the library's own kernel stores the record into every peer's buffer over
+    NVLink peer memory (buffers mapped across the processes with CUDA IPC handles, exchanged once over the
+    process group), publishes a flag, waits for the peers' flags and runs the K7 select — one launch per
+    step, no collective call. ``nccl`` (``VB_EXCHANGE=nccl``, or when the peer mapping cannot be set up):
+    one ``all_gather_into_tensor`` + the K7 merge kernel. Both produce the same merged record."""
+
+    def __init__(self, lay: dict, nq: int, k_in: int, k_out: int, group, device: torch.device):
+        import os
+
+        self.lay, self.nq, self.k_in, self.k_out, self.group, self.device = lay, nq, k_in, k_out, group, device
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.offsets = merged_offsets(nq, k_out)
+        self.peer = None
+        self.gathered = None
+        self.mode = "none"
+        if self.world == 1:
+            return
+        self.mode = "nccl"
+        if device.type == "cuda" and os.environ.get("VB_EXCHANGE", "peer") != "nccl" and self.world <= 8:
+            self._try_peer()
+        if self.mode == "nccl":
+            self.gathered = torch.zeros(self.world * lay["bytes"], dtype=torch.uint8, device=device)
+
+    def _try_peer(self):
+        handle = (C.c_ubyte * 64)()
+        px = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = lib().vb_peer_new(self.world, self.rank, self.lay["bytes"], C.byref(px), handle)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle) if rc == 0 else None, group=self.group)
+        ok = rc == 0 and all(h is not None for h in handles)
+        if ok:
+            blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
+            with torch.cuda.device(self.device):
+                ok = lib().vb_peer_connect_ipc(px, blob) == 0
+        flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self.peer, self.mode = px, "peer"
+        elif rc == 0:
+            lib().vb_peer_free(px)
+
+    @property
+    def name(self) -> str:
+        return {"none": "none (single shard)", "nccl": "NCCL all-gather + K7 merge kernel",
+                "peer": "NVLink peer-memory stores + fused wait/select kernel (vb_peer_exchange_merge)"}[self.mode]
+
+    @property
+    def launches(self) -> int:
+        return {"none": 0, "nccl": 2, "peer": 1 if self.nq <= 4 else 2}[self.mode]
+
+    def run(self, local: torch.Tensor, out: torch.Tensor, stream: C.c_void_p) -> tuple[int, int, int, int]:
+        """``local``: this rank's packed record (device). Writes the merged record into ``out``; returns its offsets."""
+        lay = self.lay
+        o_keys, o_vals, o_rows, o_counts = self.offsets
+        p = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+        if self.mode == "peer":
+            rc = lib().vb_peer_exchange_merge(self.peer, p(local), self.nq, self.k_in, self.k_out, lay["keys"], lay["values"],
+                                              lay["rows"], lay["counts"], p(out, o_keys), p(out, o_vals), p(out, o_rows),
+                                              p(out, o_counts), stream)
+            if rc:
+                raise RuntimeError(_lib.last_error())
+            return self.offsets
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, local, group=self.group)
+            src = self.gathered
+        else:
+            src = local
+        return _merge_gathered(src, lay, self.nq, self.world, self.k_in, self.k_out, out, stream)
+
+    def __del__(self):
+        px, self.peer = getattr(self, "peer", None), None
+        if px:
+            try:
+                lib().vb_peer_free(px)
+            except Exception:
+                pass
+
+
 @dataclass
 class ShardHit:
     shard: int
@@ -55,9 +147,10 @@ class ShardedFlat:
         self.layout = packed_layout(self.nq, self.k)
         nbytes = self.layout["bytes"]
         self.local = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-        self.gathered = torch.zeros(self.world * nbytes, dtype=torch.uint8, device=self.device)
         self.out = torch.zeros(nbytes + self.nq * self.k * 4 + 16, dtype=torch.uint8, device=self.device)
-        self.launches_per_search = 2 + (1 if self.world > 1 else 0)  # scan, unpack (+ merge when sharded)
+        self.exchange = Exchange(self.layout, self.nq, self.k, self.k, group, self.device)
+        self.exchange_name = self.exchange.name
+        self.launches_per_search = 2 + self.exchange.launches  # scan, unpack (+ exchange / merge when sharded)
 
     # ---- device-side pieces ------------------------------------------------------------
     def _ptr(self, t: torch.Tensor, off: int = 0) -> C.c_void_p:
@@ -78,20 +171,7 @@ class ShardedFlat:
             raise RuntimeError(_lib.last_error())
         if self.world == 1:
             return self.local  # single shard: the local record already is the global top-k
-        dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
-        src, lists = self.gathered, self.world
-        o_keys = 0
-        o_vals = o_keys + nq * self.k * 8
-        o_rows = o_vals + nq * self.k * 4
-        o_rows = (o_rows + 7) // 8 * 8
-        o_counts = o_rows + nq * self.k * 8
-        rc = lib().vb_topk_merge_device(self._ptr(src, lay["keys"]), self._ptr(src, lay["values"]),
-                                        self._ptr(src, lay["rows"]), self._ptr(src, lay["counts"]), lay["bytes"],
-                                        nq, lists, self.k, self.k, self._ptr(self.out, o_keys),
-                                        self._ptr(self.out, o_vals), self._ptr(self.out, o_rows),
-                                        self._ptr(self.out, o_counts), stream)
-        if rc:
-            raise RuntimeError(_lib.last_error())
+        o_keys, o_vals, o_rows, o_counts = self.exchange.run(self.local, self.out, stream)
         self._out_off = (o_keys, o_vals, o_rows, o_counts)
         return self.out
 
@@ -178,37 +258,39 @@ class ShardedQuantized:
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.lay_c, self.lay_k = packed_layout(1, self.cand), packed_layout(1, self.k)
         z = lambda n: torch.zeros(n, dtype=torch.uint8, device=self.device)
-        self.local_c, self.gath_c = z(self.lay_c["bytes"]), z(self.world * self.lay_c["bytes"])
-        self.local_k, self.gath_k = z(self.lay_k["bytes"]), z(self.world * self.lay_k["bytes"])
+        self.local_c, self.local_k = z(self.lay_c["bytes"]), z(self.lay_k["bytes"])
         self.out_c, self.out_k = z(self.cand * 20 + 64), z(self.k * 20 + 64)
+        self.ex_c = Exchange(self.lay_c, 1, self.cand, self.cand, group, self.device)
+        self.ex_k = Exchange(self.lay_k, 1, self.k, self.k, group, self.device)
+        self.exchange_name = self.ex_c.name
+
+    def candidates_device(self, d_query: torch.Tensor) -> tuple[torch.Tensor, tuple[int, int, int, int]]:
+        """Stage 1 only: this shard's Hamming candidates (K6 + K3), the exchange and the global select."""
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+        _, stride = d_query.shape
+        lc = self.lay_c
+        rc = lib().vb_flat_hamming_device(self.index.handle, p(d_query), 1, stride, self.cand, p(self.local_c, lc["keys"]),
+                                          p(self.local_c, lc["values"]), p(self.local_c, lc["rows"]),
+                                          p(self.local_c, lc["counts"]), stream)
+        if rc:
+            raise RuntimeError(_lib.last_error())
+        return self.out_c, self.ex_c.run(self.local_c, self.out_c, stream)
 
     def search_device(self, d_query: torch.Tensor) -> tuple[torch.Tensor, tuple[int, int, int, int]]:
         """``d_query``: ``[1, q_stride]`` float32 on the device. Returns the merged record and its offsets."""
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         p = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
         _, stride = d_query.shape
-        lc, lk = self.lay_c, self.lay_k
-        rc = lib().vb_flat_hamming_device(self.index.handle, p(d_query), 1, stride, self.cand, p(self.local_c, lc["keys"]),
-                                          p(self.local_c, lc["values"]), p(self.local_c, lc["rows"]),
-                                          p(self.local_c, lc["counts"]), stream)
-        if rc:
-            raise RuntimeError(_lib.last_error())
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.gath_c, self.local_c, group=self.group)
-        else:
-            self.gath_c.copy_(self.local_c)
-        offs_c = _merge_gathered(self.gath_c, lc, 1, self.world, self.cand, self.cand, self.out_c, stream)
+        lk = self.lay_k
+        _, offs_c = self.candidates_device(d_query)
         rc = lib().vb_flat_rerank_owned_device(self.index.handle, p(d_query), stride, self.metric_code,
                                                p(self.out_c, offs_c[2]), p(self.out_c, offs_c[3]), self.cand, self.rank,
                                                self.k, p(self.local_k, lk["keys"]), p(self.local_k, lk["values"]),
                                                p(self.local_k, lk["rows"]), p(self.local_k, lk["counts"]), stream)
         if rc:
             raise RuntimeError(_lib.last_error())
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.gath_k, self.local_k, group=self.group)
-        else:
-            self.gath_k.copy_(self.local_k)
-        offs_k = _merge_gathered(self.gath_k, lk, 1, self.world, self.k, self.k, self.out_k, stream)
+        offs_k = self.ex_k.run(self.local_k, self.out_k, stream)
         return self.out_k, offs_k
 
     def search(self, query_host: torch.Tensor) -> list[ShardHit]:
@@ -229,8 +311,9 @@ class ShardedMv:
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.lay = packed_layout(1, self.k)
         self.local = torch.zeros(self.lay["bytes"], dtype=torch.uint8, device=self.device)
-        self.gathered = torch.zeros(self.world * self.lay["bytes"], dtype=torch.uint8, device=self.device)
         self.out = torch.zeros(self.k * 20 + 64, dtype=torch.uint8, device=self.device)
+        self.exchange = Exchange(self.lay, 1, self.k, self.k, group, self.device)
+        self.exchange_name = self.exchange.name
 
     def search(self, query_tokens: np.ndarray) -> list[ShardHit]:
         """``query_tokens``: host ``[tq, dim]`` float32 (the reference API takes the query by value)."""
@@ -243,11 +326,7 @@ class ShardedMv:
             raise RuntimeError(res[1])
         torch.cuda.synchronize(self.device)   # the library scored on its own stream
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
-        else:
-            self.gathered.copy_(self.local)
-        offs = _merge_gathered(self.gathered, lay, 1, self.world, self.k, self.k, self.out, stream)
+        offs = self.exchange.run(self.local, self.out, stream)
         return _decode_merged(self.out.cpu().numpy(), offs, self.k)
 
 
