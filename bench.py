@@ -45,6 +45,7 @@ if ROOT not in sys.path:
 METRIC = "queries/sec @k=10, 1M x 768 fp32 cosine flat"
 SEED = 20_260_721  # the reference's own bench seed (bench/search_modes_bench.exs:14)
 TOL = 1e-5         # north_star: float scores within 1e-5 relative
+INGEST_CHUNK = 1_000_000   # rows generated per device chunk (one seed per chunk)
 
 
 def parse_args():
@@ -321,11 +322,11 @@ def ingest_rows_device(run: Run, index, rows: int, dim: int, base: int, seed: in
     torch = run.torch
     assert nifs.flat_reserve(index, rows) == ("ok", ())
     kept = None
-    chunk = 1_000_000
+    chunk = INGEST_CHUNK
     t0 = time.perf_counter()
     for s in range(0, rows, chunk):
         m = min(chunk, rows - s)
-        blk = make_rows_torch(m, dim, seed + 7 * (s // chunk), run.dev)
+        blk = make_rows_torch(chunk, dim, seed + 7 * (s // chunk), run.dev)[:m]   # always a whole chunk: RowRegen re-creates it
         res = nifs.flat_insert_device(index, nifs.decimal_ids(base + s, m), blk.data_ptr(), dim)
         assert res == ("ok", ()), res
         if s == 0 and keep_first:
@@ -333,6 +334,31 @@ def ingest_rows_device(run: Run, index, rows: int, dim: int, base: int, seed: in
         del blk
     torch.cuda.synchronize()
     return time.perf_counter() - t0, kept
+
+
+class RowRegen:
+    """Re-creates any row of a device-generated corpus on the host for the oracle: the corpora of configs 3-5
+    are generated chunk by chunk from per-chunk seeds (ingest_rows_device), so the chunk holding a given row
+    can be generated again on the device and the row fetched. One chunk is cached."""
+
+    def __init__(self, run: Run, dim: int, seed_of_chunk, chunk_rows: int):
+        self.run, self.dim, self.seed_of_chunk, self.chunk_rows = run, dim, seed_of_chunk, chunk_rows
+        self.cached, self.block = None, None
+
+    def rows(self, shard: int, row0: int, count: int = 1):
+        """`count` consecutive rows starting at local row `row0` of shard `shard` (all inside one chunk)."""
+        c = row0 // self.chunk_rows
+        if self.cached != (shard, c):
+            self.block = None
+            self.run.free()
+            self.block = make_rows_torch(self.chunk_rows, self.dim, self.seed_of_chunk(shard, c), self.run.dev)
+            self.cached = (shard, c)
+        o = row0 - c * self.chunk_rows
+        return self.block[o:o + count].cpu().numpy()
+
+    def close(self):
+        self.block, self.cached = None, None
+        self.run.free()
 
 
 def headline(run: Run, args, pk):
@@ -588,6 +614,16 @@ def block_c3(run: Run, args, pk):
         for qi in range(nchk):
             got = [(h.row if h.shard == 0 else 1 << 40, h.value) for h in hits[qi]]
             checked += subsample_check(got, ref[qi], kept.shape[0], True, f"c3 query {qi}")
+        # every returned value must be the oracle's inner product of the query with that very row: the best 8
+        # hits of each checked query, rows re-created from their chunk seeds (any shard)
+        regen = RowRegen(run, d, lambda shard, c: SEED + 1000 * shard + 7 * c, INGEST_CHUNK)
+        qh = queries[:nchk].cpu().numpy()
+        for qi in range(nchk):
+            for h in hits[qi][:8]:
+                st, v = oracle.compute("inner_product", qh[qi], regen.rows(h.shard, h.row)[0])
+                assert st == "ok" and close(h.value, v), ("c3 value", qi, h.shard, h.row, h.value, v)
+                checked += 1
+        regen.close()
     issued = 3 * 2.0 * nq * n * d / (local_ms * 1e-3) / 1e12
     tf32_peak = pk["bf16"] / 2
     out = {"workload": f"flat inner-product scan {total}x{d} fp32 row-sharded x{world}, batch of {nq} queries, k={k}",
@@ -602,10 +638,11 @@ def block_c3(run: Run, args, pk):
                         "frac": issued / tf32_peak, "peak_source": pk["tc_src"]},
            "speedup_vs_one_gpu_same_corpus": world * local_ms / step_ms,
            "speedup_definition": "one GPU works through the same resident corpus shard by shard: n_gpus x local_scan_ms / step_ms",
-           "exchange_bytes_per_rank": lay["bytes"], "exchange": "NCCL all-gather + K7 merge" if world > 1 else "none",
+           "exchange_bytes_per_rank": lay["bytes"], "exchange": sharded.exchange_name,
            "ingest_seconds_per_shard": round(ingest_s, 2), "ingest_rows_per_sec": n / ingest_s,
-           "parity": f"subsample property check on 4 queries vs the oracle over the first {0 if kept is None else kept.shape[0]} "
-                     f"rows of shard 0 ({checked} hits verified by value, completeness + order for all)"}
+           "parity": f"4 queries: order + completeness vs the oracle's top-{k} over the first {0 if kept is None else kept.shape[0]} "
+                     f"rows of shard 0; the best 8 hits of each re-scored by the oracle on rows re-created from their "
+                     f"chunk seeds ({checked} values verified within 1e-5)"}
     del sharded, index, queries
     run.free()
     return out
@@ -679,11 +716,17 @@ def block_c4(run: Run, args, pk):
         # the final hits must be candidates, sorted, and carry the oracle's f64 cosine for rows in the sample
         cset = {(h.shard, h.row) for h in cands}
         assert all((h.shard, h.row) in cset for h in final), "c4: final hit outside the candidate set"
-        for h in final:
-            if h.shard == 0 and h.row < kept.shape[0]:
-                st, v = oracle.cosine(qh, kept[h.row])
-                assert st == "ok" and close(h.value, v), ("c4 rerank value", h.row, h.value, v)
-                checked += 1
+        regen = RowRegen(run, d, lambda shard, c: SEED + 2000 * shard + 7 * c, INGEST_CHUNK)
+        for h in final:             # every final hit: the oracle's f64 cosine of the query with that very row
+            st, v = oracle.cosine(qh, regen.rows(h.shard, h.row)[0])
+            assert st == "ok" and close(h.value, v), ("c4 rerank value", h.shard, h.row, h.value, v)
+            checked += 1
+        for h in cands[:8] + cands[-8:]:   # best and worst candidates: exact Hamming distance of the sign codes
+            bits = np.array(oracle.compress_sign_bits(regen.rows(h.shard, h.row)[0]), dtype=np.uint64)
+            st, dist = oracle.packed_hamming(qbits, bits, d)
+            assert st == "ok" and dist == h.value, ("c4 candidate distance", h.shard, h.row, h.value, dist)
+            checked += 1
+        regen.close()
     code_bytes = n * (d // 64) * 8
     gbs = code_bytes / (ham_local_ms * 1e-3) / 1e9
     out = {"workload": f"quantized_search: {total}x{d}-bit sign codes row-sharded x{world}, {cand} candidates -> exact cosine rerank to k={k}",
@@ -703,8 +746,9 @@ def block_c4(run: Run, args, pk):
            "speedup_definition": "Hamming pass: n_gpus x local_scan_ms / step_ms (one GPU works through the same codes shard by shard)",
            "exchange": sq.exchange_name if world > 1 else "none",
            "ingest_seconds_per_shard": round(ingest_s, 2),
-           "parity": f"Hamming distances equal to the oracle's on the rows of a 50k-row sample of shard 0 and no better oracle "
-                     f"candidate missing; final hits are candidates with the oracle's f64 cosine ({checked} values verified)"}
+           "parity": f"candidates: Hamming distances EQUAL to the oracle's on a 50k-row sample of shard 0, no better oracle "
+                     f"candidate missing, best/worst 8 re-derived from re-created rows; all {k} final hits are candidates and "
+                     f"carry the oracle's f64 cosine ({checked} values verified)"}
     del sq, index, queries
     run.free()
     return out
@@ -729,7 +773,7 @@ def block_c5(run: Run, args, pk):
     t0 = time.perf_counter()
     for s in range(0, n, chunk):
         m = min(chunk, n - s)
-        x = make_rows_torch(m * td, d, SEED + 3000 * rank + 7 * (s // chunk), dev)
+        x = make_rows_torch(chunk * td, d, SEED + 3000 * rank + 7 * (s // chunk), dev)[:m * td]   # whole chunks: RowRegen
         assert nifs.mv_insert_device(index, nifs.decimal_ids(base + s, m), x.data_ptr(), td, d) == ("ok", ())
         if s == 0 and rank == 0:
             kept = x[: 2000 * td].cpu().numpy().reshape(-1, td, d)
@@ -748,6 +792,14 @@ def block_c5(run: Run, args, pk):
         _, ref = oracle.maxsim_scan_timed("inner_product", kept, q[None, :, :], k, os.cpu_count() or 1)
         got = [(h.row if h.shard == 0 else 1 << 40, h.value) for h in hits]
         checked = subsample_check(got, ref[0], kept.shape[0], True, "c5")
+        # every returned score must be the oracle's MaxSim of the query with that very document (any shard),
+        # its tokens re-created from the chunk seed
+        regen = RowRegen(run, d, lambda shard, c: SEED + 3000 * shard + 7 * c, chunk * td)
+        for h in hits:
+            st, v = oracle.multi_vector_score(q, regen.rows(h.shard, h.row * td, td), nifs.METRIC_CODE["inner_product"])
+            assert st == "ok" and close(h.value, v), ("c5 score", h.shard, h.row, h.value, v)
+            checked += 1
+        regen.close()
     alg = n * td * d * 4
     gbs = alg / (local_ms * 1e-3) / 1e9
     out = {"workload": f"multi_vector_search MaxSim: {total} docs x {td} tokens x {d} dims fp32 document-sharded x{world}, "
@@ -760,10 +812,11 @@ def block_c5(run: Run, args, pk):
            "timing": "wall clock through the by-value query call (vb_mv_search synchronises): H2D of the query, K5, D2H of the hits",
            "strong_scaling": "the 1M-document corpus is fixed; docs_per_gpu = 1M / n_gpus (compare queries_per_sec across the N lines)",
            "speedup_vs_one_gpu_same_corpus": world * local_ms / step_ms,
-           "exchange": "NCCL all-gather + K7 merge" if world > 1 else "none",
+           "exchange": smv.exchange_name, "phase_ms": smv.phase_ms(),
            "ingest_seconds_per_shard": round(ingest_s, 2),
-           "parity": f"subsample property check vs the oracle over the first {kept.shape[0] if kept is not None else 0} documents of "
-                     f"shard 0 ({checked} scores verified, completeness + order)"}
+           "parity": f"order + completeness vs the oracle's top-{k} over the first {kept.shape[0] if kept is not None else 0} "
+                     f"documents of shard 0; all {k} returned scores re-derived by the oracle from documents re-created from "
+                     f"their chunk seeds ({checked} values verified within 1e-5)"}
     del smv, index
     run.free()
     return out

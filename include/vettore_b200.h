@@ -250,6 +250,14 @@ int vb_mv_search_packed_device(vb_mv* index, const float* q_vals, const uint64_t
 int vb_mv_set_id_ranks(vb_mv* index, const uint32_t* ranks, size_t n);
 int vb_mv_info(vb_mv* index, size_t* docs, size_t* tokens, size_t* dimension);
 
+/* Additive (the step after the scan): Distance.result_values/3
+ * (lib/vettore_distance.ex:100-102, 525-543) for a whole hit list in one call — raw f32 metric values ->
+ * the (score, distance) pairs of Vettore.Result, in f64 exactly as the BEAM computes them (`raw / 1`,
+ * `1.0 - raw`, `1.0 / (1.0 + raw)`, `(raw + 1.0) / 2.0` on the widened raw). score_mode 0 = :raw,
+ * 1 = :similarity. Host arithmetic (k values): callers are left with the ETS lookups only
+ * (index/flat.ex:72-91). "unknown metric" for codes outside 0..8. */
+int vb_result_values(int metric_code, int score_mode, const float* raw, size_t n, double* score, double* distance);
+
 /* compress_sign_bits/1, nifs.rs:125-129 -> distances.rs:413-423. words[ceil(len/64)]. */
 int vb_compress_sign_bits(const float* vector, size_t len, uint64_t* words);
 

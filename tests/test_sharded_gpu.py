@@ -260,7 +260,8 @@ def _random_record(rng, lay, nq, k, shard):
 
 
 @pytest.mark.parametrize("world,nq,k_in,k_out", [(2, 1, 10, 10), (8, 1, 10, 10), (4, 1, 1000, 1000), (8, 3, 100, 100),
-                                                 (8, 64, 100, 100), (3, 300, 10, 10)])
+                                                 (8, 64, 100, 100), (3, 300, 10, 10), (2, 1, 1000, 1000),
+                                                 (8, 2, 1000, 1000), (8, 1, 1024, 100), (5, 1, 300, 300)])
 def test_peer_exchange_merge_equals_gather_then_merge(world, nq, k_in, k_out):
     L = _lib.lib()
     dev = torch.device("cuda", 0)

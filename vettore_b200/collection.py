@@ -109,12 +109,15 @@ class Collection:
         return isinstance(limit, int) and 0 < limit <= MAX_NIF_USIZE
 
     def _results(self, hits):
+        """index/flat.ex:72-91 for the whole hit list: ONE vb_result_values call shapes every raw value
+        (SURVEY.md §8(f) rank 3), then the store lookups; ids the store no longer has are dropped."""
+        st, shaped = nifs.result_values(nifs.METRIC_CODE[self.metric], [raw for _, raw in hits], self.score)
+        assert st == "ok", shaped
         out = []
-        for id_, raw in hits:
+        for (id_, _raw), (score, dist) in zip(hits, shaped):
             e = self.store.get(id_)
             if e is None:
                 continue
-            score, dist = result_values(self.metric, raw, self.score)
             out.append(Result(id_, e.value, score, dist, self.metric, e.metadata))
         return out
 

@@ -576,6 +576,26 @@ int vb_mv_info(vb_mv* index, size_t* docs, size_t* tokens, size_t* dimension) {
     return VB_OK;
 }
 
+int vb_result_values(int metric_code, int score_mode, const float* raw, size_t n, double* score, double* distance) {
+    if (metric_code < 0 || metric_code > 8) return finish(vb::Status::Ref("unknown metric"));
+    if (score_mode != 0 && score_mode != 1) return finish(vb::Status::Ref("unknown score mode"));
+    const bool similarity_metric = metric_code == vb::kCosine || metric_code == vb::kInnerProduct;   // @similarity_metrics
+    for (size_t i = 0; i < n; ++i) {
+        const double r = (double)raw[i];                     // the BEAM holds the NIF's f32 as an f64
+        if (metric_code == vb::kNegativeInnerProduct) {      // vettore_distance.ex:527-529 (both modes)
+            score[i] = -r;
+            distance[i] = r;
+        } else if (similarity_metric) {                      // :531-532, :537-538
+            distance[i] = metric_code == vb::kCosine ? 1.0 - r : -r;
+            score[i] = (score_mode == 1 && metric_code == vb::kCosine) ? (r + 1.0) / 2.0 : r;
+        } else {                                             // :534-535, :540-541
+            score[i] = score_mode == 1 ? 1.0 / (1.0 + r) : -r;
+            distance[i] = r;
+        }
+    }
+    return VB_OK;
+}
+
 int vb_compress_sign_bits(const float* vector, size_t len, uint64_t* words) {
     const size_t nw = (len + 63) / 64;
     for (size_t w = 0; w < nw; ++w) words[w] = 0;

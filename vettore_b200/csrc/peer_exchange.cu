@@ -183,6 +183,87 @@ peer_wait_merge_kernel(PeerPtrs pp, RecordLayout L, uint32_t world, uint32_t ran
                    rows_out, counts_out);
 }
 
+// ---- large lists (the 1000 Hamming candidates of quantized_search x 8 shards): rank merge ------------------
+// A single CTA pushing 8000 candidates through the collector's sort costs ~100 us. The lists are sorted and
+// keys are unique (the low word is the global id rank), so an entry's position in the merged order is simply
+// its own index plus, for every other list, the number of entries below it (a binary search): no sort, no
+// atomics, every entry independent. All lists are staged in shared memory (world x k_in x 8 B <= 64 KB) by
+// each of a few CTAs, which split the entries between them. Fused with the push and the wait like the small
+// kernel: the CTAs' pushes never wait, the last one to finish publishes the flags.
+constexpr uint32_t kRankThreads = 512;
+constexpr uint32_t kRankCtas = 8;
+
+__global__ void __launch_bounds__(kRankThreads)
+peer_exchange_rank_merge_kernel(PeerPtrs pp, const unsigned char* record, RecordLayout L, uint32_t world, uint32_t rank,
+                                uint32_t epoch, u64* keys_out, float* values_out, u64* rows_out, uint32_t* counts_out,
+                                uint32_t* ticket, uint32_t* error) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t s_cnt[kMaxPeers];
+    __shared__ uint32_t s_last;
+    u64* s_keys = reinterpret_cast<u64*>(smem);                 // [world][k_in]
+    const uint32_t parity = epoch & 1u;
+    push_record(pp, record, L.bytes, world, rank, parity, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < world) st_release_sys(pp.flags[threadIdx.x] + parity * kMaxPeers + rank, epoch);
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+    if (!wait_flags(pp.flags[rank], world, parity, epoch)) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) { *error = 1u; for (uint32_t q = 0; q < L.nq; ++q) counts_out[q] = 0u; }
+        return;
+    }
+    const unsigned char* gathered = pp.gather[rank] + (size_t)parity * world * L.bytes;
+    const uint32_t k_in = L.k_in, k_out = L.k_out;
+    for (uint32_t qi = 0; qi < L.nq; ++qi) {
+        __syncthreads();
+        if (threadIdx.x < world)
+            s_cnt[threadIdx.x] = min(ld_vol_u32(gathered + (size_t)threadIdx.x * L.bytes + L.off_counts + 4 * qi), k_in);
+        for (uint32_t s = threadIdx.x; s < world * k_in; s += blockDim.x) {
+            const uint32_t l = s / k_in, i = s - l * k_in;
+            s_keys[s] = ld_vol_u64(gathered + (size_t)l * L.bytes + L.off_keys + 8 * ((size_t)qi * k_in + i));
+        }
+        __syncthreads();
+        uint32_t total = 0;
+        for (uint32_t l = 0; l < world; ++l) total += s_cnt[l];
+        const uint32_t kept = min(total, k_out);
+        for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < world * k_in; s += gridDim.x * blockDim.x) {
+            const uint32_t l = s / k_in, i = s - l * k_in;
+            if (i >= s_cnt[l] || i >= k_out) continue;
+            const u64 key = s_keys[s];
+            uint32_t pos = i;
+            for (uint32_t m = 0; m < world && pos < k_out; ++m) {
+                if (m == l) continue;
+                const u64* lk = s_keys + m * k_in;
+                uint32_t lo = 0, hi = s_cnt[m];
+                while (lo < hi) {                       // entries of list m below `key` (keys are unique)
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (lk[mid] < key) lo = mid + 1; else hi = mid;
+                }
+                pos += lo;
+            }
+            if (pos >= k_out) continue;
+            const size_t o = (size_t)qi * k_out + pos, src = (size_t)qi * k_in + i;
+            const unsigned char* rec = gathered + (size_t)l * L.bytes;
+            keys_out[o] = key;
+            if (values_out) values_out[o] = __uint_as_float(ld_vol_u32(rec + L.off_values + 4 * src));
+            if (rows_out) rows_out[o] = ((u64)l << 32) | ld_vol_u32(rec + L.off_rows + 4 * src);
+        }
+        if (blockIdx.x == 0) {
+            for (uint32_t i = kept + threadIdx.x; i < k_out; i += blockDim.x) {
+                const size_t o = (size_t)qi * k_out + i;
+                keys_out[o] = kKeyMax;
+                if (values_out) values_out[o] = 0.0f;
+                if (rows_out) rows_out[o] = 0;
+            }
+            if (threadIdx.x == 0) counts_out[qi] = kept;
+        }
+    }
+}
+
 }  // namespace
 
 struct PeerExchange::Impl {
@@ -325,6 +406,15 @@ Status PeerExchange::exchange_merge(const void* d_record, const PeerRecord& rec,
         return wait_merge(rec, d_keys_out, d_values_out, d_rows_out, d_counts_out, stream);
     }
     ++epoch_;
+    if ((size_t)world_ * rec.k_in > 1024) {   // long lists: rank merge over a few CTAs instead of one CTA's sort
+        const size_t smem_r = (size_t)world_ * rec.k_in * sizeof(u64);
+        VB_TRY(ensure_dynamic_smem_for(peer_exchange_rank_merge_kernel, smem_r));
+        peer_exchange_rank_merge_kernel<<<kRankCtas, kRankThreads, smem_r, stream>>>(
+            impl_->pp, static_cast<const unsigned char*>(d_record), to_layout(rec), (uint32_t)world_, (uint32_t)rank_, epoch_,
+            d_keys_out, d_values_out, d_rows_out, d_counts_out, impl_->d_ticket, impl_->d_ticket + 1);
+        VB_CUDA(cudaGetLastError());
+        return Status::Ok();
+    }
     const uint32_t cap = merge_cap(rec);
     const size_t smem = (size_t)cap * 16;
     VB_TRY(ensure_dynamic_smem_for(peer_exchange_merge_kernel, smem));

@@ -281,6 +281,17 @@ def binary_top_k(vectors: Sequence[tuple], query: Sequence[int], dimensions: int
     return _err() if rc else ("ok", _take_hits(h))
 
 
+def result_values(metric_code: int, raws, score_mode: str = "raw"):
+    """Additive: ``Distance.result_values/3`` (vettore_distance.ex:525-543) over a whole hit list in one C call.
+    Returns ``("ok", [(score, distance)])``."""
+    r = _f32(raws)
+    score, dist = np.zeros(r.size, np.float64), np.zeros(r.size, np.float64)
+    _f64p = C.POINTER(C.c_double)
+    rc = lib().vb_result_values(int(metric_code), {"raw": 0, "similarity": 1}[score_mode], _ptr(r, _f32p), r.size,
+                                _ptr(score, _f64p), _ptr(dist, _f64p))
+    return _err() if rc else ("ok", list(zip(score.tolist(), dist.tolist())))
+
+
 def compress_sign_bits(vector) -> list[int]:
     """nifs.rs:125-129: bare list of u64 words."""
     v = _f32(vector)

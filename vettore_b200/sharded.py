@@ -314,20 +314,34 @@ class ShardedMv:
         self.out = torch.zeros(self.k * 20 + 64, dtype=torch.uint8, device=self.device)
         self.exchange = Exchange(self.lay, 1, self.k, self.k, group, self.device)
         self.exchange_name = self.exchange.name
+        self._t = [0.0, 0.0, 0]   # seconds in the local scan call / in exchange + read-back, calls
+
+    def phase_ms(self) -> dict:
+        """Mean host-clock milliseconds per search spent in the local scan call and in exchange + D2H."""
+        n = max(1, self._t[2])
+        return {"local_scan_call": 1e3 * self._t[0] / n, "exchange_and_readback": 1e3 * self._t[1] / n, "calls": self._t[2]}
 
     def search(self, query_tokens: np.ndarray) -> list[ShardHit]:
         """``query_tokens``: host ``[tq, dim]`` float32 (the reference API takes the query by value)."""
+        import time as _time
         lay = self.lay
         p = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+        t0 = _time.perf_counter()
         res = nifs.mv_search_packed_device(self.index, query_tokens, self.k, p(self.local, lay["keys"]),
                                            p(self.local, lay["values"]), p(self.local, lay["rows"]),
                                            p(self.local, lay["counts"]))
         if res[0] != "ok":
             raise RuntimeError(res[1])
         torch.cuda.synchronize(self.device)   # the library scored on its own stream
+        t1 = _time.perf_counter()
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         offs = self.exchange.run(self.local, self.out, stream)
-        return _decode_merged(self.out.cpu().numpy(), offs, self.k)
+        host = self.out.cpu().numpy()
+        t2 = _time.perf_counter()
+        self._t[0] += t1 - t0
+        self._t[1] += t2 - t1
+        self._t[2] += 1
+        return _decode_merged(host, offs, self.k)
 
 
 def set_global_mv_ranks(index: "nifs.MvRef", base: int, docs: int) -> None:
