@@ -59,7 +59,7 @@ int enif_get_resource(ErlNifEnv* e, ERL_NIF_TERM t, ErlNifResourceType* type, vo
     if (h->type != type) return 0;
     *objp = T(t)->obj; return 1;
 }
-ERL_NIF_TERM enif_make_atom(ErlNifEnv* e, const char* name) { (void)e; ERL_NIF_TERM t = mk(T_ATOM); T(t)->s = strdup(name); T(t)->len = strlen(name); return t; }
+ERL_NIF_TERM enif_make_atom(ErlNifEnv* e, const char* name) { (void)e; ERL_NIF_TERM t = mk(T_ATOM); T(t)->len = strlen(name); T(t)->s = (char*)malloc(T(t)->len + 1); memcpy(T(t)->s, name, T(t)->len + 1); return t; }
 ERL_NIF_TERM enif_make_double(ErlNifEnv* e, double d) { (void)e; ERL_NIF_TERM t = mk(T_DOUBLE); T(t)->d = d; return t; }
 ERL_NIF_TERM enif_make_uint64(ErlNifEnv* e, ErlNifUInt64 i) { (void)e; ERL_NIF_TERM t = mk(T_INT); T(t)->u = i; return t; }
 static ERL_NIF_TERM make_tuple_v(unsigned cnt, va_list ap) {
