@@ -73,6 +73,16 @@ void vb_hits_free(vb_hits* h);
 /* ---- resident flat index: Nifs.flat_* ------------------------------------------ */
 /* flat_new_<metric>/0, nifs.rs:200-257. The index lives on the current CUDA device. */
 int vb_flat_new(int metric_code, vb_flat** out);
+/* Additive: the same index spread over several GPUs INSIDE ONE PROCESS (the reference surface is one BEAM
+ * process holding one FlatResource, nifs.rs:297-309 — an erl_nif caller cannot fork a process per GPU).
+ * Shard s lives on CUDA device devices[s] (devices == NULL: s % device_count, so several shards may share
+ * a device); an id is owned by shard fnv1a(id) % n_shards. Each shard has its own host thread and stream;
+ * vb_flat_search / _search_batch run the fused scan + top-k on every GPU concurrently and merge the
+ * n_shards sorted lists on the calling thread by (rank.total_cmp, id bytes) — flat.rs:34-40 exactly.
+ * The returned handle works with vb_flat_insert / _insert_many / _reserve / _delete / _search /
+ * _search_batch / _info / _free; the resident pipelines and the device-level entries below answer
+ * VB_ERR_CUDA "not available on a sharded (multi-GPU) index handle". vb_hits_index = shard << 32 | row. */
+int vb_flat_new_sharded(int metric_code, int n_shards, const int* devices, vb_flat** out);
 /* Resource destructor (BEAM GC of the last reference). Frees the HBM matrix. */
 void vb_flat_free(vb_flat* index);
 /* flat_insert/3, nifs.rs:259-271 -> FlatIndex::insert, flat.rs:59-66. */

@@ -1,0 +1,141 @@
+"""The multi-GPU flat index INSIDE ONE PROCESS (vb_flat_new_sharded): the reference surface is one BEAM process
+holding one FlatResource (flat.rs:131-134, nifs.rs:297-309), so the G-GPU path must answer the ordinary
+flat_insert / flat_search calls exactly like the single-GPU index and the oracle. Shards land on device
+s % device_count: 8 shards share the one GPU of a single-GPU box and spread over the GPUs of a bigger one."""
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import METRICS, assert_hits_match
+from test_golden_fixtures import KNOWN, _run_case
+from vettore_b200 import _lib, nifs
+
+pytestmark = pytest.mark.gpu
+
+
+def _rows(n, d, seed, ints=False):
+    rng = np.random.default_rng(seed)
+    if ints:
+        return rng.integers(-2, 3, size=(n, d)).astype(np.float32)
+    return rng.standard_normal((n, d)).astype(np.float32)
+
+
+class _ShardedFlat:
+    shards = 8
+
+    def __init__(self, metric):
+        self.idx = nifs.flat_new_sharded(metric, self.shards)
+    def insert(self, i, v): return nifs.flat_insert(self.idx, i, v)
+    def insert_many(self, items): return nifs.flat_insert_many(self.idx, items)
+    def delete(self, i): return nifs.flat_delete(self.idx, i)
+    def search(self, q, k): return nifs.flat_search(self.idx, q, k)
+
+
+@pytest.mark.parametrize("case", [c for c in KNOWN if c["fn"] == "flat_script"], ids=lambda c: c["source"].split(" ")[0])
+def test_reference_flat_known_answers_through_a_sharded_handle(case):
+    """flat.rs:165-180, 208-249, 252-281 and the hardening tests: same answers from 8 shards."""
+    _run_case(case, nifs, _ShardedFlat)
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("shards,n,d,k,ints", [(2, 5000, 96, 10, False), (8, 4000, 64, 100, True), (3, 700, 33, 1000, False)])
+def test_sharded_search_equals_oracle_and_single_index(metric, shards, n, d, k, ints):
+    rows = _rows(n, d, n + d, ints)
+    if metric in ("cosine",) and not ints:
+        rows = (rows / np.linalg.norm(rows.astype(np.float64), axis=1, keepdims=True)).astype(np.float32)
+    ids = [f"{(i * 7919) % n:06d}" for i in range(n)]
+    q = _rows(1, d, 3, ints)[0]
+    sh = nifs.flat_new_sharded(metric, shards)
+    assert nifs.flat_reserve(sh, n) == ("ok", ())
+    assert nifs.flat_insert_matrix(sh, ids, rows) == ("ok", ())
+    assert nifs.flat_info(sh) == (n, d)
+    st, got = nifs.flat_search(sh, q, k)
+    assert st == "ok", got
+    st, exp = oracle.flat_search_dense(metric, rows, ids, q, k)
+    assert st == "ok"
+    assert_hits_match(got, exp, exact_ids=ints)
+    one = getattr(nifs, f"flat_new_{metric}")()
+    assert nifs.flat_insert_matrix(one, ids, rows) == ("ok", ())
+    assert nifs.flat_search(one, q, k) == ("ok", got)     # bit-identical to the single-GPU index
+
+
+def test_sharded_mutations_batches_and_errors():
+    n, d, k = 3000, 128, 10
+    rows = _rows(n, d, 11)
+    ids = [f"id-{i:05d}" for i in range(n)]
+    sh = nifs.flat_new_sharded("l2", 4)
+    assert nifs.flat_search(sh, [1.0, 2.0], 5) == ("ok", [])                      # empty index: any finite query
+    assert nifs.flat_insert_many(sh, [("a", [1.0, 2.0]), ("b", [1.0])]) == ("error", "dimension mismatch")
+    assert nifs.flat_info(sh) == (0, None)                                         # all-or-nothing across shards
+    assert nifs.flat_insert_many(sh, [("a", [1.0, float("inf")])]) == ("error", "vector contains a non-finite value")
+    assert nifs.flat_insert_matrix(sh, ids, rows) == ("ok", ())
+    assert nifs.flat_insert(sh, "x", [1.0]) == ("error", "dimension mismatch")
+    assert nifs.flat_search(sh, np.zeros(d + 1), 3) == ("error", "dimension mismatch")
+    assert nifs.flat_search(sh, [], 3) == ("error", "vector must not be empty")
+    assert nifs.flat_search(sh, np.zeros(d + 1), 0) == ("ok", [])                  # flat.rs:97-99
+    # upsert moves a row to the query; delete removes the runner-up
+    q = _rows(1, d, 5)[0]
+    assert nifs.flat_insert(sh, ids[77], q) == ("ok", ())
+    rows2 = rows.copy()
+    rows2[77] = q
+    st, got = nifs.flat_search(sh, q, k)
+    assert st == "ok" and got[0] == (ids[77], 0.0)
+    assert nifs.flat_delete(sh, got[1][0]) == ("ok", ())
+    gone = ids.index(got[1][0])
+    keep = [i for i in range(n) if i != gone]
+    st, got = nifs.flat_search(sh, q, k)
+    assert_hits_match(got, oracle.flat_search_dense("l2", rows2[keep], [ids[i] for i in keep], q, k)[1])
+    assert nifs.flat_info(sh) == (n - 1, d)
+    # a batch of queries (K2 is not eligible for l2: per-query K1 on every shard) and an inner-product batch (K2)
+    qs = _rows(40, d, 9)
+    st, res = nifs.flat_search_batch(sh, qs, k)
+    assert st == "ok"
+    for i in range(40):
+        assert_hits_match(res[i], oracle.flat_search_dense("l2", rows2[keep], [ids[j] for j in keep], qs[i], k)[1])
+    ip = nifs.flat_new_sharded("inner_product", 4)
+    assert nifs.flat_insert_matrix(ip, ids, rows) == ("ok", ())
+    st, res = nifs.flat_search_batch(ip, qs, k)
+    assert st == "ok"
+    for i in range(0, 40, 5):
+        assert_hits_match(res[i], oracle.flat_search_dense("inner_product", rows, ids, qs[i], k)[1])
+    # delete everything: the dimension resets to None (flat.rs:90-92)
+    small = nifs.flat_new_sharded("cosine", 3)
+    assert nifs.flat_insert_many(small, [("a", [1.0, 0.0]), ("b", [0.0, 1.0])]) == ("ok", ())
+    assert nifs.flat_delete(small, "a") == ("ok", ()) and nifs.flat_delete(small, "b") == ("ok", ())
+    assert nifs.flat_info(small) == (0, None)
+    assert nifs.flat_insert(small, "c", [1.0, 2.0, 3.0]) == ("ok", ())
+    # entries that need a single device answer loudly
+    assert nifs.flat_quantized_search(sh, q, 0, 10, 5)[0] == "error"
+    assert "sharded" in nifs.flat_quantized_search(sh, q, 0, 10, 5)[1]
+
+
+def test_eight_shards_driven_by_concurrent_callers():
+    n, d, k = 8000, 256, 10
+    rows = _rows(n, d, 21)
+    rows = (rows / np.linalg.norm(rows.astype(np.float64), axis=1, keepdims=True)).astype(np.float32)
+    ids = [f"{i:06d}" for i in range(n)]
+    sh = nifs.flat_new_sharded("cosine", 8)
+    assert nifs.flat_insert_matrix(sh, ids, rows) == ("ok", ())
+    qs = _rows(8, d, 22)
+    ref = [oracle.flat_search_dense("cosine", rows, ids, qs[i], k)[1] for i in range(8)]
+    errors = []
+
+    def caller(t):
+        try:
+            for _ in range(40):
+                st, hits = nifs.flat_search(sh, qs[t], k)
+                assert st == "ok"
+                assert_hits_match(hits, ref[t])
+        except Exception as e:   # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=caller, args=(t,)) for t in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]

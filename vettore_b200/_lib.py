@@ -28,6 +28,7 @@ SIGNATURES = {
     "vb_hits_export": (_sz, [_vp, C.POINTER(C.c_void_p), C.POINTER(_u64p), C.POINTER(_f32p), C.POINTER(_u64p)]),
     "vb_hits_free": (None, [_vp]),
     "vb_flat_new": (C.c_int, [C.c_int, _vpp]),
+    "vb_flat_new_sharded": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), _vpp]),
     "vb_flat_free": (None, [_vp]),
     "vb_flat_insert": (C.c_int, [_vp, C.c_char_p, _sz, _f32p, _sz]),
     "vb_flat_insert_many": (C.c_int, [_vp, _sz, C.c_char_p, _u64p, _f32p, _u64p]),

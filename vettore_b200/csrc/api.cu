@@ -12,6 +12,7 @@
 #include "runtime.h"
 #include "scan_driver.h"
 #include "select.h"
+#include "sharded_index.h"
 
 namespace {
 
@@ -98,39 +99,64 @@ int vb_flat_new(int metric_code, vb_flat** out) {
     if (vb_device_count() <= 0) return no_device();
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return no_device();
-    *out = new vb_flat{new vb::FlatIndex(metric_code, dev)};
+    *out = new vb_flat{new vb::FlatIndex(metric_code, dev), nullptr};
+    return VB_OK;
+}
+
+int vb_flat_new_sharded(int metric_code, int n_shards, const int* devices, vb_flat** out) {
+    *out = nullptr;
+    if (metric_code < 0 || metric_code > 8) return finish(vb::Status::Ref("unknown metric"));
+    const int ndev = vb_device_count();
+    if (ndev <= 0) return no_device();
+    if (n_shards < 1 || n_shards > 64) return finish(vb::Status::Cuda("sharded index: shard count must be in 1..64"));
+    std::vector<int> devs((size_t)n_shards);
+    for (int s = 0; s < n_shards; ++s) {
+        devs[s] = devices ? devices[s] : s % ndev;
+        if (devs[s] < 0 || devs[s] >= ndev) return finish(vb::Status::Cuda("sharded index: no such CUDA device"));
+    }
+    *out = new vb_flat{nullptr, new vb::ShardedFlatIndex(metric_code, devs)};
     return VB_OK;
 }
 
 void vb_flat_free(vb_flat* index) {
     if (!index) return;
     delete index->impl;
+    delete index->sharded;
     delete index;
 }
 
+#define VB_SINGLE_GPU_ONLY(index)                                                                          \
+    if (!(index)->impl) return finish(vb::Status::Cuda("not available on a sharded (multi-GPU) index handle"))
+
 int vb_flat_insert(vb_flat* index, const char* id, size_t id_len, const float* vector, size_t len) {
     const uint64_t id_off[2] = {0, id_len}, val_off[2] = {0, len};
+    if (index->sharded) return finish(index->sharded->insert_many(1, id, id_off, vector, val_off));
     return finish(index->impl->insert_many(1, id, id_off, vector, val_off, true));
 }
 
 int vb_flat_insert_many(vb_flat* index, size_t n, const char* ids, const uint64_t* id_off, const float* values,
                         const uint64_t* value_off) {
+    if (index->sharded) return finish(index->sharded->insert_many(n, ids, id_off, values, value_off));
     return finish(index->impl->insert_many(n, ids, id_off, values, value_off, false));
 }
 
-int vb_flat_reserve(vb_flat* index, size_t rows) { return finish(index->impl->reserve(rows)); }
+int vb_flat_reserve(vb_flat* index, size_t rows) {
+    return finish(index->sharded ? index->sharded->reserve(rows) : index->impl->reserve(rows));
+}
 int vb_flat_insert_many_device(vb_flat* index, size_t n, const char* ids, const uint64_t* id_off,
                                const float* d_values, size_t dimension) {
+    VB_SINGLE_GPU_ONLY(index);
     return finish(index->impl->insert_many_device(n, ids, id_off, d_values, dimension));
 }
 int vb_flat_delete(vb_flat* index, const char* id, size_t id_len) {
-    return finish(index->impl->remove(id, id_len));
+    return finish(index->sharded ? index->sharded->remove(id, id_len) : index->impl->remove(id, id_len));
 }
 
 int vb_flat_search(vb_flat* index, const float* query, size_t len, size_t limit, vb_hits** out) {
     *out = nullptr;
     std::vector<vb::Hits> hits;
-    vb::Status s = index->impl->search(query, 1, len, limit, &hits);
+    vb::Status s = index->sharded ? index->sharded->search(query, 1, len, limit, &hits)
+                                  : index->impl->search(query, 1, len, limit, &hits);
     if (!s.ok()) return finish(s);
     *out = new vb_hits{std::move(hits[0])};
     return VB_OK;
@@ -140,14 +166,16 @@ int vb_flat_search_batch(vb_flat* index, const float* queries, size_t nq, size_t
                          vb_hits** out) {
     for (size_t q = 0; q < nq; ++q) out[q] = nullptr;
     std::vector<vb::Hits> hits;
-    vb::Status s = index->impl->search(queries, nq, len, limit, &hits);
+    vb::Status s = index->sharded ? index->sharded->search(queries, nq, len, limit, &hits)
+                                  : index->impl->search(queries, nq, len, limit, &hits);
     if (!s.ok()) return finish(s);
     for (size_t q = 0; q < nq; ++q) out[q] = new vb_hits{std::move(hits[q])};
     return VB_OK;
 }
 
 int vb_flat_info(vb_flat* index, size_t* rows, size_t* dimension) {
-    index->impl->info(rows, dimension);
+    if (index->sharded) index->sharded->info(rows, dimension);
+    else index->impl->info(rows, dimension);
     return VB_OK;
 }
 
@@ -155,6 +183,7 @@ int vb_flat_prefix_top_k(vb_flat* index, size_t n_ids, const char* ids, const ui
                          const float* query, size_t len, int metric_code, size_t dimensions, size_t limit,
                          vb_hits** out) {
     *out = nullptr;
+    VB_SINGLE_GPU_ONLY(index);
     vb::Hits hits;
     vb::Status s = index->impl->prefix_top_k(n_ids == SIZE_MAX, n_ids == SIZE_MAX ? 0 : n_ids, ids, id_off, query,
                                              len, metric_code, dimensions, limit, &hits);
@@ -166,6 +195,7 @@ int vb_flat_prefix_top_k(vb_flat* index, size_t n_ids, const char* ids, const ui
 int vb_flat_funnel_search(vb_flat* index, const float* query, size_t len, int metric_code, const size_t* stages,
                           size_t n_stages, size_t candidates, size_t limit, vb_hits** out) {
     *out = nullptr;
+    VB_SINGLE_GPU_ONLY(index);
     vb::Hits hits;
     vb::Status s = index->impl->funnel_search(query, len, metric_code, stages, n_stages, candidates, limit, &hits);
     if (!s.ok()) return finish(s);
@@ -176,6 +206,7 @@ int vb_flat_funnel_search(vb_flat* index, const float* query, size_t len, int me
 int vb_flat_quantized_search(vb_flat* index, const float* query, size_t len, int metric_code, size_t candidates,
                              size_t limit, vb_hits** out) {
     *out = nullptr;
+    VB_SINGLE_GPU_ONLY(index);
     vb::Hits hits;
     vb::Status s = index->impl->quantized_search(query, len, metric_code, candidates, limit, &hits);
     if (!s.ok()) return finish(s);
@@ -185,6 +216,7 @@ int vb_flat_quantized_search(vb_flat* index, const float* query, size_t len, int
 
 int vb_flat_search_device(vb_flat* index, const float* d_queries, size_t nq, size_t q_stride, size_t limit,
                           uint64_t* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, void* stream) {
+    VB_SINGLE_GPU_ONLY(index);
     return finish(index->impl->search_device(d_queries, nq, q_stride, limit,
                                              reinterpret_cast<vb::u64*>(d_keys), d_values, d_rows, d_counts,
                                              static_cast<cudaStream_t>(stream)));
@@ -192,6 +224,7 @@ int vb_flat_search_device(vb_flat* index, const float* d_queries, size_t nq, siz
 
 int vb_flat_hamming_device(vb_flat* index, const float* d_queries, size_t nq, size_t q_stride, size_t candidates,
                            uint64_t* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, void* stream) {
+    VB_SINGLE_GPU_ONLY(index);
     return finish(index->impl->hamming_device(d_queries, nq, q_stride, candidates, reinterpret_cast<vb::u64*>(d_keys),
                                               d_values, d_rows, d_counts, static_cast<cudaStream_t>(stream)));
 }
@@ -199,13 +232,18 @@ int vb_flat_rerank_owned_device(vb_flat* index, const float* d_query, size_t q_s
                                 const uint64_t* d_global_rows, const uint32_t* d_global_count, size_t max_candidates,
                                 uint32_t shard, size_t limit, uint64_t* d_keys, float* d_values, uint32_t* d_rows,
                                 uint32_t* d_counts, void* stream) {
+    VB_SINGLE_GPU_ONLY(index);
     return finish(index->impl->rerank_owned_device(d_query, q_stride, metric_code,
                                                    reinterpret_cast<const vb::u64*>(d_global_rows), d_global_count,
                                                    max_candidates, shard, limit, reinterpret_cast<vb::u64*>(d_keys),
                                                    d_values, d_rows, d_counts, static_cast<cudaStream_t>(stream)));
 }
-int vb_flat_device_status(vb_flat* index, uint32_t* status) { return finish(index->impl->device_status(status)); }
+int vb_flat_device_status(vb_flat* index, uint32_t* status) {
+    VB_SINGLE_GPU_ONLY(index);
+    return finish(index->impl->device_status(status));
+}
 int vb_flat_set_id_ranks(vb_flat* index, const uint32_t* ranks, size_t n) {
+    VB_SINGLE_GPU_ONLY(index);
     return finish(index->impl->set_id_ranks(ranks, n));
 }
 

@@ -115,6 +115,10 @@ class FlatIndex {
 
 }  // namespace vb
 
+namespace vb { class ShardedFlatIndex; }
+
+// The C ABI handle: a single-GPU index (impl) or a multi-GPU one in the same process (sharded).
 struct vb_flat {
     vb::FlatIndex* impl;
+    vb::ShardedFlatIndex* sharded;
 };

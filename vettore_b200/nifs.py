@@ -143,6 +143,17 @@ def _flat_new(metric: str) -> FlatRef:
     return FlatRef(h, metric)
 
 
+def flat_new_sharded(metric: str, n_shards: int, devices: Sequence[int] | None = None) -> FlatRef:
+    """Additive: one index over several GPUs in this process (vb_flat_new_sharded). The handle works with
+    flat_insert / flat_insert_many / flat_delete / flat_search / flat_search_batch like any other."""
+    h = C.c_void_p()
+    devs = (C.c_int * n_shards)(*devices) if devices is not None else None
+    rc = lib().vb_flat_new_sharded(METRIC_CODE[metric], int(n_shards), devs, C.byref(h))
+    if rc:
+        raise RuntimeError(_lib.last_error())
+    return FlatRef(h, metric)
+
+
 def flat_new_l2(): return _flat_new("l2")
 def flat_new_l2_squared(): return _flat_new("l2_squared")
 def flat_new_cosine(): return _flat_new("cosine")
