@@ -199,3 +199,42 @@ def test_collection_default_candidates_with_limit_200():
     assert_hits_match([(r.id, r.score) for r in got], ref_quantized(vectors, qn, 2, 2000, 200))
     got = ok(c.funnel_search(q, limit=200, stages=[32]))
     assert_hits_match([(r.id, r.score) for r in got], ref_funnel(vectors, qn, 2, [32], 2000, 200))
+
+
+@pytest.mark.parametrize("metric,stages", [("cosine", [64, 128]), ("l2", [50]), ("inner_product", [128])])
+def test_funnel_stage_one_over_the_dense_prefix_mirror(metric, stages):
+    """Enough rows for the dense mirror of the first-stage columns (flat_index.h: prefix_wanted): same answers as
+    the reference composition, before and after inserts, an in-place upsert and deletes touch the mirror."""
+    n, d, cand, limit = 40_000, 256, 300, 10
+    rows = _rows(n, d, 1234)
+    if metric == "cosine":
+        rows = (rows / np.linalg.norm(rows.astype(np.float64), axis=1, keepdims=True)).astype(np.float32)
+    ids = [f"{(i * 104729) % n:06d}" for i in range(n)]
+    q = normalize_l2(_rows(1, d, 8)[0])
+    idx = getattr(nifs, f"flat_new_{metric}")()
+    ok(nifs.flat_insert_matrix(idx, ids, rows))
+    code = nifs.METRIC_CODE[metric]
+    vectors = {ids[i]: rows[i] for i in range(n)}
+    got = ok(nifs.flat_funnel_search(idx, q, code, stages, cand, limit))
+    assert_hits_match(got, ref_funnel(list(vectors.items()), q, code, stages, cand, limit))
+    # the mirror now exists: mutate through every path that must keep it in sync
+    best = got[0][0]
+    ok(nifs.flat_delete(idx, best))                                   # hole filled by the last row
+    del vectors[best]
+    up = got[1][0]
+    newv = normalize_l2(_rows(1, d, 99)[0])
+    ok(nifs.flat_insert(idx, up, newv))                               # in-place upsert
+    vectors[up] = newv
+    extra = _rows(50, d, 77)
+    extra[0, :stages[0]] = q[:stages[0]] * 3.0                        # a strong first-stage candidate among the appended rows
+    if metric == "cosine":
+        extra = (extra / np.linalg.norm(extra.astype(np.float64), axis=1, keepdims=True)).astype(np.float32)
+    ok(nifs.flat_insert_many(idx, [(f"new-{i:02d}", extra[i]) for i in range(50)]))
+    for i in range(50):
+        vectors[f"new-{i:02d}"] = extra[i]
+    got = ok(nifs.flat_funnel_search(idx, q, code, stages, cand, limit))
+    assert_hits_match(got, ref_funnel(list(vectors.items()), q, code, stages, cand, limit))
+    # a different first stage rebuilds the mirror with the new width
+    other = [stages[0] // 2] + stages
+    got = ok(nifs.flat_funnel_search(idx, q, code, other, cand, limit))
+    assert_hits_match(got, ref_funnel(list(vectors.items()), q, code, other, cand, limit))

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 namespace vb {
@@ -43,6 +44,7 @@ FlatIndex::~FlatIndex() {
     if (d_rows_) cudaFree(d_rows_);
     if (d_rank_) cudaFree(d_rank_);
     if (d_codes_) cudaFree(d_codes_);
+    if (d_prefix_) cudaFree(d_prefix_);
     if (d_status_) cudaFreeHost(d_status_);
 }
 
@@ -158,6 +160,13 @@ Status FlatIndex::grow(size_t need_rows) {
         cudaFree(d_codes_);
         d_codes_ = codes;
     }
+    if (d_prefix_) {
+        float* pre = nullptr;
+        VB_CUDA(cudaMalloc(&pre, new_cap * prefix_stride_ * sizeof(float)));
+        if (n_ > 0) VB_CUDA(cudaMemcpy(pre, d_prefix_, n_ * prefix_stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
+        cudaFree(d_prefix_);
+        d_prefix_ = pre;
+    }
     if (d_rows_) cudaFree(d_rows_);
     if (d_rank_) cudaFree(d_rank_);
     d_rows_ = rows;
@@ -179,11 +188,39 @@ Status FlatIndex::reserve(size_t rows) {
 }
 
 Status FlatIndex::pack_rows(size_t row0, size_t rows) {
-    if (!d_codes_ || rows == 0) return Status::Ok();
-    VB_TRY(sign_pack_device(d_rows_ + row0 * stride_, stride_, (uint32_t)rows, (uint32_t)dim_,
-                            d_codes_ + row0 * code_words_, nullptr));
+    if (rows == 0) return Status::Ok();
+    if (d_prefix_) {
+        float* dst = d_prefix_ + row0 * prefix_stride_;
+        if (prefix_stride_ != prefix_dims_) VB_CUDA(cudaMemset(dst, 0, rows * prefix_stride_ * sizeof(float)));
+        VB_CUDA(cudaMemcpy2D(dst, prefix_stride_ * sizeof(float), d_rows_ + row0 * stride_, stride_ * sizeof(float),
+                             prefix_dims_ * sizeof(float), rows, cudaMemcpyDeviceToDevice));
+    }
+    if (d_codes_)
+        VB_TRY(sign_pack_device(d_rows_ + row0 * stride_, stride_, (uint32_t)rows, (uint32_t)dim_,
+                                d_codes_ + row0 * code_words_, nullptr));
     VB_CUDA(cudaStreamSynchronize(nullptr));
     return Status::Ok();
+}
+
+bool FlatIndex::prefix_wanted(size_t dims) const {
+    // worth a mirror: a real prefix (at most half of the row, so the copy costs at most half the matrix again)
+    // over enough rows for the stage to be bandwidth- rather than latency-bound
+    return dims > 0 && 2 * dims <= dim_ && n_ >= 32768 && !std::getenv("VB_NO_PREFIX_MIRROR");
+}
+
+Status FlatIndex::ensure_prefix(size_t dims) {
+    if (d_prefix_ && prefix_dims_ == dims) return Status::Ok();
+    if (d_prefix_) { cudaFree(d_prefix_); d_prefix_ = nullptr; }
+    prefix_dims_ = dims;
+    prefix_stride_ = (dims + 3) & ~(size_t)3;
+    cudaError_t e = cudaMalloc(&d_prefix_, cap_ * prefix_stride_ * sizeof(float));
+    if (e != cudaSuccess) {   // no room for the mirror: the stage keeps reading the main matrix
+        cudaGetLastError();
+        d_prefix_ = nullptr;
+        prefix_dims_ = prefix_stride_ = 0;
+        return Status::Ok();
+    }
+    return pack_rows(0, n_);
 }
 
 Status FlatIndex::ensure_codes() {
@@ -391,10 +428,13 @@ void FlatIndex::reset_if_empty() {
     if (d_rows_) cudaFree(d_rows_);
     if (d_rank_) cudaFree(d_rank_);
     if (d_codes_) cudaFree(d_codes_);
+    if (d_prefix_) cudaFree(d_prefix_);
     d_rows_ = nullptr;
     d_rank_ = nullptr;
     d_codes_ = nullptr;
+    d_prefix_ = nullptr;
     code_words_ = 0;
+    prefix_dims_ = prefix_stride_ = 0;
     external_ranks_ = false;
     sorted_ = true;
     id_row_.clear();
@@ -418,6 +458,9 @@ Status FlatIndex::remove(const char* id, size_t id_len) {
         if (d_codes_)
             VB_CUDA(cudaMemcpy(d_codes_ + (size_t)row * code_words_, d_codes_ + (size_t)last * code_words_,
                                code_words_ * sizeof(u64), cudaMemcpyDeviceToDevice));
+        if (d_prefix_)
+            VB_CUDA(cudaMemcpy(d_prefix_ + (size_t)row * prefix_stride_, d_prefix_ + (size_t)last * prefix_stride_,
+                               prefix_stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
         row_id_[row] = std::move(row_id_[last]);
         h_rank_[row] = h_rank_[last];
         id_row_[row_id_[row]] = row;
@@ -577,6 +620,22 @@ Status FlatIndex::funnel_search(const float* query, size_t len, int metric_code,
         if (!all_finite(query, d)) return Status::Ref("vector contains a non-finite value");
     }
     std::shared_lock<std::shared_mutex> g(mu_);
+    // stage 1 scores a prefix of EVERY row: give it a dense mirror of those columns (built once, under the
+    // write lock, like the sign codes; re-checked after the read lock is back)
+    bool no_room = false;
+    while (!no_room && nstages > 0 && prefix_wanted(stages[0]) && !(d_prefix_ && prefix_dims_ == stages[0])) {
+        g.unlock();
+        {
+            std::unique_lock<std::shared_mutex> w(mu_);
+            if (prefix_wanted(stages[0]) && !(d_prefix_ && prefix_dims_ == stages[0])) {
+                VB_CUDA(cudaSetDevice(device_));
+                VB_TRY(ensure_prefix(stages[0]));
+                VB_TRY(finish_mutation());
+                no_room = d_prefix_ == nullptr;
+            }
+        }
+        g.lock();
+    }
     if (n_ == 0) return Status::Ok();
     for (size_t s = 0; s <= nstages; ++s)
         if ((s < nstages ? stages[s] : len) > dim_) return Status::Ref("dimension mismatch");
@@ -602,6 +661,13 @@ Status FlatIndex::funnel_search(const float* query, size_t len, int metric_code,
         job.dims = (uint32_t)stages[s];
         job.whole_rows = stages[s] == dim_;
         job.d_row_sel = s == 0 ? nullptr : ctx->row_sel.as<uint32_t>();
+        job.d_rows = d_rows_;
+        job.row_stride = stride_;
+        if (s == 0 && d_prefix_ && prefix_dims_ == stages[0]) {   // same row numbers, dense columns: a whole-row stream
+            job.d_rows = d_prefix_;
+            job.row_stride = prefix_stride_;
+            job.whole_rows = true;
+        }
         job.k = std::min(candidates, survivors);
         VB_TRY(run_scan_to_rows(*ctx.ctx, job, (uint32_t)s, nslots, h_err + s));
         survivors = job.k;
@@ -609,6 +675,8 @@ Status FlatIndex::funnel_search(const float* query, size_t len, int metric_code,
     job.n = (uint32_t)survivors;
     job.dims = (uint32_t)len;
     job.whole_rows = len == dim_;
+    job.d_rows = d_rows_;
+    job.row_stride = stride_;
     job.d_row_sel = nstages == 0 ? nullptr : ctx->row_sel.as<uint32_t>();
     job.k = std::max<size_t>(1, std::min(limit, survivors));
     ScanResult res;

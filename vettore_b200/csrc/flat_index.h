@@ -77,7 +77,12 @@ class FlatIndex {
   private:
     Status grow(size_t need_rows);
     Status ensure_codes();                       // builds the sign-code mirror on first use (K6)
-    Status pack_rows(size_t row0, size_t rows);  // (re)packs rows [row0, row0 + rows)
+    Status pack_rows(size_t row0, size_t rows);  // refreshes the mirrors (sign codes, dense prefix) of rows [row0, row0 + rows)
+    // Dense mirror of the first `dims` columns (funnel stage 1, search.rs:51-70 over every row): a row-major
+    // [cap, round4(dims)] matrix kept in sync like the sign codes, so the stage is a whole-row stream through
+    // the TMA ring instead of 4*dims-byte pieces at a 4*stride-byte pitch (DRAM page locality).
+    Status ensure_prefix(size_t dims);
+    bool prefix_wanted(size_t dims) const;
     Status relabel_all();
     Status assign_rank(std::map<std::string, uint32_t>::iterator it, uint32_t row, bool* relabel_needed);
     void reset_if_empty();
@@ -102,6 +107,8 @@ class FlatIndex {
     uint32_t* d_rank_ = nullptr;
     u64* d_codes_ = nullptr;   // [cap, code_words_] sign codes of the rows, kept in sync once built
     size_t code_words_ = 0;
+    float* d_prefix_ = nullptr;   // [cap, prefix_stride_] first prefix_dims_ columns of the rows, kept in sync once built
+    size_t prefix_dims_ = 0, prefix_stride_ = 0;
     std::vector<std::string> row_id_;
     std::vector<uint32_t> h_rank_;
     std::map<std::string, uint32_t> id_row_;   // general mode only (see sorted_)
