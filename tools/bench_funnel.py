@@ -17,18 +17,20 @@ ap.add_argument("--stages", default="64,256")
 ap.add_argument("--candidates", type=int, default=1000)
 ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--iters", type=int, default=50)
+ap.add_argument("--metric", default="cosine")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 stages = [int(x) for x in a.stages.split(",")]
-idx = nifs.flat_new_cosine()
+idx = getattr(nifs, f"flat_new_{a.metric}")()
 assert nifs.flat_reserve(idx, a.rows) == ("ok", ())
 for s in range(0, a.rows, 1_000_000):
     m = min(1_000_000, a.rows - s)
     blk = make_rows_torch(m, a.dim, SEED + s, dev)
     assert nifs.flat_insert_device(idx, [f"{i:09d}" for i in range(s, s + m)], blk.data_ptr(), a.dim) == ("ok", ())
 q = make_rows_torch(1, a.dim, SEED + 1, dev)[0].cpu().numpy()
-code = nifs.METRIC_CODE["cosine"]
-out = {"config": {"rows": a.rows, "dim": a.dim, "stages": stages, "candidates": a.candidates, "k": a.k}}
+code = nifs.METRIC_CODE[a.metric]
+out = {"config": {"rows": a.rows, "dim": a.dim, "stages": stages, "candidates": a.candidates, "k": a.k, "metric": a.metric,
+                  "prefix_mirror": not os.environ.get("VB_NO_PREFIX_MIRROR")}}
 def timed(fn):
     fn(); fn()
     t0 = time.perf_counter()
