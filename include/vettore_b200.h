@@ -268,6 +268,23 @@ int vb_mv_info(vb_mv* index, size_t* docs, size_t* tokens, size_t* dimension);
  * (index/flat.ex:72-91). "unknown metric" for codes outside 0..8. */
 int vb_result_values(int metric_code, int score_mode, const float* raw, size_t n, double* score, double* distance);
 
+/* Additive: muvera_encode_query/7 and muvera_encode_document/7 (nifs.rs:430-476 ->
+ * muvera::encode, muvera.rs:26-74), batched over documents on the device. Document i owns the vectors
+ * [doc_vec[i], doc_vec[i+1]) of the ragged list (vals, vec_off[nvec + 1] in elements); ndocs = 1 is exactly one
+ * reference NIF call. has_final / final_projection_dimension spell Option<usize>; mode 0 = query (sum per SimHash
+ * partition), 1 = document (running average, rounded to f32 after every vector like the reference). out: host
+ * buffer of out_capacity floats receiving [ndocs][*fde_dimension]; out == NULL validates the input the way
+ * the reference does and only reports *fde_dimension (so a binding can size its buffer). The device keeps the reference's
+ * accumulation orders, so the encoding is bit-identical to the reference arithmetic. Errors are the
+ * reference's strings: "empty vectors", "dimension must be positive", "num_repetitions must be positive",
+ * "num_simhash_projections must be < 31", "projection_dimension must be positive",
+ * "final_projection_dimension must be positive", "dimension mismatch", "vector contains a non-finite value",
+ * "fde dimension overflow", "fde dimension exceeds safety limit", "encoding overflow". */
+int vb_muvera_encode(size_t ndocs, const float* vals, const uint64_t* vec_off, const uint64_t* doc_vec, size_t dimension,
+                     size_t num_repetitions, size_t num_simhash_projections, uint64_t seed, size_t projection_dimension,
+                     int has_final, size_t final_projection_dimension, int mode, float* out, size_t out_capacity,
+                     size_t* fde_dimension);
+
 /* compress_sign_bits/1, nifs.rs:125-129 -> distances.rs:413-423. words[ceil(len/64)]. */
 int vb_compress_sign_bits(const float* vector, size_t len, uint64_t* words);
 

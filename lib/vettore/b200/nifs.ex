@@ -68,6 +68,14 @@ defmodule Vettore.B200.Nifs do
   @spec flat_search(reference(), [float()], pos_integer()) :: {:ok, [{String.t(), float()}]} | {:error, String.t()}
   def flat_search(_index, _query, _limit), do: :erlang.nif_error(:nif_not_loaded)
 
+  @spec muvera_encode_query([[float()]], pos_integer(), pos_integer(), non_neg_integer(), non_neg_integer(), pos_integer(), pos_integer() | nil) ::
+          {:ok, [float()]} | {:error, String.t()}
+  def muvera_encode_query(_vectors, _dimension, _num_repetitions, _num_simhash_projections, _seed, _projection_dimension, _final_projection_dimension), do: :erlang.nif_error(:nif_not_loaded)
+
+  @spec muvera_encode_document([[float()]], pos_integer(), pos_integer(), non_neg_integer(), non_neg_integer(), pos_integer(), pos_integer() | nil) ::
+          {:ok, [float()]} | {:error, String.t()}
+  def muvera_encode_document(_vectors, _dimension, _num_repetitions, _num_simhash_projections, _seed, _projection_dimension, _final_projection_dimension), do: :erlang.nif_error(:nif_not_loaded)
+
   # ---- additive: resident pipelines (no counterpart in Vettore.Nifs) -------------------------------
   # Capacity hint before a snapshot is streamed in (Collection.rebuild_index).
   @spec flat_reserve(reference(), non_neg_integer()) :: {:ok, {}} | {:error, String.t()}

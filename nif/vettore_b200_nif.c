@@ -13,7 +13,7 @@
  * (schedule = "DirtyCpu"); Result<T, String> -> {:ok, T} | {:error, binary}; Result<(), String> -> {:ok, {}};
  * flat_new_* return the bare resource; floats arrive as f64 (integers are accepted like Rustler's f32
  * decoder accepts them) and are narrowed to f32; u64 words may be bignums; mistyped terms -> badarg.
- * HNSW / MUVERA / the pairwise helpers stay in the Rust library behind `Vettore.Nifs`.
+ * HNSW and the pairwise helpers stay in the Rust library behind `Vettore.Nifs`.
  */
 #include <erl_nif.h>
 #include <stdlib.h>
@@ -456,6 +456,38 @@ static ERL_NIF_TERM mv_search(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[
     return hits_result(env, rc, hits);
 }
 
+/* muvera_encode_query/7 and muvera_encode_document/7 (lib/vettore_nifs.ex:219-258; nifs.rs:430-476): vectors,
+ * dimension, num_repetitions, num_simhash_projections, seed, projection_dimension, final_projection_dimension
+ * (an integer or nil = Option<usize>) -> {:ok, [float]}. One multi-vector per call like the reference; the C
+ * entry itself is batched over documents (vb_muvera_encode). */
+static ERL_NIF_TERM muvera_encode(ErlNifEnv* env, const ERL_NIF_TERM argv[], int mode) {
+    vecs v; size_t dim, reps, ks, pdim, fin = 0; ErlNifUInt64 seed; int has_final = 1; char atom[8];
+    if (!get_size(env, argv[1], &dim) || !get_size(env, argv[2], &reps) || !get_size(env, argv[3], &ks) ||
+        !enif_get_uint64(env, argv[4], &seed) || !get_size(env, argv[5], &pdim)) return enif_make_badarg(env);
+    if (!get_size(env, argv[6], &fin)) {
+        if (!enif_get_atom(env, argv[6], atom, sizeof(atom), ERL_NIF_LATIN1) || strcmp(atom, "nil") != 0) return enif_make_badarg(env);
+        has_final = 0;
+    }
+    if (!decode_vectors(env, argv[0], &v)) return enif_make_badarg(env);
+    /* the output size is known only after validation: out == NULL validates and sizes without computing */
+    size_t fde = 0;
+    const uint64_t doc_vec[2] = {0, v.n};
+    int rc = vb_muvera_encode(1, v_vals(&v), v.off.v, doc_vec, dim, reps, ks, (uint64_t)seed, pdim, has_final, fin, mode, NULL, 0, &fde);
+    float* out = NULL;
+    if (rc == VB_OK) {
+        out = (float*)malloc((fde ? fde : 1) * sizeof(float));
+        rc = vb_muvera_encode(1, v_vals(&v), v.off.v, doc_vec, dim, reps, ks, (uint64_t)seed, pdim, has_final, fin, mode, out, fde, &fde);
+    }
+    vecs_free(&v);
+    if (rc != VB_OK) { free(out); return mk_error(env); }
+    ERL_NIF_TERM list = enif_make_list(env, 0);
+    for (size_t i = fde; i-- > 0;) list = enif_make_list_cell(env, enif_make_double(env, out[i]), list);
+    free(out);
+    return mk_ok(env, list);
+}
+static ERL_NIF_TERM muvera_encode_query(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) { (void)argc; return muvera_encode(env, argv, 0); }
+static ERL_NIF_TERM muvera_encode_document(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) { (void)argc; return muvera_encode(env, argv, 1); }
+
 static int load(ErlNifEnv* env, void** priv, ERL_NIF_TERM info) {
     (void)priv; (void)info;
     FLAT_TYPE = enif_open_resource_type(env, NULL, "vettore_b200_flat", flat_dtor, ERL_NIF_RT_CREATE, NULL);
@@ -484,6 +516,8 @@ static ErlNifFunc nif_funcs[] = {
     {"flat_insert_many", 2, flat_insert_many, DIRTY},
     {"flat_delete", 2, flat_delete, DIRTY},
     {"flat_search", 3, flat_search, DIRTY},
+    {"muvera_encode_query", 7, muvera_encode_query, DIRTY},
+    {"muvera_encode_document", 7, muvera_encode_document, DIRTY},
     /* additive */
     {"flat_reserve", 2, flat_reserve, DIRTY},
     {"flat_search_shaped", 5, flat_search_shaped, DIRTY},

@@ -352,3 +352,21 @@ def maxsim_scan_timed(metric: str | int, tokens: np.ndarray, queries: np.ndarray
     if secs < 0:
         raise RuntimeError("oracle MaxSim scan failed: " + _err()[1])
     return secs, [[(int(oi[q * cap + i]), float(orr[q * cap + i])) for i in range(cap)] for q in range(nq)]
+
+
+def muvera_encode(vectors, dimension: int, num_repetitions: int, num_simhash_projections: int, seed: int,
+                  projection_dimension: int, final_projection_dimension: int | None, mode: str):
+    """muvera.rs:26-74 (nifs.rs:430-476: muvera_encode_query / muvera_encode_document). ``mode`` is "query" (sum per
+    partition) or "document" (running average). Returns ("ok", [float]) or ("error", msg)."""
+    vals, off = _ragged_f32(vectors)
+    part = 1 << min(int(num_simhash_projections), 40)
+    cap = int(final_projection_dimension) if final_projection_dimension else min(int(num_repetitions) * part *
+                                                                                max(1, int(projection_dimension)), 16777216)
+    out = np.zeros(max(1, cap), np.float32)
+    n = C.c_size_t()
+    rc = lib().vo_muvera_encode(_p(vals, C.c_float), _p(off, C.c_uint64), C.c_size_t(len(off) - 1), C.c_size_t(dimension),
+                                C.c_size_t(num_repetitions), C.c_size_t(num_simhash_projections), C.c_uint64(seed),
+                                C.c_size_t(projection_dimension), C.c_int(final_projection_dimension is not None),
+                                C.c_size_t(final_projection_dimension or 0), C.c_int({"query": 0, "document": 1}[mode]),
+                                _p(out, C.c_float), C.c_size_t(out.size), C.byref(n))
+    return _err() if rc else ("ok", out[: n.value].tolist())

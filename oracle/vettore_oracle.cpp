@@ -697,3 +697,117 @@ double vo_maxsim_scan_timed(const float* tokens, size_t ndocs, size_t td, size_t
 }
 
 }  // extern "C"
+
+// ---- MUVERA fixed-dimensional encoding: muvera.rs:26-74 and its helpers -------------
+namespace {
+// muvera.rs:215-221
+inline uint64_t mv_rotl(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+inline uint64_t mv_hash4(uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    uint64_t x = a ^ mv_rotl(b, 17) ^ mv_rotl(c, 31) ^ mv_rotl(d, 47);
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// muvera.rs:199-203: (hash as f64 / u64::MAX as f64) as f32, then * 2 - 1 in f32
+inline float mv_random_weight(uint64_t seed, uint64_t rep, uint64_t proj, uint64_t dim) {
+    const uint64_t h = mv_hash4(seed, rep, proj, dim);
+    const float unit = static_cast<float>(static_cast<double>(h) / static_cast<double>(UINT64_MAX));
+    return unit * 2.0f - 1.0f;
+}
+// muvera.rs:206-212
+inline float mv_random_sign(uint64_t seed, uint64_t rep, uint64_t proj, uint64_t dim) {
+    return (mv_hash4(seed, rep, proj, dim) & 1) == 0 ? 1.0f : -1.0f;
+}
+// muvera.rs:163-176
+inline int mv_accumulate(float* slot, double value, int mode, size_t count) {
+    const double current = static_cast<double>(*slot);
+    const double next = mode == 0 ? current + value : current + (value - current) / static_cast<double>(count);
+    if (std::isfinite(next) && next >= -static_cast<double>(std::numeric_limits<float>::max()) &&
+        next <= static_cast<double>(std::numeric_limits<float>::max())) {
+        *slot = static_cast<float>(next);
+        return 0;
+    }
+    return fail("encoding overflow");
+}
+}  // namespace
+
+extern "C" {
+
+// muvera.rs:26-74 (encode) incl. validate (:77-108) and count_sketch (:179-196). `vectors` is a ragged list
+// (vals, off[nvec + 1]); has_final = final_projection_dimension is Some(final_dim); mode 0 = Query (sum),
+// 1 = Document (running average). Writes *out_len floats to out (capacity out_cap).
+int vo_muvera_encode(const float* vals, const uint64_t* off, size_t nvec, size_t dimension, size_t num_repetitions,
+                     size_t num_simhash, uint64_t seed, size_t projection_dimension, int has_final, size_t final_dim,
+                     int mode, float* out, size_t out_cap, size_t* out_len) {
+    *out_len = 0;
+    const size_t kMaxOut = 16777216;
+    if (nvec == 0) return fail("empty vectors");
+    if (dimension == 0) return fail("dimension must be positive");
+    if (num_repetitions == 0) return fail("num_repetitions must be positive");
+    if (num_simhash >= 31) return fail("num_simhash_projections must be < 31");
+    if (projection_dimension == 0) return fail("projection_dimension must be positive");
+    if (has_final && final_dim == 0) return fail("final_projection_dimension must be positive");
+    for (size_t v = 0; v < nvec; ++v)
+        if (off[v + 1] - off[v] != dimension) return fail("dimension mismatch");
+    for (size_t v = 0; v < nvec; ++v)
+        if (!all_finite(vals + off[v], dimension)) return fail("vector contains a non-finite value");
+    const size_t partitions = static_cast<size_t>(1) << num_simhash;
+    size_t repetition_size, output_size, counts_size;
+    if (__builtin_mul_overflow(partitions, projection_dimension, &repetition_size)) return fail("fde dimension overflow");
+    if (__builtin_mul_overflow(num_repetitions, repetition_size, &output_size)) return fail("fde dimension overflow");
+    const size_t final_size = has_final ? final_dim : output_size;
+    if (output_size > kMaxOut || final_size > kMaxOut) return fail("fde dimension exceeds safety limit");
+    if (__builtin_mul_overflow(num_repetitions, partitions, &counts_size)) return fail("fde dimension overflow");
+    if (final_size > out_cap) return fail("output buffer too small");
+    std::vector<float> full(output_size, 0.0f);
+    std::vector<size_t> counts(counts_size, 0);
+    for (size_t rep = 0; rep < num_repetitions; ++rep) {
+        for (size_t v = 0; v < nvec; ++v) {
+            const float* vec = vals + off[v];
+            size_t partition = 0;                                             // muvera.rs:111-131
+            for (size_t proj = 0; proj < num_simhash; ++proj) {
+                double dot = 0.0;
+                for (size_t d = 0; d < dimension; ++d)
+                    dot += static_cast<double>(vec[d]) * static_cast<double>(mv_random_weight(seed, rep, proj, d));
+                partition = (partition << 1) + (dot >= 0.0 ? 1 : 0);
+            }
+            const size_t ci = rep * partitions + partition;
+            counts[ci] += 1;
+            const size_t base = rep * repetition_size + partition * projection_dimension;
+            if (projection_dimension == dimension) {                           // muvera.rs:142-147
+                for (size_t d = 0; d < dimension; ++d)
+                    if (mv_accumulate(&full[base + d], static_cast<double>(vec[d]), mode, counts[ci])) return 1;
+            } else {
+                for (size_t proj = 0; proj < projection_dimension; ++proj) {   // :149-160
+                    double value = 0.0;
+                    for (size_t d = 0; d < dimension; ++d)
+                        value += static_cast<double>(vec[d]) * static_cast<double>(mv_random_sign(seed + 17, rep, proj, d));
+                    if (mv_accumulate(&full[base + proj], value, mode, counts[ci])) return 1;
+                }
+            }
+        }
+    }
+    if (!has_final) {
+        std::memcpy(out, full.data(), output_size * sizeof(float));
+        *out_len = output_size;
+        return 0;
+    }
+    std::vector<float> fin(final_dim, 0.0f);                                    // muvera.rs:179-196
+    for (size_t i = 0; i < output_size; ++i) {
+        const size_t slot = static_cast<size_t>(mv_hash4(seed, 0x9E3779B97F4A7C15ull, i, 0)) % final_dim;
+        const float sign = (mv_hash4(seed, 0xD1B54A32D192ED03ull, i, slot) & 1) == 0 ? 1.0f : -1.0f;
+        const double next = static_cast<double>(fin[slot]) + static_cast<double>(sign * full[i]);
+        if (!std::isfinite(next) || next < -static_cast<double>(std::numeric_limits<float>::max()) ||
+            next > static_cast<double>(std::numeric_limits<float>::max()))
+            return fail("encoding overflow");
+        fin[slot] = static_cast<float>(next);
+    }
+    std::memcpy(out, fin.data(), final_dim * sizeof(float));
+    *out_len = final_dim;
+    return 0;
+}
+
+uint64_t vo_muvera_hash4(uint64_t a, uint64_t b, uint64_t c, uint64_t d) { return mv_hash4(a, b, c, d); }
+
+}  // extern "C"

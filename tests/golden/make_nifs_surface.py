@@ -22,7 +22,7 @@ for m in re.finditer(r"^\s*def\s+([a-z_0-9]+)\(\s*\n(.*?)\)\s*,?\s*\n?\s*do:", s
     arity = len([a for a in m.group(2).split(",") if a.strip()])
     if [name, arity] not in surface:
         surface.append([name, arity])
-scan_prefixes = ("flat_", "vector_top_k", "binary_top_k", "multi_vector_", "compress_sign_bits")
+scan_prefixes = ("flat_", "vector_top_k", "binary_top_k", "multi_vector_", "compress_sign_bits", "muvera_")   # + SURVEY.md §8(f) rank 4
 scan = [e for e in surface if e[0].startswith(scan_prefixes)]
 out = {"source": "lib/vettore_nifs.ex (reference v0.3.2)", "all": sorted(surface), "scan_path": sorted(scan)}
 json.dump(out, open(os.path.join(HERE, "nifs_surface.json"), "w"), indent=1)

@@ -48,6 +48,8 @@ int enif_get_double(ErlNifEnv*, ERL_NIF_TERM term, double* dp);
 int enif_get_long(ErlNifEnv*, ERL_NIF_TERM term, long* ip);
 int enif_get_int(ErlNifEnv*, ERL_NIF_TERM term, int* ip);
 int enif_get_uint64(ErlNifEnv*, ERL_NIF_TERM term, ErlNifUInt64* ip);
+typedef enum { ERL_NIF_LATIN1 = 1, ERL_NIF_UTF8 = 2 } ErlNifCharEncoding;
+int enif_get_atom(ErlNifEnv*, ERL_NIF_TERM atom, char* buf, unsigned len, ErlNifCharEncoding);
 int enif_get_tuple(ErlNifEnv*, ERL_NIF_TERM tpl, int* arity, const ERL_NIF_TERM** array);
 int enif_inspect_binary(ErlNifEnv*, ERL_NIF_TERM bin_term, ErlNifBinary* bin);
 int enif_get_resource(ErlNifEnv*, ERL_NIF_TERM term, ErlNifResourceType* type, void** objp);

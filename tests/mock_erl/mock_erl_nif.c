@@ -47,6 +47,10 @@ int enif_get_int(ErlNifEnv* e, ERL_NIF_TERM t, int* ip) {
 int enif_get_uint64(ErlNifEnv* e, ERL_NIF_TERM t, ErlNifUInt64* ip) {
     (void)e; if (T(t)->type != T_INT || T(t)->neg) return 0; *ip = T(t)->u; return 1;
 }
+int enif_get_atom(ErlNifEnv* e, ERL_NIF_TERM t, char* buf, unsigned len, ErlNifCharEncoding enc) {
+    (void)e; (void)enc; if (T(t)->type != T_ATOM || T(t)->len + 1 > len) return 0;
+    memcpy(buf, T(t)->s, T(t)->len + 1); return (int)T(t)->len + 1;
+}
 int enif_get_tuple(ErlNifEnv* e, ERL_NIF_TERM t, int* arity, const ERL_NIF_TERM** arr) {
     (void)e; if (T(t)->type != T_TUPLE) return 0; *arity = T(t)->arity; *arr = T(t)->elems; return 1;
 }

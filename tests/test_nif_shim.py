@@ -222,6 +222,19 @@ def test_validation_errors_that_need_no_device(nif):
     assert nif.call("multi_vector_top_k", [("b", [[1.0]]), ("a", [[2.0]])], [], 0, 10) == (OK, [("a", 0.0), ("b", 0.0)])  # :298-306
 
 
+def test_muvera_argument_decoding_and_validation(nif):
+    assert nif.call("muvera_encode_query", [], 2, 2, 1, 42, 2, Atom("nil")) == (ERROR, "empty vectors")
+    assert nif.call("muvera_encode_query", [], 0, 2, 1, 42, 2, Atom("nil")) == (ERROR, "empty vectors")   # before the config checks
+    assert nif.call("muvera_encode_query", [[1.0]], 2, 2, 1, 42, 2, Atom("nil")) == (ERROR, "dimension mismatch")
+    assert nif.call("muvera_encode_document", [[1.0, 0.0]], 2, 2, 31, 42, 2, Atom("nil")) == (ERROR, "num_simhash_projections must be < 31")
+    assert nif.call("muvera_encode_document", [[1.0, 0.0]], 2, 2, 1, 42, 2, 0) == (ERROR, "final_projection_dimension must be positive")
+    assert nif.call("muvera_encode_query", [[1.0, 0.0]], 2, 2, 30, 2 ** 64 - 1, 2, Atom("nil")) == (ERROR, "fde dimension exceeds safety limit")
+    with pytest.raises(BadArg):
+        nif.call("muvera_encode_query", [[1.0, 0.0]], 2, 2, 1, 42, 2, Atom("none"))
+    with pytest.raises(BadArg):
+        nif.call("muvera_encode_query", [[1.0, 0.0]], 2, 2, 1, -1, 2, Atom("nil"))
+
+
 def test_flat_new_without_a_device_raises_instead_of_falling_back(nif):
     import torch
     if torch.cuda.is_available():
@@ -257,6 +270,18 @@ def test_nif_level_known_answers_of_the_reference(nif):
     assert nif.call("multi_vector_score", [[1e19]] * 4, [[1e19]], 3) == (ERROR, "score overflow")                 # :251-258
     docs = [("b", [[1.0, 0.0]]), ("a", [[1.0, 0.0]]), ("c", [[-1.0, 0.0]])]
     assert nif.call("multi_vector_top_k", docs, [[1.0, 0.0]], 3, 2) == (OK, [("a", 1.0), ("b", 1.0)])           # :209-222
+
+
+@gpu
+def test_muvera_through_the_shim_equals_the_oracle(nif):
+    vectors = [[1.0, 2.0], [3.0, 4.0], [-2.0, 0.0]]                              # muvera.rs:334-355
+    assert nif.call("muvera_encode_query", vectors, 2, 1, 0, 0, 2, Atom("nil")) == (OK, [2.0, 6.0])
+    assert nif.call("muvera_encode_document", vectors, 2, 1, 0, 0, 2, Atom("nil")) == (OK, [float(np.float32(2.0 / 3.0)), 2.0])
+    rng = np.random.default_rng(1)
+    doc = rng.standard_normal((9, 16)).astype(np.float32)
+    for final in (Atom("nil"), 40):
+        got = nif.call("muvera_encode_document", [t for t in doc], 16, 4, 3, 99, 8, final)
+        assert got == oracle.muvera_encode(doc, 16, 4, 3, 99, 8, None if isinstance(final, Atom) else final, "document")
 
 
 @gpu

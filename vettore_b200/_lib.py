@@ -57,6 +57,8 @@ SIGNATURES = {
     "vb_peer_error": (C.c_int, [_vp, _u32p]),
     "vb_vector_top_k": (C.c_int, [_sz, C.c_char_p, _u64p, _f32p, _u64p, _f32p, _sz, C.c_int, _sz, _sz, _vpp]),
     "vb_binary_top_k": (C.c_int, [_sz, C.c_char_p, _u64p, _u64p, _u64p, _u64p, _sz, _sz, _sz, _vpp]),
+    "vb_muvera_encode": (C.c_int, [_sz, _f32p, _u64p, _u64p, _sz, _sz, _sz, C.c_uint64, _sz, C.c_int, _sz, C.c_int, _f32p, _sz,
+                                   C.POINTER(_sz)]),
     "vb_result_values": (C.c_int, [C.c_int, C.c_int, _f32p, _sz, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "vb_compress_sign_bits": (C.c_int, [_f32p, _sz, _u64p]),
     "vb_multi_vector_top_k": (C.c_int, [_sz, C.c_char_p, _u64p, _f32p, _u64p, _u64p, _f32p, _u64p, _sz, C.c_int, _sz, _vpp]),

@@ -8,6 +8,7 @@
 #include "flat_index.h"
 #include "hamming.h"
 #include "maxsim.h"
+#include "muvera.h"
 #include "peer_exchange.h"
 #include "runtime.h"
 #include "scan_driver.h"
@@ -612,6 +613,45 @@ int vb_mv_set_id_ranks(vb_mv* index, const uint32_t* ranks, size_t n) {
 int vb_mv_info(vb_mv* index, size_t* docs, size_t* tokens, size_t* dimension) {
     index->impl->info(docs, tokens, dimension);
     return VB_OK;
+}
+
+int vb_muvera_encode(size_t ndocs, const float* vals, const uint64_t* vec_off, const uint64_t* doc_vec, size_t dimension,
+                     size_t num_repetitions, size_t num_simhash_projections, uint64_t seed, size_t projection_dimension,
+                     int has_final, size_t final_projection_dimension, int mode, float* out, size_t out_capacity,
+                     size_t* fde_dimension) {
+    *fde_dimension = 0;
+    if (mode != 0 && mode != 1) return finish(vb::Status::Cuda("muvera: mode must be 0 (query) or 1 (document)"));
+    vb::MuveraConfig c;
+    c.dimension = dimension;
+    c.num_repetitions = num_repetitions;
+    c.num_simhash_projections = num_simhash_projections;
+    c.seed = seed;
+    c.projection_dimension = projection_dimension;
+    c.has_final = has_final != 0;
+    c.final_projection_dimension = final_projection_dimension;
+    // validation that needs no device runs first (muvera.rs:77-108), so error strings come back on any host
+    for (size_t d = 0; d < ndocs; ++d) {
+        if (doc_vec[d + 1] == doc_vec[d]) return finish(vb::Status::Ref("empty vectors"));
+        size_t a = 0, b = 0;
+        vb::Status cs = vb::muvera_output_dimension(c, &a, &b);
+        const bool size_error = !cs.ok() && (cs.msg == "fde dimension overflow" || cs.msg == "fde dimension exceeds safety limit");
+        if (!cs.ok() && !size_error) return finish(cs);
+        for (size_t v = doc_vec[d]; v < doc_vec[d + 1]; ++v)
+            if (vec_off[v + 1] - vec_off[v] != dimension) return finish(vb::Status::Ref("dimension mismatch"));
+        for (size_t v = doc_vec[d]; v < doc_vec[d + 1]; ++v)
+            if (!all_finite(vals + vec_off[v], dimension)) return finish(vb::Status::Ref("vector contains a non-finite value"));
+        if (size_error) return finish(cs);
+    }
+    size_t full = 0, fin = 0;
+    vb::Status cs = vb::muvera_output_dimension(c, &full, &fin);
+    if (!cs.ok()) return finish(cs);
+    *fde_dimension = fin;
+    if (ndocs == 0 || out == nullptr) return VB_OK;   // out == NULL: validate and size only
+    if (vb_device_count() <= 0) return no_device();
+    vb::CtxLease ctx;
+    vb::Status s = ctx.get();
+    if (!s.ok()) return finish(s);
+    return finish(vb::muvera_encode_batch(*ctx.ctx, c, ndocs, vals, vec_off, doc_vec, mode, out, out_capacity));
 }
 
 int vb_result_values(int metric_code, int score_mode, const float* raw, size_t n, double* score, double* distance) {

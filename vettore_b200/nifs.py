@@ -292,6 +292,46 @@ def binary_top_k(vectors: Sequence[tuple], query: Sequence[int], dimensions: int
     return _err() if rc else ("ok", _take_hits(h))
 
 
+def muvera_encode_batch(documents: Sequence, dimension: int, num_repetitions: int, num_simhash_projections: int, seed: int,
+                        projection_dimension: int, final_projection_dimension: int | None, mode: str):
+    """Additive: MUVERA fixed-dimensional encodings of MANY multi-vectors in one device
+    call (muvera.rs:26-74 per document). ``mode``: "query" (sum) or "document" (average). Returns
+    ``("ok", ndarray [ndocs, fde_dim])`` or ``("error", msg)``."""
+    toks, doc_vec = [], np.zeros(len(documents) + 1, dtype=np.uint64)
+    for i, vs in enumerate(documents):
+        toks.extend(vs)
+        doc_vec[i + 1] = len(toks)
+    vals, off = _ragged(toks, np.float32)
+    part = 1 << min(int(num_simhash_projections), 40)
+    fde = int(final_projection_dimension) if final_projection_dimension else min(
+        int(num_repetitions) * part * max(1, int(projection_dimension)), 16777216)
+    out = np.zeros((max(1, len(documents)), max(1, fde)), dtype=np.float32)
+    n = C.c_size_t()
+    rc = lib().vb_muvera_encode(len(documents), _ptr(vals, _f32p), _ptr(off, _u64p), _ptr(doc_vec, _u64p), int(dimension),
+                                int(num_repetitions), int(num_simhash_projections), int(seed), int(projection_dimension),
+                                int(final_projection_dimension is not None), int(final_projection_dimension or 0),
+                                {"query": 0, "document": 1}[mode], _ptr(out, _f32p), out.size, C.byref(n))
+    if rc:
+        return _err()
+    return ("ok", out.reshape(-1)[: len(documents) * n.value].reshape(len(documents), n.value))
+
+
+def muvera_encode_query(vectors, dimension, num_repetitions, num_simhash_projections, seed, projection_dimension,
+                        final_projection_dimension):
+    """nifs.rs:430-452 (one multi-vector, summed per partition): ``("ok", [float])``."""
+    res = muvera_encode_batch([vectors], dimension, num_repetitions, num_simhash_projections, seed, projection_dimension,
+                              final_projection_dimension, "query")
+    return res if res[0] != "ok" else ("ok", res[1][0].tolist())
+
+
+def muvera_encode_document(vectors, dimension, num_repetitions, num_simhash_projections, seed, projection_dimension,
+                           final_projection_dimension):
+    """nifs.rs:455-476 (one multi-vector, averaged per partition): ``("ok", [float])``."""
+    res = muvera_encode_batch([vectors], dimension, num_repetitions, num_simhash_projections, seed, projection_dimension,
+                              final_projection_dimension, "document")
+    return res if res[0] != "ok" else ("ok", res[1][0].tolist())
+
+
 def result_values(metric_code: int, raws, score_mode: str = "raw"):
     """Additive: ``Distance.result_values/3`` (vettore_distance.ex:525-543) over a whole hit list in one C call.
     Returns ``("ok", [(score, distance)])``."""
