@@ -21,9 +21,18 @@ def _rows(n, d, seed):
     return (x / np.linalg.norm(x.astype(np.float64), axis=1, keepdims=True)).astype(np.float32)
 
 
+@pytest.fixture(params=["auto", "1", "3"])
+def gemm_terms(request, monkeypatch):
+    """K2 precision mode: one TF32 pass with a wide candidate margin (k <= 32 by default), 3xTF32 otherwise; both
+    are filters in front of the exact re-scoring, so every test must pass in either mode."""
+    if request.param != "auto":
+        monkeypatch.setenv("VB_GEMM_TERMS", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("metric", ["cosine", "inner_product", "negative_inner_product"])
 @pytest.mark.parametrize("n,d,nq,k", [(5000, 128, 40, 10), (20000, 768, 300, 10), (3000, 64, 16, 100), (9000, 96, 513, 1)])
-def test_batched_search_matches_oracle(metric, n, d, nq, k):
+def test_batched_search_matches_oracle(metric, n, d, nq, k, gemm_terms):
     rows = _rows(n, d, n + d)
     queries = _rows(nq, d, 17)
     queries[3] = rows[42]            # an exact duplicate: self-match must rank first
@@ -37,7 +46,7 @@ def test_batched_search_matches_oracle(metric, n, d, nq, k):
         assert_hits_match(got[qi], exp)
 
 
-def test_batched_and_single_query_kernels_agree(monkeypatch):
+def test_batched_and_single_query_kernels_agree(monkeypatch, gemm_terms):
     n, d, nq, k = 12000, 256, 64, 10
     rows, queries = _rows(n, d, 1), _rows(nq, d, 2)
     ids = [f"{i:06d}" for i in range(n)]
@@ -50,7 +59,7 @@ def test_batched_and_single_query_kernels_agree(monkeypatch):
         assert_hits_match(a, b)
 
 
-def test_batched_search_ties_resolve_by_id():
+def test_batched_search_ties_resolve_by_id(gemm_terms):
     """Small-integer rows: many exact score ties inside and across tiles."""
     rng = np.random.default_rng(5)
     n, d, nq, k = 4000, 32, 32, 25
@@ -65,7 +74,7 @@ def test_batched_search_ties_resolve_by_id():
 
 
 @pytest.mark.parametrize("k", [40, 100])
-def test_batched_search_large_k_many_tiles_per_cta(k):
+def test_batched_search_large_k_many_tiles_per_cta(k, gemm_terms):
     """Enough rows per CTA that the per-(CTA, query) candidate lists are cut back several times
     (value-bisection select), with a continuous score distribution."""
     n, d, nq = 250_000, 64, 16
@@ -79,7 +88,7 @@ def test_batched_search_large_k_many_tiles_per_cta(k):
 
 
 @pytest.mark.parametrize("k", [25, 100])
-def test_batched_search_large_k_ties_at_the_cut(k):
+def test_batched_search_large_k_ties_at_the_cut(k, gemm_terms):
     """Small-integer rows over many tiles: the cut of a candidate list falls inside large groups of equal
     scores, so the id word decides which of them survive (second bisection)."""
     rng = np.random.default_rng(6)
@@ -92,3 +101,24 @@ def test_batched_search_large_k_ties_at_the_cut(k):
     got = ok(nifs.flat_search_batch(idx, queries, k))
     for qi in range(nq):
         assert got[qi] == ok(oracle.flat_search_dense("inner_product", rows, ids, queries[qi], k))
+
+
+def test_single_pass_filter_is_complete_on_adversarial_near_ties(monkeypatch):
+    """Rows packed within the single-pass error bound of each other (all-positive, nearly parallel vectors at d = 32
+    and 64: ADVICE r1): the kept candidate set cannot be proven complete from TF32 scores alone, so the queries must
+    come back exact anyway (flagged and redone by the single-query kernel)."""
+    rng = np.random.default_rng(11)
+    for d in (32, 64):
+        n, nq, k = 6000, 20, 10
+        base = np.abs(rng.standard_normal(d)).astype(np.float32) + 1.0
+        rows = (base[None, :] * (1.0 + 2e-4 * rng.standard_normal((n, d)))).astype(np.float32)
+        rows = (rows / np.linalg.norm(rows.astype(np.float64), axis=1, keepdims=True)).astype(np.float32)
+        queries = rows[:nq] + 1e-4 * rng.standard_normal((nq, d)).astype(np.float32)
+        ids = [f"{(i * 7919) % n:05d}" for i in range(n)]
+        for terms in ("1", "3"):
+            monkeypatch.setenv("VB_GEMM_TERMS", terms)
+            idx = nifs.flat_new_cosine()
+            ok(nifs.flat_insert_matrix(idx, ids, rows))
+            got = ok(nifs.flat_search_batch(idx, queries, k))
+            for qi in range(nq):
+                assert_hits_match(got[qi], ok(oracle.flat_search_dense("cosine", rows, ids, queries[qi], k)))

@@ -41,11 +41,11 @@ def corpus_1m():
     return idx, rows
 
 
-@pytest.mark.parametrize("k", [10, 100])
+@pytest.mark.parametrize("k", [10, 100, 1000])
 def test_k1_single_query_1m_x_768_cosine(corpus_1m, k):
     """configs[1], batch of 1: every hit of 16 queries equals the oracle's over the whole 1M-row corpus."""
     idx, rows = corpus_1m
-    q = _normal_rows(16, 768, SEED + 1, torch.device("cuda", 0)).cpu().numpy()
+    q = _normal_rows(16 if k <= 100 else 4, 768, SEED + 1, torch.device("cuda", 0)).cpu().numpy()   # k = 1000: merge tree + rank merge
     _, ref = oracle.flat_scan_timed("cosine", rows, q, k, THREADS)
     for qi in range(q.shape[0]):
         st, hits = nifs.flat_search(idx, q[qi], k)

@@ -2,6 +2,7 @@
 # Round-2 profiling pass (one GPU): launch list of the quantized pipeline shard, full captures of K2 (1024 queries)
 # and of funnel stage 1 over the dense prefix mirror, funnel bench for a float metric with / without the mirror.
 mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_muvera.py tests/test_nif_shim.py tests/test_sharded_gpu.py -m gpu -x -q > gpurun_out/pytest_new.log 2>&1; tail -3 gpurun_out/pytest_new.log
 for m in inner_product l2; do
   timeout 300 python tools/bench_funnel.py --metric $m --stages 128,384 --candidates 100 --iters 50 > gpurun_out/funnel_${m}_mirror.log 2>&1; tail -1 gpurun_out/funnel_${m}_mirror.log | cut -c1-420
   VB_NO_PREFIX_MIRROR=1 timeout 300 python tools/bench_funnel.py --metric $m --stages 128,384 --candidates 100 --iters 50 > gpurun_out/funnel_${m}_nomirror.log 2>&1; tail -1 gpurun_out/funnel_${m}_nomirror.log | cut -c1-420

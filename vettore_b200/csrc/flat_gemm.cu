@@ -335,6 +335,193 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned
     if (warp == kGmMmaWarp) tc::tmem_dealloc(tbase, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K2 single-pass variant. The tensor-core scores are only a FILTER (every kept candidate is re-scored exactly
+// by flat_gemm_rescore_kernel and the kept set is proven complete against an error bound), so fp32 accuracy is
+// not needed HERE: one TF32 pass with a wider candidate margin returns bit-identical final results for a third
+// of the MMA work. That also removes what throttled the 3xTF32 kernel (ncu, 1024 queries: tensor pipe 58 %
+// active, every warp role waiting): no hi/lo split warps, one 32 KB query chunk instead of 64 KB per K chunk
+// (the ring holds 4 stages instead of 2 — the 80 KB stages left ~1 stage in flight against a ~2-3k-cycle L2
+// latency), both operands straight from shared memory (SS mode, the hardware reads fp32 words as TF32), and
+// the whole of TMEM for TWO accumulators, released as soon as a tile's scores sit in registers.
+// Error bound: operands lose < 2^-10 relative each, so |approx - exact| <= 2^-9 * |q| * |row| (+ fp32
+// accumulation): 2e-3 for unit vectors. The candidate margin k' - k covers the rows that can sit that close to
+// the k-th score; it is used for k <= 32 (k' = k + 32), larger k keeps the 3xTF32 kernel above.
+constexpr int kG1EpiWarps = 8, kG1ProducerWarp = 8, kG1MmaWarp = 9;
+constexpr int kG1Threads = (kG1MmaWarp + 1) * 32;        // warps 0-7 epilogue, 8 producer, 9 MMA
+constexpr int kG1Stages = 4;
+constexpr uint32_t kG1StageBytes = 16384 + 32768;         // A chunk [128 x 32] + query chunk [256 x 32], fp32, SW128
+
+__global__ void __launch_bounds__(kG1Threads, 1)
+flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned char* __restrict__ q_blobs,
+                       const GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char gsmem[];
+    __shared__ __align__(8) uint64_t full_bar[kG1Stages], empty_bar[kG1Stages], d_full[2], d_free[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ u64 s_thr[kGmN];
+    __shared__ float s_thr_rank[kGmN];
+    __shared__ uint32_t s_cnt[kGmN];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t qb = blockIdx.x % p.qblocks, rr = blockIdx.x / p.qblocks;
+    const bool active = rr < p.ranges;
+    const uint32_t tiles_total = (p.n + kGmTile - 1) / kGmTile;
+    const uint32_t tile0 = active ? (uint32_t)((uint64_t)tiles_total * rr / p.ranges) : 0;
+    const uint32_t tile1 = active ? (uint32_t)((uint64_t)tiles_total * (rr + 1) / p.ranges) : 0;
+    const uint32_t chunks = p.dims / 32;
+
+    for (int q = tid; q < kGmN; q += kG1Threads) { s_thr[q] = kKeyMax; s_thr_rank[q] = INFINITY; s_cnt[q] = 0; }
+    if (tid == 0) {
+        for (int s = 0; s < kG1Stages; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);          // the MMA commit frees both operands of the stage
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&d_full[b], 1);
+            tc::mbar_init(&d_free[b], kG1EpiWarps);
+        }
+        tc::mbar_fence_init();
+    }
+    if (warp == kG1MmaWarp) tc::tmem_alloc(&tmem_slot, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+
+    if (warp == kG1ProducerWarp) {
+        if (lane == 0) {
+            uint32_t cc = 0;
+            for (uint32_t tile = tile0; tile < tile1; ++tile) {
+                for (uint32_t kc = 0; kc < chunks; ++kc, ++cc) {
+                    const uint32_t s = cc % kG1Stages, ph = (cc / kG1Stages) & 1u;
+                    unsigned char* st = gsmem + (size_t)s * kG1StageBytes;
+                    tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+                    tc::mbar_arrive_expect_tx(&full_bar[s], kG1StageBytes);
+                    tc::tma_load_2d(st, &tmap_a, kc * 32, tile * kGmTile, &full_bar[s]);
+                    tma_bulk_g2s(st + 16384, q_blobs + ((size_t)qb * chunks + kc) * 32768u, 32768u, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == kG1MmaWarp) {
+        const uint32_t idesc = tc::umma_idesc_tf32(kGmTile, kGmN);
+        uint32_t cc = 0, it = 0;
+        for (uint32_t tile = tile0; tile < tile1; ++tile, ++it) {
+            const uint32_t buf = it & 1u;
+            tc::mbar_wait(&d_free[buf], ((it >> 1) & 1u) ^ 1u);     // the epilogue took this accumulator's last tile
+            tc::fence_after_sync();
+            const uint32_t d_addr = tbase + buf * (uint32_t)kGmN;
+            for (uint32_t kc = 0; kc < chunks; ++kc, ++cc) {
+                const uint32_t s = cc % kG1Stages, ph = (cc / kG1Stages) & 1u;
+                tc::mbar_wait(&full_bar[s], ph);
+                tc::fence_after_sync();
+                const uint32_t st_addr = tc::smem_addr(gsmem + (size_t)s * kG1StageBytes);
+                const uint64_t a0 = tc::umma_smem_desc_sw128(st_addr);
+                const uint64_t b0 = tc::umma_smem_desc_sw128(st_addr + 16384);
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 4; ++ks)
+                        tc::umma_tf32_ss(d_addr, a0 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc, (kc | ks) != 0u);
+                    tc::umma_commit(&empty_bar[s]);
+                    if (kc + 1 == chunks) tc::umma_commit(&d_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue warps 0-7: TMEM lanes of quarter (w & 3), query columns of half (w >> 2) =====
+        const uint32_t quarter = warp & 3u, half = warp >> 2;
+        const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
+        const size_t list_base = (size_t)blockIdx.x * kGmN;
+        const float bias = p.metric == kCosine ? 1.0f : 0.0f;
+        uint32_t it = 0;
+        for (uint32_t tile = tile0; tile < tile1; ++tile, ++it) {
+            const uint32_t buf = it & 1u;
+            const uint32_t row = tile * kGmTile + quarter * 32u + lane;
+            const bool valid = row < p.n;
+            const uint32_t idr = valid ? (p.id_rank ? __ldg(p.id_rank + row) : row) : 0u;
+            tc::mbar_wait(&d_full[buf], (it >> 1) & 1u);
+            tc::fence_after_sync();
+            // the warp's 32 rows x 128 columns into registers at once, then the accumulator is free again
+            uint32_t r[4][32];
+#pragma unroll
+            for (uint32_t g = 0; g < 4; ++g) tc::tmem_ld32(lane_addr + buf * (uint32_t)kGmN + (half * 4u + g) * 32u, r[g]);
+            tc::tmem_ld_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&d_free[buf]);
+            uint32_t worst_bits = 0;
+#pragma unroll
+            for (uint32_t g = 0; g < 4; ++g) {
+                const uint32_t cg = half * 4u + g;
+                if (qb * kGmN + cg * 32u >= p.nq) break;       // padded query columns (warp-uniform)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t q = cg * 32u + j;
+                    const float dot = __uint_as_float(r[g][j]);
+                    worst_bits = max(worst_bits, r[g][j] & 0x7fffffffu);
+                    const float rankv = fmaf(dot, -1.0f, bias);
+                    if (rankv <= s_thr_rank[q] && valid && qb * kGmN + q < p.nq) {
+                        const u64 key = ((u64)order_key(rankv) << 32) | idr;
+                        if (key < s_thr[q]) {
+                            const float raw = p.metric == kNegativeInnerProduct ? -dot : dot;
+                            const uint32_t slot = atomicAdd(&s_cnt[q], 1u);
+                            if (slot < p.list_cap) {
+                                p.list_keys[(list_base + q) * p.list_cap + slot] = key;
+                                p.list_pays[(list_base + q) * p.list_cap + slot] = ((u64)__float_as_uint(raw) << 32) | row;
+                            }
+                        }
+                    }
+                }
+            }
+            if (valid && worst_bits >= 0x7f800000u) *p.bad = 1u;
+            // lists that could overflow during the next tile are cut back to their best k
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            for (uint32_t q = warp; q < kGmN; q += kG1EpiWarps) {
+                const uint32_t cnt = min(s_cnt[q], p.list_cap);
+                if (cnt + kGmTile > p.list_cap) {
+                    u64* lkeys = p.list_keys + (list_base + q) * p.list_cap;
+                    u64* lpays = p.list_pays + (list_base + q) * p.list_cap;
+                    const u64 kth = p.list_cap == kGmListSmall ? warp_select_list<8>(lkeys, lpays, cnt, p.k, lane)
+                                                               : warp_select_list<16>(lkeys, lpays, cnt, p.k, lane);
+                    if (lane == 0) {
+                        s_cnt[q] = min(cnt, p.k);
+                        s_thr[q] = kth;
+                        s_thr_rank[q] = kth == kKeyMax ? INFINITY : rank_from_key(kth);
+                    }
+                }
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+        for (uint32_t q = warp; q < kGmN; q += kG1EpiWarps) {
+            const uint32_t cnt = min(s_cnt[q], p.list_cap);
+            u64* lkeys = p.list_keys + (list_base + q) * p.list_cap;
+            u64* lpays = p.list_pays + (list_base + q) * p.list_cap;
+            if (cnt > 0) {
+                if (p.list_cap == kGmListSmall) warp_select_list<8>(lkeys, lpays, cnt, p.k, lane);
+                else warp_select_list<16>(lkeys, lpays, cnt, p.k, lane);
+            }
+            if (lane == 0) p.list_counts[list_base + q] = min(cnt, p.k);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == kG1MmaWarp) tc::tmem_dealloc(tbase, 512);
+}
+
+// queries [nq, dims] -> per (query block, 32-dim chunk) a 32 KB image [256 x 32] fp32 in the UMMA K-major
+// SWIZZLE_128B shared-memory layout (zero rows beyond nq); the tensor core reads the words as TF32.
+__global__ void pack_queries_kernel(const float* q, uint32_t nq, uint32_t qblocks, uint32_t dims, unsigned char* blobs) {
+    const uint32_t chunks = dims / 32;
+    const size_t total = (size_t)qblocks * kGmN * dims;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)(i % dims);
+        const size_t row = i / dims;
+        const uint32_t qb = (uint32_t)(row / kGmN), n = (uint32_t)(row % kGmN);
+        unsigned char* blob = blobs + ((size_t)qb * chunks + k / 32u) * 32768u;
+        *reinterpret_cast<float*>(blob + tc::sw128_offset(n, k % 32u)) = row < nq ? q[row * dims + k] : 0.0f;
+    }
+}
+
 // Per query: merge the sorted lists of the CTAs that served its query block.
 __global__ void __launch_bounds__(128)
 flat_gemm_merge_kernel(const GemmParams p, uint32_t cap, u64* out_keys, u64* out_pays, uint32_t* out_counts) {
@@ -526,13 +713,21 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     const uint32_t qblocks_total = (uint32_t)((nq + kGmN - 1) / kGmN);
     const uint32_t group = std::min<uint32_t>(qblocks_total, (uint32_t)sms);   // query blocks per launch
     const size_t nq_pad = (size_t)qblocks_total * kGmN;
-    const size_t kprime = std::min<size_t>(std::min<size_t>(k + std::max<size_t>(8, k / 4), 128), n);   // approximate candidates kept
+    // single TF32 pass (wide margin) for small k, 3xTF32 (narrow margin) otherwise; VB_GEMM_TERMS forces either
+    int terms = k <= 32 ? 1 : 3;
+    if (const char* e = std::getenv("VB_GEMM_TERMS")) {
+        const int t = std::atoi(e);
+        if (t == 3 || (t == 1 && k <= 96)) terms = t;
+    }
+    const size_t margin = terms == 1 ? 32 : std::max<size_t>(8, k / 4);
+    const size_t kprime = std::min<size_t>(std::min<size_t>(k + margin, 128), n);   // approximate candidates kept
     RescoreKernel rescore = rescore_lookup(metric);
     if (!rescore) return Status::Cuda("metric not served by the batched kernel");
 
     VB_TRY(ctx.staging.reserve(2 * nq_pad * dims * sizeof(float)));
     unsigned char* q_blobs = ctx.staging.as<unsigned char>();
-    split_queries_kernel<<<148 * 4, 256, 0, stream>>>(d_queries, (uint32_t)nq, qblocks_total, (uint32_t)dims, q_blobs);
+    if (terms == 1) pack_queries_kernel<<<148 * 4, 256, 0, stream>>>(d_queries, (uint32_t)nq, qblocks_total, (uint32_t)dims, q_blobs);
+    else split_queries_kernel<<<148 * 4, 256, 0, stream>>>(d_queries, (uint32_t)nq, qblocks_total, (uint32_t)dims, q_blobs);
     VB_CUDA(cudaGetLastError());
 
     const size_t max_ctas = (size_t)sms;
@@ -544,8 +739,10 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     VB_TRY(ctx.dump_pays.reserve(nq_pad * kprime * sizeof(u64)));
     VB_TRY(ctx.staging_rank.reserve(nq_pad * sizeof(uint32_t)));
 
-    const size_t smem_bytes = (size_t)kGmStages * kGmStageBytes + 1024;
-    VB_TRY(ensure_dynamic_smem_for(flat_gemm_topk_kernel, smem_bytes));
+    const size_t smem_bytes = terms == 1 ? (size_t)kG1Stages * kG1StageBytes + 1024 : (size_t)kGmStages * kGmStageBytes + 1024;
+    if (terms == 1) VB_TRY(ensure_dynamic_smem_for(flat_gemm1_topk_kernel, smem_bytes));
+    else VB_TRY(ensure_dynamic_smem_for(flat_gemm_topk_kernel, smem_bytes));
+    const size_t blob_bytes = terms == 1 ? 32768u : 65536u;
 
     CUtensorMap tmap_a;
     VB_TRY(make_tmap_rows_sw128(d_rows, n, stride, kGmTile, &tmap_a));
@@ -577,8 +774,10 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
         p.bad = d_bad;
         { const char* dbg = std::getenv("VB_GEMM_DEBUG"); p.debug = dbg ? (uint32_t)std::atoi(dbg) : 0u; }
         const uint32_t grid = p.qblocks * p.ranges;
-        flat_gemm_topk_kernel<<<grid, kGmThreads, smem_bytes, stream>>>(
-            tmap_a, q_blobs + (size_t)qb0 * (dims / 32) * 65536u, p);
+        if (terms == 1)
+            flat_gemm1_topk_kernel<<<grid, kG1Threads, smem_bytes, stream>>>(tmap_a, q_blobs + (size_t)qb0 * (dims / 32) * blob_bytes, p);
+        else
+            flat_gemm_topk_kernel<<<grid, kGmThreads, smem_bytes, stream>>>(tmap_a, q_blobs + (size_t)qb0 * (dims / 32) * blob_bytes, p);
         VB_CUDA(cudaGetLastError());
         flat_gemm_merge_kernel<<<nq_here, 128, (size_t)cap * 16, stream>>>(p, cap, apx_keys + q0 * kprime,
                                                                           apx_pays + q0 * kprime, apx_counts + q0);
@@ -596,7 +795,11 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     rp.cand_keys = apx_keys;
     rp.cand_pays = apx_pays;
     rp.cand_counts = apx_counts;
-    rp.err_coeff = 1.0e-7f * (float)(3 * dims / 8);
+    // |approx - exact| <= err_coeff * |q| * max|row|. One pass: both operands are cut to TF32 (< 2^-10 relative
+    // each => 2^-9 on every product, Cauchy-Schwarz over the sum). 3xTF32: the dropped lo*lo term and the
+    // truncation of the two lo operands (<= 2^-20 each, with head-room), plus fp32 accumulation over dims / 8
+    // MMA steps per term in both cases.
+    rp.err_coeff = (terms == 1 ? 1.96e-3f : 4.0e-6f) + 1.0e-7f * (float)(3 * dims / 8);
     rp.max_row_norm = max_row_norm;
     rp.out_keys = d_out_keys;
     rp.out_pays = d_out_pays;

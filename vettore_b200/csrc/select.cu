@@ -3,6 +3,8 @@
 // values and rows are gathered once for the k_out survivors.
 #include "select.h"
 
+#include <cstdlib>
+
 #include "runtime.h"
 #include "topk.cuh"
 
@@ -120,6 +122,62 @@ topk_tree_merge_kernel(const u64* keys_in, const u64* pays_in, const uint32_t* c
     }
 }
 
+// Final level for LONG lists (k in the hundreds: the 1000 Hamming candidates of quantized_search, funnel stages):
+// one CTA pushing 10 x 1000 entries through the collector's sorts cost 43 us on a 265 us scan. The lists are
+// sorted and keys are unique (the low word is the id rank), so an entry's place in the merged order is its own
+// index plus, per other list, the number of entries below it — a binary search each, no sort, no atomics,
+// every entry independent. Each of a few CTAs stages all keys in shared memory and ranks its share.
+constexpr uint32_t kRankMergeThreads = 512;
+constexpr uint32_t kRankMergeCtas = 8;
+constexpr uint32_t kRankMergeMaxEntries = 24576;   // lists * k keys of 8 bytes: 192 KB of shared memory
+
+__global__ void __launch_bounds__(kRankMergeThreads)
+topk_rank_merge_kernel(const u64* keys_in, const u64* pays_in, const uint32_t* counts_in, uint32_t lists_in, uint32_t k,
+                       u64* keys_out, u64* pays_out, uint32_t* counts_out, uint32_t* err_row, uint32_t* out_err,
+                       u64* g_thresh) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    u64* s_keys = reinterpret_cast<u64*>(smem);                       // [lists_in][k]
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_keys + (size_t)lists_in * k);
+    const uint32_t qi = blockIdx.y;
+    const u64* qk = keys_in + (size_t)qi * lists_in * k;
+    const u64* qp = pays_in + (size_t)qi * lists_in * k;
+    const uint32_t* qc = counts_in + (size_t)qi * lists_in;
+    for (uint32_t l = threadIdx.x; l < lists_in; l += blockDim.x) s_cnt[l] = min(qc[l], k);
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < lists_in * k; s += blockDim.x) {
+        const uint32_t l = s / k, i = s - l * k;
+        if (i < s_cnt[l]) s_keys[s] = qk[s];
+    }
+    __syncthreads();
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < lists_in * k; s += gridDim.x * blockDim.x) {
+        const uint32_t l = s / k, i = s - l * k;
+        if (i >= s_cnt[l]) continue;
+        const u64 key = s_keys[s];
+        uint32_t pos = i;
+        for (uint32_t m = 0; m < lists_in && pos < k; ++m) {
+            if (m == l) continue;
+            const u64* lk = s_keys + (size_t)m * k;
+            uint32_t lo = 0, hi = s_cnt[m];
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (lk[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            pos += lo;
+        }
+        if (pos < k) {
+            keys_out[(size_t)qi * k + pos] = key;
+            pays_out[(size_t)qi * k + pos] = qp[s];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (uint32_t l = 0; l < lists_in; ++l) total += s_cnt[l];
+        counts_out[qi] = min(total, k);
+        if (out_err) { out_err[qi] = err_row[qi]; err_row[qi] = kNoError; }   // what the last CTA of the scan would have done
+        if (g_thresh) g_thresh[qi] = kKeyMax;
+    }
+}
+
 Status run_merge_tree(const TopkWorkspace& ws, uint32_t nq, uint32_t lists, DeviceBuf& scratch, cudaStream_t stream) {
     const uint32_t k = ws.k;
     uint32_t cap = 256;
@@ -139,7 +197,17 @@ Status run_merge_tree(const TopkWorkspace& ws, uint32_t nq, uint32_t lists, Devi
     const uint32_t* cin = ws.cand_counts;
     uint32_t lin = lists;
     int level = 0;
+    const bool rank_final = k >= 128 && !std::getenv("VB_NO_RANK_MERGE");
     for (;;) {
+        if (rank_final && level > 0 && (size_t)lin * k <= kRankMergeMaxEntries) {
+            // the remaining lists are sorted outputs of the previous level: rank-merge them straight into the result
+            const size_t smem_r = (size_t)lin * k * sizeof(u64) + (size_t)lin * sizeof(uint32_t) + 16;
+            VB_TRY(ensure_dynamic_smem_for(topk_rank_merge_kernel, smem_r));
+            topk_rank_merge_kernel<<<dim3(kRankMergeCtas, nq), kRankMergeThreads, smem_r, stream>>>(
+                kin, pin, cin, lin, k, ws.out_keys, ws.out_pays, ws.out_counts, ws.err_row, ws.out_err, ws.g_thresh);
+            VB_CUDA(cudaGetLastError());
+            break;
+        }
         const uint32_t lout = (lin + kTreeGroup - 1) / kTreeGroup;
         u64 *kout, *pout;
         uint32_t* cout;

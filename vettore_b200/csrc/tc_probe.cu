@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const __grid_constant__ C
     for (int idx = t; idx < 32 * K; idx += 128) {
         const int n = idx / K, k = idx % K;
         const float x = B[idx];
-        const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        const float hi = mode == 11 ? x : __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);   // 11: raw fp32 words, the hardware cuts them to TF32
         const uint32_t off = (uint32_t)(k / 32) * 4096u + tc::sw128_offset(n, k % 32);
         *reinterpret_cast<float*>(b_hi + off) = hi;
         *reinterpret_cast<float*>(b_lo + off) = x - hi;
@@ -121,6 +121,11 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const __grid_constant__ C
                 const uint64_t bh = tc::umma_smem_desc_sw128(tc::smem_addr(b_hi + kb * 4096 + ks * 32));
                 const uint64_t bl = tc::umma_smem_desc_sw128(tc::smem_addr(b_lo + kb * 4096 + ks * 32));
                 const uint32_t ah = tbase + kb * 32 + ks * 8, al = tbase + 128 + kb * 32 + ks * 8;
+                if (mode == 11) {   // SS: A straight from the TMA-swizzled shared-memory tile, unmasked
+                    tc::umma_tf32_ss(d_tmem, tc::umma_smem_desc_sw128(tc::smem_addr(a_tile + (size_t)kb * 16384 + ks * 32)), bh, idesc, acc);
+                    acc = 1;
+                    continue;
+                }
                 tc::umma_tf32_ts(d_tmem, ah, bh, idesc, acc);
                 acc = 1;
                 if (mode == 3) {
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const __grid_constant__ C
 }  // namespace vb
 
 // Self-test entry (not part of the drop-in ABI): host A[128][K], B[32][K] -> host D[128][32].
-// mode 1 = single TF32 pass, 3 = 3xTF32. Returns 0 or a cudaError_t / -1.
+// mode 1 = single TF32 pass (A from TMEM), 3 = 3xTF32, 11 = single pass with both operands from shared memory (SS). Returns 0 or a cudaError_t / -1.
 extern "C" int vb_debug_tc_probe(const float* hA, const float* hB, int K, int mode, float* hD) {
     if (K <= 0 || K > 128 || K % 32) return -1;
     float *dA = nullptr, *dB = nullptr, *dD = nullptr;
