@@ -283,7 +283,12 @@ static ERL_NIF_TERM multi_vector_top_k(ErlNifEnv* env, int argc, const ERL_NIF_T
  * constructors cannot fail, and an index that silently does nothing would be worse. */
 static ERL_NIF_TERM flat_new(ErlNifEnv* env, int metric) {
     vb_flat* index = NULL;
-    if (vb_flat_new(metric, &index) != VB_OK) return enif_raise_exception(env, mk_error(env));
+    /* VETTORE_B200_GPUS=N (N > 1): the same resource spread over N GPUs of the box (vb_flat_new_sharded);
+     * the callers cannot tell the difference. */
+    const char* gpus = getenv("VETTORE_B200_GPUS");
+    const int n_gpus = gpus ? atoi(gpus) : 1;
+    const int rc = n_gpus > 1 ? vb_flat_new_sharded(metric, n_gpus, NULL, &index) : vb_flat_new(metric, &index);
+    if (rc != VB_OK) return enif_raise_exception(env, mk_error(env));
     flat_res* r = (flat_res*)enif_alloc_resource(FLAT_TYPE, sizeof(flat_res));
     r->index = index;
     ERL_NIF_TERM t = enif_make_resource(env, r);

@@ -344,3 +344,26 @@ def test_multi_vector_resident_index_through_the_shim(nif):
     st, hits2 = nif.call("mv_search", mv, [t for t in qv], 8)
     assert st == OK and hits2[0][0] != hits[0][0]
     nif.L.mock_release(mv.term)
+
+
+@gpu
+def test_sharded_resource_behind_the_same_nifs(nif, monkeypatch):
+    """VETTORE_B200_GPUS=N: flat_new_* returns ONE resource spread over N shards (one per GPU; they share the
+    device of a single-GPU box); insert / search / delete answer exactly like the single-GPU resource."""
+    rng = np.random.default_rng(13)
+    n, d = 2000, 48
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    ids = [f"{(i * 7919) % n:05d}" for i in range(n)]
+    q = rng.standard_normal(d).astype(np.float32)
+    one = nif.call("flat_new_l2")
+    monkeypatch.setenv("VETTORE_B200_GPUS", "4")
+    many = nif.call("flat_new_l2")
+    for idx in (one, many):
+        assert nif.call("flat_insert_many", idx, [(ids[i], rows[i]) for i in range(n)]) == (OK, ())
+        assert nif.call("flat_delete", idx, ids[5]) == (OK, ())
+    a, b = nif.call("flat_search", one, q, 12), nif.call("flat_search", many, q, 12)
+    assert a == b and a[0] == OK
+    keep = [i for i in range(n) if i != 5]
+    assert_hits_match(a[1], oracle.flat_search_dense("l2", rows[keep], [ids[i] for i in keep], q, 12)[1])
+    nif.L.mock_release(one.term)
+    nif.L.mock_release(many.term)

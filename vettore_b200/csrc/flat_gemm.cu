@@ -46,6 +46,10 @@ struct GemmParams {
     u64* list_pays;
     uint32_t* list_counts;         // [cta][256]
     uint32_t* bad;                 // set when a non-finite score shows up (caller falls back)
+    // optional: per query of this launch, the merged best-k list of a PRE-PASS over a sample of the rows. Its
+    // k-th key bounds the final k-th key from above, so every CTA starts with a tight filter instead of an open one.
+    const u64* init_keys;          // [nq][k] ascending, or null
+    const uint32_t* init_counts;   // [nq]
     uint32_t debug;                // timing experiments only (VB_GEMM_DEBUG): 1 skip A loads, 2 skip B loads, 4 skip split, 8 skip epilogue, 16 skip MMA
 };
 
@@ -148,7 +152,14 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned
     const uint32_t tile1 = active ? (uint32_t)((uint64_t)tiles_total * (rr + 1) / p.ranges) : 0;
     const uint32_t chunks = p.dims / 32;
 
-    for (int q = tid; q < kGmN; q += kGmThreads) { s_thr[q] = kKeyMax; s_thr_rank[q] = INFINITY; s_cnt[q] = 0; }
+    for (int q = tid; q < kGmN; q += kGmThreads) {
+        u64 thr = kKeyMax;
+        const uint32_t qg = qb * kGmN + q;
+        if (p.init_keys != nullptr && qg < p.nq && p.init_counts[qg] >= p.k) thr = p.init_keys[(size_t)qg * p.k + p.k - 1u];
+        s_thr[q] = thr == kKeyMax ? kKeyMax : thr + 1u;             // keys are unique: "<= k-th" is "< k-th + 1"
+        s_thr_rank[q] = thr == kKeyMax ? INFINITY : rank_from_key(thr);
+        s_cnt[q] = 0;
+    }
     if (tid == 0) {
         for (int s = 0; s < kGmStages; ++s) {
             tc::mbar_init(&full_bar[s], 1);
@@ -349,14 +360,17 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned
 // the k-th score; it is used for k <= 32 (k' = k + 32), larger k keeps the 3xTF32 kernel above.
 constexpr int kG1EpiWarps = 8, kG1ProducerWarp = 8, kG1MmaWarp = 9;
 constexpr int kG1Threads = (kG1MmaWarp + 1) * 32;        // warps 0-7 epilogue, 8 producer, 9 MMA
-constexpr int kG1Stages = 4;
-constexpr uint32_t kG1StageBytes = 16384 + 32768;         // A chunk [128 x 32] + query chunk [256 x 32], fp32, SW128
+constexpr int kG1Stages = 3;
+// One stage = the same 32-dim chunk of TWO consecutive row tiles + the query chunk: the query operand is what
+// the kernel streams most (it is re-read from L2 for every row tile, ~7-8 TB/s measured = the L2->SM limit), so
+// every query chunk is used for 256 rows — one tile per TMEM accumulator — instead of 128.
+constexpr uint32_t kG1StageBytes = 2 * 16384 + 32768;     // A chunks of tile 2t, 2t+1 [128 x 32] + query chunk [256 x 32], fp32, SW128
 
 __global__ void __launch_bounds__(kG1Threads, 1)
 flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned char* __restrict__ q_blobs,
                        const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char gsmem[];
-    __shared__ __align__(8) uint64_t full_bar[kG1Stages], empty_bar[kG1Stages], d_full[2], d_free[2];
+    __shared__ __align__(8) uint64_t full_bar[kG1Stages], empty_bar[kG1Stages], d_full, d_free[2];
     __shared__ uint32_t tmem_slot;
     __shared__ u64 s_thr[kGmN];
     __shared__ float s_thr_rank[kGmN];
@@ -366,20 +380,27 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
     const uint32_t qb = blockIdx.x % p.qblocks, rr = blockIdx.x / p.qblocks;
     const bool active = rr < p.ranges;
     const uint32_t tiles_total = (p.n + kGmTile - 1) / kGmTile;
-    const uint32_t tile0 = active ? (uint32_t)((uint64_t)tiles_total * rr / p.ranges) : 0;
-    const uint32_t tile1 = active ? (uint32_t)((uint64_t)tiles_total * (rr + 1) / p.ranges) : 0;
+    const uint32_t pairs_total = (tiles_total + 1) / 2;
+    const uint32_t pair0 = active ? (uint32_t)((uint64_t)pairs_total * rr / p.ranges) : 0;
+    const uint32_t pair1 = active ? (uint32_t)((uint64_t)pairs_total * (rr + 1) / p.ranges) : 0;
     const uint32_t chunks = p.dims / 32;
 
-    for (int q = tid; q < kGmN; q += kG1Threads) { s_thr[q] = kKeyMax; s_thr_rank[q] = INFINITY; s_cnt[q] = 0; }
+    for (int q = tid; q < kGmN; q += kG1Threads) {
+        u64 thr = kKeyMax;
+        const uint32_t qg = qb * kGmN + q;
+        if (p.init_keys != nullptr && qg < p.nq && p.init_counts[qg] >= p.k) thr = p.init_keys[(size_t)qg * p.k + p.k - 1u];
+        s_thr[q] = thr == kKeyMax ? kKeyMax : thr + 1u;             // keys are unique: "<= k-th" is "< k-th + 1"
+        s_thr_rank[q] = thr == kKeyMax ? INFINITY : rank_from_key(thr);
+        s_cnt[q] = 0;
+    }
     if (tid == 0) {
         for (int s = 0; s < kG1Stages; ++s) {
             tc::mbar_init(&full_bar[s], 1);
-            tc::mbar_init(&empty_bar[s], 1);          // the MMA commit frees both operands of the stage
+            tc::mbar_init(&empty_bar[s], 1);          // the MMA commit frees the three operands of the stage
         }
-        for (int b = 0; b < 2; ++b) {
-            tc::mbar_init(&d_full[b], 1);
-            tc::mbar_init(&d_free[b], kG1EpiWarps);
-        }
+        tc::mbar_init(&d_full, 1);
+        tc::mbar_init(&d_free[0], kG1EpiWarps);
+        tc::mbar_init(&d_free[1], kG1EpiWarps);
         tc::mbar_fence_init();
     }
     if (warp == kG1MmaWarp) tc::tmem_alloc(&tmem_slot, 512);
@@ -391,98 +412,112 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
     if (warp == kG1ProducerWarp) {
         if (lane == 0) {
             uint32_t cc = 0;
-            for (uint32_t tile = tile0; tile < tile1; ++tile) {
+            for (uint32_t pair = pair0; pair < pair1; ++pair) {
                 for (uint32_t kc = 0; kc < chunks; ++kc, ++cc) {
                     const uint32_t s = cc % kG1Stages, ph = (cc / kG1Stages) & 1u;
                     unsigned char* st = gsmem + (size_t)s * kG1StageBytes;
                     tc::mbar_wait(&empty_bar[s], ph ^ 1u);
                     tc::mbar_arrive_expect_tx(&full_bar[s], kG1StageBytes);
-                    tc::tma_load_2d(st, &tmap_a, kc * 32, tile * kGmTile, &full_bar[s]);
-                    tma_bulk_g2s(st + 16384, q_blobs + ((size_t)qb * chunks + kc) * 32768u, 32768u, &full_bar[s]);
+                    // rows past the end of a partial tile are zero-filled by the tensor map and still count; an odd
+                    // tile count leaves the last pair without a second tile: load the first again (its rows are
+                    // masked out in the epilogue) rather than a box that lies entirely outside the matrix
+                    const uint32_t tile_b = min(2u * pair + 1u, tiles_total - 1u);
+                    tc::tma_load_2d(st, &tmap_a, kc * 32, (2u * pair) * kGmTile, &full_bar[s]);
+                    tc::tma_load_2d(st + 16384, &tmap_a, kc * 32, tile_b * kGmTile, &full_bar[s]);
+                    tma_bulk_g2s(st + 32768, q_blobs + ((size_t)qb * chunks + kc) * 32768u, 32768u, &full_bar[s]);
                 }
             }
         }
     } else if (warp == kG1MmaWarp) {
         const uint32_t idesc = tc::umma_idesc_tf32(kGmTile, kGmN);
         uint32_t cc = 0, it = 0;
-        for (uint32_t tile = tile0; tile < tile1; ++tile, ++it) {
-            const uint32_t buf = it & 1u;
-            tc::mbar_wait(&d_free[buf], ((it >> 1) & 1u) ^ 1u);     // the epilogue took this accumulator's last tile
-            tc::fence_after_sync();
-            const uint32_t d_addr = tbase + buf * (uint32_t)kGmN;
+        for (uint32_t pair = pair0; pair < pair1; ++pair, ++it) {
             for (uint32_t kc = 0; kc < chunks; ++kc, ++cc) {
                 const uint32_t s = cc % kG1Stages, ph = (cc / kG1Stages) & 1u;
                 tc::mbar_wait(&full_bar[s], ph);
+                if (kc == 0) tc::mbar_wait(&d_free[0], (it & 1u) ^ 1u);   // accumulator 0's scores sit in registers
                 tc::fence_after_sync();
                 const uint32_t st_addr = tc::smem_addr(gsmem + (size_t)s * kG1StageBytes);
                 const uint64_t a0 = tc::umma_smem_desc_sw128(st_addr);
-                const uint64_t b0 = tc::umma_smem_desc_sw128(st_addr + 16384);
+                const uint64_t a1 = tc::umma_smem_desc_sw128(st_addr + 16384);
+                const uint64_t b0 = tc::umma_smem_desc_sw128(st_addr + 32768);
                 if (tc::elect_one()) {
 #pragma unroll
                     for (uint32_t ks = 0; ks < 4; ++ks)
-                        tc::umma_tf32_ss(d_addr, a0 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc, (kc | ks) != 0u);
+                        tc::umma_tf32_ss(tbase, a0 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc, (kc | ks) != 0u);
+                }
+                __syncwarp();
+                if (kc == 0) { tc::mbar_wait(&d_free[1], (it & 1u) ^ 1u); tc::fence_after_sync(); }
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 4; ++ks)
+                        tc::umma_tf32_ss(tbase + (uint32_t)kGmN, a1 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc,
+                                         (kc | ks) != 0u);
                     tc::umma_commit(&empty_bar[s]);
-                    if (kc + 1 == chunks) tc::umma_commit(&d_full[buf]);
+                    if (kc + 1 == chunks) tc::umma_commit(&d_full);
                 }
                 __syncwarp();
             }
         }
     } else {
-        // ===== epilogue warps 0-7: TMEM lanes of quarter (w & 3), query columns of half (w >> 2) =====
+        // ===== epilogue warps 0-7: TMEM lanes of quarter (w & 3), query columns of half (w >> 2), both accumulators =====
         const uint32_t quarter = warp & 3u, half = warp >> 2;
         const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
         const size_t list_base = (size_t)blockIdx.x * kGmN;
         const float bias = p.metric == kCosine ? 1.0f : 0.0f;
         uint32_t it = 0;
-        for (uint32_t tile = tile0; tile < tile1; ++tile, ++it) {
-            const uint32_t buf = it & 1u;
-            const uint32_t row = tile * kGmTile + quarter * 32u + lane;
-            const bool valid = row < p.n;
-            const uint32_t idr = valid ? (p.id_rank ? __ldg(p.id_rank + row) : row) : 0u;
-            tc::mbar_wait(&d_full[buf], (it >> 1) & 1u);
+        for (uint32_t pair = pair0; pair < pair1; ++pair, ++it) {
+            tc::mbar_wait(&d_full, it & 1u);
             tc::fence_after_sync();
-            // the warp's 32 rows x 128 columns into registers at once, then the accumulator is free again
-            uint32_t r[4][32];
-#pragma unroll
-            for (uint32_t g = 0; g < 4; ++g) tc::tmem_ld32(lane_addr + buf * (uint32_t)kGmN + (half * 4u + g) * 32u, r[g]);
-            tc::tmem_ld_wait();
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&d_free[buf]);
             uint32_t worst_bits = 0;
+            bool any_valid = false;
+#pragma unroll 1
+            for (uint32_t acc = 0; acc < 2; ++acc) {
+                const uint32_t row = (2u * pair + acc) * kGmTile + quarter * 32u + lane;
+                const bool valid = row < p.n;
+                any_valid |= valid;
+                const uint32_t idr = valid ? (p.id_rank ? __ldg(p.id_rank + row) : row) : 0u;
+                // the warp's 32 rows x 128 columns into registers at once, then this accumulator is free again
+                uint32_t r[4][32];
 #pragma unroll
-            for (uint32_t g = 0; g < 4; ++g) {
-                const uint32_t cg = half * 4u + g;
-                if (qb * kGmN + cg * 32u >= p.nq) break;       // padded query columns (warp-uniform)
+                for (uint32_t g = 0; g < 4; ++g) tc::tmem_ld32(lane_addr + acc * (uint32_t)kGmN + (half * 4u + g) * 32u, r[g]);
+                tc::tmem_ld_wait();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&d_free[acc]);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const uint32_t q = cg * 32u + j;
-                    const float dot = __uint_as_float(r[g][j]);
-                    worst_bits = max(worst_bits, r[g][j] & 0x7fffffffu);
-                    const float rankv = fmaf(dot, -1.0f, bias);
-                    if (rankv <= s_thr_rank[q] && valid && qb * kGmN + q < p.nq) {
-                        const u64 key = ((u64)order_key(rankv) << 32) | idr;
-                        if (key < s_thr[q]) {
-                            const float raw = p.metric == kNegativeInnerProduct ? -dot : dot;
-                            const uint32_t slot = atomicAdd(&s_cnt[q], 1u);
-                            if (slot < p.list_cap) {
-                                p.list_keys[(list_base + q) * p.list_cap + slot] = key;
-                                p.list_pays[(list_base + q) * p.list_cap + slot] = ((u64)__float_as_uint(raw) << 32) | row;
+                for (uint32_t g = 0; g < 4; ++g) {
+                    const uint32_t cg = half * 4u + g;
+                    if (qb * kGmN + cg * 32u >= p.nq) break;       // padded query columns (warp-uniform)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const uint32_t q = cg * 32u + j;
+                        const float dot = __uint_as_float(r[g][j]);
+                        worst_bits = max(worst_bits, valid ? (r[g][j] & 0x7fffffffu) : 0u);
+                        const float rankv = fmaf(dot, -1.0f, bias);
+                        if (rankv <= s_thr_rank[q] && valid && qb * kGmN + q < p.nq) {
+                            const u64 key = ((u64)order_key(rankv) << 32) | idr;
+                            if (key < s_thr[q]) {
+                                const float raw = p.metric == kNegativeInnerProduct ? -dot : dot;
+                                const uint32_t slot = atomicAdd(&s_cnt[q], 1u);
+                                if (slot < p.list_cap) {
+                                    p.list_keys[(list_base + q) * p.list_cap + slot] = key;
+                                    p.list_pays[(list_base + q) * p.list_cap + slot] = ((u64)__float_as_uint(raw) << 32) | row;
+                                }
                             }
                         }
                     }
                 }
             }
-            if (valid && worst_bits >= 0x7f800000u) *p.bad = 1u;
-            // lists that could overflow during the next tile are cut back to their best k
+            if (any_valid && worst_bits >= 0x7f800000u) *p.bad = 1u;
+            // lists that could overflow during the next pair of tiles are cut back to their best k
             asm volatile("bar.sync 2, 256;" ::: "memory");
             for (uint32_t q = warp; q < kGmN; q += kG1EpiWarps) {
                 const uint32_t cnt = min(s_cnt[q], p.list_cap);
-                if (cnt + kGmTile > p.list_cap) {
+                if (cnt + 2 * kGmTile > p.list_cap) {
                     u64* lkeys = p.list_keys + (list_base + q) * p.list_cap;
                     u64* lpays = p.list_pays + (list_base + q) * p.list_cap;
-                    const u64 kth = p.list_cap == kGmListSmall ? warp_select_list<8>(lkeys, lpays, cnt, p.k, lane)
-                                                               : warp_select_list<16>(lkeys, lpays, cnt, p.k, lane);
+                    const u64 kth = warp_select_list<16>(lkeys, lpays, cnt, p.k, lane);
                     if (lane == 0) {
                         s_cnt[q] = min(cnt, p.k);
                         s_thr[q] = kth;
@@ -496,10 +531,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
             const uint32_t cnt = min(s_cnt[q], p.list_cap);
             u64* lkeys = p.list_keys + (list_base + q) * p.list_cap;
             u64* lpays = p.list_pays + (list_base + q) * p.list_cap;
-            if (cnt > 0) {
-                if (p.list_cap == kGmListSmall) warp_select_list<8>(lkeys, lpays, cnt, p.k, lane);
-                else warp_select_list<16>(lkeys, lpays, cnt, p.k, lane);
-            }
+            if (cnt > 0) warp_select_list<16>(lkeys, lpays, cnt, p.k, lane);
             if (lane == 0) p.list_counts[list_base + q] = min(cnt, p.k);
         }
     }
@@ -731,7 +763,7 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     VB_CUDA(cudaGetLastError());
 
     const size_t max_ctas = (size_t)sms;
-    const uint32_t list_cap = kprime <= 64 ? kGmListSmall : kGmListLarge;
+    const uint32_t list_cap = (kprime <= 64 && terms != 1) ? kGmListSmall : kGmListLarge;   // single pass: 256 rows between cuts
     VB_TRY(ctx.cand_keys.reserve(max_ctas * kGmN * list_cap * sizeof(u64)));
     VB_TRY(ctx.cand_pays.reserve(max_ctas * kGmN * list_cap * sizeof(u64)));
     VB_TRY(ctx.cand_counts.reserve(max_ctas * kGmN * sizeof(uint32_t) + 16));
@@ -754,12 +786,28 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     VB_CUDA(cudaMemsetAsync(d_out_flags, 0, nq * sizeof(uint32_t), stream));
     VB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), stream));
 
+    // Pre-pass over a sample of the rows: with 148 CTAs sharing ~4 query blocks, a CTA sees only 1/37 of the rows
+    // of its queries, so a filter built from ITS rows lets ~k' ln(n) / (n / 37) of them through — with 32 rows per
+    // warp that sent 20-40 % of all (warp, query) pairs down the append path, and the epilogue, not the tensor
+    // pipe, set the pace (ncu: 20 % of the first-level branches taken). The k'-th best score of ANY subset of the
+    // rows bounds the final k'-th from above: one small launch over the first rows + its merge gives every CTA of
+    // the main launch a filter at quantile k' / sample from its first tile on.
+    const size_t sample = std::min<size_t>(32768, std::max<size_t>(4096, (n / 16) & ~(size_t)255));
+    const bool prepass = n >= 65536 && !std::getenv("VB_GEMM_NO_PREPASS");
+    u64* pre_keys = nullptr;
+    uint32_t* pre_counts = nullptr;
+    if (prepass) {
+        VB_TRY(ctx.dump_keys2.reserve(nq_pad * kprime * sizeof(u64)));
+        VB_TRY(ctx.dump_pays2.reserve(nq_pad * kprime * sizeof(u64)));
+        VB_TRY(ctx.hist.reserve(nq_pad * sizeof(uint32_t)));
+        pre_keys = ctx.dump_keys2.as<u64>();
+        pre_counts = ctx.hist.as<uint32_t>();
+    }
     for (uint32_t qb0 = 0; qb0 < qblocks_total; qb0 += group) {
         const uint32_t qblocks = std::min(group, qblocks_total - qb0);
         const size_t q0 = (size_t)qb0 * kGmN;
         const uint32_t nq_here = (uint32_t)std::min<size_t>(nq - q0, (size_t)qblocks * kGmN);
         GemmParams p{};
-        p.n = (uint32_t)n;
         p.dims = (uint32_t)dims;
         p.nq = nq_here;
         p.k = (uint32_t)kprime;
@@ -774,14 +822,22 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
         p.bad = d_bad;
         { const char* dbg = std::getenv("VB_GEMM_DEBUG"); p.debug = dbg ? (uint32_t)std::atoi(dbg) : 0u; }
         const uint32_t grid = p.qblocks * p.ranges;
-        if (terms == 1)
-            flat_gemm1_topk_kernel<<<grid, kG1Threads, smem_bytes, stream>>>(tmap_a, q_blobs + (size_t)qb0 * (dims / 32) * blob_bytes, p);
-        else
-            flat_gemm_topk_kernel<<<grid, kGmThreads, smem_bytes, stream>>>(tmap_a, q_blobs + (size_t)qb0 * (dims / 32) * blob_bytes, p);
-        VB_CUDA(cudaGetLastError());
-        flat_gemm_merge_kernel<<<nq_here, 128, (size_t)cap * 16, stream>>>(p, cap, apx_keys + q0 * kprime,
-                                                                          apx_pays + q0 * kprime, apx_counts + q0);
-        VB_CUDA(cudaGetLastError());
+        const unsigned char* blobs = q_blobs + (size_t)qb0 * (dims / 32) * blob_bytes;
+        for (int pass = prepass ? 0 : 1; pass < 2; ++pass) {
+            p.n = pass == 0 ? (uint32_t)sample : (uint32_t)n;
+            p.init_keys = pass == 0 ? nullptr : (prepass ? pre_keys + q0 * kprime : nullptr);
+            p.init_counts = pass == 0 ? nullptr : (prepass ? pre_counts + q0 : nullptr);
+            if (terms == 1) flat_gemm1_topk_kernel<<<grid, kG1Threads, smem_bytes, stream>>>(tmap_a, blobs, p);
+            else flat_gemm_topk_kernel<<<grid, kGmThreads, smem_bytes, stream>>>(tmap_a, blobs, p);
+            VB_CUDA(cudaGetLastError());
+            if (pass == 0)
+                flat_gemm_merge_kernel<<<nq_here, 128, (size_t)cap * 16, stream>>>(p, cap, pre_keys + q0 * kprime,
+                                                                                  ctx.dump_pays2.as<u64>() + q0 * kprime, pre_counts + q0);
+            else
+                flat_gemm_merge_kernel<<<nq_here, 128, (size_t)cap * 16, stream>>>(p, cap, apx_keys + q0 * kprime,
+                                                                                  apx_pays + q0 * kprime, apx_counts + q0);
+            VB_CUDA(cudaGetLastError());
+        }
     }
     RescoreParams rp{};
     rp.rows = d_rows;
