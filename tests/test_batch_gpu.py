@@ -30,7 +30,7 @@ def gemm_terms(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("metric", ["cosine", "inner_product", "negative_inner_product"])
+@pytest.mark.parametrize("metric", ["cosine", "inner_product", "negative_inner_product", "l2", "l2_squared"])
 @pytest.mark.parametrize("n,d,nq,k", [(5000, 128, 40, 10), (20000, 768, 300, 10), (3000, 64, 16, 100), (9000, 96, 513, 1)])
 def test_batched_search_matches_oracle(metric, n, d, nq, k, gemm_terms):
     rows = _rows(n, d, n + d)
@@ -122,3 +122,31 @@ def test_single_pass_filter_is_complete_on_adversarial_near_ties(monkeypatch):
             got = ok(nifs.flat_search_batch(idx, queries, k))
             for qi in range(nq):
                 assert_hits_match(got[qi], ok(oracle.flat_search_dense("cosine", rows, ids, queries[qi], k)))
+
+
+@pytest.mark.parametrize("metric", ["l2", "l2_squared"])
+def test_batched_l2_family_unnormalised_rows_and_mutations(metric, gemm_terms):
+    """The L2 family goes through the tensor cores as |x|^2 - 2 q.x with a row-norm mirror: rows of very different
+    norms, an exact duplicate of a query (distance 0), and mutations that must refresh the mirror."""
+    rng = np.random.default_rng(21)
+    n, d, nq, k = 70_000, 64, 48, 10
+    rows = (rng.standard_normal((n, d)) * rng.uniform(0.2, 5.0, size=(n, 1))).astype(np.float32)
+    queries = (rng.standard_normal((nq, d)) * 2.0).astype(np.float32)
+    queries[5] = rows[1234]
+    ids = [f"{(i * 7919) % n:06d}" for i in range(n)]
+    idx = getattr(nifs, f"flat_new_{metric}")()
+    ok(nifs.flat_insert_matrix(idx, ids, rows))
+    got = ok(nifs.flat_search_batch(idx, queries, k))
+    for qi in range(nq):
+        assert_hits_match(got[qi], ok(oracle.flat_search_dense(metric, rows, ids, queries[qi], k)))
+    assert got[5][0] == (ids[1234], 0.0)
+    # delete the duplicate, upsert another row onto a query: the mirror must follow
+    ok(nifs.flat_delete(idx, ids[1234]))
+    ok(nifs.flat_insert(idx, ids[77], queries[9]))
+    rows2 = rows.copy()
+    rows2[77] = queries[9]
+    keep = [i for i in range(n) if i != 1234]
+    got = ok(nifs.flat_search_batch(idx, queries, k))
+    for qi in (5, 9, 20, nq - 1):
+        assert_hits_match(got[qi], ok(oracle.flat_search_dense(metric, rows2[keep], [ids[i] for i in keep], queries[qi], k)))
+    assert got[9][0] == (ids[77], 0.0)

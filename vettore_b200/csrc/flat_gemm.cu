@@ -38,7 +38,12 @@ constexpr uint32_t kGmACol = 256;        // TMEM: D at [0,256), A buffer u at 25
 
 struct GemmParams {
     uint32_t n, dims, nq, k;
-    int metric;                    // kCosine / kInnerProduct / kNegativeInnerProduct
+    int metric;                    // kCosine / kInnerProduct / kNegativeInnerProduct / kL2 / kL2Squared
+    // rank of a score: fma(dot, rank_scale, row bias). Dot family: scale -1, bias 1 (cosine: 1 - dot) or 0. L2 family:
+    // scale -2, bias |row|^2 from the row-norm mirror, i.e. |x|^2 - 2 q.x = |x - q|^2 - |q|^2 — the squared distance up
+    // to a per-query constant, which is all a per-query filter needs (distances.rs:140-152 via the exact re-scoring).
+    float rank_scale;
+    const float* row_norm2;        // [n] or null
     uint32_t qblocks, ranges;      // query blocks, row ranges (qblocks * ranges CTAs do work)
     const uint32_t* id_rank;       // [n] or null
     uint32_t list_cap;             // kGmListSmall / kGmListLarge
@@ -274,12 +279,12 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned
         const size_t list_base = (size_t)blockIdx.x * kGmN;
         // rank = fma(dot, -1, bias): cosine 1 - dot (one rounding, == 1.0f - raw), inner product / negative
         // inner product -dot (distances.rs:113-119 with raw = dot resp. -dot)
-        const float bias = p.metric == kCosine ? 1.0f : 0.0f;
         uint32_t it = 0;
         for (uint32_t tile = tile0; tile < tile1; ++tile, ++it) {
             const uint32_t row = tile * kGmTile + quarter * 32u + lane;
             const bool valid = row < p.n;
             const uint32_t idr = valid ? (p.id_rank ? __ldg(p.id_rank + row) : row) : 0u;
+            const float bias = p.row_norm2 ? (valid ? __ldg(p.row_norm2 + row) : 0.0f) : (p.metric == kCosine ? 1.0f : 0.0f);
             tc::mbar_wait(&d_full, it & 1u);
             tc::fence_after_sync();
             uint32_t worst_bits = 0;   // max |score| bits: >= 0x7f800000 means a non-finite score
@@ -293,11 +298,11 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned
                     const uint32_t q = cg * 32u + j;
                     const float dot = __uint_as_float(r[j]);
                     worst_bits = max(worst_bits, r[j] & 0x7fffffffu);
-                    const float rankv = fmaf(dot, -1.0f, bias);
+                    const float rankv = fmaf(dot, p.rank_scale, bias);
                     if (rankv <= s_thr_rank[q] && valid && qb * kGmN + q < p.nq) {   // first-level filter: one compare
                         const u64 key = ((u64)order_key(rankv) << 32) | idr;
                         if (key < s_thr[q]) {
-                            const float raw = p.metric == kNegativeInnerProduct ? -dot : dot;
+                            const float raw = p.row_norm2 ? rankv : (p.metric == kNegativeInnerProduct ? -dot : dot);
                             const uint32_t slot = atomicAdd(&s_cnt[q], 1u);
                             if (slot < p.list_cap) {
                                 p.list_keys[(list_base + q) * p.list_cap + slot] = key;
@@ -391,6 +396,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
         if (p.init_keys != nullptr && qg < p.nq && p.init_counts[qg] >= p.k) thr = p.init_keys[(size_t)qg * p.k + p.k - 1u];
         s_thr[q] = thr == kKeyMax ? kKeyMax : thr + 1u;             // keys are unique: "<= k-th" is "< k-th + 1"
         s_thr_rank[q] = thr == kKeyMax ? INFINITY : rank_from_key(thr);
+        if (qg >= p.nq) { s_thr[q] = 0ull; s_thr_rank[q] = -INFINITY; }   // padded query column: nothing ever passes
         s_cnt[q] = 0;
     }
     if (tid == 0) {
@@ -465,18 +471,19 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
         const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
         const size_t list_base = (size_t)blockIdx.x * kGmN;
         const float bias = p.metric == kCosine ? 1.0f : 0.0f;
+        const float scale = p.rank_scale;
         uint32_t it = 0;
         for (uint32_t pair = pair0; pair < pair1; ++pair, ++it) {
             tc::mbar_wait(&d_full, it & 1u);
             tc::fence_after_sync();
-            uint32_t worst_bits = 0;
-            bool any_valid = false;
+            float poison = 0.0f;       // stays +-0 unless a score is Inf / NaN (x * 0 is NaN for those)
 #pragma unroll 1
             for (uint32_t acc = 0; acc < 2; ++acc) {
                 const uint32_t row = (2u * pair + acc) * kGmTile + quarter * 32u + lane;
                 const bool valid = row < p.n;
-                any_valid |= valid;
                 const uint32_t idr = valid ? (p.id_rank ? __ldg(p.id_rank + row) : row) : 0u;
+                // a row past the end never passes the filter: its rank is NaN (one compare per score, no row test)
+                const float row_bias = valid ? (p.row_norm2 ? __ldg(p.row_norm2 + row) : bias) : __int_as_float(0x7fc00000);
                 // the warp's 32 rows x 128 columns into registers at once, then this accumulator is free again
                 uint32_t r[4][32];
 #pragma unroll
@@ -493,12 +500,12 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                     for (int j = 0; j < 32; ++j) {
                         const uint32_t q = cg * 32u + j;
                         const float dot = __uint_as_float(r[g][j]);
-                        worst_bits = max(worst_bits, valid ? (r[g][j] & 0x7fffffffu) : 0u);
-                        const float rankv = fmaf(dot, -1.0f, bias);
-                        if (rankv <= s_thr_rank[q] && valid && qb * kGmN + q < p.nq) {
+                        if (valid) poison = fmaf(dot, 0.0f, poison);
+                        const float rankv = fmaf(dot, scale, row_bias);
+                        if (rankv <= s_thr_rank[q]) {               // first-level filter: one compare
                             const u64 key = ((u64)order_key(rankv) << 32) | idr;
                             if (key < s_thr[q]) {
-                                const float raw = p.metric == kNegativeInnerProduct ? -dot : dot;
+                                const float raw = p.row_norm2 ? rankv : (p.metric == kNegativeInnerProduct ? -dot : dot);
                                 const uint32_t slot = atomicAdd(&s_cnt[q], 1u);
                                 if (slot < p.list_cap) {
                                     p.list_keys[(list_base + q) * p.list_cap + slot] = key;
@@ -509,7 +516,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                     }
                 }
             }
-            if (any_valid && worst_bits >= 0x7f800000u) *p.bad = 1u;
+            if (poison != poison) *p.bad = 1u;
             // lists that could overflow during the next pair of tiles are cut back to their best k
             asm volatile("bar.sync 2, 256;" ::: "memory");
             for (uint32_t q = warp; q < kGmN; q += kG1EpiWarps) {
@@ -594,8 +601,9 @@ struct RescoreParams {
     const u64* cand_keys;        // [nq][kprime] approximate keys, ascending
     const u64* cand_pays;        // [nq][kprime]
     const uint32_t* cand_counts; // [nq]
-    float err_coeff;             // bound = err_coeff * |query| * max |row|
+    float err_coeff;             // |approx dot - exact dot| <= err_coeff * |query| * max |row|
     float max_row_norm;
+    int l2_family;               // approximate ranks are |x|^2 - 2 q.x (squared distance minus |q|^2)
     u64* out_keys;               // [nq][k] exact keys (optional)
     u64* out_pays;               // [nq][k]
     uint32_t* out_counts;        // [nq]
@@ -653,9 +661,17 @@ __global__ void __launch_bounds__(128) flat_gemm_rescore_kernel(const RescorePar
         p.out_counts[q] = kept;
         // completeness check (see above); only needed when candidates were actually dropped
         if (cnt == p.kprime && p.kprime < p.n && kept == p.k) {
-            const float bound = p.err_coeff * sqrtf(qn2) * p.max_row_norm;
-            const float worst_kept_approx = rank_from_key(p.cand_keys[(size_t)q * p.kprime + cnt - 1]);
-            const float exact_kth = rank_from_key(col.keys[p.k - 1]);
+            float bound = p.err_coeff * sqrtf(qn2) * p.max_row_norm;
+            float worst_kept_approx = rank_from_key(p.cand_keys[(size_t)q * p.kprime + cnt - 1]);
+            float exact_kth = rank_from_key(col.keys[p.k - 1]);
+            if (p.l2_family) {
+                // compare squared distances: the approximate rank lacks |q|^2, carries twice the dot error and the
+                // fp32 rounding of the row-norm mirror and of the subtraction
+                worst_kept_approx += qn2;
+                bound = 2.0f * bound + 1.0e-6f * (p.max_row_norm * p.max_row_norm + qn2);
+                if (M == kL2) exact_kth = exact_kth * exact_kth;
+                exact_kth *= 1.000001f;   // the exact value's own rounding (and the square of the rounded root)
+            }
             if (!(worst_kept_approx - bound > exact_kth) && p.flags[q] == 0u) p.flags[q] = 1u;
         }
     }
@@ -683,7 +699,9 @@ __global__ void split_queries_kernel(const float* q, uint32_t nq, uint32_t qbloc
 
 bool flat_gemm_eligible(int metric, size_t dims, size_t stride, size_t nq, size_t k, size_t n) {
     if (std::getenv("VB_FLAT_NO_GEMM")) return false;
-    if (metric != kCosine && metric != kInnerProduct && metric != kNegativeInnerProduct) return false;
+    if (metric != kCosine && metric != kInnerProduct && metric != kNegativeInnerProduct && metric != kL2 &&
+        metric != kL2Squared)
+        return false;
     if (dims % 32 != 0 || stride != dims) return false;
     const char* min_env = std::getenv("VB_FLAT_GEMM_MIN_BATCH");
     const size_t min_batch = min_env ? (size_t)std::atoi(min_env) : 16;
@@ -693,7 +711,8 @@ bool flat_gemm_eligible(int metric, size_t dims, size_t stride, size_t nq, size_
 }
 
 // max over rows of |row| (f32 from an f64 sum), one warp per row; non-negative floats order like uints
-__global__ void row_norm_max_kernel(const float* rows, size_t stride, uint32_t dims, uint32_t n, uint32_t* out_bits) {
+__global__ void row_norm_max_kernel(const float* rows, size_t stride, uint32_t dims, uint32_t n, uint32_t* out_bits,
+                                    float* norm2_out) {
     const uint32_t lane = threadIdx.x & 31;
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     float best = 0.0f;
@@ -705,15 +724,17 @@ __global__ void row_norm_max_kernel(const float* rows, size_t stride, uint32_t d
         }
         s = warp_sum(s);
         best = fmaxf(best, (float)sqrt(s) * 1.0000002f);
+        if (norm2_out && lane == 0) norm2_out[r] = (float)s;
     }
     if (lane == 0) atomicMax(out_bits, __float_as_uint(best));
 }
 
-Status flat_gemm_max_row_norm(SearchCtx& ctx, const float* d_rows, size_t stride, size_t n, size_t dims, float* out) {
+Status flat_gemm_max_row_norm(SearchCtx& ctx, const float* d_rows, size_t stride, size_t n, size_t dims, float* out,
+                              float* d_norm2_out) {
     VB_TRY(ctx.q_norms.reserve(16));
     uint32_t* d_bits = ctx.q_norms.as<uint32_t>() + 2;
     VB_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t), ctx.stream));
-    row_norm_max_kernel<<<148 * 8, 256, 0, ctx.stream>>>(d_rows, stride, (uint32_t)dims, (uint32_t)n, d_bits);
+    row_norm_max_kernel<<<148 * 8, 256, 0, ctx.stream>>>(d_rows, stride, (uint32_t)dims, (uint32_t)n, d_bits, d_norm2_out);
     uint32_t bits = 0;
     VB_CUDA(cudaMemcpyAsync(&bits, d_bits, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
     VB_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -727,6 +748,8 @@ static RescoreKernel rescore_lookup(int metric) {
         case kCosine: return flat_gemm_rescore_kernel<kCosine>;
         case kInnerProduct: return flat_gemm_rescore_kernel<kInnerProduct>;
         case kNegativeInnerProduct: return flat_gemm_rescore_kernel<kNegativeInnerProduct>;
+        case kL2: return flat_gemm_rescore_kernel<kL2>;
+        case kL2Squared: return flat_gemm_rescore_kernel<kL2Squared>;
     }
     return nullptr;
 }
@@ -737,7 +760,7 @@ static RescoreKernel rescore_lookup(int metric) {
 // score was non-finite (redo the whole batch). No host synchronisation.
 Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, size_t stride,
                                const uint32_t* d_id_rank, size_t n, size_t dims, float max_row_norm,
-                               const float* d_queries, size_t nq, size_t k, u64* d_out_keys, u64* d_out_pays,
+                               const float* d_row_norm2, const float* d_queries, size_t nq, size_t k, u64* d_out_keys, u64* d_out_pays,
                                uint32_t* d_out_counts, uint32_t* d_out_flags, uint32_t* d_bad, cudaStream_t stream) {
     int dev = 0, sms = 0;
     VB_CUDA(cudaGetDevice(&dev));
@@ -755,6 +778,8 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     const size_t kprime = std::min<size_t>(std::min<size_t>(k + margin, 128), n);   // approximate candidates kept
     RescoreKernel rescore = rescore_lookup(metric);
     if (!rescore) return Status::Cuda("metric not served by the batched kernel");
+    const bool l2_family = metric == kL2 || metric == kL2Squared;
+    if (l2_family && d_row_norm2 == nullptr) return Status::Cuda("batched L2 search needs the row-norm mirror");
 
     VB_TRY(ctx.staging.reserve(2 * nq_pad * dims * sizeof(float)));
     unsigned char* q_blobs = ctx.staging.as<unsigned char>();
@@ -812,6 +837,8 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
         p.nq = nq_here;
         p.k = (uint32_t)kprime;
         p.metric = metric;
+        p.rank_scale = l2_family ? -2.0f : -1.0f;
+        p.row_norm2 = l2_family ? d_row_norm2 : nullptr;
         p.qblocks = qblocks;
         p.ranges = std::max<uint32_t>(1, (uint32_t)sms / qblocks);
         p.id_rank = d_id_rank;
@@ -857,6 +884,7 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     // MMA steps per term in both cases.
     rp.err_coeff = (terms == 1 ? 1.96e-3f : 4.0e-6f) + 1.0e-7f * (float)(3 * dims / 8);
     rp.max_row_norm = max_row_norm;
+    rp.l2_family = l2_family ? 1 : 0;
     rp.out_keys = d_out_keys;
     rp.out_pays = d_out_pays;
     rp.out_counts = d_out_counts;
@@ -867,8 +895,8 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
 }
 
 Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t stride, const uint32_t* d_id_rank,
-                        size_t n, size_t dims, float max_row_norm, const float* h_queries, size_t nq, size_t k,
-                        GemmResult* out) {
+                        size_t n, size_t dims, float max_row_norm, const float* d_row_norm2, const float* h_queries, size_t nq,
+                        size_t k, GemmResult* out) {
     const size_t qbytes = nq * dims * sizeof(float);
     VB_TRY(ctx.h_queries.reserve(qbytes));
     VB_TRY(ctx.queries.reserve(qbytes));
@@ -881,7 +909,7 @@ Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t 
     uint32_t* out_counts = reinterpret_cast<uint32_t*>(out_pays + nq * k);
     uint32_t* out_flags = out_counts + nq;
     uint32_t* d_bad = out_flags + nq;
-    Status s = flat_gemm_search_device(ctx, metric, d_rows, stride, d_id_rank, n, dims, max_row_norm,
+    Status s = flat_gemm_search_device(ctx, metric, d_rows, stride, d_id_rank, n, dims, max_row_norm, d_row_norm2,
                                        ctx.queries.as<float>(), nq, k, nullptr, out_pays, out_counts, out_flags, d_bad,
                                        ctx.stream);
     if (!s.ok()) { ctx.poison(); return s; }

@@ -45,6 +45,7 @@ FlatIndex::~FlatIndex() {
     if (d_rank_) cudaFree(d_rank_);
     if (d_codes_) cudaFree(d_codes_);
     if (d_prefix_) cudaFree(d_prefix_);
+    if (d_norm2_) cudaFree(d_norm2_);
     if (d_status_) cudaFreeHost(d_status_);
 }
 
@@ -78,6 +79,21 @@ Status FlatIndex::device_status(uint32_t* out) {
     *out = *reinterpret_cast<volatile uint32_t*>(d_status_);
     d_status_[0] = 0u;
     return Status::Ok();
+}
+
+// Callers hold the read lock; norm_mu_ serialises the lazy (re)computation among concurrent batched searches.
+Status FlatIndex::ensure_norms(SearchCtx& ctx) {
+    std::lock_guard<std::mutex> ng(norm_mu_);
+    if (max_norm_ >= 0.0f) return Status::Ok();
+    const bool l2_family = metric_ == kL2 || metric_ == kL2Squared;
+    if (l2_family && norm2_cap_ < n_) {
+        if (d_norm2_) cudaFree(d_norm2_);
+        d_norm2_ = nullptr;
+        norm2_cap_ = 0;
+        VB_CUDA(cudaMalloc(&d_norm2_, cap_ * sizeof(float)));
+        norm2_cap_ = cap_;
+    }
+    return flat_gemm_max_row_norm(ctx, d_rows_, stride_, n_, dim_, &max_norm_, l2_family ? d_norm2_ : nullptr);
 }
 
 int64_t FlatIndex::find_row(const std::string& id) const {
@@ -429,6 +445,10 @@ void FlatIndex::reset_if_empty() {
     if (d_rank_) cudaFree(d_rank_);
     if (d_codes_) cudaFree(d_codes_);
     if (d_prefix_) cudaFree(d_prefix_);
+    if (d_norm2_) cudaFree(d_norm2_);
+    d_norm2_ = nullptr;
+    norm2_cap_ = 0;
+    max_norm_ = -1.0f;
     d_rows_ = nullptr;
     d_rank_ = nullptr;
     d_codes_ = nullptr;
@@ -449,6 +469,7 @@ Status FlatIndex::remove(const char* id, size_t id_len) {
     if (dev_ctx_) VB_CUDA(cudaDeviceSynchronize());
     const uint32_t row = (uint32_t)found;
     const uint32_t last = (uint32_t)(n_ - 1);
+    if (d_norm2_) max_norm_ = -1.0f;        // the row-norm mirror follows the rows: recomputed by the next batched search
     if (row != last) leave_sorted_mode();   // the hole is filled by the last row: rows leave id order
     if (!sorted_) id_row_.erase(key);
     if (row != last) {  // move the last row into the hole; its rank label travels with it
@@ -487,12 +508,9 @@ Status FlatIndex::search(const float* queries, size_t nq, size_t len, size_t lim
     const size_t kk = std::min(limit, n_);
     if (flat_gemm_eligible(metric_, dim_, stride_, nq, kk, n_)) {
         // K2: the batch is one dense contraction on the tensor cores (+ exact re-scoring)
-        {
-            std::lock_guard<std::mutex> ng(norm_mu_);
-            if (max_norm_ < 0.0f) VB_TRY(flat_gemm_max_row_norm(*ctx.ctx, d_rows_, stride_, n_, dim_, &max_norm_));
-        }
+        VB_TRY(ensure_norms(*ctx.ctx));
         GemmResult gr;
-        VB_TRY(flat_gemm_search(*ctx.ctx, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, queries, nq, kk, &gr));
+        VB_TRY(flat_gemm_search(*ctx.ctx, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, d_norm2_, queries, nq, kk, &gr));
         if (!gr.non_finite) {
             std::vector<size_t> redo;
             for (size_t q = 0; q < nq; ++q) {
@@ -789,7 +807,7 @@ Status FlatIndex::search_device(const float* d_queries, size_t nq, size_t q_stri
         // are resolved HERE, like FlatIndex::search does: one small D2H read of the flag words, then
         // the flagged queries are redone by the single-query kernel into the same output slots — so a
         // batch through this entry (the row-sharded path) is exactly as complete as the host-facing one.
-        if (max_norm_ < 0.0f) VB_TRY(flat_gemm_max_row_norm(*dev_ctx_, d_rows_, stride_, n_, dim_, &max_norm_));
+        VB_TRY(ensure_norms(*dev_ctx_));
         SearchCtx& c = *dev_ctx_;
         VB_TRY(c.result.reserve(nq * kk * sizeof(u64) + 2 * nq * sizeof(uint32_t) + 16));
         VB_TRY(c.out_keys.reserve(nq * kk * sizeof(u64)));
@@ -797,7 +815,7 @@ Status FlatIndex::search_device(const float* d_queries, size_t nq, size_t q_stri
         u64* pays = c.result.as<u64>();
         uint32_t* counts = reinterpret_cast<uint32_t*>(pays + nq * kk);
         uint32_t* flags = counts + nq;
-        VB_TRY(flat_gemm_search_device(c, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, d_queries, nq, kk,
+        VB_TRY(flat_gemm_search_device(c, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, d_norm2_, d_queries, nq, kk,
                                        c.out_keys.as<u64>(), pays, counts, flags, flags + nq, stream));
         VB_TRY(unpack_device_results(c.out_keys.as<u64>(), pays, counts, (uint32_t)nq, (uint32_t)kk, d_keys, d_values,
                                      d_rows, d_counts, stream));

@@ -116,6 +116,9 @@ class FlatIndex {
     bool external_ranks_ = false;
     std::mutex norm_mu_;
     float max_norm_ = -1.0f;   // max |row| (device reduction, lazily), < 0 = unknown
+    float* d_norm2_ = nullptr; // [norm2_cap_] |row|^2 (L2-family indexes: batched searches), valid while max_norm_ >= 0
+    size_t norm2_cap_ = 0;
+    Status ensure_norms(SearchCtx& ctx);   // (re)computes max_norm_ (and the row-norm mirror for the L2 family)
     SearchCtx* dev_ctx_ = nullptr;  // workspace of the stream-ordered device-level entry
     uint32_t* d_status_ = nullptr;  // sticky status word of the device-level entries
 };
