@@ -371,6 +371,9 @@ constexpr int kG1Stages = 3;
 // every query chunk is used for 256 rows — one tile per TMEM accumulator — instead of 128.
 constexpr uint32_t kG1StageBytes = 2 * 16384 + 32768;     // A chunks of tile 2t, 2t+1 [128 x 32] + query chunk [256 x 32], fp32, SW128
 
+// (Tried and dropped: warp-aggregated appends — one vote + ballot + a single shared-memory atomic per (warp, query
+// column). The vote costs an instruction on EVERY score: the main pass went from 2.67 to 5.25 ms, and even the
+// pre-pass, where nearly every score passes, got slower: 736 vs 618 us.)
 __global__ void __launch_bounds__(kG1Threads, 1)
 flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned char* __restrict__ q_blobs,
                        const GemmParams p) {
@@ -817,8 +820,13 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     // pipe, set the pace (ncu: 20 % of the first-level branches taken). The k'-th best score of ANY subset of the
     // rows bounds the final k'-th from above: one small launch over the first rows + its merge gives every CTA of
     // the main launch a filter at quantile k' / sample from its first tile on.
-    const size_t sample = std::min<size_t>(32768, std::max<size_t>(4096, (n / 16) & ~(size_t)255));
-    const bool prepass = n >= 65536 && !std::getenv("VB_GEMM_NO_PREPASS");
+    // Sample = 256 rows per CTA of the launch (one tile pair): while thresholds are open EVERY score is appended, and
+    // that phase costs ~170 us per pair per CTA, so a longer sample buys a tighter filter at a steep price
+    // (measured at 1M x 768, Q = 1024: 9.5k rows 313k queries/s, 19k 287k, 33k 282k, 66k 272k).
+    const uint32_t ranges_full = std::max<uint32_t>(1, (uint32_t)sms / group);
+    size_t sample = std::min<size_t>(n / 8, (size_t)ranges_full * 256);
+    if (const char* e = std::getenv("VB_GEMM_SAMPLE")) sample = std::min<size_t>(n, std::max<size_t>(1024, (size_t)std::atol(e)));
+    const bool prepass = n >= 65536 && sample >= 2048 && !std::getenv("VB_GEMM_NO_PREPASS");
     u64* pre_keys = nullptr;
     uint32_t* pre_counts = nullptr;
     if (prepass) {
