@@ -65,6 +65,20 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_tf32_peak():
+    """Dense TF32 tensor-pipe peak of this device, measured live with a bare tcgen05.mma kind::tf32 loop
+    (vb_debug_tf32_peak, csrc/tc_probe.cu): the denominator SURVEY.md §8(d) asks for. None when it cannot run."""
+    try:
+        from vettore_b200._lib import lib
+        fn = lib().vb_debug_tf32_peak
+        fn.restype = C.c_int
+        out = C.c_float(0.0)
+        rc = fn(C.c_int(20000), C.byref(out))
+        return float(out.value) if rc == 0 and out.value > 0 else None
+    except Exception:
+        return None
+
+
 def workload_string(rows, dim, k):
     return f"flat cosine exact scan {rows}x{dim} fp32 per GPU, batch of 1 query, k={k}"
 
@@ -496,7 +510,7 @@ def headline(run: Run, args, pk):
         rows_h, vals_h = brows.cpu().numpy().reshape(nqb, k), bvals.cpu().numpy().reshape(nqb, k)
         for qi in range(nchk):
             assert_hits_match([(int(rows_h[qi, i]), float(vals_h[qi, i])) for i in range(k)], bref[qi], f"batch query {qi}")
-        tf32_peak = pk["bf16"] / 2
+        tf32_peak = pk["tf32"]
         terms = int(os.environ.get("VB_GEMM_TERMS", "1" if k <= 32 else "3"))
         alg = 2.0 * nqb * n * d / (bms * 1e-3) / 1e12
         issued = terms * alg
@@ -630,7 +644,7 @@ def block_c3(run: Run, args, pk):
                 checked += 1
         regen.close()
     issued = 3 * 2.0 * nq * n * d / (local_ms * 1e-3) / 1e12
-    tf32_peak = pk["bf16"] / 2
+    tf32_peak = pk["tf32"]
     out = {"workload": f"flat inner-product scan {total}x{d} fp32 row-sharded x{world}, batch of {nq} queries, k={k}",
            "rows_per_gpu": n, "corpus_rows_resident": n * world, "full_corpus": n * world == total,
            "fits_note": None if n * world == total else
@@ -860,6 +874,11 @@ def cpu_samples(args):
 def run_b200(args):
     run = Run()
     pk = peaks()
+    tf32 = measured_tf32_peak()
+    if tf32:   # the tensor-bound rooflines are stated against the pipe's own measured TF32 rate
+        pk["tf32"], pk["tc_src"] = tf32, "measured on this device: bare tcgen05.mma kind::tf32 loop (vb_debug_tf32_peak)"
+    else:
+        pk["tf32"] = pk["bf16"] / 2
     args.cfgs = [c for c in args.configs.split(",") if c]
     line = headline(run, args, pk)
     blocks = {}

@@ -178,3 +178,67 @@ extern "C" int vb_debug_tc_probe(const float* hA, const float* hB, int K, int mo
     cudaFree(dD);
     return rc;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Measured dense TF32 tensor-pipe peak of THIS device ("measure TF32 directly on the box"): one
+// persistent CTA per SM issues back-to-back tcgen05.mma kind::tf32 (M = 128, N = 256, K = 8, both operands from
+// shared memory, two TMEM accumulators alternating) with no loads, no epilogue and no waits in between. Not part
+// of the drop-in ABI; bench.py uses it as the denominator of the tensor-bound rooflines.
+namespace vb {
+__global__ void __launch_bounds__(128) tf32_peak_kernel(int iters) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
+    if (t == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    tc::fence_proxy_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    if (t == 0) {
+        const uint32_t idesc = tc::umma_idesc_tf32(128, 256);
+        const uint64_t a0 = tc::umma_smem_desc_sw128(tc::smem_addr(smem));
+        const uint64_t b0 = tc::umma_smem_desc_sw128(tc::smem_addr(smem + 16384));
+        for (int i = 0; i < iters; ++i)
+#pragma unroll
+            for (uint32_t ks = 0; ks < 4; ++ks)
+                tc::umma_tf32_ss(tbase + (uint32_t)(i & 1) * 256u, a0 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc, 1u);
+        tc::umma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+}  // namespace vb
+
+extern "C" int vb_debug_tf32_peak(int iters, float* tflops) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = 16384 + 32768 + 1024;
+    if (cudaFuncSetAttribute(vb::tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    vb::tf32_peak_kernel<<<sms, 128, smem>>>(iters / 8 + 1);            // warm-up
+    float best = 0.0f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        vb::tf32_peak_kernel<<<sms, 128, smem>>>(iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) return -3;
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = (double)sms * iters * 4.0 * 2.0 * 128.0 * 256.0 * 8.0;
+        best = fmaxf(best, (float)(flops / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
