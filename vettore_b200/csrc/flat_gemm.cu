@@ -764,7 +764,8 @@ static RescoreKernel rescore_lookup(int metric) {
 Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, size_t stride,
                                const uint32_t* d_id_rank, size_t n, size_t dims, float max_row_norm,
                                const float* d_row_norm2, const float* d_queries, size_t nq, size_t k, u64* d_out_keys, u64* d_out_pays,
-                               uint32_t* d_out_counts, uint32_t* d_out_flags, uint32_t* d_bad, cudaStream_t stream) {
+                               uint32_t* d_out_counts, uint32_t* d_out_flags, uint32_t* d_bad, cudaStream_t stream,
+                               int force_terms, int* terms_used) {
     int dev = 0, sms = 0;
     VB_CUDA(cudaGetDevice(&dev));
     VB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -777,6 +778,8 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
         const int t = std::atoi(e);
         if (t == 3 || (t == 1 && k <= 96)) terms = t;
     }
+    if (force_terms == 3) terms = 3;
+    if (terms_used) *terms_used = terms;
     const size_t margin = terms == 1 ? 32 : std::max<size_t>(8, k / 4);
     const size_t kprime = std::min<size_t>(std::min<size_t>(k + margin, 128), n);   // approximate candidates kept
     RescoreKernel rescore = rescore_lookup(metric);
@@ -904,7 +907,7 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
 
 Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t stride, const uint32_t* d_id_rank,
                         size_t n, size_t dims, float max_row_norm, const float* d_row_norm2, const float* h_queries, size_t nq,
-                        size_t k, GemmResult* out) {
+                        size_t k, GemmResult* out, int force_terms) {
     const size_t qbytes = nq * dims * sizeof(float);
     VB_TRY(ctx.h_queries.reserve(qbytes));
     VB_TRY(ctx.queries.reserve(qbytes));
@@ -919,7 +922,7 @@ Status flat_gemm_search(SearchCtx& ctx, int metric, const float* d_rows, size_t 
     uint32_t* d_bad = out_flags + nq;
     Status s = flat_gemm_search_device(ctx, metric, d_rows, stride, d_id_rank, n, dims, max_row_norm, d_row_norm2,
                                        ctx.queries.as<float>(), nq, k, nullptr, out_pays, out_counts, out_flags, d_bad,
-                                       ctx.stream);
+                                       ctx.stream, force_terms, &out->terms);
     if (!s.ok()) { ctx.poison(); return s; }
     VB_TRY(ctx.h_result.reserve(res_bytes));
     cudaError_t e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, res_bytes, cudaMemcpyDeviceToHost, ctx.stream);

@@ -511,6 +511,13 @@ Status FlatIndex::search(const float* queries, size_t nq, size_t len, size_t lim
         VB_TRY(ensure_norms(*ctx.ctx));
         GemmResult gr;
         VB_TRY(flat_gemm_search(*ctx.ctx, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, d_norm2_, queries, nq, kk, &gr));
+        if (!gr.non_finite && gr.terms == 1) {
+            size_t flagged = 0;
+            for (size_t q = 0; q < nq; ++q) flagged += gr.flags[q] == 1;
+            if (flagged >= kGemmRedoAsBatch)   // too dense for the single-pass margin: one 3xTF32 batch, not `flagged` scans
+                VB_TRY(flat_gemm_search(*ctx.ctx, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, d_norm2_, queries, nq,
+                                        kk, &gr, 3));
+        }
         if (!gr.non_finite) {
             std::vector<size_t> redo;
             for (size_t q = 0; q < nq; ++q) {
@@ -815,13 +822,20 @@ Status FlatIndex::search_device(const float* d_queries, size_t nq, size_t q_stri
         u64* pays = c.result.as<u64>();
         uint32_t* counts = reinterpret_cast<uint32_t*>(pays + nq * kk);
         uint32_t* flags = counts + nq;
-        VB_TRY(flat_gemm_search_device(c, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, d_norm2_, d_queries, nq, kk,
-                                       c.out_keys.as<u64>(), pays, counts, flags, flags + nq, stream));
+        uint32_t* h_flags = c.h_misc.as<uint32_t>();
+        for (int force = 0;; force = 3) {
+            int terms_used = 3;
+            VB_TRY(flat_gemm_search_device(c, metric_, d_rows_, stride_, d_rank_, n_, dim_, max_norm_, d_norm2_, d_queries, nq, kk,
+                                           c.out_keys.as<u64>(), pays, counts, flags, flags + nq, stream, force, &terms_used));
+            VB_CUDA(cudaMemcpyAsync(h_flags, flags, (nq + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            VB_CUDA(cudaStreamSynchronize(stream));
+            size_t flagged = 0;
+            for (size_t q = 0; q < nq; ++q) flagged += h_flags[q] == 1;
+            if (terms_used == 1 && h_flags[nq] == 0 && flagged >= kGemmRedoAsBatch) continue;   // redo as one 3xTF32 batch
+            break;
+        }
         VB_TRY(unpack_device_results(c.out_keys.as<u64>(), pays, counts, (uint32_t)nq, (uint32_t)kk, d_keys, d_values,
                                      d_rows, d_counts, stream));
-        uint32_t* h_flags = c.h_misc.as<uint32_t>();
-        VB_CUDA(cudaMemcpyAsync(h_flags, flags, (nq + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        VB_CUDA(cudaStreamSynchronize(stream));
         if (h_flags[nq] != 0) {
             // a non-finite tensor-core score: the f64 recovery lives in the per-query kernel, redo all
             return run_scan_device(c, job, d_queries, q_stride, nullptr, d_keys, d_values, d_rows, d_counts, d_status_,
