@@ -2,7 +2,7 @@
 // memory instead of a collective library call: every rank STORES its packed top-k record straight into a
 // slot of every peer's gather buffer (P2P stores through NVLink / NVSwitch), publishes a flag, waits for
 // the peers' flags on its own memory and runs the K7 select — for a single query all of it in ONE
-// one-CTA kernel (push + wait + merge), so a sharded step is scan -> unpack -> exchange_merge with no
+// kernel (push + wait + rank merge), so a sharded step is scan -> unpack -> exchange_merge with no
 // NCCL launch, no stream hand-off and no separate merge launch. Records of many queries (a 1024-query
 // batch is 1.6 MB) take two launches: a multi-CTA push (which never waits, so it cannot deadlock against
 // a peer's waiting CTAs) and the per-query wait + merge.
@@ -130,28 +130,6 @@ __device__ __forceinline__ void merge_gathered(unsigned char* smem, const unsign
     if (threadIdx.x == 0) counts_out[qi] = total;
 }
 
-// Single query (or a handful): push + flag + wait + merge in one one-CTA launch.
-__global__ void __launch_bounds__(256)
-peer_exchange_merge_kernel(PeerPtrs pp, const unsigned char* record, RecordLayout L, uint32_t world, uint32_t rank,
-                           uint32_t epoch, uint32_t cap, u64* keys_out, float* values_out, u64* rows_out,
-                           uint32_t* counts_out, uint32_t* error) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t parity = epoch & 1u;
-    push_record(pp, record, L.bytes, world, rank, parity, threadIdx.x, blockDim.x);
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < world) st_release_sys(pp.flags[threadIdx.x] + parity * kMaxPeers + rank, epoch);
-    if (!wait_flags(pp.flags[rank], world, parity, epoch)) {
-        if (threadIdx.x == 0) { *error = 1u; for (uint32_t q = 0; q < L.nq; ++q) counts_out[q] = 0u; }
-        return;
-    }
-    const unsigned char* gathered = pp.gather[rank] + (size_t)parity * world * L.bytes;
-    for (uint32_t qi = 0; qi < L.nq; ++qi) {
-        merge_gathered(smem, gathered, L, world, cap, qi, keys_out, values_out, rows_out, counts_out);
-        __syncthreads();
-    }
-}
-
 // Large records, launch 1: every CTA copies its share; the last one to finish publishes the flags.
 __global__ void __launch_bounds__(256)
 peer_push_kernel(PeerPtrs pp, const unsigned char* record, uint32_t bytes, uint32_t world, uint32_t rank, uint32_t epoch,
@@ -183,13 +161,13 @@ peer_wait_merge_kernel(PeerPtrs pp, RecordLayout L, uint32_t world, uint32_t ran
                    rows_out, counts_out);
 }
 
-// ---- large lists (the 1000 Hamming candidates of quantized_search x 8 shards): rank merge ------------------
-// A single CTA pushing 8000 candidates through the collector's sort costs ~100 us. The lists are sorted and
-// keys are unique (the low word is the global id rank), so an entry's position in the merged order is simply
-// its own index plus, for every other list, the number of entries below it (a binary search): no sort, no
-// atomics, every entry independent. All lists are staged in shared memory (world x k_in x 8 B <= 64 KB) by
-// each of a few CTAs, which split the entries between them. Fused with the push and the wait like the small
-// kernel: the CTAs' pushes never wait, the last one to finish publishes the flags.
+// ---- one query (or a handful): push + flag + wait + RANK MERGE in one launch ---------------------------------
+// The lists are sorted and keys are unique (the low word is the global id rank), so an entry's position in the
+// merged order is simply its own index plus, for every other list, the number of entries below it (a binary
+// search): no sort, no atomics, every entry independent. All lists are staged in shared memory (world x k_in x
+// 8 B <= 64 KB). k = 10 from 8 shards is one 128-thread CTA; the 1000 Hamming candidates of quantized_search x 8
+// shards (a single CTA pushing 8000 entries through a sorting collector cost ~100 us) are split over 8 CTAs: their
+// pushes never wait, the last one to finish publishes the flags, then every CTA waits and ranks its share.
 constexpr uint32_t kRankThreads = 512;
 constexpr uint32_t kRankCtas = 8;
 
@@ -406,21 +384,14 @@ Status PeerExchange::exchange_merge(const void* d_record, const PeerRecord& rec,
         return wait_merge(rec, d_keys_out, d_values_out, d_rows_out, d_counts_out, stream);
     }
     ++epoch_;
-    if ((size_t)world_ * rec.k_in > 1024) {   // long lists: rank merge over a few CTAs instead of one CTA's sort
-        const size_t smem_r = (size_t)world_ * rec.k_in * sizeof(u64);
-        VB_TRY(ensure_dynamic_smem_for(peer_exchange_rank_merge_kernel, smem_r));
-        peer_exchange_rank_merge_kernel<<<kRankCtas, kRankThreads, smem_r, stream>>>(
-            impl_->pp, static_cast<const unsigned char*>(d_record), to_layout(rec), (uint32_t)world_, (uint32_t)rank_, epoch_,
-            d_keys_out, d_values_out, d_rows_out, d_counts_out, impl_->d_ticket, impl_->d_ticket + 1);
-        VB_CUDA(cudaGetLastError());
-        return Status::Ok();
-    }
-    const uint32_t cap = merge_cap(rec);
-    const size_t smem = (size_t)cap * 16;
-    VB_TRY(ensure_dynamic_smem_for(peer_exchange_merge_kernel, smem));
-    peer_exchange_merge_kernel<<<1, 256, smem, stream>>>(impl_->pp, static_cast<const unsigned char*>(d_record), to_layout(rec),
-                                                         (uint32_t)world_, (uint32_t)rank_, epoch_, cap, d_keys_out,
-                                                         d_values_out, d_rows_out, d_counts_out, impl_->d_ticket + 1);
+    // one fused launch: push + flag + wait + rank merge. Short lists (k = 10 from 8 shards) need one small CTA; long
+    // ones (1000 candidates x 8) are ranked by 8 CTAs.
+    const bool many = (size_t)world_ * rec.k_in > 1024;
+    const size_t smem_r = (size_t)world_ * rec.k_in * sizeof(u64);
+    VB_TRY(ensure_dynamic_smem_for(peer_exchange_rank_merge_kernel, smem_r));
+    peer_exchange_rank_merge_kernel<<<many ? kRankCtas : 1, many ? kRankThreads : 128, smem_r, stream>>>(
+        impl_->pp, static_cast<const unsigned char*>(d_record), to_layout(rec), (uint32_t)world_, (uint32_t)rank_, epoch_,
+        d_keys_out, d_values_out, d_rows_out, d_counts_out, impl_->d_ticket, impl_->d_ticket + 1);
     VB_CUDA(cudaGetLastError());
     return Status::Ok();
 }
