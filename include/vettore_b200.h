@@ -244,6 +244,10 @@ int vb_mv_reserve(vb_mv* index, size_t docs, size_t tokens, size_t dimension);
  * the same GPU). Validation (finite values) and the per-token norms run on the device. */
 int vb_mv_insert_many_device(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off,
                              const float* d_tokens, size_t tokens_per_doc, size_t dimension);
+/* Same for ragged documents: document i owns rows [doc_tok[i], doc_tok[i + 1]) of the device matrix
+ * (doc_tok: HOST array of ndocs + 1 ascending row offsets; a document may be empty). */
+int vb_mv_insert_ragged_device(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off,
+                               const float* d_tokens, const uint64_t* doc_tok, size_t dimension);
 int vb_mv_delete(vb_mv* index, const char* id, size_t id_len);
 int vb_mv_search(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit,
                  vb_hits** out);

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--metric", default="inner_product")
     ap.add_argument("--general", action="store_true")
+    ap.add_argument("--ragged", default=None, metavar="LO,HI",
+                    help="document lengths uniform in [LO, HI] (ragged tensor-core kernel); --docs counts documents")
     ap.add_argument("--check", type=int, default=2000, help="docs re-scored by the oracle for a parity spot check")
     args = ap.parse_args()
     if args.general:
@@ -30,25 +32,39 @@ def main():
     import numpy as np
     import torch
 
-    from vettore_b200 import nifs
+    from vettore_b200 import _lib, nifs
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     g = torch.Generator(device=dev)
     g.manual_seed(20_260_721)
     idx = nifs.mv_new(args.metric)
-    assert nifs.mv_reserve(idx, args.docs, args.docs * args.tokens, args.dim) == ("ok", ())
+    lens = None
+    if args.ragged:
+        lo, hi = (int(v) for v in args.ragged.split(","))
+        lens = np.random.default_rng(7).integers(lo, hi + 1, args.docs)
+    total_tokens = int(lens.sum()) if lens is not None else args.docs * args.tokens
+    assert nifs.mv_reserve(idx, args.docs, total_tokens, args.dim) == ("ok", ())
     chunk = 20_000
     first = None
     t0 = time.perf_counter()
     for s in range(0, args.docs, chunk):
         n = min(chunk, args.docs - s)
-        x = torch.randn(n * args.tokens, args.dim, generator=g, device=dev)
+        rows = int(lens[s:s + n].sum()) if lens is not None else n * args.tokens
+        x = torch.randn(rows, args.dim, generator=g, device=dev)
         x = (x.double() / x.double().norm(dim=1, keepdim=True)).float().contiguous()
         ids = [f"{s + i:09d}" for i in range(n)]
-        assert nifs.mv_insert_device(idx, ids, x.data_ptr(), args.tokens, args.dim) == ("ok", ())
-        if first is None:
-            first = x[: args.check * args.tokens].cpu().numpy().reshape(-1, args.tokens, args.dim)
+        if lens is not None:
+            doc_tok = np.concatenate([[0], np.cumsum(lens[s:s + n])]).astype(np.uint64)
+            assert nifs.mv_insert_ragged_device(idx, ids, x.data_ptr(), doc_tok, args.dim) == ("ok", ())
+            if first is None:
+                c = min(args.check, n)
+                host = x[: int(doc_tok[c])].cpu().numpy()
+                first = [host[int(doc_tok[i]):int(doc_tok[i + 1])] for i in range(c)]
+        else:
+            assert nifs.mv_insert_device(idx, ids, x.data_ptr(), args.tokens, args.dim) == ("ok", ())
+            if first is None:
+                first = list(x[: args.check * args.tokens].cpu().numpy().reshape(-1, args.tokens, args.dim))
         del x
     torch.cuda.synchronize()
     ingest = time.perf_counter() - t0
@@ -59,11 +75,11 @@ def main():
     assert st == "ok", hits
     # parity spot check on the first `check` docs
     import oracle
-    docs = [(f"{i:09d}", first[i]) for i in range(first.shape[0])]
+    docs = [(f"{i:09d}", first[i]) for i in range(len(first))]
     ref = oracle.multi_vector_top_k(docs, q, nifs.METRIC_CODE[args.metric], args.k)[1]
     ref_d = dict(ref)
     for hid, s in hits:
-        if int(hid) < first.shape[0]:
+        if int(hid) < len(first):
             assert hid in ref_d and abs(ref_d[hid] - s) <= 1e-5 * max(1.0, abs(s)), (hid, s, ref_d.get(hid))
 
     for _ in range(3):
@@ -74,16 +90,17 @@ def main():
         nifs.mv_search(idx, q, args.k)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / args.steps
-    alg = args.docs * args.tokens * args.dim * 4
+    alg = total_tokens * args.dim * 4
+    path = {0: "general", 1: "tcgen05 3xTF32 (uniform)", 2: "tcgen05 3xTF32 (ragged)"}.get(_lib.lib().vb_debug_maxsim_path(), "?")
     peak = 6545.0
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    flops = 2.0 * args.tq * args.docs * args.tokens * args.dim
+    flops = 2.0 * args.tq * total_tokens * args.dim
     print(json.dumps({"metric": "maxsim queries/s (e2e through vb_mv_search)", "value": 1.0 / dt, "ms_per_query": dt * 1e3,
                       "config": {"docs": args.docs, "tokens": args.tokens, "dim": args.dim, "tq": args.tq, "k": args.k,
-                                 "metric": args.metric, "kernel": "general" if args.general else "tcgen05 3xTF32"},
+                                 "metric": args.metric, "ragged": args.ragged, "tokens_total": total_tokens, "kernel": path},
                       "roofline": {"bound": "hbm", "achieved": alg / dt / 1e9, "peak": peak, "unit": "GB/s",
                                    "frac": alg / dt / 1e9 / peak, "algorithmic_tflops": flops / dt / 1e12},
                       "ingest_seconds": round(ingest, 2), "top1": hits[0]}))

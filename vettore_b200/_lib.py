@@ -68,6 +68,7 @@ SIGNATURES = {
     "vb_mv_insert_many": (C.c_int, [_vp, _sz, C.c_char_p, _u64p, _f32p, _u64p, _u64p]),
     "vb_mv_reserve": (C.c_int, [_vp, _sz, _sz, _sz]),
     "vb_mv_insert_many_device": (C.c_int, [_vp, _sz, C.c_char_p, _u64p, _vp, _sz, _sz]),
+    "vb_mv_insert_ragged_device": (C.c_int, [_vp, _sz, C.c_char_p, _u64p, _vp, _u64p, _sz]),
     "vb_mv_delete": (C.c_int, [_vp, C.c_char_p, _sz]),
     "vb_mv_search": (C.c_int, [_vp, _f32p, _u64p, _sz, _sz, _vpp]),
     "vb_mv_search_packed_device": (C.c_int, [_vp, _f32p, _u64p, _sz, _sz, _vp, _vp, _vp, _vp, _vpp]),

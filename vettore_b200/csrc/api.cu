@@ -459,28 +459,49 @@ vb::Status maxsim_by_value(size_t ndocs, const float* tok_vals, const uint64_t* 
     const size_t stride = (dim + 3) & ~(size_t)3;
     const size_t ntok = doc_tok[ndocs] - doc_tok[0];
     if (ntok >= 0xFFFFFFFFull || ndocs >= 0xFFFFFFFEull) return vb::Status::Cuda("batch too large");
+    // Side arrays next to the token rows: doc_off[ndocs + 1] | doc_rank[ndocs] | tok_doc[ntok] | 1/|token| [ntok]
+    // (the last two feed the ragged tensor-core kernel, maxsim_tcr.cu).
+    const size_t side_words = 2 * ndocs + 1 + 2 * ntok;
     vb::PinnedBuf hb;
-    VB_TRY(hb.reserve(std::max<size_t>(ntok, 1) * stride * sizeof(float) + (2 * ndocs + 1) * sizeof(uint32_t)));
+    VB_TRY(hb.reserve(std::max<size_t>(ntok, 1) * stride * sizeof(float) + side_words * sizeof(uint32_t)));
     float* hrows = hb.as<float>();
     uint32_t* hoff = reinterpret_cast<uint32_t*>(hrows + std::max<size_t>(ntok, 1) * stride);
     uint32_t* hrank = hoff + ndocs + 1;
+    uint32_t* howner = hrank + ndocs;
+    float* hinv = reinterpret_cast<float*>(howner + ntok);
     for (size_t t = 0; t < ntok; ++t) {
-        std::memcpy(hrows + t * stride, tok_vals + tok_off[doc_tok[0] + t], dim * sizeof(float));
+        const float* src = tok_vals + tok_off[doc_tok[0] + t];
+        std::memcpy(hrows + t * stride, src, dim * sizeof(float));
         for (size_t c = dim; c < stride; ++c) hrows[t * stride + c] = 0.0f;
+        double nn = 0.0;   // distances.rs:166: f64_dot(right, right).sqrt()
+        for (size_t c = 0; c < dim; ++c) nn += (double)src[c] * (double)src[c];
+        hinv[t] = nn > 0.0 ? (float)(1.0 / std::sqrt(nn)) : 0.0f;
     }
+    uint32_t min_td = 0;
+    bool has_empty = false;
     for (size_t d = 0; d <= ndocs; ++d) hoff[d] = (uint32_t)(doc_tok[d] - doc_tok[0]);
+    for (size_t d = 0; d < ndocs; ++d) {
+        const uint32_t cnt = hoff[d + 1] - hoff[d];
+        if (cnt == 0) has_empty = true;
+        else if (min_td == 0 || cnt < min_td) min_td = cnt;
+        for (uint32_t t = hoff[d]; t < hoff[d + 1]; ++t) howner[t] = (uint32_t)d;
+    }
     std::memcpy(hrank, ranks, ndocs * sizeof(uint32_t));
     VB_TRY(ctx->staging.reserve(std::max<size_t>(ntok, 1) * stride * sizeof(float)));
-    VB_TRY(ctx->staging_rank.reserve((2 * ndocs + 1) * sizeof(uint32_t)));
+    VB_TRY(ctx->staging_rank.reserve(side_words * sizeof(uint32_t)));
     VB_CUDA(cudaMemcpyAsync(ctx->staging.p, hrows, ntok * stride * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    VB_CUDA(cudaMemcpyAsync(ctx->staging_rank.p, hoff, (2 * ndocs + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                            ctx->stream));
+    VB_CUDA(cudaMemcpyAsync(ctx->staging_rank.p, hoff, side_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     vb::MaxSimJob job;
     job.metric = metric_code == vb::kCosine ? vb::kCosineTrue : metric_code;   // multi_vector.rs:74-75
     job.d_tokens = ctx->staging.as<float>();
     job.stride = stride;
     job.d_doc_off = ctx->staging_rank.as<uint32_t>();
     job.d_doc_rank = job.d_doc_off + ndocs + 1;
+    job.d_tok_doc = job.d_doc_rank + ndocs;
+    job.d_inv_dnorm = reinterpret_cast<const float*>(job.d_tok_doc + ntok);
+    job.ntok = ntok;
+    job.min_td = min_td;
+    job.has_empty = has_empty;
     job.ndocs = ndocs;
     job.dims = (uint32_t)dim;
     job.h_query = q_vals;
@@ -587,6 +608,11 @@ int vb_mv_reserve(vb_mv* index, size_t docs, size_t tokens, size_t dimension) {
 int vb_mv_insert_many_device(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off,
                              const float* d_tokens, size_t tokens_per_doc, size_t dimension) {
     return finish(index->impl->insert_many_device(ndocs, ids, id_off, d_tokens, tokens_per_doc, dimension));
+}
+int vb_mv_insert_ragged_device(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off,
+                               const float* d_tokens, const uint64_t* doc_tok, size_t dimension) {
+    if (!doc_tok) return finish(vb::Status::Cuda("document token offsets required"));
+    return finish(index->impl->insert_many_device(ndocs, ids, id_off, d_tokens, 0, dimension, doc_tok));
 }
 int vb_mv_delete(vb_mv* index, const char* id, size_t id_len) { return finish(index->impl->remove(id, id_len)); }
 int vb_mv_search(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, vb_hits** out) {

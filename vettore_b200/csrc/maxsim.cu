@@ -225,15 +225,64 @@ static MaxSimKernel maxsim_lookup(int metric) {
     return nullptr;
 }
 
+Status maxsim_collect_result(SearchCtx& ctx, const MaxSimJob& job, const TopkWorkspace& ws, uint32_t k, cudaError_t e,
+                             MaxSimResult* out) {
+    if (e == cudaSuccess && job.d_keys_out) {
+        Status u = unpack_device_results(ws.out_keys, ws.out_pays, ws.out_counts, 1, k, job.d_keys_out, job.d_values_out,
+                                         job.d_rows_out, job.d_counts_out, ctx.stream);
+        if (!u.ok()) { ctx.poison(); return u; }
+    }
+    const size_t bytes = (size_t)k * sizeof(u64) + 8;
+    if (e == cudaSuccess) e = ctx.h_result.reserve(bytes).ok() ? cudaSuccess : cudaErrorMemoryAllocation;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, bytes, cudaMemcpyDeviceToHost, ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx.stream);
+    if (e != cudaSuccess) {
+        ctx.poison();
+        return Status::Cuda(cudaGetErrorString(e));
+    }
+    const u64* pays = ctx.h_result.as<u64>();
+    const uint32_t* tail = reinterpret_cast<const uint32_t*>(pays + k);
+    const uint32_t count = tail[0];
+    out->err = tail[1];
+    out->rows.resize(count);
+    out->scores.resize(count);
+    for (uint32_t i = 0; i < count; ++i) {
+        uint32_t bits = (uint32_t)(pays[i] >> 32);
+        std::memcpy(&out->scores[i], &bits, 4);
+        out->rows[i] = (uint32_t)pays[i];
+    }
+    return Status::Ok();
+}
+
+// Which kernel answered this thread's last maxsim_top_k (tests): 0 general, 1 tensor-core uniform, 2 tensor-core
+// ragged, 3 / 4 = 1 / 2 flagged a non-finite score and the general kernel repeated the query.
+static thread_local int t_last_path = 0;
+extern "C" int vb_debug_maxsim_path() { return t_last_path; }
+
 Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out) {
+    t_last_path = 0;
     out->rows.clear();
     out->scores.clear();
     out->err = kNoError;
     if (job.ndocs == 0 || job.k == 0 || job.tq == 0) return Status::Cuda("empty maxsim job");
     const uint32_t k = (uint32_t)std::min<size_t>(job.k, job.ndocs);
     if (k > (uint32_t)kMaxFusedK) return Status::Cuda("multi-vector limit beyond the fused collector (1024)");
-    if (maxsim_tc_eligible(job, job.uniform_td) && (job.metric != kCosineTrue || job.d_inv_dnorm))
-        return maxsim_tc_top_k(ctx, job, job.uniform_td, job.d_inv_dnorm, out);
+    // Tensor-core kernels first. They raise the error word for a non-finite pair or sum; which of the reference's
+    // two overflow errors that is (or whether f64 recovery rescues the pair, distances.rs:59-98) is decided by
+    // repeating the query on the general kernel below.
+    if (maxsim_tc_eligible(job, job.uniform_td) && (job.metric != kCosineTrue || job.d_inv_dnorm)) {
+        VB_TRY(maxsim_tc_top_k(ctx, job, job.uniform_td, job.d_inv_dnorm, out));
+        t_last_path = 1;
+        if (out->err == kNoError) return Status::Ok();
+    } else if (maxsim_tcr_eligible(job)) {
+        VB_TRY(maxsim_tcr_top_k(ctx, job, out));
+        t_last_path = 2;
+        if (out->err == kNoError) return Status::Ok();
+    }
+    t_last_path = t_last_path ? t_last_path + 2 : 0;   // 3 / 4: a tensor-core kernel flagged the query, redone here
+    out->rows.clear();
+    out->scores.clear();
+    out->err = kNoError;
     MaxSimKernel kernel = maxsim_lookup(job.metric);
     if (!kernel) return Status::Ref("unknown metric");
 
@@ -299,32 +348,7 @@ Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out) {
     p.ws.err_row = ctx.err_row();
     p.ws.out_err = p.ws.out_counts + 1;
     kernel<<<grid, kMsThreads, smem, ctx.stream>>>(p);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && job.d_keys_out) {
-        Status u = unpack_device_results(p.ws.out_keys, p.ws.out_pays, p.ws.out_counts, 1, k, job.d_keys_out, job.d_values_out,
-                                         job.d_rows_out, job.d_counts_out, ctx.stream);
-        if (!u.ok()) { ctx.poison(); return u; }
-    }
-    const size_t bytes = (size_t)k * sizeof(u64) + 8;
-    if (e == cudaSuccess) e = ctx.h_result.reserve(bytes).ok() ? cudaSuccess : cudaErrorMemoryAllocation;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, bytes, cudaMemcpyDeviceToHost, ctx.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx.stream);
-    if (e != cudaSuccess) {
-        ctx.poison();
-        return Status::Cuda(cudaGetErrorString(e));
-    }
-    const u64* pays = ctx.h_result.as<u64>();
-    const uint32_t* tail = reinterpret_cast<const uint32_t*>(pays + k);
-    const uint32_t count = tail[0];
-    out->err = tail[1];
-    out->rows.resize(count);
-    out->scores.resize(count);
-    for (uint32_t i = 0; i < count; ++i) {
-        uint32_t bits = (uint32_t)(pays[i] >> 32);
-        std::memcpy(&out->scores[i], &bits, 4);
-        out->rows[i] = (uint32_t)pays[i];
-    }
-    return Status::Ok();
+    return maxsim_collect_result(ctx, job, p.ws, k, cudaGetLastError(), out);
 }
 
 }  // namespace vb

@@ -23,24 +23,10 @@
 
 #include <cstdlib>
 #include "scan_driver.h"
-#include "tc.cuh"
+#include "maxsim_tc.cuh"
 #include "topk.cuh"
 
 namespace vb {
-
-constexpr int kTcEpiWarps = 8, kTcSplitWarps = 8;   // epilogue: two groups of 4 warps, alternating tiles
-constexpr int kTcEpiGroupWarps = 4;
-constexpr int kTcProducerWarp = kTcEpiWarps + kTcSplitWarps, kTcMmaWarp = kTcProducerWarp + 1;
-constexpr int kTcThreads = (kTcMmaWarp + 1) * 32;
-constexpr int kTcStages = 4;     // ring stages of one chunk (<= 2 K blocks = 32 KB) each
-constexpr int kTcAccBufs = 2;     // accumulator buffers (MMA <-> epilogue double buffering)
-constexpr int kTcChains = 4;      // independent accumulators per buffer: consecutive MMAs never depend on each other
-constexpr int kTcTile = 128;     // tokens per tile (UMMA M)
-constexpr int kTcN = 32;         // query tokens (UMMA N), zero padded
-constexpr uint32_t kTcChunkBytes = 2 * 16384;   // 2 K blocks of [128 rows x 128 B]
-// TMEM columns: A operand double-buffered per chunk, buffer u at [128 u, +128): hi [0,64) lo [64,128);
-// accumulator buffer b at 256 + 128 b: kTcChains partial accumulators of 32 columns (summed by the epilogue).
-constexpr uint32_t kTcAccCol = 256;
 
 struct MaxSimTcParams {
     uint32_t ndocs, td, dims, tq;
@@ -54,37 +40,6 @@ struct MaxSimTcParams {
     uint32_t debug;               // timing experiments only (VB_MAXSIM_DEBUG): 1 skip MMAs, 2 skip the split work, 4 skip the TMA loads, 8 skip the epilogue math
     TopkWorkspace ws;
 };
-
-// Max over the 32 lanes of a warp for 32 per-lane values at once: after the butterfly lane q
-// holds max over lanes of v[q]. 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
-__device__ __forceinline__ float warp_transpose_max(float (&v)[32], int lane) {
-#pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
-        const bool hi = (lane & half) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const float send = hi ? v[i] : v[i + half];
-            const float keep = hi ? v[i + half] : v[i];
-            v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, half));
-        }
-    }
-    return v[0];
-}
-
-// Same for 16 per-lane values: 8 + 4 + 2 + 1 exchanges, then one plain step; lanes 2c and 2c + 1 hold column c.
-__device__ __forceinline__ float warp_transpose_max16(float (&v)[16], int lane) {
-#pragma unroll
-    for (int half = 8; half >= 1; half >>= 1) {
-        const bool hi = (lane & (half * 2)) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const float send = hi ? v[i] : v[i + half];
-            const float keep = hi ? v[i + half] : v[i];
-            v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, half * 2));
-        }
-    }
-    return fmaxf(v[0], __shfl_xor_sync(0xffffffffu, v[0], 1));
-}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams p) {
@@ -336,7 +291,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcParams 
 }
 
 bool maxsim_tc_eligible(const MaxSimJob& job, uint32_t uniform_td) {
-    if (std::getenv("VB_MAXSIM_NO_TC")) return false;
+    if (std::getenv("VB_MAXSIM_NO_TC") || std::getenv("VB_MAXSIM_NO_TCU")) return false;
     if (job.metric != kInnerProduct && job.metric != kNegativeInnerProduct && job.metric != kCosineTrue) return false;
     if (job.dims % 32 != 0 || job.dims > 128 || job.stride != job.dims) return false;
     if (job.tq == 0 || job.tq > (uint32_t)kTcN) return false;
@@ -416,31 +371,7 @@ Status maxsim_tc_top_k(SearchCtx& ctx, const MaxSimJob& job, uint32_t td, const 
     p.ws.err_row = ctx.err_row();
     p.ws.out_err = p.ws.out_counts + 1;
     maxsim_tc_kernel<<<grid, kTcThreads, smem, ctx.stream>>>(tmap, p);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && job.d_keys_out) {
-        Status u = unpack_device_results(p.ws.out_keys, p.ws.out_pays, p.ws.out_counts, 1, k, job.d_keys_out, job.d_values_out,
-                                         job.d_rows_out, job.d_counts_out, ctx.stream);
-        if (!u.ok()) { ctx.poison(); return u; }
-    }
-    const size_t bytes = (size_t)k * sizeof(u64) + 8;
-    if (e == cudaSuccess && !ctx.h_result.reserve(bytes).ok()) e = cudaErrorMemoryAllocation;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx.h_result.p, ctx.result.p, bytes, cudaMemcpyDeviceToHost, ctx.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx.stream);
-    if (e != cudaSuccess) {
-        ctx.poison();
-        return Status::Cuda(cudaGetErrorString(e));
-    }
-    const u64* pays = ctx.h_result.as<u64>();
-    const uint32_t* tail = reinterpret_cast<const uint32_t*>(pays + k);
-    out->err = tail[1];
-    out->rows.resize(tail[0]);
-    out->scores.resize(tail[0]);
-    for (uint32_t i = 0; i < tail[0]; ++i) {
-        uint32_t bits = (uint32_t)(pays[i] >> 32);
-        std::memcpy(&out->scores[i], &bits, 4);
-        out->rows[i] = (uint32_t)pays[i];
-    }
-    return Status::Ok();
+    return maxsim_collect_result(ctx, job, p.ws, k, cudaGetLastError(), out);
 }
 
 }  // namespace vb

@@ -20,6 +20,7 @@ MvIndex::~MvIndex() {
     cudaSetDevice(device_);
     if (d_tokens_) cudaFree(d_tokens_);
     if (d_inv_norm_) cudaFree(d_inv_norm_);
+    if (d_tok_doc_) cudaFree(d_tok_doc_);
     if (d_doc_off_) cudaFree(d_doc_off_);
     if (d_doc_rank_) cudaFree(d_doc_rank_);
 }
@@ -43,15 +44,20 @@ Status MvIndex::reserve_tokens(size_t need) {
     }
     if (e != cudaSuccess) return Status::Cuda(cudaGetErrorString(e));
     float* inv = nullptr;
+    uint32_t* owner = nullptr;
     VB_CUDA(cudaMalloc(&inv, cap * sizeof(float)));
+    VB_CUDA(cudaMalloc(&owner, cap * sizeof(uint32_t)));
     if (ntok_) {
         VB_CUDA(cudaMemcpy(t, d_tokens_, ntok_ * stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
         VB_CUDA(cudaMemcpy(inv, d_inv_norm_, ntok_ * sizeof(float), cudaMemcpyDeviceToDevice));
+        VB_CUDA(cudaMemcpy(owner, d_tok_doc_, ntok_ * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
     }
     if (d_tokens_) cudaFree(d_tokens_);
     if (d_inv_norm_) cudaFree(d_inv_norm_);
+    if (d_tok_doc_) cudaFree(d_tok_doc_);
     d_tokens_ = t;
     d_inv_norm_ = inv;
+    d_tok_doc_ = owner;
     tok_cap_ = cap;
     return Status::Ok();
 }
@@ -84,6 +90,9 @@ Status MvIndex::compact() {
     const size_t live = ntok_ - dead_tok_;
     VB_CUDA(cudaMalloc(&fresh, std::max<size_t>(live, 1) * stride_ * sizeof(float)));
     VB_CUDA(cudaMalloc(&fresh_inv, std::max<size_t>(live, 1) * sizeof(float)));
+    uint32_t* fresh_owner = nullptr;
+    VB_CUDA(cudaMalloc(&fresh_owner, std::max<size_t>(live, 1) * sizeof(uint32_t)));
+    std::vector<uint32_t> owner(live);
     std::vector<uint32_t> off{0};
     std::vector<uint32_t> rank;
     std::vector<std::string> ids;
@@ -96,17 +105,23 @@ Status MvIndex::compact() {
                                cudaMemcpyDeviceToDevice));
             VB_CUDA(cudaMemcpy(fresh_inv + cursor, d_inv_norm_ + t0, cnt * sizeof(float), cudaMemcpyDeviceToDevice));
         }
+        for (size_t t = 0; t < cnt; ++t) owner[cursor + t] = (uint32_t)ids.size();
         cursor += cnt;
         id_doc_[doc_id_[d]] = (uint32_t)ids.size();
         ids.push_back(std::move(doc_id_[d]));
         rank.push_back(h_rank_[d]);
         off.push_back((uint32_t)cursor);
     }
+    if (live) VB_CUDA(cudaMemcpy(fresh_owner, owner.data(), live * sizeof(uint32_t), cudaMemcpyHostToDevice));
     cudaFree(d_tokens_);
     cudaFree(d_inv_norm_);
+    cudaFree(d_tok_doc_);
     d_tokens_ = fresh;
     d_inv_norm_ = fresh_inv;
+    d_tok_doc_ = fresh_owner;
     uniform_known_ = false;   // recomputed from the surviving documents below
+    min_td_ = 0;
+    has_empty_ = false;
     tok_cap_ = std::max<size_t>(live, 1);
     ntok_ = live;
     dead_tok_ = 0;
@@ -118,6 +133,7 @@ Status MvIndex::compact() {
         const uint32_t cnt = h_doc_off_[d + 1] - h_doc_off_[d];
         if (!uniform_known_) { uniform_td_ = cnt; uniform_known_ = true; }
         else if (uniform_td_ != cnt) uniform_td_ = 0;
+        note_doc_length(cnt);
     }
     return Status::Ok();
 }
@@ -154,6 +170,12 @@ Status MvIndex::insert_many(size_t ndocs, const char* ids, const uint64_t* id_of
         VB_TRY(stage.reserve(chunk_rows * stride_ * sizeof(float)));
         float* sb = stage.as<float>();
         std::vector<float> inv(chunk_rows);
+        {   // owning document slot of every new token
+            std::vector<uint32_t> owner(new_tok);
+            for (size_t d = 0; d < ndocs; ++d)
+                for (size_t t = doc_tok[d]; t < doc_tok[d + 1]; ++t) owner[t - doc_tok[0]] = (uint32_t)(ndocs_ + d);
+            VB_CUDA(cudaMemcpy(d_tok_doc_ + ntok_, owner.data(), new_tok * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
         size_t done = 0;
         while (done < new_tok) {
             const size_t n = std::min(chunk_rows, new_tok - done);
@@ -191,6 +213,7 @@ Status MvIndex::insert_many(size_t ndocs, const char* ids, const uint64_t* id_of
             const uint32_t cnt = (uint32_t)(doc_tok[d + 1] - doc_tok[d]);
             if (!uniform_known_) { uniform_td_ = cnt; uniform_known_ = true; }
             else if (uniform_td_ != cnt) uniform_td_ = 0;
+            note_doc_length(cnt);
         }
         ntok_ += doc_tok[d + 1] - doc_tok[d];
         h_doc_off_.push_back((uint32_t)ntok_);
@@ -224,6 +247,17 @@ __global__ void token_inv_norm_kernel(const float* tokens, size_t stride, uint32
     }
 }
 
+// tok_doc for `ndocs` uniform documents of `td` tokens appended at document slot `doc0`.
+__global__ void fill_tok_doc_kernel(uint32_t* tok_doc, size_t ntok, uint32_t td, uint32_t doc0) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntok; t += (size_t)gridDim.x * blockDim.x)
+        tok_doc[t] = doc0 + (uint32_t)(t / td);
+}
+
+void MvIndex::note_doc_length(uint32_t cnt) {
+    if (cnt == 0) has_empty_ = true;
+    else if (min_td_ == 0 || cnt < min_td_) min_td_ = cnt;
+}
+
 Status MvIndex::reserve(size_t docs, size_t tokens, size_t dim) {
     std::unique_lock<std::shared_mutex> g(mu_);
     VB_CUDA(cudaSetDevice(device_));
@@ -245,14 +279,19 @@ Status MvIndex::reserve(size_t docs, size_t tokens, size_t dim) {
 }
 
 Status MvIndex::insert_many_device(size_t ndocs, const char* ids, const uint64_t* id_off, const float* d_tokens,
-                                   size_t td, size_t dim) {
+                                   size_t td, size_t dim, const uint64_t* doc_tok) {
     std::unique_lock<std::shared_mutex> g(mu_);
     VB_CUDA(cudaSetDevice(device_));
     if (ndocs == 0) return Status::Ok();
-    if (dim == 0 || td == 0) return Status::Ref("vectors must not be empty");
+    if (dim == 0 || (!doc_tok && td == 0)) return Status::Ref("vectors must not be empty");
     if (dim_ != 0 && dim != dim_) return Status::Ref("dimension mismatch");
     if (dim % 4 != 0) return Status::Cuda("device ingest needs a dimension that is a multiple of 4");
-    const size_t new_tok = ndocs * td;
+    // doc_tok (host, [ndocs + 1], ascending) makes the batch ragged: document i owns rows [doc_tok[i], doc_tok[i+1]).
+    if (doc_tok)
+        for (size_t d = 0; d < ndocs; ++d)
+            if (doc_tok[d + 1] < doc_tok[d]) return Status::Cuda("document token offsets must ascend");
+    const size_t new_tok = doc_tok ? (size_t)(doc_tok[ndocs] - doc_tok[0]) : ndocs * td;
+    if (doc_tok) d_tokens += (size_t)doc_tok[0] * dim;
     if (ntok_ + new_tok >= 0xFFFFFFFFull || ndocs_ + ndocs >= 0xFFFFFFFEull)
         return Status::Cuda("multi-vector index limit (2^32 tokens) exceeded");
     if (dim_ == 0) {
@@ -265,12 +304,21 @@ Status MvIndex::insert_many_device(size_t ndocs, const char* ids, const uint64_t
     VB_CUDA(cudaMalloc(&d_bad, sizeof(uint32_t)));
     VB_CUDA(cudaMemset(d_bad, 0, sizeof(uint32_t)));
     token_inv_norm_kernel<<<148 * 8, 256>>>(d_tokens, dim, (uint32_t)dim, (uint32_t)new_tok, d_inv_norm_ + ntok_, d_bad);
+    if (!doc_tok) {
+        fill_tok_doc_kernel<<<148 * 4, 256>>>(d_tok_doc_ + ntok_, new_tok, (uint32_t)td, (uint32_t)ndocs_);
+    } else if (new_tok) {
+        std::vector<uint32_t> owner(new_tok);
+        for (size_t d = 0; d < ndocs; ++d)
+            for (uint64_t t = doc_tok[d]; t < doc_tok[d + 1]; ++t) owner[t - doc_tok[0]] = (uint32_t)(ndocs_ + d);
+        VB_CUDA(cudaMemcpy(d_tok_doc_ + ntok_, owner.data(), new_tok * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     uint32_t bad = 0;
     cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost);
     cudaFree(d_bad);
     if (e != cudaSuccess) return Status::Cuda(cudaGetErrorString(e));
     if (bad) return Status::Ref("vector contains a non-finite value");
-    VB_CUDA(cudaMemcpy(d_tokens_ + ntok_ * stride_, d_tokens, new_tok * stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
+    if (new_tok)
+        VB_CUDA(cudaMemcpy(d_tokens_ + ntok_ * stride_, d_tokens, new_tok * stride_ * sizeof(float), cudaMemcpyDeviceToDevice));
     for (size_t d = 0; d < ndocs; ++d) {
         std::string id(ids + id_off[d], ids + id_off[d + 1]);
         auto hint = id_doc_.end();
@@ -290,9 +338,11 @@ Status MvIndex::insert_many_device(size_t ndocs, const char* ids, const uint64_t
         }
         doc_id_.push_back(std::move(id));
         h_rank_.push_back(0);
-        if (!uniform_known_) { uniform_td_ = (uint32_t)td; uniform_known_ = true; }
-        else if (uniform_td_ != td) uniform_td_ = 0;
-        ntok_ += td;
+        const size_t cnt = doc_tok ? (size_t)(doc_tok[d + 1] - doc_tok[d]) : td;
+        if (!uniform_known_) { uniform_td_ = (uint32_t)cnt; uniform_known_ = true; }
+        else if (uniform_td_ != cnt) uniform_td_ = 0;
+        note_doc_length((uint32_t)cnt);
+        ntok_ += cnt;
         h_doc_off_.push_back((uint32_t)ntok_);
         ++ndocs_;
     }
@@ -320,10 +370,14 @@ Status MvIndex::remove(const char* id, size_t id_len) {
         ndocs_ = 0;
         if (d_tokens_) cudaFree(d_tokens_);
         if (d_inv_norm_) cudaFree(d_inv_norm_);
+        if (d_tok_doc_) cudaFree(d_tok_doc_);
         d_tokens_ = nullptr;
         d_inv_norm_ = nullptr;
+        d_tok_doc_ = nullptr;
         uniform_known_ = false;
         uniform_td_ = 0;
+        min_td_ = 0;
+        has_empty_ = false;
         h_doc_off_.assign(1, 0);
         h_rank_.clear();
         doc_id_.clear();
@@ -399,6 +453,10 @@ Status MvIndex::search_impl(const float* q_vals, const uint64_t* q_off, size_t t
     job.k = k;
     job.uniform_td = uniform_known_ ? uniform_td_ : 0;
     job.d_inv_dnorm = d_inv_norm_;
+    job.d_tok_doc = d_tok_doc_;
+    job.ntok = ntok_;
+    job.min_td = min_td_;
+    job.has_empty = has_empty_;
     job.d_keys_out = d_keys;
     job.d_values_out = d_values;
     job.d_rows_out = d_rows;

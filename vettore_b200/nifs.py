@@ -450,6 +450,16 @@ def mv_insert_device(index: MvRef, ids: Sequence, device_ptr: int, tokens_per_do
     return _err() if rc else ("ok", ())
 
 
+def mv_insert_ragged_device(index: MvRef, ids: Sequence, device_ptr: int, doc_tok, dimension: int):
+    """Ragged documents whose tokens are already in device memory: document ``i`` owns rows
+    ``[doc_tok[i], doc_tok[i + 1])`` of the row-major ``[tokens, dimension]`` float32 matrix at ``device_ptr``."""
+    blob, ioff = _ids_blob(ids)
+    dt = np.ascontiguousarray(doc_tok, dtype=np.uint64)
+    rc = lib().vb_mv_insert_ragged_device(index.handle, len(ids), blob, _ptr(ioff, _u64p), C.c_void_p(device_ptr),
+                                          _ptr(dt, _u64p), int(dimension))
+    return _err() if rc else ("ok", ())
+
+
 def mv_delete(index: MvRef, id):
     b = _enc(id)
     rc = lib().vb_mv_delete(index.handle, b, len(b))
