@@ -35,6 +35,8 @@ struct MaxSimParams {
     uint32_t tq;
     uint32_t cap;
     uint32_t* err;             // atomicMin of (doc << 1 | kind): kind 0 metric overflow, 1 score overflow
+    u64* dump_keys;            // limit beyond the fused collector: every live document's key / payload goes to
+    u64* dump_pays;            // [ndocs] arrays (pre-filled with kKeyMax) and the host radix-sorts them
     TopkWorkspace ws;
 };
 
@@ -201,11 +203,13 @@ __global__ void __launch_bounds__(kMsThreads) maxsim_kernel(const MaxSimParams p
             }
             // descending score (total order), ascending id: multi_vector.rs:22-31
             const u64 key = ((u64)(~order_key(total)) << 32) | rank;
-            if (key < col.threshold()) col.push(key, ((u64)__float_as_uint(total) << 32) | doc);
+            const u64 pay = ((u64)__float_as_uint(total) << 32) | doc;
+            if (p.dump_keys) { p.dump_keys[doc] = key; p.dump_pays[doc] = pay; }
+            else if (key < col.threshold()) col.push(key, pay);
         }
-        if ((iter & 63u) == 63u) collector_checkpoint(col, p.ws, 0, 64, g_prefetch);
+        if (!p.dump_keys && (iter & 63u) == 63u) collector_checkpoint(col, p.ws, 0, 64, g_prefetch);
     }
-    collector_publish_and_merge(col, p.ws, 0, &s_last);
+    if (!p.dump_keys) collector_publish_and_merge(col, p.ws, 0, &s_last);
 }
 
 typedef void (*MaxSimKernel)(const MaxSimParams);
@@ -225,6 +229,38 @@ static MaxSimKernel maxsim_lookup(int metric) {
     return nullptr;
 }
 
+// Dump mode (limit > 1024): [ndocs] key / payload arrays pre-filled with kKeyMax (deleted documents write nothing).
+Status maxsim_prepare_dump(SearchCtx& ctx, size_t ndocs) {
+    VB_TRY(ctx.dump_keys.reserve(ndocs * sizeof(u64)));
+    VB_TRY(ctx.dump_pays.reserve(ndocs * sizeof(u64)));
+    VB_TRY(ctx.dump_keys2.reserve(ndocs * sizeof(u64)));
+    VB_TRY(ctx.dump_pays2.reserve(ndocs * sizeof(u64)));
+    VB_CUDA(cudaMemsetAsync(ctx.dump_keys.p, 0xFF, ndocs * sizeof(u64), ctx.stream));
+    return Status::Ok();
+}
+
+static void maxsim_decode(SearchCtx& ctx, uint32_t k, MaxSimResult* out) {
+    const u64* pays = ctx.h_result.as<u64>();
+    const uint32_t* tail = reinterpret_cast<const uint32_t*>(pays + k);
+    const uint32_t count = tail[0];
+    out->err = tail[1];
+    out->rows.resize(count);
+    out->scores.resize(count);
+    for (uint32_t i = 0; i < count; ++i) {
+        uint32_t bits = (uint32_t)(pays[i] >> 32);
+        std::memcpy(&out->scores[i], &bits, 4);
+        out->rows[i] = (uint32_t)pays[i];
+    }
+}
+
+Status maxsim_collect_dump(SearchCtx& ctx, size_t ndocs, uint32_t k, cudaError_t e, MaxSimResult* out) {
+    if (e != cudaSuccess) { ctx.poison(); return Status::Cuda(cudaGetErrorString(e)); }
+    Status s = sort_dump_and_fetch(ctx, ndocs, k);
+    if (!s.ok()) { ctx.poison(); return s; }
+    maxsim_decode(ctx, k, out);
+    return Status::Ok();
+}
+
 Status maxsim_collect_result(SearchCtx& ctx, const MaxSimJob& job, const TopkWorkspace& ws, uint32_t k, cudaError_t e,
                              MaxSimResult* out) {
     if (e == cudaSuccess && job.d_keys_out) {
@@ -240,17 +276,7 @@ Status maxsim_collect_result(SearchCtx& ctx, const MaxSimJob& job, const TopkWor
         ctx.poison();
         return Status::Cuda(cudaGetErrorString(e));
     }
-    const u64* pays = ctx.h_result.as<u64>();
-    const uint32_t* tail = reinterpret_cast<const uint32_t*>(pays + k);
-    const uint32_t count = tail[0];
-    out->err = tail[1];
-    out->rows.resize(count);
-    out->scores.resize(count);
-    for (uint32_t i = 0; i < count; ++i) {
-        uint32_t bits = (uint32_t)(pays[i] >> 32);
-        std::memcpy(&out->scores[i], &bits, 4);
-        out->rows[i] = (uint32_t)pays[i];
-    }
+    maxsim_decode(ctx, k, out);
     return Status::Ok();
 }
 
@@ -266,7 +292,9 @@ Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out) {
     out->err = kNoError;
     if (job.ndocs == 0 || job.k == 0 || job.tq == 0) return Status::Cuda("empty maxsim job");
     const uint32_t k = (uint32_t)std::min<size_t>(job.k, job.ndocs);
-    if (k > (uint32_t)kMaxFusedK) return Status::Cuda("multi-vector limit beyond the fused collector (1024)");
+    // A limit beyond the fused collector (1024): every live document's score is written out and radix-sorted.
+    const bool dump = k > (uint32_t)kMaxFusedK;
+    if (dump && job.d_keys_out) return Status::Cuda("sharded multi-vector search is limited to 1024 hits per shard");
     // Tensor-core kernels first. They raise the error word for a non-finite pair or sum; which of the reference's
     // two overflow errors that is (or whether f64 recovery rescues the pair, distances.rs:59-98) is decided by
     // repeating the query on the general kernel below.
@@ -305,8 +333,9 @@ Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out) {
     VB_CUDA(cudaMemcpyAsync(ctx.queries.p, hq, qbytes, cudaMemcpyHostToDevice, ctx.stream));
     VB_CUDA(cudaMemcpyAsync(ctx.q_norms.p, hn, job.tq * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
 
+    const uint32_t kc = dump ? 1u : k;   // the collector is idle in dump mode
     uint32_t cap = 256;
-    while (cap < 2 * k || cap < k + 64) cap <<= 1;
+    while (cap < 2 * kc || cap < kc + 64) cap <<= 1;
     const size_t smem = (size_t)cap * 16 + (size_t)job.tq * sizeof(float);
     if (smem > 160 * 1024) return Status::Cuda("too many query tokens for the multi-vector kernel");
     VB_TRY(ensure_dynamic_smem_for(kernel, smem));
@@ -318,13 +347,16 @@ Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out) {
     const uint32_t grid = (uint32_t)std::min<size_t>(job.ndocs, (size_t)sms * per_sm);
 
     VB_TRY(ctx.arm_ctrl(1));
-    VB_TRY(ctx.cand_keys.reserve((size_t)grid * k * sizeof(u64)));
-    VB_TRY(ctx.cand_pays.reserve((size_t)grid * k * sizeof(u64)));
+    VB_TRY(ctx.cand_keys.reserve((size_t)grid * kc * sizeof(u64)));
+    VB_TRY(ctx.cand_pays.reserve((size_t)grid * kc * sizeof(u64)));
     VB_TRY(ctx.cand_counts.reserve((size_t)grid * sizeof(uint32_t)));
-    VB_TRY(ctx.out_keys.reserve((size_t)k * sizeof(u64)));
-    VB_TRY(ctx.result.reserve((size_t)k * sizeof(u64) + 8));
+    VB_TRY(ctx.out_keys.reserve((size_t)kc * sizeof(u64)));
+    VB_TRY(ctx.result.reserve((size_t)kc * sizeof(u64) + 8));
+    if (dump) VB_TRY(maxsim_prepare_dump(ctx, job.ndocs));
 
     MaxSimParams p{};
+    p.dump_keys = dump ? ctx.dump_keys.as<u64>() : nullptr;
+    p.dump_pays = dump ? ctx.dump_pays.as<u64>() : nullptr;
     p.tokens = job.d_tokens;
     p.stride = job.stride;
     p.doc_off = job.d_doc_off;
@@ -336,7 +368,7 @@ Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out) {
     p.tq = job.tq;
     p.cap = cap;
     p.err = ctx.err_row();
-    p.ws.k = k;
+    p.ws.k = kc;
     p.ws.cand_keys = ctx.cand_keys.as<u64>();
     p.ws.cand_pays = ctx.cand_pays.as<u64>();
     p.ws.cand_counts = ctx.cand_counts.as<uint32_t>();
@@ -344,10 +376,11 @@ Status maxsim_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out) {
     p.ws.g_thresh = ctx.g_thresh();
     p.ws.out_keys = ctx.out_keys.as<u64>();
     p.ws.out_pays = ctx.result.as<u64>();
-    p.ws.out_counts = reinterpret_cast<uint32_t*>(ctx.result.as<u64>() + k);
+    p.ws.out_counts = reinterpret_cast<uint32_t*>(ctx.result.as<u64>() + kc);
     p.ws.err_row = ctx.err_row();
     p.ws.out_err = p.ws.out_counts + 1;
     kernel<<<grid, kMsThreads, smem, ctx.stream>>>(p);
+    if (dump) return maxsim_collect_dump(ctx, job.ndocs, k, cudaGetLastError(), out);
     return maxsim_collect_result(ctx, job, p.ws, k, cudaGetLastError(), out);
 }
 

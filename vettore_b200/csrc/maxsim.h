@@ -52,6 +52,8 @@ Status maxsim_tc_top_k(SearchCtx& ctx, const MaxSimJob& job, uint32_t td, const 
 // at most 64 query tokens; needs d_tok_doc.
 bool maxsim_tcr_eligible(const MaxSimJob& job);
 Status maxsim_tcr_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out);
+Status maxsim_prepare_dump(SearchCtx& ctx, size_t ndocs);
+Status maxsim_collect_dump(SearchCtx& ctx, size_t ndocs, uint32_t k, cudaError_t launch, MaxSimResult* out);
 struct TopkWorkspace;
 // Common tail of the three launchers: optional device-side unpack, D2H of the sorted list, stream sync, decode.
 Status maxsim_collect_result(SearchCtx& ctx, const MaxSimJob& job, const TopkWorkspace& ws, uint32_t k, cudaError_t launch,

@@ -46,6 +46,8 @@ struct MaxSimTcrParams {
     uint32_t cap, stages;
     uint32_t ckpt_tiles, slack;   // both epilogue groups meet every ckpt_tiles tiles (even); pushes in between <= slack
     uint32_t has_empty;           // some document has no token
+    u64* dump_keys;               // limit beyond the fused collector: every live document's key / payload goes to
+    u64* dump_pays;               // [ndocs] arrays (pre-filled with kKeyMax) and the host radix-sorts them
     uint32_t* err;
     TopkWorkspace ws;
 };
@@ -282,18 +284,39 @@ maxsim_tcr_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcrParam
         const uint32_t C = p.ckpt_tiles;
         float* fin = s_fin[warp];
         u64 g_prefetch = kKeyMax;
+        uint32_t d_next = 0, before_next = 0xFFFFFFFFu, after_next = 0xFFFFFFFFu;
+        {
+            const uint32_t s0 = T0 + (group * 4u + quarter) * 32u;          // this warp's first chunk
+            if (s0 < T1) {
+                d_next = __ldg(p.tok_doc + min(s0 + (uint32_t)lane, T1 - 1u));
+                before_next = s0 > T0 ? __ldg(p.tok_doc + s0 - 1u) : 0xFFFFFFFFu;
+                after_next = s0 + 32u < T1 ? __ldg(p.tok_doc + s0 + 32u) : 0xFFFFFFFFu;
+            }
+        }
         for (uint32_t it = group; it < my_tiles; it += 2u) {
             const uint32_t chunk = it * 4u + quarter;            // CTA-local chunk number
             const uint32_t s_tok = T0 + chunk * 32u;             // first token of the chunk
             const uint32_t token = s_tok + (uint32_t)lane;
             const bool valid = token < T1;
-            // Lanes past the CTA's range borrow the last valid token's document (they are masked to -inf below).
-            const uint32_t d = __ldg(p.tok_doc + (valid ? token : T1 - 1u));
-            const uint32_t db = __ldg(p.doc_off + d), de = __ldg(p.doc_off + d + 1u);
+            // Document of every lane (loaded one tile ahead, below); lanes past the CTA's range borrow the last
+            // valid token's document (they are masked to -inf). The neighbours just outside the chunk tell whether
+            // its first document began earlier / its last one goes on: no dependent doc_off gather on the chain.
+            const uint32_t d = d_next, d_before = before_next, d_after = after_next;
+            {
+                const uint32_t nchunk = chunk + 8u, ns = T0 + nchunk * 32u;   // this warp's chunk of tile it + 2
+                if (ns < T1) {
+                    d_next = __ldg(p.tok_doc + min(ns + (uint32_t)lane, T1 - 1u));
+                    before_next = __ldg(p.tok_doc + ns - 1u);                  // ns > T0: nchunk >= 8
+                    after_next = ns + 32u < T1 ? __ldg(p.tok_doc + ns + 32u) : 0xFFFFFFFFu;
+                }
+            }
             const uint32_t rank = p.doc_rank ? __ldg(p.doc_rank + d) : d;
             const float inv_dn = cosine ? (valid ? __ldg(p.inv_dnorm + token) : 0.0f) : 1.0f;
             const uint32_t dprev = __shfl_up_sync(0xffffffffu, d, 1);
             const uint32_t heads = s_tok < T1 ? __ballot_sync(0xffffffffu, lane == 0 || d != dprev) : 0u;
+            const uint32_t d_first = __shfl_sync(0xffffffffu, d, 0), d_last = __shfl_sync(0xffffffffu, d, 31);
+            const bool first_continues = s_tok > T0 && d_before == d_first;   // same document as the token before the chunk
+            const bool last_continues = d_after == d_last;                    // ... as the token after it (none: 0xFFFFFFFF)
 
             tc::mbar_wait(&d_full[b], (it / kTcAccBufs) & 1u);
             tc::fence_after_sync();
@@ -345,9 +368,8 @@ maxsim_tcr_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcrParam
                     const uint32_t l1 = hm ? (uint32_t)__ffs(hm) - 1u : 32u;
                     float m = heads == 1u ? warp_transpose_max(v, lane)
                                           : warp_transpose_max_masked(v, (uint32_t)lane >= l0 && (uint32_t)lane < l1, lane);
-                    const uint32_t sdb = __shfl_sync(0xffffffffu, db, l0), sde = __shfl_sync(0xffffffffu, de, l0);
                     const uint32_t sd = __shfl_sync(0xffffffffu, d, l0), srank = __shfl_sync(0xffffffffu, rank, l0);
-                    const bool starts_here = sdb >= s_tok, ends_here = sde <= s_tok + 32u;
+                    const bool starts_here = l0 != 0u || !first_continues, ends_here = l1 != 32u || !last_continues;
                     if (!starts_here) {                                       // the document began in an earlier chunk
                         const uint32_t slot = (chunk - 1u) % kTcrCarrySlots;
                         while (ld_acquire_smem(&s_flag[slot][h]) != chunk) {}
@@ -387,25 +409,29 @@ maxsim_tcr_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcrParam
                 // a non-finite running sum can never become finite again, so one check suffices
                 if (!isfinite(my_total)) { atomicMin(p.err, (my_doc << 1) | 1u); my_total = 0.0f; }
                 const u64 key = ((u64)(~order_key(my_total)) << 32) | my_rank;
-                if (key < col.threshold()) col.push(key, ((u64)__float_as_uint(my_total) << 32) | my_doc);
+                const u64 pay = ((u64)__float_as_uint(my_total) << 32) | my_doc;
+                if (p.dump_keys) { p.dump_keys[my_doc] = key; p.dump_pays[my_doc] = pay; }
+                else if (key < col.threshold()) col.push(key, pay);
             }
             // Both groups meet (all 8 warps) each time the CTA has finished another C tiles; a window only
             // counts when it lies inside this CTA's tiles, so both groups pass the same number of checkpoints.
-            if ((it + 2u) / C != it / C && (it / C + 1u) * C <= my_tiles)
+            if (!p.dump_keys && (it + 2u) / C != it / C && (it / C + 1u) * C <= my_tiles)
                 collector_checkpoint(col, p.ws, 0, p.slack, g_prefetch);
         }
         if (p.has_empty) {
             for (uint32_t d0 = D0; d0 < D1; d0 += kTcrEmptyRound) {
-                collector_checkpoint(col, p.ws, 0, kTcrEmptyRound, g_prefetch);
+                if (!p.dump_keys) collector_checkpoint(col, p.ws, 0, kTcrEmptyRound, g_prefetch);
                 const uint32_t d = d0 + (uint32_t)tid;
                 if (d < D1 && __ldg(p.doc_off + d) == __ldg(p.doc_off + d + 1u)) {
                     const uint32_t rank = p.doc_rank ? __ldg(p.doc_rank + d) : d;
                     const u64 key = ((u64)(~order_key(0.0f)) << 32) | rank;
-                    if (rank != 0xFFFFFFFFu && key < col.threshold()) col.push(key, (u64)d);
+                    if (rank == 0xFFFFFFFFu) continue;
+                    if (p.dump_keys) { p.dump_keys[d] = key; p.dump_pays[d] = (u64)d; }
+                    else if (key < col.threshold()) col.push(key, (u64)d);
                 }
             }
         }
-        collector_publish_and_merge(col, p.ws, 0, &s_last);
+        if (!p.dump_keys) collector_publish_and_merge(col, p.ws, 0, &s_last);
     }
     // teardown: every role is done with TMEM before it is released
     tc::fence_before_sync();
@@ -421,7 +447,7 @@ bool maxsim_tcr_eligible(const MaxSimJob& job) {
     if (job.dims == 0 || job.dims > 128 || job.stride % 4 != 0) return false;
     if (job.tq == 0 || job.tq > 64) return false;
     if (job.ntok == 0 || job.ntok >= (1ull << 31)) return false;   // TMA coordinates are signed 32-bit
-    if (std::min<size_t>(job.k, job.ndocs) > (size_t)kMaxFusedK) return false;
+    if (std::min<size_t>(job.k, job.ndocs) > (size_t)kMaxFusedK && job.d_keys_out) return false;
     return true;
 }
 
@@ -429,7 +455,9 @@ Status maxsim_tcr_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out)
     out->rows.clear();
     out->scores.clear();
     out->err = kNoError;
-    const uint32_t k = (uint32_t)std::min<size_t>(job.k, job.ndocs);
+    const uint32_t k_out = (uint32_t)std::min<size_t>(job.k, job.ndocs);
+    const bool dump = k_out > (uint32_t)kMaxFusedK;   // every live document's score is written out and radix-sorted
+    const uint32_t k = dump ? 1u : k_out;              // the collector is idle in dump mode
     const uint32_t KB = (job.dims + 31) / 32;
     const uint32_t N = job.tq <= 32 ? 32u : 64u;
     // query tokens + their inverse norms (f64 norm, reference distances.rs:165)
@@ -480,8 +508,11 @@ Status maxsim_tcr_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out)
     VB_TRY(ctx.cand_counts.reserve((size_t)grid * sizeof(uint32_t)));
     VB_TRY(ctx.out_keys.reserve((size_t)k * sizeof(u64)));
     VB_TRY(ctx.result.reserve((size_t)k * sizeof(u64) + 8));
+    if (dump) VB_TRY(maxsim_prepare_dump(ctx, job.ndocs));
 
     MaxSimTcrParams p{};
+    p.dump_keys = dump ? ctx.dump_keys.as<u64>() : nullptr;
+    p.dump_pays = dump ? ctx.dump_pays.as<u64>() : nullptr;
     p.ndocs = (uint32_t)job.ndocs;
     p.ntok = (uint32_t)job.ntok;
     p.dims = job.dims;
@@ -511,6 +542,7 @@ Status maxsim_tcr_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out)
     p.ws.err_row = ctx.err_row();
     p.ws.out_err = p.ws.out_counts + 1;
     kernel<<<grid, kTcThreads, smem, ctx.stream>>>(tmap, p);
+    if (dump) return maxsim_collect_dump(ctx, job.ndocs, k_out, cudaGetLastError(), out);
     return maxsim_collect_result(ctx, job, p.ws, k, cudaGetLastError(), out);
 }
 

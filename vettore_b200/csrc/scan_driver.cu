@@ -170,6 +170,30 @@ static Status dump_and_sort(SearchCtx& ctx, const ScanJob& job, const float* d_q
     return Status::Ok();
 }
 
+// Dump mode of kernels outside this file (MaxSim with a limit beyond the fused collector): sorts the n pairs a
+// kernel left in ctx.dump_keys / ctx.dump_pays (absent entries hold kKeyMax) and brings the best k payloads to
+// ctx.h_result in the fused collector's result layout (k payloads | count | error word). Synchronises the stream.
+Status sort_dump_and_fetch(SearchCtx& ctx, size_t n, size_t k) {
+    size_t tmp_bytes = 0;
+    VB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx.dump_keys.as<u64>(), ctx.dump_keys2.as<u64>(),
+                                            ctx.dump_pays.as<u64>(), ctx.dump_pays2.as<u64>(), (int64_t)n, 0, 64,
+                                            ctx.stream));
+    VB_TRY(ctx.sort_tmp.reserve(tmp_bytes));
+    VB_CUDA(cub::DeviceRadixSort::SortPairs(ctx.sort_tmp.p, tmp_bytes, ctx.dump_keys.as<u64>(), ctx.dump_keys2.as<u64>(),
+                                            ctx.dump_pays.as<u64>(), ctx.dump_pays2.as<u64>(), (int64_t)n, 0, 64,
+                                            ctx.stream));
+    VB_TRY(ctx.misc.reserve(17 * sizeof(uint32_t)));
+    collect_err_kernel<<<1, 32, 0, ctx.stream>>>(ctx.err_row(), ctx.misc.as<uint32_t>(), 1);
+    VB_CUDA(cudaGetLastError());
+    VB_TRY(ctx.h_result.reserve(k * sizeof(u64) + 8));
+    uint32_t* tail = reinterpret_cast<uint32_t*>(ctx.h_result.as<u64>() + k);
+    VB_CUDA(cudaMemcpyAsync(ctx.h_result.p, ctx.dump_pays2.p, k * sizeof(u64), cudaMemcpyDeviceToHost, ctx.stream));
+    VB_CUDA(cudaMemcpyAsync(tail + 1, ctx.misc.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
+    VB_CUDA(cudaStreamSynchronize(ctx.stream));
+    tail[0] = (uint32_t)k;
+    return Status::Ok();
+}
+
 // Scratch word receiving the overflow flag of a dump scan.
 static Status dump_err_word(SearchCtx& ctx, uint32_t** out, uint32_t nslots = 1) {
     VB_TRY(ctx.misc.reserve(((size_t)nslots + 16) * sizeof(uint32_t)));   // same size for every stage of a pipeline

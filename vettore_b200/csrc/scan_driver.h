@@ -51,6 +51,9 @@ Status run_scan_device(SearchCtx& ctx, const ScanJob& job, const float* d_querie
                        uint32_t* d_counts, uint32_t* d_status, cudaStream_t stream);
 
 // (key, payload) pairs -> separate keys / values / rows arrays (device, on `stream`).
+// Sorts the n (key, payload) pairs a dump-mode kernel left in ctx.dump_keys / ctx.dump_pays and fetches the best k
+// payloads + the error word into ctx.h_result (fused-collector result layout). Synchronises ctx.stream.
+Status sort_dump_and_fetch(SearchCtx& ctx, size_t n, size_t k);
 Status unpack_device_results(const u64* d_keys_in, const u64* d_pays, const uint32_t* d_counts_in, uint32_t nq, uint32_t k,
                              u64* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream);
 
