@@ -52,9 +52,9 @@ struct MaxSimTcrParams {
     TopkWorkspace ws;
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_smem(const uint32_t* p) {
+__device__ __forceinline__ uint32_t ld_acquire_smem(uint32_t smem_address) {
     uint32_t v;
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(tc::smem_addr(p)) : "memory");
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_address) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_smem(uint32_t* p, uint32_t v) {
@@ -361,18 +361,22 @@ maxsim_tcr_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcrParam
                 }
                 if (valid && !(fabsf(chk) <= FLT_MAX)) atomicMin(p.err, 0u);
 
-                uint32_t hm = heads, j = 0;
+                // Segments are taken LAST to FIRST: the chunk's open last segment is published before the first
+                // segment waits for the previous chunk, so only chunks that lie wholly inside one document (wait ->
+                // max -> publish) are links of the serial carry chain; every butterfly stays off it.
+                uint32_t hm = heads, j = 0, l1 = 32u;
                 while (hm) {                                                  // warp-uniform: one round per segment
-                    const uint32_t l0 = (uint32_t)__ffs(hm) - 1u;
-                    hm &= hm - 1u;
-                    const uint32_t l1 = hm ? (uint32_t)__ffs(hm) - 1u : 32u;
+                    const uint32_t l0 = 31u - (uint32_t)__clz(hm);
+                    hm &= ~(1u << l0);
                     float m = heads == 1u ? warp_transpose_max(v, lane)
                                           : warp_transpose_max_masked(v, (uint32_t)lane >= l0 && (uint32_t)lane < l1, lane);
                     const uint32_t sd = __shfl_sync(0xffffffffu, d, l0), srank = __shfl_sync(0xffffffffu, rank, l0);
                     const bool starts_here = l0 != 0u || !first_continues, ends_here = l1 != 32u || !last_continues;
+                    l1 = l0;
                     if (!starts_here) {                                       // the document began in an earlier chunk
                         const uint32_t slot = (chunk - 1u) % kTcrCarrySlots;
-                        while (ld_acquire_smem(&s_flag[slot][h]) != chunk) {}
+                        const uint32_t flag = tc::smem_addr(&s_flag[slot][h]);
+                        while (ld_acquire_smem(flag) != chunk) {}
                         m = fmaxf(m, s_carry[slot][h * 32u + lane]);
                     }
                     if (!ends_here) {                                         // ... and goes on in the next one
