@@ -511,7 +511,7 @@ def headline(run: Run, args, pk):
         for qi in range(nchk):
             assert_hits_match([(int(rows_h[qi, i]), float(vals_h[qi, i])) for i in range(k)], bref[qi], f"batch query {qi}")
         tf32_peak = pk["tf32"]
-        terms = int(os.environ.get("VB_GEMM_TERMS", "1" if k <= 32 else "3"))
+        terms = int(lib().vb_debug_gemm_terms())   # TF32 passes of the last batch (3 = it fell back to the 3xTF32 tier)
         alg = 2.0 * nqb * n * d / (bms * 1e-3) / 1e12
         issued = terms * alg
         batch = {"workload": f"flat cosine exact scan {n}x{d} fp32, batch of {nqb} queries, k={k}",
@@ -520,8 +520,9 @@ def headline(run: Run, args, pk):
                  "roofline": {"bound": "tensor", "achieved": issued, "peak": tf32_peak, "unit": "TFLOP/s",
                               "frac": issued / tf32_peak, "peak_source": pk["tc_src"],
                               "note": "the tensor-core pass is a candidate filter in front of the exact fp32 re-scoring: ONE "
-                                      "TF32 pass for k <= 32 (issued = algorithmic flops), 3xTF32 above (3x issued); the "
-                                      "sample pre-pass, list merges and re-scoring launches are inside ms_per_batch"},
+                                      "TF32 pass (issued = algorithmic flops), 3xTF32 only as the fallback tier for queries whose "
+                                      "candidate set could not be proven complete; the sample pre-pass, list merges and "
+                                      "re-scoring launches are inside ms_per_batch"},
                  "parity_checked": nchk,
                  "kernel": "vb::flat_gemm1_topk_kernel (tcgen05 kind::tf32, SS mode, fused top-k filter) + exact re-scoring"
                            if terms == 1 else "vb::flat_gemm_topk_kernel (tcgen05 3xTF32) + exact re-scoring"}
@@ -643,7 +644,8 @@ def block_c3(run: Run, args, pk):
                 assert st == "ok" and close(h.value, v), ("c3 value", qi, h.shard, h.row, h.value, v)
                 checked += 1
         regen.close()
-    issued = 3 * 2.0 * nq * n * d / (local_ms * 1e-3) / 1e12
+    terms = int(lib().vb_debug_gemm_terms())   # 1: single TF32 filter pass; 3: the batch fell back to the 3xTF32 tier
+    issued = terms * 2.0 * nq * n * d / (local_ms * 1e-3) / 1e12
     tf32_peak = pk["tf32"]
     out = {"workload": f"flat inner-product scan {total}x{d} fp32 row-sharded x{world}, batch of {nq} queries, k={k}",
            "rows_per_gpu": n, "corpus_rows_resident": n * world, "full_corpus": n * world == total,
@@ -652,7 +654,9 @@ def block_c3(run: Run, args, pk):
             f"{total // world} rows x {d} fp32 = {total // world * d * 4 / 1e9:.0f} GB per GPU does not fit next to the "
             f"workspaces: {n} rows per GPU resident"),
            "local_scan_ms": local_ms, "step_ms": step_ms, "queries_per_sec": nq / (step_ms * 1e-3),
-           "tf32_passes": 3, "per_gpu_tf32_tflops_issued": issued, "per_gpu_algorithmic_tflops": issued / 3,
+           "tf32_passes": terms, "per_gpu_tf32_tflops_issued": issued, "per_gpu_algorithmic_tflops": issued / terms,
+           "kernel": ("vb::flat_gemm1_topk_kernel (one TF32 pass as a candidate filter, k' = 192 kept per query)" if terms == 1
+                      else "vb::flat_gemm_topk_kernel (3xTF32)") + " + exact fp32 re-scoring",
            "roofline": {"bound": "tensor", "achieved": issued, "peak": tf32_peak, "unit": "TFLOP/s",
                         "frac": issued / tf32_peak, "peak_source": pk["tc_src"]},
            "speedup_vs_one_gpu_same_corpus": world * local_ms / step_ms,

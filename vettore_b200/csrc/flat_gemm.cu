@@ -362,7 +362,8 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned
 // the whole of TMEM for TWO accumulators, released as soon as a tile's scores sit in registers.
 // Error bound: operands lose < 2^-10 relative each, so |approx - exact| <= 2^-9 * |q| * |row| (+ fp32
 // accumulation): 2e-3 for unit vectors. The candidate margin k' - k covers the rows that can sit that close to
-// the k-th score; it is used for k <= 32 (k' = k + 32), larger k keeps the 3xTF32 kernel above.
+// the k-th score: k' = k + 32 up to k = 32, k' = min(3k, 192) >= k + 64 above (flat_gemm_search_device); queries whose
+// kept set cannot be proven complete are redone by the caller on the 3xTF32 kernel above (second tier).
 constexpr int kG1EpiWarps = 8, kG1ProducerWarp = 8, kG1MmaWarp = 9;
 constexpr int kG1Threads = (kG1MmaWarp + 1) * 32;        // warps 0-7 epilogue, 8 producer, 9 MMA
 constexpr int kG1Stages = 3;
@@ -374,6 +375,22 @@ constexpr uint32_t kG1StageBytes = 2 * 16384 + 32768;     // A chunks of tile 2t
 // (Tried and dropped: warp-aggregated appends — one vote + ballot + a single shared-memory atomic per (warp, query
 // column). The vote costs an instruction on EVERY score: the main pass went from 2.67 to 5.25 ms, and even the
 // pre-pass, where nearly every score passes, got slower: 736 vs 618 us.)
+// Second-level filter + append of one score that passed the rank compare (rare: a fraction of a percent of the scores).
+// The payload carries the approximate rank next to the row; only the row is read downstream (the candidates are
+// re-scored exactly).
+__device__ __noinline__ void gemm1_append(const u64* s_thr, uint32_t* s_cnt, u64* list_keys, u64* list_pays, uint32_t list_cap,
+                                          uint32_t list_base, uint32_t q, float rankv, uint32_t idr, uint32_t row) {
+    const u64 key = ((u64)order_key(rankv) << 32) | idr;
+    if (key < s_thr[q]) {
+        const uint32_t slot = atomicAdd(&s_cnt[q], 1u);
+        if (slot < list_cap) {
+            const size_t at = ((size_t)list_base + q) * list_cap + slot;
+            list_keys[at] = key;
+            list_pays[at] = ((u64)__float_as_uint(rankv) << 32) | row;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kG1Threads, 1)
 flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned char* __restrict__ q_blobs,
                        const GemmParams p) {
@@ -381,7 +398,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
     __shared__ __align__(8) uint64_t full_bar[kG1Stages], empty_bar[kG1Stages], d_full, d_free[2];
     __shared__ uint32_t tmem_slot;
     __shared__ u64 s_thr[kGmN];
-    __shared__ float s_thr_rank[kGmN];
+    __shared__ __align__(16) float s_thr_rank[kGmN];
     __shared__ uint32_t s_cnt[kGmN];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -487,34 +504,53 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                 const uint32_t idr = valid ? (p.id_rank ? __ldg(p.id_rank + row) : row) : 0u;
                 // a row past the end never passes the filter: its rank is NaN (one compare per score, no row test)
                 const float row_bias = valid ? (p.row_norm2 ? __ldg(p.row_norm2 + row) : bias) : __int_as_float(0x7fc00000);
-                // the warp's 32 rows x 128 columns into registers at once, then this accumulator is free again
-                uint32_t r[4][32];
-#pragma unroll
-                for (uint32_t g = 0; g < 4; ++g) tc::tmem_ld32(lane_addr + acc * (uint32_t)kGmN + (half * 4u + g) * 32u, r[g]);
-                tc::tmem_ld_wait();
-                tc::fence_before_sync();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&d_free[acc]);
-#pragma unroll
+                // One group of 32 query columns at a time: scores and the group's 32 bounds in registers (thresholds
+                // only move in the cut phase below, behind the barrier, so reading them once per group is exact).
+                // The per-score work is branch-free — FFMA, compare, a predicated bit and a predicated copy of the
+                // passing rank — and the append code exists once, out of line. (The earlier form, a shared-memory
+                // load + branch per score with 128 inlined copies of the append path, had 27 % of the kernel's samples
+                // on the load wait and 11 % on instruction-cache misses; holding all 128 scores AND the bounds in
+                // registers spilled.) The accumulator is released once its last group sits in registers.
+#pragma unroll 1
                 for (uint32_t g = 0; g < 4; ++g) {
                     const uint32_t cg = half * 4u + g;
-                    if (qb * kGmN + cg * 32u >= p.nq) break;       // padded query columns (warp-uniform)
+                    uint32_t r[32];
+                    tc::tmem_ld32(lane_addr + acc * (uint32_t)kGmN + cg * 32u, r);
+                    float thr[32];
+                    {
+                        const float4* t4 = reinterpret_cast<const float4*>(&s_thr_rank[cg * 32u]);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 t = t4[i];
+                            thr[4 * i] = t.x; thr[4 * i + 1] = t.y; thr[4 * i + 2] = t.z; thr[4 * i + 3] = t.w;
+                        }
+                    }
+                    tc::tmem_ld_wait();
+                    if (g == 3u) {
+                        tc::fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&d_free[acc]);
+                    }
+                    // (padded query columns carry a -inf bound: nothing passes)
+                    uint32_t mask = 0u;
+                    float one_rank = 0.0f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const uint32_t q = cg * 32u + j;
-                        const float dot = __uint_as_float(r[g][j]);
-                        if (valid) poison = fmaf(dot, 0.0f, poison);
+                        const float dot = __uint_as_float(r[j]);
+                        poison = fmaf(dot, 0.0f, poison);              // rows past the end are zero-filled by the tensor map: finite
                         const float rankv = fmaf(dot, scale, row_bias);
-                        if (rankv <= s_thr_rank[q]) {               // first-level filter: one compare
-                            const u64 key = ((u64)order_key(rankv) << 32) | idr;
-                            if (key < s_thr[q]) {
-                                const float raw = p.row_norm2 ? rankv : (p.metric == kNegativeInnerProduct ? -dot : dot);
-                                const uint32_t slot = atomicAdd(&s_cnt[q], 1u);
-                                if (slot < p.list_cap) {
-                                    p.list_keys[(list_base + q) * p.list_cap + slot] = key;
-                                    p.list_pays[(list_base + q) * p.list_cap + slot] = ((u64)__float_as_uint(raw) << 32) | row;
-                                }
-                            }
+                        if (rankv <= thr[j]) { mask |= 1u << j; one_rank = rankv; }   // first-level filter: one compare
+                    }
+                    if (mask != 0u) {
+                        if ((mask & (mask - 1u)) == 0u) {                  // the usual case: one score of the 32 passed
+                            gemm1_append(s_thr, s_cnt, p.list_keys, p.list_pays, p.list_cap, (uint32_t)list_base,
+                                         cg * 32u + (uint32_t)__ffs(mask) - 1u, one_rank, idr, row);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (mask & (1u << j))
+                                    gemm1_append(s_thr, s_cnt, p.list_keys, p.list_pays, p.list_cap, (uint32_t)list_base, cg * 32u + j,
+                                                 fmaf(__uint_as_float(r[j]), scale, row_bias), idr, row);
                         }
                     }
                 }
@@ -709,7 +745,7 @@ bool flat_gemm_eligible(int metric, size_t dims, size_t stride, size_t nq, size_
     const char* min_env = std::getenv("VB_FLAT_GEMM_MIN_BATCH");
     const size_t min_batch = min_env ? (size_t)std::atoi(min_env) : 16;
     if (nq < min_batch) return false;
-    if (k == 0 || k > 100 || n < 1024) return false;   // k' = k + max(8, k/4) <= 128 candidates kept per query
+    if (k == 0 || k > 100 || n < 1024) return false;   // k' <= 192 (one pass) / 128 (3xTF32) candidates kept per query
     return true;
 }
 
@@ -757,6 +793,10 @@ static RescoreKernel rescore_lookup(int metric) {
     return nullptr;
 }
 
+// TF32 passes of this thread's most recent batched search (bench.py reports issued flops from it).
+static thread_local int t_gemm_terms = 0;
+extern "C" int vb_debug_gemm_terms() { return t_gemm_terms; }
+
 // Device part: queries already in device memory ([nq, dims]); leaves, on `stream`, the exact top-k
 // payloads [nq][k] (raw bits << 32 | row), optional exact keys, counts [nq] and flags [nq]
 // (0 ok, 1 redo on the single-query path, 2 metric overflow); *d_bad != 0 when a tensor-core
@@ -772,16 +812,23 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     const uint32_t qblocks_total = (uint32_t)((nq + kGmN - 1) / kGmN);
     const uint32_t group = std::min<uint32_t>(qblocks_total, (uint32_t)sms);   // query blocks per launch
     const size_t nq_pad = (size_t)qblocks_total * kGmN;
-    // single TF32 pass (wide margin) for small k, 3xTF32 (narrow margin) otherwise; VB_GEMM_TERMS forces either
-    int terms = k <= 32 ? 1 : 3;
+    // One TF32 pass with a wide candidate margin; 3xTF32 (narrow margin) only when forced — VB_GEMM_TERMS=3, or the
+    // caller's second tier for the queries whose single-pass candidate set could not be proven complete.
+    // Margins: the kept set must reach `bound` (2e-3 |q| |row| for one pass) below the exact k-th score. For unit
+    // vectors of 768 dims the scores of a 12.5M-row shard put ~30 rows that close to the 100th best, so k' = 192
+    // candidates for k = 100 (k' = k + 32 up to k = 32) leave a wide reserve; denser corpora flag and take tier two.
+    // k' stays 64 below the point where a list is cut (256 of its 512 slots): a cut must buy room for many appends
+    // (k' = 256 cut every list after every tile pair: 168 ms instead of 40 per batch on the C3 shard).
+    int terms = 1;
     if (const char* e = std::getenv("VB_GEMM_TERMS")) {
         const int t = std::atoi(e);
-        if (t == 3 || (t == 1 && k <= 96)) terms = t;
+        if (t == 3 || t == 1) terms = t;
     }
     if (force_terms == 3) terms = 3;
     if (terms_used) *terms_used = terms;
-    const size_t margin = terms == 1 ? 32 : std::max<size_t>(8, k / 4);
-    const size_t kprime = std::min<size_t>(std::min<size_t>(k + margin, 128), n);   // approximate candidates kept
+    t_gemm_terms = terms;
+    const size_t margin = terms == 1 ? (k <= 32 ? 32 : std::max<size_t>(64, 2 * k)) : std::max<size_t>(8, k / 4);
+    const size_t kprime = std::min<size_t>(std::min<size_t>(k + margin, terms == 1 ? 192 : 128), n);   // approximate candidates kept
     RescoreKernel rescore = rescore_lookup(metric);
     if (!rescore) return Status::Cuda("metric not served by the batched kernel");
     const bool l2_family = metric == kL2 || metric == kL2Squared;
