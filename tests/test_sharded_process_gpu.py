@@ -139,3 +139,64 @@ def test_eight_shards_driven_by_concurrent_callers():
     for t in ts:
         t.join()
     assert not errors, errors[:3]
+
+
+# ------------------------------------------------------------------ resident pipelines over the sharded corpus
+def _pipeline_pair(metric, shards, n, d, seed):
+    rows = _rows(n, d, seed)
+    rows = (rows / np.linalg.norm(rows.astype(np.float64), axis=1, keepdims=True)).astype(np.float32)
+    ids = [f"{(i * 7919) % n:06d}" for i in range(n)]
+    single = getattr(nifs, f"flat_new_{metric}")()
+    sharded = nifs.flat_new_sharded(metric, shards)
+    for idx in (single, sharded):
+        assert nifs.flat_insert_matrix(idx, ids, rows) == ("ok", ())
+    return rows, ids, single, sharded
+
+
+@pytest.mark.parametrize("metric_code", [2, 3, 0, 5])
+@pytest.mark.parametrize("shards", [2, 8])
+def test_sharded_funnel_and_prefix_equal_the_single_index_and_the_oracle(metric_code, shards):
+    n, d = 6000, 96
+    rows, ids, single, sharded = _pipeline_pair("cosine", shards, n, d, 11)
+    q = _rows(1, d, 5)[0]
+    for stages, cand, limit in (([16, 48], 200, 10), ([32], 1500, 25), ([], 50, 7), ([8, 24, 64], 64, 64)):
+        a = nifs.flat_funnel_search(single, q, metric_code, stages, cand, limit)
+        b = nifs.flat_funnel_search(sharded, q, metric_code, stages, cand, limit)
+        assert a[0] == b[0] == "ok"
+        assert a[1] == b[1], (stages, cand, limit)
+    # vector_top_k over all rows / a listed subset (search.rs:38-73) against the oracle
+    vectors = [(ids[i], rows[i]) for i in range(n)]
+    for dims, limit in ((24, 50), (d, 10)):
+        exp = oracle.vector_top_k(vectors, q, metric_code, dims, limit)
+        got = nifs.flat_prefix_top_k(sharded, None, q, metric_code, dims, limit)
+        assert got[0] == exp[0] == "ok"
+        assert_hits_match(got[1], exp[1])
+    some = ids[::7] + ["no-such-id"]
+    exp = oracle.vector_top_k([(i, rows[ids.index(i)]) for i in ids[::7]], q, metric_code, 40, 30)
+    assert_hits_match(nifs.flat_prefix_top_k(sharded, some, q, metric_code, 40, 30)[1], exp[1])
+    # error strings and degenerate limits behave like the single index
+    for args in ((q, metric_code, [200], 10, 5), (q, 9, [16], 10, 5), (q, metric_code, [16], 0, 5), (q, metric_code, [16], 10, 0)):
+        assert nifs.flat_funnel_search(sharded, *args) == nifs.flat_funnel_search(single, *args)
+    assert nifs.flat_prefix_top_k(sharded, None, q, metric_code, 0, 5) == nifs.flat_prefix_top_k(single, None, q, metric_code, 0, 5)
+
+
+@pytest.mark.parametrize("shards", [2, 8])
+def test_sharded_quantized_search_equals_the_single_index(shards):
+    n, d = 20000, 128
+    rows, ids, single, sharded = _pipeline_pair("cosine", shards, n, d, 23)
+    q = _rows(1, d, 9)[0]
+    for code in (2, 3, 0):
+        for cand, limit in ((100, 10), (1500, 40), (5, 10), (n + 5, 3)):
+            a = nifs.flat_quantized_search(single, q, code, cand, limit)
+            b = nifs.flat_quantized_search(sharded, q, code, cand, limit)
+            assert a[0] == b[0] == "ok"
+            assert a[1] == b[1], (code, cand, limit)
+    # and the oracle's composition: binary_top_k over the sign codes, then vector_top_k over the candidates
+    codes = [(ids[i], oracle.compress_sign_bits(rows[i])) for i in range(n)]
+    st, cands = oracle.binary_top_k(codes, oracle.compress_sign_bits(q), d, 300)
+    assert st == "ok"
+    pos = {i: r for r, i in enumerate(ids)}
+    exp = oracle.vector_top_k([(i, rows[pos[i]]) for i, _ in cands], q, 2, d, 10)
+    assert_hits_match(nifs.flat_quantized_search(sharded, q, 2, 300, 10)[1], exp[1])
+    for args in ((q[:5], 2, 10, 5), (q, 9, 10, 5), (q, 2, 0, 5), (q, 2, 10, 0)):
+        assert nifs.flat_quantized_search(sharded, *args) == nifs.flat_quantized_search(single, *args)

@@ -184,10 +184,12 @@ int vb_flat_prefix_top_k(vb_flat* index, size_t n_ids, const char* ids, const ui
                          const float* query, size_t len, int metric_code, size_t dimensions, size_t limit,
                          vb_hits** out) {
     *out = nullptr;
-    VB_SINGLE_GPU_ONLY(index);
     vb::Hits hits;
-    vb::Status s = index->impl->prefix_top_k(n_ids == SIZE_MAX, n_ids == SIZE_MAX ? 0 : n_ids, ids, id_off, query,
-                                             len, metric_code, dimensions, limit, &hits);
+    const bool all = n_ids == SIZE_MAX;
+    vb::Status s = index->sharded ? index->sharded->prefix_top_k(all, all ? 0 : n_ids, ids, id_off, query, len, metric_code,
+                                                                 dimensions, limit, &hits)
+                                  : index->impl->prefix_top_k(all, all ? 0 : n_ids, ids, id_off, query, len, metric_code,
+                                                              dimensions, limit, &hits);
     if (!s.ok()) return finish(s);
     *out = new vb_hits{std::move(hits)};
     return VB_OK;
@@ -196,9 +198,9 @@ int vb_flat_prefix_top_k(vb_flat* index, size_t n_ids, const char* ids, const ui
 int vb_flat_funnel_search(vb_flat* index, const float* query, size_t len, int metric_code, const size_t* stages,
                           size_t n_stages, size_t candidates, size_t limit, vb_hits** out) {
     *out = nullptr;
-    VB_SINGLE_GPU_ONLY(index);
     vb::Hits hits;
-    vb::Status s = index->impl->funnel_search(query, len, metric_code, stages, n_stages, candidates, limit, &hits);
+    vb::Status s = index->sharded ? index->sharded->funnel_search(query, len, metric_code, stages, n_stages, candidates, limit, &hits)
+                                  : index->impl->funnel_search(query, len, metric_code, stages, n_stages, candidates, limit, &hits);
     if (!s.ok()) return finish(s);
     *out = new vb_hits{std::move(hits)};
     return VB_OK;
@@ -207,9 +209,9 @@ int vb_flat_funnel_search(vb_flat* index, const float* query, size_t len, int me
 int vb_flat_quantized_search(vb_flat* index, const float* query, size_t len, int metric_code, size_t candidates,
                              size_t limit, vb_hits** out) {
     *out = nullptr;
-    VB_SINGLE_GPU_ONLY(index);
     vb::Hits hits;
-    vb::Status s = index->impl->quantized_search(query, len, metric_code, candidates, limit, &hits);
+    vb::Status s = index->sharded ? index->sharded->quantized_search(query, len, metric_code, candidates, limit, &hits)
+                                  : index->impl->quantized_search(query, len, metric_code, candidates, limit, &hits);
     if (!s.ok()) return finish(s);
     *out = new vb_hits{std::move(hits)};
     return VB_OK;

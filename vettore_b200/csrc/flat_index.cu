@@ -788,6 +788,40 @@ Status FlatIndex::quantized_search(const float* query, size_t len, int metric_co
     return Status::Ok();
 }
 
+Status FlatIndex::hamming_candidates(const float* query, size_t len, size_t candidates, Hits* out) {
+    *out = Hits{};
+    if (len == 0) return Status::Ref("vector must not be empty");
+    if (!all_finite(query, len)) return Status::Ref("vector contains a non-finite value");
+    std::shared_lock<std::shared_mutex> g(mu_);
+    while (n_ > 0 && !d_codes_) {   // first use builds the code mirror (see quantized_search)
+        g.unlock();
+        {
+            std::unique_lock<std::shared_mutex> w(mu_);
+            if (n_ > 0 && !d_codes_) {
+                VB_CUDA(cudaSetDevice(device_));
+                VB_TRY(ensure_codes());
+                VB_TRY(finish_mutation());
+            }
+        }
+        g.lock();
+    }
+    if (n_ == 0) return Status::Ok();
+    if (len != dim_) return Status::Ref("dimension mismatch");
+    const size_t cand = std::min(candidates, n_);
+    if (cand == 0) return Status::Ok();
+    VB_CUDA(cudaSetDevice(device_));
+    CtxLease ctx;
+    VB_TRY(ctx.get());
+    std::vector<uint64_t> code(code_words_, 0);     // query sign code (distances.rs:413-423)
+    for (size_t i = 0; i < len; ++i)
+        if (query[i] >= 0.0f) code[i / 64] |= 1ull << (i % 64);
+    std::vector<uint32_t> rows;
+    std::vector<float> vals;
+    VB_TRY(hamming_top_k_resident(*ctx.ctx, d_codes_, n_, code_words_, dim_, d_rank_, code.data(), cand, &rows, &vals));
+    for (size_t i = 0; i < rows.size(); ++i) out->add(row_id_[rows[i]].data(), row_id_[rows[i]].size(), vals[i], rows[i]);
+    return Status::Ok();
+}
+
 Status FlatIndex::search_device(const float* d_queries, size_t nq, size_t q_stride, size_t limit, u64* d_keys,
                                 float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream) {
     if (limit == 0 || nq == 0) return Status::Cuda("device search needs limit >= 1 and nq >= 1");

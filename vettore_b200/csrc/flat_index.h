@@ -50,6 +50,10 @@ class FlatIndex {
     // mirror of the rows (K3), then the exact rerank of those rows (K4).
     Status quantized_search(const float* query, size_t len, int metric_code, size_t candidates, size_t limit,
                             Hits* out);
+    // Stage 1 of quantized_search on its own (search.rs:76-92 over the resident code mirror): the best
+    // `candidates` rows by (Hamming distance of the sign codes, id), distances as f32. The multi-GPU handle
+    // merges the shards' candidate lists before the owners rerank (sharded_index.cu).
+    Status hamming_candidates(const float* query, size_t len, size_t candidates, Hits* out);
     Status search_device(const float* d_queries, size_t nq, size_t q_stride, size_t limit, u64* d_keys,
                          float* d_values, uint32_t* d_rows, uint32_t* d_counts, cudaStream_t stream);
     // Row-sharded quantized_search, stage 1: sign-packs the device queries and scans this shard's

@@ -212,4 +212,145 @@ Status ShardedFlatIndex::search(const float* queries, size_t nq, size_t len, siz
     return Status::Ok();
 }
 
+namespace {
+
+// Merges per-shard sorted lists into the best `limit` by (order key of the rank, id bytes) — FlatHit's /
+// SearchHit's order (flat.rs:34-40, search.rs:22-31). `rank_of` maps a hit's value to its rank.
+template <typename RankFn>
+void merge_parts(const std::vector<Hits>& part, size_t limit, RankFn rank_of, Hits* dst) {
+    struct Ref { uint32_t key; uint32_t shard; uint32_t pos; };
+    std::vector<Ref> pool;
+    for (size_t s = 0; s < part.size(); ++s)
+        for (size_t i = 0; i < part[s].size(); ++i)
+            pool.push_back(Ref{order_key(rank_of(part[s].values[i])), (uint32_t)s, (uint32_t)i});
+    auto id_of = [&](const Ref& r, size_t* n) {
+        const Hits& h = part[r.shard];
+        *n = (size_t)(h.off[r.pos + 1] - h.off[r.pos]);
+        return h.blob.data() + h.off[r.pos];
+    };
+    std::sort(pool.begin(), pool.end(), [&](const Ref& a, const Ref& b) {
+        if (a.key != b.key) return a.key < b.key;
+        size_t la, lb;
+        const char* ia = id_of(a, &la);
+        const char* ib = id_of(b, &lb);
+        const int c = std::memcmp(ia, ib, std::min(la, lb));
+        return c != 0 ? c < 0 : la < lb;
+    });
+    const size_t take = std::min(limit, pool.size());
+    for (size_t i = 0; i < take; ++i) {
+        size_t il;
+        const char* id = id_of(pool[i], &il);
+        const Hits& h = part[pool[i].shard];
+        dst->add(id, il, h.values[pool[i].pos], ((uint64_t)pool[i].shard << 32) | (uint32_t)h.index[pool[i].pos]);
+    }
+}
+
+float rank_of_metric(int metric_code, float raw) {   // distances.rs:113-119
+    if (metric_code == kCosine) return 1.0f - raw;
+    if (metric_code == kInnerProduct) return -raw;
+    return raw;
+}
+
+bool finite_prefix(const float* v, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (!std::isfinite(v[i])) return false;
+    return true;
+}
+
+}  // namespace
+
+Status ShardedFlatIndex::stage_top_k(const Hits* from, const float* query, size_t len, int metric_code, size_t dimensions,
+                                     size_t limit, Hits* out) {
+    const size_t G = shards_.size();
+    // survivors of the previous stage, regrouped by owner shard (the shard is in the upper half of a hit's index)
+    struct IdList { std::string blob; std::vector<uint64_t> off{0}; };
+    std::vector<IdList> own(G);
+    if (from) {
+        for (size_t i = 0; i < from->size(); ++i) {
+            IdList& l = own[(size_t)(from->index[i] >> 32)];
+            l.blob.append(from->blob.data() + from->off[i], (size_t)(from->off[i + 1] - from->off[i]));
+            l.off.push_back(l.blob.size());
+        }
+    }
+    std::vector<Hits> part(G);
+    std::vector<Status> st(G);
+    for_each_shard([&](size_t s) {
+        if (from && own[s].off.size() == 1) return;   // owns none of the survivors
+        st[s] = shards_[s]->prefix_top_k(from == nullptr, from ? own[s].off.size() - 1 : 0, own[s].blob.data(),
+                                         own[s].off.data(), query, len, metric_code, dimensions, limit, &part[s]);
+    });
+    for (auto& x : st) VB_TRY(x);
+    *out = Hits{};
+    merge_parts(part, limit, [metric_code](float raw) { return rank_of_metric(metric_code, raw); }, out);
+    return Status::Ok();
+}
+
+Status ShardedFlatIndex::prefix_top_k(bool all_rows, size_t n_ids, const char* ids, const uint64_t* id_off,
+                                      const float* query, size_t len, int metric_code, size_t dimensions, size_t limit,
+                                      Hits* out) {
+    *out = Hits{};
+    if (metric_code < 0 || metric_code > 8) return Status::Ref("unknown metric");              // nifs.rs:160
+    if (dimensions == 0 || dimensions > len) return Status::Ref("invalid prefix dimensions");    // search.rs:45-47
+    if (!finite_prefix(query, dimensions)) return Status::Ref("vector contains a non-finite value");
+    std::shared_lock<std::shared_mutex> g(mu_);
+    if (rows_ == 0) return Status::Ok();
+    if (all_rows) {
+        if (dimensions > dim_) return Status::Ref("dimension mismatch");                       // search.rs:52-54
+        return stage_top_k(nullptr, query, len, metric_code, dimensions, limit, out);
+    }
+    // the listed ids, each on its owner shard: reuse the stage path with a synthetic survivor list
+    Hits listed;
+    for (size_t i = 0; i < n_ids; ++i) {
+        const char* id = ids + id_off[i];
+        const size_t il = (size_t)(id_off[i + 1] - id_off[i]);
+        listed.add(id, il, 0.0f, (uint64_t)shard_of(id, il) << 32);
+    }
+    if (listed.size() == 0) return Status::Ok();
+    return stage_top_k(&listed, query, len, metric_code, dimensions, limit, out);
+}
+
+Status ShardedFlatIndex::funnel_search(const float* query, size_t len, int metric_code, const size_t* stages,
+                                       size_t nstages, size_t candidates, size_t limit, Hits* out) {
+    *out = Hits{};
+    if (metric_code < 0 || metric_code > 8) return Status::Ref("unknown metric");
+    for (size_t s = 0; s <= nstages; ++s) {   // every stage is a vector_top_k call: validated in the order the reference meets them
+        const size_t d = s < nstages ? stages[s] : len;
+        if (d == 0 || d > len) return Status::Ref("invalid prefix dimensions");
+        if (!finite_prefix(query, d)) return Status::Ref("vector contains a non-finite value");
+    }
+    std::shared_lock<std::shared_mutex> g(mu_);
+    if (rows_ == 0) return Status::Ok();
+    for (size_t s = 0; s <= nstages; ++s)
+        if ((s < nstages ? stages[s] : len) > dim_) return Status::Ref("dimension mismatch");
+    if (candidates == 0) return Status::Ok();   // vector_top_k(limit 0) -> [] at the first stage (search.rs:48)
+    Hits cur, next;
+    for (size_t s = 0; s < nstages; ++s) {
+        VB_TRY(stage_top_k(s == 0 ? nullptr : &cur, query, len, metric_code, stages[s], candidates, &next));
+        std::swap(cur, next);
+        if (cur.size() == 0) return Status::Ok();
+    }
+    return stage_top_k(nstages == 0 ? nullptr : &cur, query, len, metric_code, len, limit, out);   // exact rerank
+}
+
+Status ShardedFlatIndex::quantized_search(const float* query, size_t len, int metric_code, size_t candidates, size_t limit,
+                                          Hits* out) {
+    *out = Hits{};
+    if (metric_code < 0 || metric_code > 8) return Status::Ref("unknown metric");
+    if (len == 0) return Status::Ref("vector must not be empty");
+    if (!finite_prefix(query, len)) return Status::Ref("vector contains a non-finite value");
+    std::shared_lock<std::shared_mutex> g(mu_);
+    if (rows_ == 0) return Status::Ok();
+    if (len != dim_) return Status::Ref("dimension mismatch");
+    if (std::min(candidates, rows_) == 0) return Status::Ok();   // binary_top_k(limit 0) -> [] (search.rs:95-97)
+    const size_t G = shards_.size();
+    std::vector<Hits> part(G);
+    std::vector<Status> st(G);
+    for_each_shard([&](size_t s) { st[s] = shards_[s]->hamming_candidates(query, len, candidates, &part[s]); });
+    for (auto& x : st) VB_TRY(x);
+    Hits cand;   // global candidate set: (distance, id bytes) ascending, search.rs:87-90
+    merge_parts(part, candidates, [](float d) { return d; }, &cand);
+    if (cand.size() == 0) return Status::Ok();
+    return stage_top_k(&cand, query, len, metric_code, len, limit, out);   // exact rerank on the owners
+}
+
 }  // namespace vb

@@ -49,9 +49,20 @@ class ShardedFlatIndex {
     Status reserve(size_t rows);
     Status remove(const char* id, size_t id_len);
     Status search(const float* queries, size_t nq, size_t len, size_t limit, std::vector<Hits>* out);
+    // The resident pipelines over the whole sharded corpus (same semantics as the single-GPU index): every stage
+    // runs on all shards at once, the shards' sorted lists are merged on the calling thread in the reference's
+    // order, and the next stage re-scores each survivor on the shard that owns it.
+    Status prefix_top_k(bool all_rows, size_t n_ids, const char* ids, const uint64_t* id_off, const float* query,
+                        size_t len, int metric_code, size_t dimensions, size_t limit, Hits* out);
+    Status funnel_search(const float* query, size_t len, int metric_code, const size_t* stages, size_t nstages,
+                         size_t candidates, size_t limit, Hits* out);
+    Status quantized_search(const float* query, size_t len, int metric_code, size_t candidates, size_t limit, Hits* out);
     void info(size_t* rows, size_t* dim);
 
   private:
+    // One vector_top_k (search.rs:38-73) over all rows, or over the ids of `from` (each on its owner shard).
+    Status stage_top_k(const Hits* from, const float* query, size_t len, int metric_code, size_t dimensions, size_t limit,
+                       Hits* out);
     size_t shard_of(const char* id, size_t len) const;
     // Runs fn(shard) for every shard: shard 0 on the calling thread, the others on their workers.
     void for_each_shard(const std::function<void(size_t)>& fn);
