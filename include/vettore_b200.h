@@ -80,8 +80,11 @@ int vb_flat_new(int metric_code, vb_flat** out);
  * vb_flat_search / _search_batch run the fused scan + top-k on every GPU concurrently and merge the
  * n_shards sorted lists on the calling thread by (rank.total_cmp, id bytes) — flat.rs:34-40 exactly.
  * The returned handle works with vb_flat_insert / _insert_many / _reserve / _delete / _search /
- * _search_batch / _info / _free; the resident pipelines and the device-level entries below answer
- * VB_ERR_CUDA "not available on a sharded (multi-GPU) index handle". vb_hits_index = shard << 32 | row. */
+ * _search_batch / _info / _free AND the resident pipelines vb_flat_prefix_top_k / _funnel_search /
+ * _quantized_search (every stage runs on all shards at once, the sorted lists are merged on the calling
+ * thread, survivors are re-scored on the shard that owns them); the stream-ordered device-level entries
+ * below (one process per GPU) answer VB_ERR_CUDA "not available on a sharded (multi-GPU) index handle".
+ * vb_hits_index = shard << 32 | row. */
 int vb_flat_new_sharded(int metric_code, int n_shards, const int* devices, vb_flat** out);
 /* Resource destructor (BEAM GC of the last reference). Frees the HBM matrix. */
 void vb_flat_free(vb_flat* index);

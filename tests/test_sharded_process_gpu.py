@@ -108,9 +108,9 @@ def test_sharded_mutations_batches_and_errors():
     assert nifs.flat_delete(small, "a") == ("ok", ()) and nifs.flat_delete(small, "b") == ("ok", ())
     assert nifs.flat_info(small) == (0, None)
     assert nifs.flat_insert(small, "c", [1.0, 2.0, 3.0]) == ("ok", ())
-    # entries that need a single device answer loudly
-    assert nifs.flat_quantized_search(sh, q, 0, 10, 5)[0] == "error"
-    assert "sharded" in nifs.flat_quantized_search(sh, q, 0, 10, 5)[1]
+    # the stream-ordered device-level entries need a single device and answer loudly
+    rc = _lib.lib().vb_flat_device_status(sh.handle, None)
+    assert rc != 0 and "sharded" in _lib.last_error()
 
 
 def test_eight_shards_driven_by_concurrent_callers():
