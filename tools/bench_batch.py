@@ -12,6 +12,7 @@ ap.add_argument("--nq", type=int, default=1024)
 ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--no-gemm", action="store_true")
+ap.add_argument("--no-check", action="store_true", help="timing experiments with VB_GEMM_DEBUG: results are garbage by design")
 a = ap.parse_args()
 if a.no_gemm:
     os.environ["VB_FLAT_NO_GEMM"] = "1"
@@ -28,10 +29,10 @@ idx = nifs.flat_new_cosine()
 assert nifs.flat_insert_matrix(idx, ids, rows) == ("ok", ())
 queries = make_rows_torch(a.nq, a.dim, SEED + 1, dev).cpu().numpy()
 st, hits = nifs.flat_search_batch(idx, queries, a.k)
-assert st == "ok", hits
+assert st == "ok" or a.no_check, hits
 # parity spot check of 3 queries against the oracle on a 200k-row prefix
 sub = min(a.rows, 200_000)
-for qi in (0, a.nq // 2, a.nq - 1):
+for qi in (() if a.no_check else (0, a.nq // 2, a.nq - 1)):
     ref = dict(oracle.flat_search_dense("cosine", rows[:sub], ids[:sub], queries[qi], a.k)[1])
     for hid, v in hits[qi]:
         if int(hid) < sub:
@@ -66,7 +67,7 @@ torch.cuda.synchronize()
 dev_ms = e0.elapsed_time(e1) / a.steps
 # the device path must agree with the host path
 hv = vals.cpu().numpy().reshape(a.nq, a.k)
-for qi in (0, a.nq - 1):
+for qi in (() if a.no_check else (0, a.nq - 1)):
     assert all(abs(hv[qi, i] - hits[qi][i][1]) <= 1e-6 for i in range(a.k)), (qi, hv[qi], hits[qi])
 flops = 2.0 * a.nq * a.rows * a.dim
 print(json.dumps({"metric": "batched flat queries/s (e2e through vb_flat_search_batch)", "value": a.nq / dt,

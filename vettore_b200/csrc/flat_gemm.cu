@@ -55,7 +55,7 @@ struct GemmParams {
     // k-th key bounds the final k-th key from above, so every CTA starts with a tight filter instead of an open one.
     const u64* init_keys;          // [nq][k] ascending, or null
     const uint32_t* init_counts;   // [nq]
-    uint32_t debug;                // timing experiments only (VB_GEMM_DEBUG): 1 skip A loads, 2 skip B loads, 4 skip split, 8 skip epilogue, 16 skip MMA
+    uint32_t debug;                // timing experiments only (VB_GEMM_DEBUG): 1 / 2 skip operand loads, 4 skip split, 8 skip the filter, 16 skip MMA
 };
 
 __device__ __forceinline__ float rank_from_key(u64 key) {
@@ -443,6 +443,10 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                     const uint32_t s = cc % kG1Stages, ph = (cc / kG1Stages) & 1u;
                     unsigned char* st = gsmem + (size_t)s * kG1StageBytes;
                     tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+                    if ((p.debug & 3u) && cc >= (uint32_t)kG1Stages) {   // timing experiments: the operands stay what the first fills left
+                        tc::mbar_arrive_expect_tx(&full_bar[s], 0u);
+                        continue;
+                    }
                     tc::mbar_arrive_expect_tx(&full_bar[s], kG1StageBytes);
                     // rows past the end of a partial tile are zero-filled by the tensor map and still count; an odd
                     // tile count leaves the last pair without a second tile: load the first again (its rows are
@@ -467,7 +471,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                 const uint64_t a0 = tc::umma_smem_desc_sw128(st_addr);
                 const uint64_t a1 = tc::umma_smem_desc_sw128(st_addr + 16384);
                 const uint64_t b0 = tc::umma_smem_desc_sw128(st_addr + 32768);
-                if (tc::elect_one()) {
+                if (tc::elect_one() && !(p.debug & 16u)) {
 #pragma unroll
                     for (uint32_t ks = 0; ks < 4; ++ks)
                         tc::umma_tf32_ss(tbase, a0 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc, (kc | ks) != 0u);
@@ -477,8 +481,9 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                 if (tc::elect_one()) {
 #pragma unroll
                     for (uint32_t ks = 0; ks < 4; ++ks)
-                        tc::umma_tf32_ss(tbase + (uint32_t)kGmN, a1 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc,
-                                         (kc | ks) != 0u);
+                        if (!(p.debug & 16u))
+                            tc::umma_tf32_ss(tbase + (uint32_t)kGmN, a1 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc,
+                                             (kc | ks) != 0u);
                     tc::umma_commit(&empty_bar[s]);
                     if (kc + 1 == chunks) tc::umma_commit(&d_full);
                 }
@@ -531,6 +536,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                         __syncwarp();
                         if (lane == 0) tc::mbar_arrive(&d_free[acc]);
                     }
+                    if (p.debug & 8u) continue;
                     // (padded query columns carry a -inf bound: nothing passes)
                     uint32_t mask = 0u;
                     float one_rank = 0.0f;
