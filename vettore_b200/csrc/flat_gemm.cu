@@ -55,6 +55,12 @@ struct GemmParams {
     // k-th key bounds the final k-th key from above, so every CTA starts with a tight filter instead of an open one.
     const u64* init_keys;          // [nq][k] ascending, or null
     const uint32_t* init_counts;   // [nq]
+    // single-pass kernel: the pre-pass as a dense dump. score_dump != null: the rank of every (query, sample row) goes
+    // to score_dump[query][dump_stride] (coalesced, no lists, no filter) and gemm1_sample_select_kernel finds each
+    // query's k-th smallest; init_rank != null: the main pass starts from those rank bounds.
+    float* score_dump;
+    uint32_t dump_stride;
+    const float* init_rank;        // [nq] or null; +inf = no bound
     uint32_t debug;                // timing experiments only (VB_GEMM_DEBUG): 1 / 2 skip operand loads, 4 skip split, 8 skip the filter, 16 skip MMA
 };
 
@@ -416,6 +422,13 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
         if (p.init_keys != nullptr && qg < p.nq && p.init_counts[qg] >= p.k) thr = p.init_keys[(size_t)qg * p.k + p.k - 1u];
         s_thr[q] = thr == kKeyMax ? kKeyMax : thr + 1u;             // keys are unique: "<= k-th" is "< k-th + 1"
         s_thr_rank[q] = thr == kKeyMax ? INFINITY : rank_from_key(thr);
+        if (p.init_rank != nullptr && qg < p.nq) {                  // a rank bound: every key of that rank or better passes
+            const float r = p.init_rank[qg];
+            const uint32_t rk = order_key(r);
+            s_thr_rank[q] = r;
+            s_thr[q] = (r == INFINITY || rk == 0xFFFFFFFFu) ? kKeyMax : ((u64)(rk + 1u) << 32);
+            if (s_thr[q] == kKeyMax) s_thr_rank[q] = INFINITY;
+        }
         if (qg >= p.nq) { s_thr[q] = 0ull; s_thr_rank[q] = -INFINITY; }   // padded query column: nothing ever passes
         s_cnt[q] = 0;
     }
@@ -537,6 +550,13 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                         if (lane == 0) tc::mbar_arrive(&d_free[acc]);
                     }
                     if (p.debug & 8u) continue;
+                    if (p.score_dump != nullptr) {   // pre-pass: ranks of this warp's 32 rows x 32 queries, 128 contiguous bytes per query
+                        float* dst = p.score_dump + (size_t)(qb * kGmN + cg * 32u) * p.dump_stride + row;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (row < p.dump_stride) dst[(size_t)j * p.dump_stride] = valid ? fmaf(__uint_as_float(r[j]), scale, row_bias) : INFINITY;
+                        continue;
+                    }
                     // (padded query columns carry a -inf bound: nothing passes)
                     uint32_t mask = 0u;
                     float one_rank = 0.0f;
@@ -603,6 +623,36 @@ __global__ void pack_queries_kernel(const float* q, uint32_t nq, uint32_t qblock
         const uint32_t qb = (uint32_t)(row / kGmN), n = (uint32_t)(row % kGmN);
         unsigned char* blob = blobs + ((size_t)qb * chunks + k / 32u) * 32768u;
         *reinterpret_cast<float*>(blob + tc::sw128_offset(n, k % 32u)) = row < nq ? q[row * dims + k] : 0.0f;
+    }
+}
+
+// Pre-pass select (single-pass kernel): the k-th smallest rank among a query's `n` sample scores, by bisection on the
+// order key with the scores held in shared memory. One CTA per query. Fewer than k sample rows: no bound (+inf).
+__global__ void __launch_bounds__(128) gemm1_sample_select_kernel(const float* dump, uint32_t stride, uint32_t n, uint32_t k,
+                                                                  float* out_rank) {
+    extern __shared__ __align__(1024) unsigned char gsmem[];
+    __shared__ uint32_t s_part[4];
+    uint32_t* keys = reinterpret_cast<uint32_t*>(gsmem);
+    const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* src = dump + (size_t)q * stride;
+    for (uint32_t i = tid; i < n; i += 128) keys[i] = order_key(src[i]);
+    __syncthreads();
+    if (n < k) { if (tid == 0) out_rank[q] = INFINITY; return; }
+    uint32_t lo = 0u, hi = 0xFFFFFFFFu;
+    while (lo < hi) {                          // smallest H with #(key <= H) >= k
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        uint32_t c = 0;
+        for (uint32_t i = tid; i < n; i += 128) c += keys[i] <= mid ? 1u : 0u;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) s_part[warp] = c;
+        __syncthreads();
+        c = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+        __syncthreads();
+        if (c >= k) hi = mid; else lo = mid + 1u;
+    }
+    if (tid == 0) {
+        const uint32_t bits = (lo & 0x80000000u) ? (lo ^ 0x80000000u) : ~lo;   // inverse of order_key
+        out_rank[q] = __uint_as_float(bits);
     }
 }
 
@@ -883,9 +933,22 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     size_t sample = std::min<size_t>(n / 8, (size_t)ranges_full * 256);
     if (const char* e = std::getenv("VB_GEMM_SAMPLE")) sample = std::min<size_t>(n, std::max<size_t>(1024, (size_t)std::atol(e)));
     const bool prepass = n >= 65536 && sample >= 2048 && !std::getenv("VB_GEMM_NO_PREPASS");
+    // Single-pass kernel: the pre-pass is a dense dump — ranks of [queries x sample rows] straight to HBM (coalesced, no
+    // lists), then one small CTA per query bisects its k'-th smallest. (Through the list machinery the same pass cost
+    // 290 us + a 70 us merge per 1024-query batch: with the bounds open every score took the append path.)
+    const bool dense_prepass = prepass && terms == 1 && sample <= 12288 && !std::getenv("VB_GEMM_LIST_PREPASS");
     u64* pre_keys = nullptr;
     uint32_t* pre_counts = nullptr;
-    if (prepass) {
+    float* pre_dump = nullptr;
+    float* pre_rank = nullptr;
+    const uint32_t dump_stride = (uint32_t)((sample + 3) & ~(size_t)3);
+    if (dense_prepass) {
+        VB_TRY(ctx.dump_keys2.reserve(nq_pad * (size_t)dump_stride * sizeof(float)));
+        VB_TRY(ctx.hist.reserve(nq_pad * sizeof(float)));
+        pre_dump = ctx.dump_keys2.as<float>();
+        pre_rank = ctx.hist.as<float>();
+        VB_TRY(ensure_dynamic_smem_for(gemm1_sample_select_kernel, (size_t)dump_stride * sizeof(uint32_t)));
+    } else if (prepass) {
         VB_TRY(ctx.dump_keys2.reserve(nq_pad * kprime * sizeof(u64)));
         VB_TRY(ctx.dump_pays2.reserve(nq_pad * kprime * sizeof(u64)));
         VB_TRY(ctx.hist.reserve(nq_pad * sizeof(uint32_t)));
@@ -916,12 +979,18 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
         const unsigned char* blobs = q_blobs + (size_t)qb0 * (dims / 32) * blob_bytes;
         for (int pass = prepass ? 0 : 1; pass < 2; ++pass) {
             p.n = pass == 0 ? (uint32_t)sample : (uint32_t)n;
-            p.init_keys = pass == 0 ? nullptr : (prepass ? pre_keys + q0 * kprime : nullptr);
-            p.init_counts = pass == 0 ? nullptr : (prepass ? pre_counts + q0 : nullptr);
+            p.init_keys = pass == 0 || dense_prepass ? nullptr : (prepass ? pre_keys + q0 * kprime : nullptr);
+            p.init_counts = pass == 0 || dense_prepass ? nullptr : (prepass ? pre_counts + q0 : nullptr);
+            p.score_dump = pass == 0 && dense_prepass ? pre_dump + q0 * dump_stride : nullptr;
+            p.dump_stride = dump_stride;
+            p.init_rank = pass == 1 && dense_prepass ? pre_rank + q0 : nullptr;
             if (terms == 1) flat_gemm1_topk_kernel<<<grid, kG1Threads, smem_bytes, stream>>>(tmap_a, blobs, p);
             else flat_gemm_topk_kernel<<<grid, kGmThreads, smem_bytes, stream>>>(tmap_a, blobs, p);
             VB_CUDA(cudaGetLastError());
-            if (pass == 0)
+            if (pass == 0 && dense_prepass)
+                gemm1_sample_select_kernel<<<nq_here, 128, (size_t)dump_stride * sizeof(uint32_t), stream>>>(
+                    pre_dump + q0 * dump_stride, dump_stride, (uint32_t)sample, (uint32_t)kprime, pre_rank + q0);
+            else if (pass == 0)
                 flat_gemm_merge_kernel<<<nq_here, 128, (size_t)cap * 16, stream>>>(p, cap, pre_keys + q0 * kprime,
                                                                                   ctx.dump_pays2.as<u64>() + q0 * kprime, pre_counts + q0);
             else
