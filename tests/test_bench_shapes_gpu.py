@@ -10,7 +10,7 @@ import torch
 
 import oracle
 from helpers import assert_hits_match
-from vettore_b200 import nifs
+from vettore_b200 import _lib, nifs
 
 pytestmark = pytest.mark.gpu
 
@@ -128,3 +128,39 @@ def test_k5_maxsim_tc_50k_docs_128x128_32_query_tokens(metric):
     assert st == "ok", hits
     ref = _oracle_maxsim_parallel(metric, host, q, k)
     assert_hits_match([(int(i), s) for i, s in hits], ref)
+
+
+@pytest.mark.parametrize("metric", ["inner_product", "cosine"])
+def test_k5_ragged_maxsim_30k_docs_of_40_to_180_tokens(metric):
+    """The C5 shape with ragged documents (the ragged tensor-core kernel, csrc/maxsim_tcr.cu): 30k documents of 40-180
+    tokens x 128 dims (3.3M tokens, 1.7 GB), 32-token query, device ingest; the oracle scores every document."""
+    dev = torch.device("cuda", 0)
+    nd, d, tq, k = 30_000, 128, 32, 10
+    lens = np.random.default_rng(3).integers(40, 181, nd)
+    idx = nifs.mv_new(metric)
+    assert nifs.mv_reserve(idx, nd, int(lens.sum()), d) == ("ok", ())
+    docs = []
+    for s in range(0, nd, 10_000):
+        doc_tok = np.concatenate([[0], np.cumsum(lens[s:s + 10_000])]).astype(np.uint64)
+        x = _normal_rows(int(doc_tok[-1]), d, SEED + s, dev)
+        assert nifs.mv_insert_ragged_device(idx, nifs.decimal_ids(s, 10_000), x.data_ptr(), doc_tok, d) == ("ok", ())
+        host = x.cpu().numpy()
+        docs.extend(host[int(doc_tok[i]):int(doc_tok[i + 1])] for i in range(10_000))
+        del x
+    q = _normal_rows(tq, d, SEED + 5, dev).cpu().numpy()
+    st, hits = nifs.mv_search(idx, q, k)
+    assert st == "ok", hits
+    assert _lib.lib().vb_debug_maxsim_path() == 2
+    code = nifs.METRIC_CODE[metric]
+    bounds = np.linspace(0, nd, THREADS + 1).astype(int)
+
+    def part(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        r = oracle.multi_vector_top_k([(f"{j:09d}", docs[j]) for j in range(lo, hi)], q, code, k)
+        assert r[0] == "ok"
+        return r[1]
+
+    with ThreadPoolExecutor(THREADS) as ex:
+        pool = [e for p in ex.map(part, range(THREADS)) for e in p]
+    pool.sort(key=lambda e: (-e[1], e[0]))
+    assert_hits_match(hits, pool[:k])
