@@ -157,8 +157,10 @@ class ClockSampler:
         mask = 0
         for s in self.samples:
             mask |= s[1]
-        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz,
-                "reasons": [n for b, n in self.REASONS.items() if mask & b], "samples": len(self.samples)}
+        capped = sum(1 for s in self.samples if s[1] & 0x4)
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_min_mhz": mhz[0], "sm_max_mhz": self.max_mhz,
+                "reasons": [n for b, n in self.REASONS.items() if mask & b], "samples": len(self.samples),
+                "power_cap_sample_frac": round(capped / len(self.samples), 3)}
 
 
 def make_rows_torch(rows: int, dim: int, seed: int, device):
@@ -623,7 +625,8 @@ def block_c3(run: Run, args, pk):
                                          C.c_void_p(sharded.local.data_ptr() + lay["counts"]), run.stream)
         assert rc == 0
 
-    local_ms = run.dev_timed(local_only, 3, 1)
+    with ClockSampler(run.local_rank) as c3_clocks:
+        local_ms = run.dev_timed(local_only, 5, 1)
     step_ms = run.dev_timed(lambda: sharded.search_device(queries), 3, 1) if world > 1 else local_ms
     out_host = sharded.search_device(queries).cpu().numpy()
     hits = sharded.decode(out_host, nq)
@@ -662,6 +665,7 @@ def block_c3(run: Run, args, pk):
            "speedup_vs_one_gpu_same_corpus": world * local_ms / step_ms,
            "speedup_definition": "one GPU works through the same resident corpus shard by shard: n_gpus x local_scan_ms / step_ms",
            "exchange_bytes_per_rank": lay["bytes"], "exchange": sharded.exchange_name,
+           "clocks_during_local_scan": c3_clocks.summary(),
            "ingest_seconds_per_shard": round(ingest_s, 2), "ingest_rows_per_sec": n / ingest_s,
            "parity": f"4 queries: order + completeness vs the oracle's top-{k} over the first {0 if kept is None else kept.shape[0]} "
                      f"rows of shard 0; the best 8 hits of each re-scored by the oracle on rows re-created from their "
@@ -807,7 +811,8 @@ def block_c5(run: Run, args, pk):
         set_global_mv_ranks(index, base, n)
     q = make_rows_torch(tq, d, SEED + 5, dev).cpu().numpy()
     smv = ShardedMv(index, k, device=dev)
-    local_ms = run.wall_timed(lambda: nifs.mv_search(index, q, k), 10, 2)
+    with ClockSampler(run.local_rank) as c5_clocks:            # the 65 GB scan runs under combined tensor + HBM load
+        local_ms = run.wall_timed(lambda: nifs.mv_search(index, q, k), 20 if world == 1 else 40, 2)
     step_ms = run.wall_timed(lambda: smv.search(q), 10, 2) if world > 1 else local_ms
     hits = smv.search(q)
     checked = 0
@@ -836,6 +841,7 @@ def block_c5(run: Run, args, pk):
            "strong_scaling": "the 1M-document corpus is fixed; docs_per_gpu = 1M / n_gpus (compare queries_per_sec across the N lines)",
            "speedup_vs_one_gpu_same_corpus": world * local_ms / step_ms,
            "exchange": smv.exchange_name, "phase_ms": smv.phase_ms(),
+           "clocks_during_local_scan": c5_clocks.summary(),
            "ingest_seconds_per_shard": round(ingest_s, 2),
            "parity": f"order + completeness vs the oracle's top-{k} over the first {kept.shape[0] if kept is not None else 0} "
                      f"documents of shard 0; all {k} returned scores re-derived by the oracle from documents re-created from "

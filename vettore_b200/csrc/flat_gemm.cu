@@ -44,7 +44,9 @@ struct GemmParams {
     // to a per-query constant, which is all a per-query filter needs (distances.rs:140-152 via the exact re-scoring).
     float rank_scale;
     const float* row_norm2;        // [n] or null
-    uint32_t qblocks, ranges;      // query blocks, row ranges (qblocks * ranges CTAs do work)
+    uint32_t qblocks, ranges;      // query blocks, row ranges (qblocks * ranges CTAs — or CTA pairs — do work)
+    uint32_t pair;                 // 1: the single-pass kernel runs as CTA pairs (cta_group::2)
+    uint32_t nblk;                 // queries per block: 256, or 128 for the CTA-pair form
     const uint32_t* id_rank;       // [n] or null
     uint32_t list_cap;             // kGmListSmall / kGmListLarge
     u64* list_keys;                // [cta][256][list_cap]
@@ -378,6 +380,9 @@ constexpr int kG1Stages = 3;
 // every query chunk is used for 256 rows — one tile per TMEM accumulator — instead of 128.
 constexpr uint32_t kG1StageBytes = 2 * 16384 + 32768;     // A chunks of tile 2t, 2t+1 [128 x 32] + query chunk [256 x 32], fp32, SW128
 
+constexpr int kG2N = 128;      // CTA-pair form: queries per block (UMMA N), two accumulator sets in TMEM
+constexpr int kG2Stages = 4;   // ... and its ring: A chunks of the CTA's two tiles (32 KB) + its half of the query chunk (8 KB)
+
 // (Tried and dropped: warp-aggregated appends — one vote + ballot + a single shared-memory atomic per (warp, query
 // column). The vote costs an instruction on EVERY score: the main pass went from 2.67 to 5.25 ms, and even the
 // pre-pass, where nearly every score passes, got slower: 736 vs 618 us.)
@@ -397,28 +402,46 @@ __device__ __noinline__ void gemm1_append(const u64* s_thr, uint32_t* s_cnt, u64
     }
 }
 
+// kPair: two CTAs of a cluster work as one (tcgen05 cta_group::2, UMMA M = 256). The pair serves one query block; each
+// CTA streams the rows of ITS two tiles and only HALF of the query chunk (the MMA reads the other half from the
+// peer's shared memory), so a stage is 48 KB instead of 64 and the ring holds four of them: three stages in flight
+// behind the one the tensor cores read, where the single-CTA form had two and ran the MMA stream at 0.73 of the
+// pipe. The leader (cluster rank 0) issues every MMA; its commits arrive on both CTAs' barriers; the peer's idle
+// MMA warp relays "my stage landed" to the leader, and the peer's epilogue warps release the accumulators there.
+template <bool kPair>
 __global__ void __launch_bounds__(kG1Threads, 1)
 flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned char* __restrict__ q_blobs,
                        const GemmParams p) {
+    constexpr int kStages = kPair ? kG2Stages : kG1Stages;
+    constexpr uint32_t kN = kPair ? (uint32_t)kG2N : (uint32_t)kGmN;   // queries per block = UMMA N
+    constexpr uint32_t kSets = kPair ? 2u : 1u;                        // accumulator sets (2 x kN columns each) in TMEM
+    constexpr uint32_t kGroups = kN / 64u;                             // 32-column groups per epilogue warp and accumulator
+    constexpr uint32_t kBBytes = kPair ? kN * 128u / 2u : kN * 128u;   // this CTA's part of a query chunk
+    constexpr uint32_t kStageBytes = 2u * 16384u + kBBytes;
     extern __shared__ __align__(1024) unsigned char gsmem[];
-    __shared__ __align__(8) uint64_t full_bar[kG1Stages], empty_bar[kG1Stages], d_full, d_free[2];
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], peer_full[kStages], d_full[kSets], d_free[kSets][2];
     __shared__ uint32_t tmem_slot;
-    __shared__ u64 s_thr[kGmN];
-    __shared__ __align__(16) float s_thr_rank[kGmN];
-    __shared__ uint32_t s_cnt[kGmN];
+    __shared__ u64 s_thr[kN];
+    __shared__ __align__(16) float s_thr_rank[kN];
+    __shared__ uint32_t s_cnt[kN];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t qb = blockIdx.x % p.qblocks, rr = blockIdx.x / p.qblocks;
+    // Work units: a tile pair per CTA; a CTA pair takes two consecutive tile pairs per unit (leader the even one).
+    const uint32_t crank = kPair ? tc::cluster_ctarank() : 0u;
+    const uint32_t wid = kPair ? blockIdx.x / 2u : blockIdx.x;           // work-group index: CTA, or CTA pair
+    const uint32_t qb = wid % p.qblocks, rr = wid / p.qblocks;
     const bool active = rr < p.ranges;
     const uint32_t tiles_total = (p.n + kGmTile - 1) / kGmTile;
     const uint32_t pairs_total = (tiles_total + 1) / 2;
-    const uint32_t pair0 = active ? (uint32_t)((uint64_t)pairs_total * rr / p.ranges) : 0;
-    const uint32_t pair1 = active ? (uint32_t)((uint64_t)pairs_total * (rr + 1) / p.ranges) : 0;
+    const uint32_t units_total = kPair ? (pairs_total + 1) / 2 : pairs_total;
+    const uint32_t unit0 = active ? (uint32_t)((uint64_t)units_total * rr / p.ranges) : 0;
+    const uint32_t unit1 = active ? (uint32_t)((uint64_t)units_total * (rr + 1) / p.ranges) : 0;
+    auto pair_of = [crank](uint32_t unit) { return kPair ? 2u * unit + crank : unit; };
     const uint32_t chunks = p.dims / 32;
 
-    for (int q = tid; q < kGmN; q += kG1Threads) {
+    for (int q = tid; q < (int)kN; q += kG1Threads) {
         u64 thr = kKeyMax;
-        const uint32_t qg = qb * kGmN + q;
+        const uint32_t qg = qb * kN + q;
         if (p.init_keys != nullptr && qg < p.nq && p.init_counts[qg] >= p.k) thr = p.init_keys[(size_t)qg * p.k + p.k - 1u];
         s_thr[q] = thr == kKeyMax ? kKeyMax : thr + 1u;             // keys are unique: "<= k-th" is "< k-th + 1"
         s_thr_rank[q] = thr == kKeyMax ? INFINITY : rank_from_key(thr);
@@ -433,86 +456,124 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
         s_cnt[q] = 0;
     }
     if (tid == 0) {
-        for (int s = 0; s < kG1Stages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             tc::mbar_init(&full_bar[s], 1);
             tc::mbar_init(&empty_bar[s], 1);          // the MMA commit frees the three operands of the stage
+            tc::mbar_init(&peer_full[s], 1);          // pair, leader: the peer's stage has landed
         }
-        tc::mbar_init(&d_full, 1);
-        tc::mbar_init(&d_free[0], kG1EpiWarps);
-        tc::mbar_init(&d_free[1], kG1EpiWarps);
+        for (uint32_t st = 0; st < kSets; ++st) {
+            tc::mbar_init(&d_full[st], 1);
+            tc::mbar_init(&d_free[st][0], kPair ? 2 * kG1EpiWarps : kG1EpiWarps);   // pair, leader: both CTAs' epilogue warps
+            tc::mbar_init(&d_free[st][1], kPair ? 2 * kG1EpiWarps : kG1EpiWarps);
+        }
         tc::mbar_fence_init();
     }
-    if (warp == kG1MmaWarp) tc::tmem_alloc(&tmem_slot, 512);
+    if (warp == kG1MmaWarp) {
+        if constexpr (kPair) tc::tmem_alloc2(&tmem_slot, 512); else tc::tmem_alloc(&tmem_slot, 512);
+    }
     tc::fence_before_sync();
     __syncthreads();
+    if constexpr (kPair) tc::cluster_sync_all();      // the peer's barriers exist before anything arrives on them
     tc::fence_after_sync();
     const uint32_t tbase = tmem_slot;
 
     if (warp == kG1ProducerWarp) {
         if (lane == 0) {
             uint32_t cc = 0;
-            for (uint32_t pair = pair0; pair < pair1; ++pair) {
+            for (uint32_t unit = unit0; unit < unit1; ++unit) {
+                const uint32_t pair = pair_of(unit);
                 for (uint32_t kc = 0; kc < chunks; ++kc, ++cc) {
-                    const uint32_t s = cc % kG1Stages, ph = (cc / kG1Stages) & 1u;
-                    unsigned char* st = gsmem + (size_t)s * kG1StageBytes;
+                    const uint32_t s = cc % kStages, ph = (cc / kStages) & 1u;
+                    unsigned char* st = gsmem + (size_t)s * kStageBytes;
                     tc::mbar_wait(&empty_bar[s], ph ^ 1u);
-                    if ((p.debug & 3u) && cc >= (uint32_t)kG1Stages) {   // timing experiments: the operands stay what the first fills left
+                    if ((p.debug & 3u) && cc >= (uint32_t)kStages) {   // timing experiments: the operands stay what the first fills left
                         tc::mbar_arrive_expect_tx(&full_bar[s], 0u);
                         continue;
                     }
-                    tc::mbar_arrive_expect_tx(&full_bar[s], kG1StageBytes);
+                    tc::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
                     // rows past the end of a partial tile are zero-filled by the tensor map and still count; an odd
                     // tile count leaves the last pair without a second tile: load the first again (its rows are
                     // masked out in the epilogue) rather than a box that lies entirely outside the matrix
-                    const uint32_t tile_b = min(2u * pair + 1u, tiles_total - 1u);
-                    tc::tma_load_2d(st, &tmap_a, kc * 32, (2u * pair) * kGmTile, &full_bar[s]);
+                    const uint32_t tile_a = min(2u * pair, tiles_total - 1u), tile_b = min(2u * pair + 1u, tiles_total - 1u);
+                    tc::tma_load_2d(st, &tmap_a, kc * 32, tile_a * kGmTile, &full_bar[s]);
                     tc::tma_load_2d(st + 16384, &tmap_a, kc * 32, tile_b * kGmTile, &full_bar[s]);
-                    tma_bulk_g2s(st + 32768, q_blobs + ((size_t)qb * chunks + kc) * 32768u, 32768u, &full_bar[s]);
+                    tma_bulk_g2s(st + 32768, q_blobs + ((size_t)qb * chunks + kc) * (kN * 128u) + crank * kBBytes, kBBytes, &full_bar[s]);
                 }
             }
         }
     } else if (warp == kG1MmaWarp) {
-        const uint32_t idesc = tc::umma_idesc_tf32(kGmTile, kGmN);
-        uint32_t cc = 0, it = 0;
-        for (uint32_t pair = pair0; pair < pair1; ++pair, ++it) {
-            for (uint32_t kc = 0; kc < chunks; ++kc, ++cc) {
-                const uint32_t s = cc % kG1Stages, ph = (cc / kG1Stages) & 1u;
-                tc::mbar_wait(&full_bar[s], ph);
-                if (kc == 0) tc::mbar_wait(&d_free[0], (it & 1u) ^ 1u);   // accumulator 0's scores sit in registers
-                tc::fence_after_sync();
-                const uint32_t st_addr = tc::smem_addr(gsmem + (size_t)s * kG1StageBytes);
-                const uint64_t a0 = tc::umma_smem_desc_sw128(st_addr);
-                const uint64_t a1 = tc::umma_smem_desc_sw128(st_addr + 16384);
-                const uint64_t b0 = tc::umma_smem_desc_sw128(st_addr + 32768);
-                if (tc::elect_one() && !(p.debug & 16u)) {
-#pragma unroll
-                    for (uint32_t ks = 0; ks < 4; ++ks)
-                        tc::umma_tf32_ss(tbase, a0 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc, (kc | ks) != 0u);
+        if (kPair && crank != 0u) {
+            // ===== pair, peer CTA: no MMAs to issue — tell the leader when each of my stages has landed =====
+            uint32_t cc = 0;
+            for (uint32_t unit = unit0; unit < unit1; ++unit) {
+                for (uint32_t kc = 0; kc < chunks; ++kc, ++cc) {
+                    const uint32_t s = cc % kStages, ph = (cc / kStages) & 1u;
+                    tc::mbar_wait(&full_bar[s], ph);
+                    if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_shared(&peer_full[s], 0u));
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (kc == 0) { tc::mbar_wait(&d_free[1], (it & 1u) ^ 1u); tc::fence_after_sync(); }
-                if (tc::elect_one()) {
+            }
+        } else {
+            const uint32_t idesc = tc::umma_idesc_tf32(kPair ? 2 * kGmTile : kGmTile, kN);
+            uint32_t cc = 0, it = 0;
+            for (uint32_t unit = unit0; unit < unit1; ++unit, ++it) {
+                // pair: set it & 1 — while the epilogues filter the scores of unit it out of one set, the MMAs of
+                // unit it + 1 fill the other
+                const uint32_t set = it % kSets, free_par = ((it / kSets) & 1u) ^ 1u;
+                const uint32_t acc0 = tbase + set * 2u * kN, acc1 = acc0 + kN;
+                for (uint32_t kc = 0; kc < chunks; ++kc, ++cc) {
+                    const uint32_t s = cc % kStages, ph = (cc / kStages) & 1u;
+                    tc::mbar_wait(&full_bar[s], ph);
+                    if constexpr (kPair) tc::mbar_wait(&peer_full[s], ph);
+                    if (kc == 0) tc::mbar_wait(&d_free[set][0], free_par);   // accumulator 0's scores sit in registers (both CTAs of a pair)
+                    tc::fence_after_sync();
+                    const uint32_t st_addr = tc::smem_addr(gsmem + (size_t)s * kStageBytes);
+                    const uint64_t a0 = tc::umma_smem_desc_sw128(st_addr);
+                    const uint64_t a1 = tc::umma_smem_desc_sw128(st_addr + 16384);
+                    const uint64_t b0 = tc::umma_smem_desc_sw128(st_addr + 32768);
+                    if (tc::elect_one() && !(p.debug & 16u)) {
 #pragma unroll
-                    for (uint32_t ks = 0; ks < 4; ++ks)
-                        if (!(p.debug & 16u))
-                            tc::umma_tf32_ss(tbase + (uint32_t)kGmN, a1 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc,
-                                             (kc | ks) != 0u);
-                    tc::umma_commit(&empty_bar[s]);
-                    if (kc + 1 == chunks) tc::umma_commit(&d_full);
+                        for (uint32_t ks = 0; ks < 4; ++ks) {
+                            if constexpr (kPair) tc::umma_tf32_ss2(acc0, a0 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc, (kc | ks) != 0u);
+                            else tc::umma_tf32_ss(acc0, a0 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc, (kc | ks) != 0u);
+                        }
+                    }
+                    __syncwarp();
+                    if (kc == 0) {
+                        tc::mbar_wait(&d_free[set][1], free_par);
+                        tc::fence_after_sync();
+                    }
+                    if (tc::elect_one()) {
+#pragma unroll
+                        for (uint32_t ks = 0; ks < 4; ++ks)
+                            if (!(p.debug & 16u)) {
+                                if constexpr (kPair) tc::umma_tf32_ss2(acc1, a1 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc, (kc | ks) != 0u);
+                                else tc::umma_tf32_ss(acc1, a1 + (uint64_t)(ks * 2u), b0 + (uint64_t)(ks * 2u), idesc, (kc | ks) != 0u);
+                            }
+                        if constexpr (kPair) {
+                            tc::umma_commit2(&empty_bar[s], 3);
+                            if (kc + 1 == chunks) tc::umma_commit2(&d_full[set], 3);
+                        } else {
+                            tc::umma_commit(&empty_bar[s]);
+                            if (kc + 1 == chunks) tc::umma_commit(&d_full[set]);
+                        }
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
-        // ===== epilogue warps 0-7: TMEM lanes of quarter (w & 3), query columns of half (w >> 2), both accumulators =====
+        // ===== epilogue warps 0-7: TMEM lanes of quarter (w & 3), query columns of half (w >> 2), both accumulators of the set =====
         const uint32_t quarter = warp & 3u, half = warp >> 2;
         const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
-        const size_t list_base = (size_t)blockIdx.x * kGmN;
+        const size_t list_base = (size_t)blockIdx.x * kN;
         const float bias = p.metric == kCosine ? 1.0f : 0.0f;
         const float scale = p.rank_scale;
         uint32_t it = 0;
-        for (uint32_t pair = pair0; pair < pair1; ++pair, ++it) {
-            tc::mbar_wait(&d_full, it & 1u);
+        for (uint32_t unit = unit0; unit < unit1; ++unit, ++it) {
+            const uint32_t pair = pair_of(unit);
+            const uint32_t set = it % kSets;
+            tc::mbar_wait(&d_full[set], (it / kSets) & 1u);
             tc::fence_after_sync();
             float poison = 0.0f;       // stays +-0 unless a score is Inf / NaN (x * 0 is NaN for those)
 #pragma unroll 1
@@ -530,10 +591,10 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                 // on the load wait and 11 % on instruction-cache misses; holding all 128 scores AND the bounds in
                 // registers spilled.) The accumulator is released once its last group sits in registers.
 #pragma unroll 1
-                for (uint32_t g = 0; g < 4; ++g) {
-                    const uint32_t cg = half * 4u + g;
+                for (uint32_t g = 0; g < kGroups; ++g) {
+                    const uint32_t cg = half * kGroups + g;
                     uint32_t r[32];
-                    tc::tmem_ld32(lane_addr + acc * (uint32_t)kGmN + cg * 32u, r);
+                    tc::tmem_ld32(lane_addr + set * 2u * kN + acc * kN + cg * 32u, r);
                     float thr[32];
                     {
                         const float4* t4 = reinterpret_cast<const float4*>(&s_thr_rank[cg * 32u]);
@@ -544,14 +605,16 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                         }
                     }
                     tc::tmem_ld_wait();
-                    if (g == 3u) {
+                    if (g + 1u == kGroups) {
                         tc::fence_before_sync();
                         __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&d_free[acc]);
+                        if (lane == 0) {
+                            if constexpr (kPair) tc::mbar_arrive_cluster(tc::mapa_shared(&d_free[set][acc], 0u)); else tc::mbar_arrive(&d_free[set][acc]);
+                        }
                     }
                     if (p.debug & 8u) continue;
                     if (p.score_dump != nullptr) {   // pre-pass: ranks of this warp's 32 rows x 32 queries, 128 contiguous bytes per query
-                        float* dst = p.score_dump + (size_t)(qb * kGmN + cg * 32u) * p.dump_stride + row;
+                        float* dst = p.score_dump + (size_t)(qb * kN + cg * 32u) * p.dump_stride + row;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (row < p.dump_stride) dst[(size_t)j * p.dump_stride] = valid ? fmaf(__uint_as_float(r[j]), scale, row_bias) : INFINITY;
@@ -584,7 +647,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
             if (poison != poison) *p.bad = 1u;
             // lists that could overflow during the next pair of tiles are cut back to their best k
             asm volatile("bar.sync 2, 256;" ::: "memory");
-            for (uint32_t q = warp; q < kGmN; q += kG1EpiWarps) {
+            for (uint32_t q = warp; q < kN; q += kG1EpiWarps) {
                 const uint32_t cnt = min(s_cnt[q], p.list_cap);
                 if (cnt + 2 * kGmTile > p.list_cap) {
                     u64* lkeys = p.list_keys + (list_base + q) * p.list_cap;
@@ -599,7 +662,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
             }
             asm volatile("bar.sync 2, 256;" ::: "memory");
         }
-        for (uint32_t q = warp; q < kGmN; q += kG1EpiWarps) {
+        for (uint32_t q = warp; q < kN; q += kG1EpiWarps) {
             const uint32_t cnt = min(s_cnt[q], p.list_cap);
             u64* lkeys = p.list_keys + (list_base + q) * p.list_cap;
             u64* lpays = p.list_pays + (list_base + q) * p.list_cap;
@@ -609,19 +672,22 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == kG1MmaWarp) tc::tmem_dealloc(tbase, 512);
+    if constexpr (kPair) tc::cluster_sync_all();      // neither CTA leaves (or frees TMEM) while the other may still signal it
+    if (warp == kG1MmaWarp) {
+        if constexpr (kPair) tc::tmem_dealloc2(tbase, 512); else tc::tmem_dealloc(tbase, 512);
+    }
 }
 
 // queries [nq, dims] -> per (query block, 32-dim chunk) a 32 KB image [256 x 32] fp32 in the UMMA K-major
 // SWIZZLE_128B shared-memory layout (zero rows beyond nq); the tensor core reads the words as TF32.
-__global__ void pack_queries_kernel(const float* q, uint32_t nq, uint32_t qblocks, uint32_t dims, unsigned char* blobs) {
+__global__ void pack_queries_kernel(const float* q, uint32_t nq, uint32_t qblocks, uint32_t nblk, uint32_t dims, unsigned char* blobs) {
     const uint32_t chunks = dims / 32;
-    const size_t total = (size_t)qblocks * kGmN * dims;
+    const size_t total = (size_t)qblocks * nblk * dims;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t k = (uint32_t)(i % dims);
         const size_t row = i / dims;
-        const uint32_t qb = (uint32_t)(row / kGmN), n = (uint32_t)(row % kGmN);
-        unsigned char* blob = blobs + ((size_t)qb * chunks + k / 32u) * 32768u;
+        const uint32_t qb = (uint32_t)(row / nblk), n = (uint32_t)(row % nblk);
+        unsigned char* blob = blobs + ((size_t)qb * chunks + k / 32u) * (nblk * 128u);
         *reinterpret_cast<float*>(blob + tc::sw128_offset(n, k % 32u)) = row < nq ? q[row * dims + k] : 0.0f;
     }
 }
@@ -662,14 +728,18 @@ flat_gemm_merge_kernel(const GemmParams p, uint32_t cap, u64* out_keys, u64* out
     extern __shared__ __align__(1024) unsigned char gsmem[];
     __shared__ u64 s_thresh;
     __shared__ uint32_t s_count;
-    const uint32_t q = blockIdx.x, qb = q / kGmN, ql = q % kGmN;
+    const uint32_t q = blockIdx.x, qb = q / p.nblk, ql = q % p.nblk;
     Collector col;
     col.init(gsmem, &s_thresh, &s_count, cap, p.k);
     __syncthreads();
     const GemmParams pp = p;
-    auto list_of = [pp, qb, ql](uint32_t l) { return ((size_t)(l * pp.qblocks + qb) * kGmN + ql); };
+    // list l of this query: CTA l * qblocks + qb, or — CTA pairs — CTA 2 * ((l / 2) * qblocks + qb) + l % 2
+    auto list_of = [pp, qb, ql](uint32_t l) {
+        const size_t cta = pp.pair ? 2 * ((size_t)(l >> 1) * pp.qblocks + qb) + (l & 1u) : (size_t)l * pp.qblocks + qb;
+        return cta * pp.nblk + ql;
+    };
     collector_merge_lists(
-        col, p.ranges, p.k, [&](uint32_t l) { return pp.list_counts[list_of(l)]; },
+        col, pp.pair ? 2 * p.ranges : p.ranges, p.k, [&](uint32_t l) { return pp.list_counts[list_of(l)]; },
         [&](uint32_t l, uint32_t i) { return pp.list_keys[list_of(l) * pp.list_cap + i]; },
         [&](uint32_t l, uint32_t i) { return pp.list_pays[list_of(l) * pp.list_cap + i]; });
     const uint32_t total = *col.count;
@@ -865,9 +935,6 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     int dev = 0, sms = 0;
     VB_CUDA(cudaGetDevice(&dev));
     VB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const uint32_t qblocks_total = (uint32_t)((nq + kGmN - 1) / kGmN);
-    const uint32_t group = std::min<uint32_t>(qblocks_total, (uint32_t)sms);   // query blocks per launch
-    const size_t nq_pad = (size_t)qblocks_total * kGmN;
     // One TF32 pass with a wide candidate margin; 3xTF32 (narrow margin) only when forced — VB_GEMM_TERMS=3, or the
     // caller's second tier for the queries whose single-pass candidate set could not be proven complete.
     // Margins: the kept set must reach `bound` (2e-3 |q| |row| for one pass) below the exact k-th score. For unit
@@ -883,6 +950,14 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     if (force_terms == 3) terms = 3;
     if (terms_used) *terms_used = terms;
     t_gemm_terms = terms;
+    // VB_GEMM_PAIR=1: the single-pass kernel as CTA pairs (clusters of 2, tcgen05 cta_group::2, two accumulator sets).
+    // Measured slower than the single-CTA form (3.22 vs 2.99 ms per 1024 x 1M x 768 batch), so it is opt-in; see DESIGN.md.
+    const bool pair = terms == 1 && sms >= 2 && std::getenv("VB_GEMM_PAIR") != nullptr;
+    const uint32_t nblk = pair ? (uint32_t)kG2N : (uint32_t)kGmN;            // queries per block
+    const uint32_t qblocks_total = (uint32_t)((nq + nblk - 1) / nblk);
+    const size_t nq_pad = (size_t)qblocks_total * nblk;
+    const uint32_t workers = pair ? (uint32_t)sms / 2u : (uint32_t)sms;      // CTAs, or CTA pairs, that can be resident
+    const uint32_t group = std::min<uint32_t>(qblocks_total, workers);         // query blocks per launch
     const size_t margin = terms == 1 ? (k <= 32 ? 32 : std::max<size_t>(64, 2 * k)) : std::max<size_t>(8, k / 4);
     const size_t kprime = std::min<size_t>(std::min<size_t>(k + margin, terms == 1 ? 192 : 128), n);   // approximate candidates kept
     RescoreKernel rescore = rescore_lookup(metric);
@@ -892,23 +967,25 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
 
     VB_TRY(ctx.staging.reserve(2 * nq_pad * dims * sizeof(float)));
     unsigned char* q_blobs = ctx.staging.as<unsigned char>();
-    if (terms == 1) pack_queries_kernel<<<148 * 4, 256, 0, stream>>>(d_queries, (uint32_t)nq, qblocks_total, (uint32_t)dims, q_blobs);
+    if (terms == 1) pack_queries_kernel<<<148 * 4, 256, 0, stream>>>(d_queries, (uint32_t)nq, qblocks_total, nblk, (uint32_t)dims, q_blobs);
     else split_queries_kernel<<<148 * 4, 256, 0, stream>>>(d_queries, (uint32_t)nq, qblocks_total, (uint32_t)dims, q_blobs);
     VB_CUDA(cudaGetLastError());
 
     const size_t max_ctas = (size_t)sms;
     const uint32_t list_cap = (kprime <= 64 && terms != 1) ? kGmListSmall : kGmListLarge;   // single pass: 256 rows between cuts
-    VB_TRY(ctx.cand_keys.reserve(max_ctas * kGmN * list_cap * sizeof(u64)));
-    VB_TRY(ctx.cand_pays.reserve(max_ctas * kGmN * list_cap * sizeof(u64)));
-    VB_TRY(ctx.cand_counts.reserve(max_ctas * kGmN * sizeof(uint32_t) + 16));
+    VB_TRY(ctx.cand_keys.reserve(max_ctas * nblk * list_cap * sizeof(u64)));
+    VB_TRY(ctx.cand_pays.reserve(max_ctas * nblk * list_cap * sizeof(u64)));
+    VB_TRY(ctx.cand_counts.reserve(max_ctas * nblk * sizeof(uint32_t) + 16));
     VB_TRY(ctx.dump_keys.reserve(nq_pad * kprime * sizeof(u64)));
     VB_TRY(ctx.dump_pays.reserve(nq_pad * kprime * sizeof(u64)));
     VB_TRY(ctx.staging_rank.reserve(nq_pad * sizeof(uint32_t)));
 
-    const size_t smem_bytes = terms == 1 ? (size_t)kG1Stages * kG1StageBytes + 1024 : (size_t)kGmStages * kGmStageBytes + 1024;
-    if (terms == 1) VB_TRY(ensure_dynamic_smem_for(flat_gemm1_topk_kernel, smem_bytes));
+    const size_t smem_bytes = pair ? (size_t)kG2Stages * (2 * 16384 + kG2N * 128 / 2) + 1024
+                            : terms == 1 ? (size_t)kG1Stages * kG1StageBytes + 1024 : (size_t)kGmStages * kGmStageBytes + 1024;
+    if (pair) VB_TRY(ensure_dynamic_smem_for(flat_gemm1_topk_kernel<true>, smem_bytes));
+    else if (terms == 1) VB_TRY(ensure_dynamic_smem_for(flat_gemm1_topk_kernel<false>, smem_bytes));
     else VB_TRY(ensure_dynamic_smem_for(flat_gemm_topk_kernel, smem_bytes));
-    const size_t blob_bytes = terms == 1 ? 32768u : 65536u;
+    const size_t blob_bytes = terms == 1 ? (size_t)nblk * 128u : 65536u;
 
     CUtensorMap tmap_a;
     VB_TRY(make_tmap_rows_sw128(d_rows, n, stride, kGmTile, &tmap_a));
@@ -929,8 +1006,8 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     // Sample = 256 rows per CTA of the launch (one tile pair): while thresholds are open EVERY score is appended, and
     // that phase costs ~170 us per pair per CTA, so a longer sample buys a tighter filter at a steep price
     // (measured at 1M x 768, Q = 1024: 9.5k rows 313k queries/s, 19k 287k, 33k 282k, 66k 272k).
-    const uint32_t ranges_full = std::max<uint32_t>(1, (uint32_t)sms / group);
-    size_t sample = std::min<size_t>(n / 8, (size_t)ranges_full * 256);
+    const uint32_t ranges_full = std::max<uint32_t>(1, workers / group);
+    size_t sample = std::min<size_t>(n / 8, (size_t)ranges_full * (pair ? 512 : 256));   // one work unit per CTA / CTA pair
     if (const char* e = std::getenv("VB_GEMM_SAMPLE")) sample = std::min<size_t>(n, std::max<size_t>(1024, (size_t)std::atol(e)));
     const bool prepass = n >= 65536 && sample >= 2048 && !std::getenv("VB_GEMM_NO_PREPASS");
     // Single-pass kernel: the pre-pass is a dense dump — ranks of [queries x sample rows] straight to HBM (coalesced, no
@@ -957,8 +1034,8 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     }
     for (uint32_t qb0 = 0; qb0 < qblocks_total; qb0 += group) {
         const uint32_t qblocks = std::min(group, qblocks_total - qb0);
-        const size_t q0 = (size_t)qb0 * kGmN;
-        const uint32_t nq_here = (uint32_t)std::min<size_t>(nq - q0, (size_t)qblocks * kGmN);
+        const size_t q0 = (size_t)qb0 * nblk;
+        const uint32_t nq_here = (uint32_t)std::min<size_t>(nq - q0, (size_t)qblocks * nblk);
         GemmParams p{};
         p.dims = (uint32_t)dims;
         p.nq = nq_here;
@@ -967,7 +1044,9 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
         p.rank_scale = l2_family ? -2.0f : -1.0f;
         p.row_norm2 = l2_family ? d_row_norm2 : nullptr;
         p.qblocks = qblocks;
-        p.ranges = std::max<uint32_t>(1, (uint32_t)sms / qblocks);
+        p.pair = pair ? 1u : 0u;
+        p.nblk = nblk;
+        p.ranges = std::max<uint32_t>(1, workers / qblocks);
         p.id_rank = d_id_rank;
         p.list_cap = list_cap;
         p.list_keys = ctx.cand_keys.as<u64>();
@@ -975,7 +1054,7 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
         p.list_counts = ctx.cand_counts.as<uint32_t>();
         p.bad = d_bad;
         { const char* dbg = std::getenv("VB_GEMM_DEBUG"); p.debug = dbg ? (uint32_t)std::atoi(dbg) : 0u; }
-        const uint32_t grid = p.qblocks * p.ranges;
+        const uint32_t grid = p.qblocks * p.ranges * (pair ? 2u : 1u);
         const unsigned char* blobs = q_blobs + (size_t)qb0 * (dims / 32) * blob_bytes;
         for (int pass = prepass ? 0 : 1; pass < 2; ++pass) {
             p.n = pass == 0 ? (uint32_t)sample : (uint32_t)n;
@@ -984,8 +1063,25 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
             p.score_dump = pass == 0 && dense_prepass ? pre_dump + q0 * dump_stride : nullptr;
             p.dump_stride = dump_stride;
             p.init_rank = pass == 1 && dense_prepass ? pre_rank + q0 : nullptr;
-            if (terms == 1) flat_gemm1_topk_kernel<<<grid, kG1Threads, smem_bytes, stream>>>(tmap_a, blobs, p);
-            else flat_gemm_topk_kernel<<<grid, kGmThreads, smem_bytes, stream>>>(tmap_a, blobs, p);
+            if (pair) {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(grid);
+                cfg.blockDim = dim3(kG1Threads);
+                cfg.dynamicSmemBytes = smem_bytes;
+                cfg.stream = stream;
+                cudaLaunchAttribute attr{};
+                attr.id = cudaLaunchAttributeClusterDimension;
+                attr.val.clusterDim.x = 2;
+                attr.val.clusterDim.y = 1;
+                attr.val.clusterDim.z = 1;
+                cfg.attrs = &attr;
+                cfg.numAttrs = 1;
+                VB_CUDA(cudaLaunchKernelEx(&cfg, flat_gemm1_topk_kernel<true>, tmap_a, blobs, p));
+            } else if (terms == 1) {
+                flat_gemm1_topk_kernel<false><<<grid, kG1Threads, smem_bytes, stream>>>(tmap_a, blobs, p);
+            } else {
+                flat_gemm_topk_kernel<<<grid, kGmThreads, smem_bytes, stream>>>(tmap_a, blobs, p);
+            }
             VB_CUDA(cudaGetLastError());
             if (pass == 0 && dense_prepass)
                 gemm1_sample_select_kernel<<<nq_here, 128, (size_t)dump_stride * sizeof(uint32_t), stream>>>(

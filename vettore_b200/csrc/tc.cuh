@@ -157,6 +157,52 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ---- CTA pair (cta_group::2): two CTAs of one cluster share an MMA of M = 256 -----------------------
+// Both CTAs of the pair execute alloc / dealloc (one warp each); only the leader (cluster rank 0) issues MMAs and
+// commits; the commit arrives on the barrier at the same shared-memory offset in every CTA of `cta_mask`.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Shared-memory address of `p` (own CTA) as seen in CTA `rank` of the cluster.
+__device__ __forceinline__ uint32_t mapa_shared(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// (Waits on barriers the other CTA arrives on use the plain mbar_wait: an acquire at CLUSTER scope makes ptxas put a
+// CCTL.IVALL — a full L1 invalidate — behind every successful wait, which made the paired K2 kernel 2.3x slower on
+// its load path alone. No generic-proxy data crosses the CTAs here: the barriers order async-proxy TMA writes, tensor
+// core reads and tcgen05.ld completions, which carry their own fences.)
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(slot_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem, both CTAs] (+)= A[smem of each CTA: its 128 rows] * B[smem of each CTA: its half of N]^T, M = 256.
+__device__ __forceinline__ void umma_tf32_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_addr(bar)), "h"(cta_mask) : "memory");
+}
+
 // 3xTF32 split: the tensor core reads the top 19 bits of an fp32 word (truncation), so
 // hi is x itself and lo = x - trunc19(x), exact in fp32.
 __device__ __forceinline__ float tf32_lo(float x) {
