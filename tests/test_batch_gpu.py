@@ -150,3 +150,20 @@ def test_batched_l2_family_unnormalised_rows_and_mutations(metric, gemm_terms):
     for qi in (5, 9, 20, nq - 1):
         assert_hits_match(got[qi], ok(oracle.flat_search_dense(metric, rows2[keep], [ids[i] for i in keep], queries[qi], k)))
     assert got[9][0] == (ids[77], 0.0)
+
+
+@pytest.mark.parametrize("metric,n,d,nq,k", [("cosine", 70000, 768, 300, 10), ("l2", 9000, 96, 513, 100), ("inner_product", 3000, 64, 16, 1)])
+def test_cta_pair_form_matches_oracle(monkeypatch, metric, n, d, nq, k):
+    """VB_GEMM_PAIR=1: the single-pass kernel as CTA pairs (clusters of 2, tcgen05 cta_group::2, 128-query blocks, two
+    accumulator sets). Opt-in (measured slower than the single-CTA form), but it must stay exact."""
+    monkeypatch.setenv("VB_GEMM_PAIR", "1")
+    rows = _rows(n, d, n + d)
+    if metric == "l2":
+        rows = (rows * np.linspace(0.5, 2.0, n, dtype=np.float32)[:, None]).astype(np.float32)
+    ids = [f"{(i * 7919) % n:06d}" for i in range(n)]
+    queries = _rows(nq, d, 5)
+    idx = getattr(nifs, f"flat_new_{metric}")()
+    ok(nifs.flat_insert_matrix(idx, ids, rows))
+    got = ok(nifs.flat_search_batch(idx, queries, k))
+    for qi in list(range(0, nq, max(1, nq // 24))) + [nq - 1]:
+        assert_hits_match(got[qi], ok(oracle.flat_search_dense(metric, rows, ids, queries[qi], k)))
