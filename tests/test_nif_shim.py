@@ -365,5 +365,9 @@ def test_sharded_resource_behind_the_same_nifs(nif, monkeypatch):
     assert a == b and a[0] == OK
     keep = [i for i in range(n) if i != 5]
     assert_hits_match(a[1], oracle.flat_search_dense("l2", rows[keep], [ids[i] for i in keep], q, 12)[1])
+    # the resident pipelines answer through the sharded resource too (every stage on all shards, merged per stage)
+    for call in (("flat_funnel_search", q, 0, [16, 32], 100, 8), ("flat_quantized_search", q, 2, 300, 8)):
+        x, y = nif.call(call[0], one, *call[1:]), nif.call(call[0], many, *call[1:])
+        assert x == y and x[0] == OK and len(x[1]) == 8
     nif.L.mock_release(one.term)
     nif.L.mock_release(many.term)

@@ -150,68 +150,6 @@ Status ShardedFlatIndex::remove(const char* id, size_t id_len) {
     return Status::Ok();
 }
 
-Status ShardedFlatIndex::search(const float* queries, size_t nq, size_t len, size_t limit, std::vector<Hits>* out) {
-    out->assign(nq, Hits{});
-    if (limit == 0 || nq == 0) return Status::Ok();   // flat.rs:97-99: before any validation
-    std::shared_lock<std::shared_mutex> g(mu_);
-    for (size_t q = 0; q < nq; ++q) {                  // flat.rs:101 against the dimension of the whole index
-        if (len == 0) return Status::Ref("vector must not be empty");
-        if (dim_ != 0 && len != dim_) return Status::Ref("dimension mismatch");
-        const float* v = queries + q * len;
-        for (size_t c = 0; c < len; ++c)
-            if (!std::isfinite(v[c])) return Status::Ref("vector contains a non-finite value");
-    }
-    if (rows_ == 0) return Status::Ok();
-    const size_t G = shards_.size();
-    std::vector<std::vector<Hits>> part(G);
-    std::vector<Status> st(G);
-    for_each_shard([&](size_t s) {
-        size_t r = 0, d = 0;
-        shards_[s]->info(&r, &d);
-        if (r == 0) { part[s].assign(nq, Hits{}); return; }   // an empty shard has no dimension to check against
-        st[s] = shards_[s]->search(queries, nq, len, limit, &part[s]);
-    });
-    for (auto& x : st) VB_TRY(x);   // "metric overflow" of any shard aborts the search (flat.rs:105)
-    // merge: FlatHit order = (rank.total_cmp, id bytes), flat.rs:34-40; rank per distances.rs:113-119
-    struct Ref { uint32_t key; uint32_t shard; uint32_t pos; };
-    std::vector<Ref> pool;
-    for (size_t q = 0; q < nq; ++q) {
-        pool.clear();
-        for (size_t s = 0; s < G; ++s) {
-            const Hits& h = part[s][q];
-            for (size_t i = 0; i < h.size(); ++i) {
-                const float raw = h.values[i];
-                float rank = raw;
-                if (metric_ == kCosine) rank = 1.0f - raw;
-                else if (metric_ == kInnerProduct) rank = -raw;
-                pool.push_back(Ref{order_key(rank), (uint32_t)s, (uint32_t)i});
-            }
-        }
-        auto id_of = [&](const Ref& r, size_t* n) {
-            const Hits& h = part[r.shard][q];
-            *n = (size_t)(h.off[r.pos + 1] - h.off[r.pos]);
-            return h.blob.data() + h.off[r.pos];
-        };
-        std::sort(pool.begin(), pool.end(), [&](const Ref& a, const Ref& b) {
-            if (a.key != b.key) return a.key < b.key;
-            size_t la, lb;
-            const char* ia = id_of(a, &la);
-            const char* ib = id_of(b, &lb);
-            const int c = std::memcmp(ia, ib, std::min(la, lb));
-            return c != 0 ? c < 0 : la < lb;
-        });
-        Hits& dst = (*out)[q];
-        const size_t take = std::min(limit, pool.size());
-        for (size_t i = 0; i < take; ++i) {
-            size_t il;
-            const char* id = id_of(pool[i], &il);
-            const Hits& h = part[pool[i].shard][q];
-            dst.add(id, il, h.values[pool[i].pos], ((uint64_t)pool[i].shard << 32) | h.index[pool[i].pos]);
-        }
-    }
-    return Status::Ok();
-}
-
 namespace {
 
 // Merges per-shard sorted lists into the best `limit` by (order key of the rank, id bytes) — FlatHit's /
@@ -258,6 +196,39 @@ bool finite_prefix(const float* v, size_t n) {
 }
 
 }  // namespace
+
+Status ShardedFlatIndex::search(const float* queries, size_t nq, size_t len, size_t limit, std::vector<Hits>* out) {
+    out->assign(nq, Hits{});
+    if (limit == 0 || nq == 0) return Status::Ok();   // flat.rs:97-99: before any validation
+    std::shared_lock<std::shared_mutex> g(mu_);
+    for (size_t q = 0; q < nq; ++q) {                  // flat.rs:101 against the dimension of the whole index
+        if (len == 0) return Status::Ref("vector must not be empty");
+        if (dim_ != 0 && len != dim_) return Status::Ref("dimension mismatch");
+        const float* v = queries + q * len;
+        for (size_t c = 0; c < len; ++c)
+            if (!std::isfinite(v[c])) return Status::Ref("vector contains a non-finite value");
+    }
+    if (rows_ == 0) return Status::Ok();
+    const size_t G = shards_.size();
+    std::vector<std::vector<Hits>> part(G);
+    std::vector<Status> st(G);
+    for_each_shard([&](size_t s) {
+        size_t r = 0, d = 0;
+        shards_[s]->info(&r, &d);
+        if (r == 0) { part[s].assign(nq, Hits{}); return; }   // an empty shard has no dimension to check against
+        st[s] = shards_[s]->search(queries, nq, len, limit, &part[s]);
+    });
+    for (auto& x : st) VB_TRY(x);   // "metric overflow" of any shard aborts the search (flat.rs:105)
+    // merge: FlatHit order = (rank.total_cmp, id bytes), flat.rs:34-40; rank per distances.rs:113-119
+    std::vector<Hits> lists(G);
+    for (size_t q = 0; q < nq; ++q) {
+        for (size_t s = 0; s < G; ++s) lists[s] = std::move(part[s][q]);
+        const int metric = metric_;
+        merge_parts(lists, limit, [metric](float raw) { return rank_of_metric(metric, raw); }, &(*out)[q]);
+    }
+    return Status::Ok();
+}
+
 
 Status ShardedFlatIndex::stage_top_k(const Hits* from, const float* query, size_t len, int metric_code, size_t dimensions,
                                      size_t limit, Hits* out) {
