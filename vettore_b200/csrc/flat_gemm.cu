@@ -372,8 +372,12 @@ flat_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned
 // accumulation): 2e-3 for unit vectors. The candidate margin k' - k covers the rows that can sit that close to
 // the k-th score: k' = k + 32 up to k = 32, k' = min(3k, 192) >= k + 64 above (flat_gemm_search_device); queries whose
 // kept set cannot be proven complete are redone by the caller on the 3xTF32 kernel above (second tier).
-constexpr int kG1EpiWarps = 8, kG1ProducerWarp = 8, kG1MmaWarp = 9;
-constexpr int kG1Threads = (kG1MmaWarp + 1) * 32;        // warps 0-7 epilogue, 8 producer, 9 MMA
+// Sixteen epilogue warps (four per TMEM lane quarter, a quarter of the query columns each): with eight, each warp had
+// eight 32-column groups to pull out of TMEM and filter per tile pair, two warps per scheduler could not hide the
+// latencies, and the ~8 us before both accumulators were released again were added to every pair's MMA time.
+constexpr int kG1EpiWarps = 16, kG1ProducerWarp = 16, kG1MmaWarp = 17;
+constexpr int kG1ColParts = kG1EpiWarps / 4;             // column parts per accumulator (one per epilogue warp of a lane quarter)
+constexpr int kG1Threads = (kG1MmaWarp + 1) * 32;        // warps 0-15 epilogue, 16 producer, 17 MMA
 constexpr int kG1Stages = 3;
 // One stage = the same 32-dim chunk of TWO consecutive row tiles + the query chunk: the query operand is what
 // the kernel streams most (it is re-read from L2 for every row tile, ~7-8 TB/s measured = the L2->SM limit), so
@@ -415,7 +419,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
     constexpr int kStages = kPair ? kG2Stages : kG1Stages;
     constexpr uint32_t kN = kPair ? (uint32_t)kG2N : (uint32_t)kGmN;   // queries per block = UMMA N
     constexpr uint32_t kSets = kPair ? 2u : 1u;                        // accumulator sets (2 x kN columns each) in TMEM
-    constexpr uint32_t kGroups = kN / 64u;                             // 32-column groups per epilogue warp and accumulator
+    constexpr uint32_t kGroups = kN / (32u * kG1ColParts);              // 32-column groups per epilogue warp and accumulator
     constexpr uint32_t kBBytes = kPair ? kN * 128u / 2u : kN * 128u;   // this CTA's part of a query chunk
     constexpr uint32_t kStageBytes = 2u * 16384u + kBBytes;
     extern __shared__ __align__(1024) unsigned char gsmem[];
@@ -563,8 +567,8 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
             }
         }
     } else {
-        // ===== epilogue warps 0-7: TMEM lanes of quarter (w & 3), query columns of half (w >> 2), both accumulators of the set =====
-        const uint32_t quarter = warp & 3u, half = warp >> 2;
+        // ===== epilogue warps: TMEM lanes of quarter (w & 3), query columns of part (w >> 2), both accumulators of the set =====
+        const uint32_t quarter = warp & 3u, half = warp >> 2;   // `half`: this warp's column part (0 .. kG1ColParts - 1)
         const uint32_t lane_addr = tbase + ((quarter * 32u) << 16);
         const size_t list_base = (size_t)blockIdx.x * kN;
         const float bias = p.metric == kCosine ? 1.0f : 0.0f;
@@ -595,15 +599,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                     const uint32_t cg = half * kGroups + g;
                     uint32_t r[32];
                     tc::tmem_ld32(lane_addr + set * 2u * kN + acc * kN + cg * 32u, r);
-                    float thr[32];
-                    {
-                        const float4* t4 = reinterpret_cast<const float4*>(&s_thr_rank[cg * 32u]);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 t = t4[i];
-                            thr[4 * i] = t.x; thr[4 * i + 1] = t.y; thr[4 * i + 2] = t.z; thr[4 * i + 3] = t.w;
-                        }
-                    }
+                    const float4* t4 = reinterpret_cast<const float4*>(&s_thr_rank[cg * 32u]);
                     tc::tmem_ld_wait();
                     if (g + 1u == kGroups) {
                         tc::fence_before_sync();
@@ -624,11 +620,17 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                     uint32_t mask = 0u;
                     float one_rank = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float dot = __uint_as_float(r[j]);
-                        poison = fmaf(dot, 0.0f, poison);              // rows past the end are zero-filled by the tensor map: finite
-                        const float rankv = fmaf(dot, scale, row_bias);
-                        if (rankv <= thr[j]) { mask |= 1u << j; one_rank = rankv; }   // first-level filter: one compare
+                    for (int j4 = 0; j4 < 8; ++j4) {                       // the group's bounds, four at a time (registers are scarce at 576 threads)
+                        const float4 t = t4[j4];
+                        const float thr[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = 4 * j4 + e;
+                            const float dot = __uint_as_float(r[j]);
+                            poison = fmaf(dot, 0.0f, poison);              // rows past the end are zero-filled by the tensor map: finite
+                            const float rankv = fmaf(dot, scale, row_bias);
+                            if (rankv <= thr[e]) { mask |= 1u << j; one_rank = rankv; }   // first-level filter: one compare
+                        }
                     }
                     if (mask != 0u) {
                         if ((mask & (mask - 1u)) == 0u) {                  // the usual case: one score of the 32 passed
@@ -646,7 +648,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
             }
             if (poison != poison) *p.bad = 1u;
             // lists that could overflow during the next pair of tiles are cut back to their best k
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(kG1EpiWarps * 32) : "memory");
             for (uint32_t q = warp; q < kN; q += kG1EpiWarps) {
                 const uint32_t cnt = min(s_cnt[q], p.list_cap);
                 if (cnt + 2 * kGmTile > p.list_cap) {
@@ -660,7 +662,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                     }
                 }
             }
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(kG1EpiWarps * 32) : "memory");
         }
         for (uint32_t q = warp; q < kN; q += kG1EpiWarps) {
             const uint32_t cnt = min(s_cnt[q], p.list_cap);
