@@ -167,3 +167,28 @@ def test_cta_pair_form_matches_oracle(monkeypatch, metric, n, d, nq, k):
     got = ok(nifs.flat_search_batch(idx, queries, k))
     for qi in list(range(0, nq, max(1, nq // 24))) + [nq - 1]:
         assert_hits_match(got[qi], ok(oracle.flat_search_dense(metric, rows, ids, queries[qi], k)))
+
+
+@pytest.mark.parametrize("metric", ["inner_product", "l2_squared"])
+def test_batched_search_keeps_the_overflow_semantics(metric):
+    """distances.rs:59-98 through the batched path: magnitudes at which |q| * |row| can overflow fp32 send the batch to the
+    exact kernels (f64 recovery, "metric overflow"), so the answers equal the oracle's, error string included."""
+    n, d, nq, k = 3000, 64, 24, 5
+    rng = np.random.default_rng(2)
+    rows = (rng.standard_normal((n, d)) * 1.0e18).astype(np.float32)
+    ids = [f"{i:05d}" for i in range(n)]
+    idx = getattr(nifs, f"flat_new_{metric}")()
+    ok(nifs.flat_insert_matrix(idx, ids, rows))
+    small_q = rng.standard_normal((nq, d)).astype(np.float32)            # finite scores (~1e19): recovered, not an error
+    got = nifs.flat_search_batch(idx, small_q, k)
+    for qi in (0, nq - 1):
+        exp = oracle.flat_search_dense(metric, rows, ids, small_q[qi], k)
+        assert exp[0] == "ok"
+        if metric == "inner_product":
+            assert_hits_match(ok(got)[qi], exp[1])
+    big_q = (rng.standard_normal((nq, d)) * 1.0e20).astype(np.float32)    # |q| |row| ~ 6e39: beyond fp32, and beyond f32 after f64 recovery
+    exp = oracle.flat_search_dense(metric, rows, ids, big_q[0], k)
+    got = nifs.flat_search_batch(idx, big_q, k)
+    assert got[0] == exp[0]
+    if exp[0] == "error":
+        assert got[1] == exp[1]

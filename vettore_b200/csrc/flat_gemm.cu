@@ -412,6 +412,18 @@ __device__ __noinline__ void gemm1_append(const u64* s_thr, uint32_t* s_cnt, u64
 // behind the one the tensor cores read, where the single-CTA form had two and ran the MMA stream at 0.73 of the
 // pipe. The leader (cluster rank 0) issues every MMA; its commits arrive on both CTAs' barriers; the peer's idle
 // MMA warp relays "my stage landed" to the leader, and the peer's epilogue warps release the accumulators there.
+// First-level bound of the single-pass filter for a rank threshold `thr`. L2 family: the rank itself (the kernel
+// computes |x|^2 - 2 q.x per score). Dot family (rank = bias - dot): the smallest dot that can still reach the
+// threshold, lowered by a few ulps so that rounding of bias - dot can never exclude a row the exact key test would
+// keep (that test, in gemm1_append, decides).
+__device__ __forceinline__ float filter_bound(float thr, bool dot_family, float bias) {
+    if (!dot_family) return thr;
+    if (thr == INFINITY) return -INFINITY;
+    if (thr == -INFINITY) return INFINITY;
+    const float t = bias - thr;
+    return t - 4.8e-7f * fmaxf(1.0f, fabsf(t));
+}
+
 template <bool kPair>
 __global__ void __launch_bounds__(kG1Threads, 1)
 flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigned char* __restrict__ q_blobs,
@@ -426,7 +438,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], peer_full[kStages], d_full[kSets], d_free[kSets][2];
     __shared__ uint32_t tmem_slot;
     __shared__ u64 s_thr[kN];
-    __shared__ __align__(16) float s_thr_rank[kN];
+    __shared__ __align__(16) float s_thr_rank[kN];   // first-level bound, see filter_bound()
     __shared__ uint32_t s_cnt[kN];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -442,6 +454,8 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
     const uint32_t unit1 = active ? (uint32_t)((uint64_t)units_total * (rr + 1) / p.ranges) : 0;
     auto pair_of = [crank](uint32_t unit) { return kPair ? 2u * unit + crank : unit; };
     const uint32_t chunks = p.dims / 32;
+    const bool dot_family = p.row_norm2 == nullptr;            // rank = bias - dot: the filter compares the dot itself
+    const float dot_bias = p.metric == kCosine ? 1.0f : 0.0f;
 
     for (int q = tid; q < (int)kN; q += kG1Threads) {
         u64 thr = kKeyMax;
@@ -457,6 +471,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
             if (s_thr[q] == kKeyMax) s_thr_rank[q] = INFINITY;
         }
         if (qg >= p.nq) { s_thr[q] = 0ull; s_thr_rank[q] = -INFINITY; }   // padded query column: nothing ever passes
+        s_thr_rank[q] = filter_bound(s_thr_rank[q], dot_family, dot_bias);
         s_cnt[q] = 0;
     }
     if (tid == 0) {
@@ -579,13 +594,11 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
             const uint32_t set = it % kSets;
             tc::mbar_wait(&d_full[set], (it / kSets) & 1u);
             tc::fence_after_sync();
-            float poison = 0.0f;       // stays +-0 unless a score is Inf / NaN (x * 0 is NaN for those)
 #pragma unroll 1
             for (uint32_t acc = 0; acc < 2; ++acc) {
                 const uint32_t row = (2u * pair + acc) * kGmTile + quarter * 32u + lane;
                 const bool valid = row < p.n;
                 const uint32_t idr = valid ? (p.id_rank ? __ldg(p.id_rank + row) : row) : 0u;
-                // a row past the end never passes the filter: its rank is NaN (one compare per score, no row test)
                 const float row_bias = valid ? (p.row_norm2 ? __ldg(p.row_norm2 + row) : bias) : __int_as_float(0x7fc00000);
                 // One group of 32 query columns at a time: scores and the group's 32 bounds in registers (thresholds
                 // only move in the cut phase below, behind the barrier, so reading them once per group is exact).
@@ -616,26 +629,42 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                             if (row < p.dump_stride) dst[(size_t)j * p.dump_stride] = valid ? fmaf(__uint_as_float(r[j]), scale, row_bias) : INFINITY;
                         continue;
                     }
-                    // (padded query columns carry a -inf bound: nothing passes)
+                    // (padded query columns carry a bound nothing passes.) Dot family: rank = bias - dot, so the score
+                    // is compared with a dot bound directly — compare + two predicated moves per score, no arithmetic.
+                    // Non-finite scores cannot occur: the re-scoring kernel sends the batch to the exact path when
+                    // |q| * max|row| could overflow (Cauchy-Schwarz bounds every partial sum).
                     uint32_t mask = 0u;
-                    float one_rank = 0.0f;
+                    float one_dot = 0.0f;
+                    if (dot_family) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {                       // the group's bounds, four at a time (registers are scarce at 576 threads)
-                        const float4 t = t4[j4];
-                        const float thr[4] = {t.x, t.y, t.z, t.w};
+                        for (int j4 = 0; j4 < 8; ++j4) {                   // the group's bounds, four at a time (registers are scarce at 576 threads)
+                            const float4 t = t4[j4];
+                            const float tb[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int j = 4 * j4 + e;
-                            const float dot = __uint_as_float(r[j]);
-                            poison = fmaf(dot, 0.0f, poison);              // rows past the end are zero-filled by the tensor map: finite
-                            const float rankv = fmaf(dot, scale, row_bias);
-                            if (rankv <= thr[e]) { mask |= 1u << j; one_rank = rankv; }   // first-level filter: one compare
+                            for (int e = 0; e < 4; ++e) {
+                                const int j = 4 * j4 + e;
+                                const float dot = __uint_as_float(r[j]);
+                                if (dot >= tb[e]) { mask |= 1u << j; one_dot = dot; }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 t = t4[j4];
+                            const float tb[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int j = 4 * j4 + e;
+                                const float dot = __uint_as_float(r[j]);
+                                if (fmaf(dot, scale, row_bias) <= tb[e]) { mask |= 1u << j; one_dot = dot; }
+                            }
                         }
                     }
+                    if (!valid) mask = 0u;                                 // rows past the end of the matrix
                     if (mask != 0u) {
                         if ((mask & (mask - 1u)) == 0u) {                  // the usual case: one score of the 32 passed
                             gemm1_append(s_thr, s_cnt, p.list_keys, p.list_pays, p.list_cap, (uint32_t)list_base,
-                                         cg * 32u + (uint32_t)__ffs(mask) - 1u, one_rank, idr, row);
+                                         cg * 32u + (uint32_t)__ffs(mask) - 1u, fmaf(one_dot, scale, row_bias), idr, row);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
@@ -646,7 +675,6 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                     }
                 }
             }
-            if (poison != poison) *p.bad = 1u;
             // lists that could overflow during the next pair of tiles are cut back to their best k
             asm volatile("bar.sync 2, %0;" ::"n"(kG1EpiWarps * 32) : "memory");
             for (uint32_t q = warp; q < kN; q += kG1EpiWarps) {
@@ -658,7 +686,7 @@ flat_gemm1_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const unsigne
                     if (lane == 0) {
                         s_cnt[q] = min(cnt, p.k);
                         s_thr[q] = kth;
-                        s_thr_rank[q] = kth == kKeyMax ? INFINITY : rank_from_key(kth);
+                        s_thr_rank[q] = filter_bound(kth == kKeyMax ? INFINITY : rank_from_key(kth), dot_family, dot_bias);
                     }
                 }
             }
@@ -775,6 +803,7 @@ struct RescoreParams {
     u64* out_pays;               // [nq][k]
     uint32_t* out_counts;        // [nq]
     uint32_t* flags;             // [nq]: 1 = redo on the single-query path, 2 = metric overflow
+    uint32_t* bad;               // raised when |q| * max|row| could overflow fp32 inside the tensor-core pass
 };
 
 
@@ -819,6 +848,12 @@ __global__ void __launch_bounds__(128) flat_gemm_rescore_kernel(const RescorePar
         }
     }
     if (fatal_any && lane == 0) p.flags[q] = 2u;
+    // The single-pass filter does not test its scores for Inf / NaN: every partial sum of a dot product is bounded by
+    // |q| |row| (and |x|^2 by max|row|^2), so below these magnitudes none can occur; above them the whole batch is
+    // redone on the exact path (distances.rs:59-98 recovery semantics live there).
+    if (threadIdx.x == 0 && p.bad != nullptr &&
+        !(sqrtf(qn2) * p.max_row_norm < 1.0e37f && p.max_row_norm < 1.0e18f && qn2 < 1.0e36f))
+        *p.bad = 1u;
     const uint32_t kept = col.compact();
     for (uint32_t i = threadIdx.x; i < kept; i += blockDim.x) {
         p.out_pays[(size_t)q * p.k + i] = col.pays[i];
@@ -1120,6 +1155,7 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     rp.out_pays = d_out_pays;
     rp.out_counts = d_out_counts;
     rp.flags = d_out_flags;
+    rp.bad = d_bad;
     rescore<<<(unsigned)nq, 128, 0, stream>>>(rp);
     VB_CUDA(cudaGetLastError());
     return Status::Ok();
