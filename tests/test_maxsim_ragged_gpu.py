@@ -156,3 +156,51 @@ def test_ragged_device_ingest_equals_host_ingest():
     assert path() == 2
     assert a == b
     assert_hits_match(a, ok(oracle.multi_vector_top_k(docs, q, 2, 300)))
+
+
+def test_compaction_rebuilds_the_token_owner_map():
+    """Deleting most of a ragged index compacts the token matrix (tombstones outweigh live tokens): the per-token
+    owner map and the document offsets must be rebuilt consistently, and later inserts must extend them."""
+    dim, tq = 64, 16
+    lens = lengths("colbert", 400, seed=21)
+    docs = ragged_docs(lens, dim, seed=22)
+    q = query(tq, dim, seed=23)
+    idx = nifs.mv_new("inner_product")
+    assert nifs.mv_insert_many(idx, docs) == ("ok", ())
+    keep = docs[::5]
+    for d in docs:
+        if d[0] not in {k[0] for k in keep}:
+            assert nifs.mv_delete(idx, d[0]) == ("ok", ())
+    # an upsert after the deletes triggers the compaction check inside insert_many
+    extra = ragged_docs([3, 77, 0, 140], dim, seed=24)
+    extra = [(f"extra-{i}", v) for i, (_, v) in enumerate(extra)]
+    assert nifs.mv_insert_many(idx, extra) == ("ok", ())
+    live = keep + extra
+    assert nifs.mv_info(idx)[0] == len(live)
+    got = ok(nifs.mv_search(idx, q, 50))
+    assert path() == 2
+    assert_hits_match(got, ok(oracle.multi_vector_top_k(live, q, 3, 50)))
+
+
+@pytest.mark.parametrize("tq", [32, 33, 64])
+@pytest.mark.parametrize("dim", [4, 100, 128])
+def test_query_token_and_dimension_boundaries(tq, dim):
+    docs = ragged_docs(lengths("mixed", 300, seed=tq + dim), dim, seed=dim)
+    q = query(tq, dim, seed=tq)
+    idx = nifs.mv_new("cosine")
+    assert nifs.mv_insert_many(idx, docs) == ("ok", ())
+    got = ok(nifs.mv_search(idx, q, 40))
+    assert path() == 2
+    assert_hits_match(got, ok(oracle.multi_vector_top_k(docs, q, 2, 40)))
+
+
+def test_by_value_limit_beyond_the_fused_collector_and_more_than_64_query_tokens():
+    docs = ragged_docs(lengths("tiny", 3000, seed=31), 32, seed=32)
+    q = query(8, 32, seed=33)
+    got = ok(nifs.multi_vector_top_k(docs, q, 3, 2500))        # k > 1024: every score dumped and radix-sorted
+    assert path() == 2 and len(got) == 2500
+    assert_hits_match(got, ok(oracle.multi_vector_top_k(docs, q, 3, 2500)))
+    q65 = query(65, 32, seed=34)                                # more than 64 query tokens: the general kernel
+    got = ok(nifs.multi_vector_top_k(docs[:500], q65, 3, 10))
+    assert path() == 0
+    assert_hits_match(got, ok(oracle.multi_vector_top_k(docs[:500], q65, 3, 10)))
