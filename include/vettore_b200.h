@@ -237,6 +237,11 @@ int vb_multi_vector_score(const float* q_vals, const uint64_t* q_off, size_t tq,
  * vb_multi_vector_top_k; documents are upserted by id like the flat index. ---------------- */
 typedef struct vb_mv vb_mv;
 int vb_mv_new(int metric_code, vb_mv** out);
+/* Additive: the same collection spread over several GPUs inside ONE process (see vb_flat_new_sharded): a document
+ * lives on shard fnv1a(id) % n_shards, vb_mv_search scores every shard's documents on its own GPU concurrently and
+ * merges the sorted lists by (score descending, id bytes), multi_vector.rs:22-31. Works with vb_mv_insert_many /
+ * _delete / _search / _info / _free; the device-ingest and stream-ordered entries answer VB_ERR_CUDA. */
+int vb_mv_new_sharded(int metric_code, int n_shards, const int* devices, vb_mv** out);
 void vb_mv_free(vb_mv* index);
 int vb_mv_insert_many(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off,
                       const float* tok_vals, const uint64_t* tok_off, const uint64_t* doc_tok);

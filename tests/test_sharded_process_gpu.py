@@ -200,3 +200,41 @@ def test_sharded_quantized_search_equals_the_single_index(shards):
     assert_hits_match(nifs.flat_quantized_search(sharded, q, 2, 300, 10)[1], exp[1])
     for args in ((q[:5], 2, 10, 5), (q, 9, 10, 5), (q, 2, 0, 5), (q, 2, 10, 0)):
         assert nifs.flat_quantized_search(sharded, *args) == nifs.flat_quantized_search(single, *args)
+
+
+# ------------------------------------------------------------------ multi-vector collection over several GPUs
+def _mv_docs(n, tmin, tmax, dim, seed):
+    rng = np.random.default_rng(seed)
+    docs = []
+    for i in range(n):
+        t = int(rng.integers(tmin, tmax + 1))
+        docs.append((f"doc-{(i * 7919) % n:05d}", rng.standard_normal((t, dim)).astype(np.float32)))
+    return docs
+
+
+@pytest.mark.parametrize("metric", ["inner_product", "cosine", "l2", "manhattan"])
+@pytest.mark.parametrize("shards", [2, 8])
+def test_sharded_multi_vector_collection_equals_single_and_oracle(metric, shards):
+    dim, tq = 64, 12
+    docs = _mv_docs(900, 0, 90, dim, shards + len(metric))
+    q = np.random.default_rng(4).standard_normal((tq, dim)).astype(np.float32)
+    single, sharded = nifs.mv_new(metric), nifs.mv_new_sharded(metric, shards)
+    for idx in (single, sharded):
+        assert nifs.mv_insert_many(idx, docs) == ("ok", ())
+    assert nifs.mv_info(sharded) == nifs.mv_info(single)
+    code = nifs.METRIC_CODE[metric]
+    for limit in (1, 10, 200, 2000):
+        a, b = nifs.mv_search(single, q, limit), nifs.mv_search(sharded, q, limit)
+        assert a[0] == b[0] == "ok"
+        assert a[1] == b[1], limit
+        assert_hits_match(b[1], oracle.multi_vector_top_k(docs, q, code, limit)[1])
+    # upsert, delete, empty query, validation errors: like the single collection
+    best = nifs.mv_search(single, q, 1)[1][0][0]
+    for idx in (single, sharded):
+        assert nifs.mv_insert_many(idx, [(best, np.zeros((2, dim), dtype=np.float32))]) == ("ok", ())
+        assert nifs.mv_delete(idx, docs[3][0]) == ("ok", ())
+    assert nifs.mv_search(sharded, q, 25) == nifs.mv_search(single, q, 25)
+    assert nifs.mv_search(sharded, [], 5) == nifs.mv_search(single, [], 5)
+    assert nifs.mv_search(sharded, q[:, :5], 5) == nifs.mv_search(single, q[:, :5], 5) == ("error", "dimension mismatch")
+    assert nifs.mv_insert_many(sharded, [("x", np.zeros((1, dim + 1), dtype=np.float32))]) == ("error", "dimension mismatch")
+    assert nifs.mv_info(sharded) == nifs.mv_info(single)

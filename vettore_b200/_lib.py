@@ -64,6 +64,7 @@ SIGNATURES = {
     "vb_multi_vector_top_k": (C.c_int, [_sz, C.c_char_p, _u64p, _f32p, _u64p, _u64p, _f32p, _u64p, _sz, C.c_int, _sz, _vpp]),
     "vb_multi_vector_score": (C.c_int, [_f32p, _u64p, _sz, _f32p, _u64p, _sz, C.c_int, _f32p]),
     "vb_mv_new": (C.c_int, [C.c_int, _vpp]),
+    "vb_mv_new_sharded": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), _vpp]),
     "vb_mv_free": (None, [_vp]),
     "vb_mv_insert_many": (C.c_int, [_vp, _sz, C.c_char_p, _u64p, _f32p, _u64p, _u64p]),
     "vb_mv_reserve": (C.c_int, [_vp, _sz, _sz, _sz]),

@@ -592,35 +592,59 @@ int vb_mv_new(int metric_code, vb_mv** out) {
     if (vb_device_count() <= 0) return no_device();
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return no_device();
-    *out = new vb_mv{new vb::MvIndex(metric_code, dev)};
+    *out = new vb_mv{new vb::MvIndex(metric_code, dev), nullptr};
+    return VB_OK;
+}
+int vb_mv_new_sharded(int metric_code, int n_shards, const int* devices, vb_mv** out) {
+    *out = nullptr;
+    if (metric_code < 0 || metric_code > 8) return finish(vb::Status::Ref("unknown metric"));
+    const int ndev = vb_device_count();
+    if (ndev <= 0) return no_device();
+    if (n_shards < 1 || n_shards > 64) return finish(vb::Status::Cuda("sharded collection: shard count must be in 1..64"));
+    std::vector<int> devs((size_t)n_shards);
+    for (int s = 0; s < n_shards; ++s) {
+        devs[s] = devices ? devices[s] : s % ndev;
+        if (devs[s] < 0 || devs[s] >= ndev) return finish(vb::Status::Cuda("sharded collection: no such CUDA device"));
+    }
+    *out = new vb_mv{nullptr, new vb::ShardedMvIndex(metric_code, devs)};
     return VB_OK;
 }
 void vb_mv_free(vb_mv* index) {
     if (!index) return;
     delete index->impl;
+    delete index->sharded;
     delete index;
 }
+#define VB_MV_SINGLE_GPU_ONLY(index)                                                                          \
+    if (!(index)->impl) return finish(vb::Status::Cuda("not available on a sharded (multi-GPU) collection handle"))
 int vb_mv_insert_many(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off, const float* tok_vals,
                       const uint64_t* tok_off, const uint64_t* doc_tok) {
+    if (index->sharded) return finish(index->sharded->insert_many(ndocs, ids, id_off, tok_vals, tok_off, doc_tok));
     return finish(index->impl->insert_many(ndocs, ids, id_off, tok_vals, tok_off, doc_tok));
 }
 int vb_mv_reserve(vb_mv* index, size_t docs, size_t tokens, size_t dimension) {
+    VB_MV_SINGLE_GPU_ONLY(index);
     return finish(index->impl->reserve(docs, tokens, dimension));
 }
 int vb_mv_insert_many_device(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off,
                              const float* d_tokens, size_t tokens_per_doc, size_t dimension) {
+    VB_MV_SINGLE_GPU_ONLY(index);
     return finish(index->impl->insert_many_device(ndocs, ids, id_off, d_tokens, tokens_per_doc, dimension));
 }
 int vb_mv_insert_ragged_device(vb_mv* index, size_t ndocs, const char* ids, const uint64_t* id_off,
                                const float* d_tokens, const uint64_t* doc_tok, size_t dimension) {
+    VB_MV_SINGLE_GPU_ONLY(index);
     if (!doc_tok) return finish(vb::Status::Cuda("document token offsets required"));
     return finish(index->impl->insert_many_device(ndocs, ids, id_off, d_tokens, 0, dimension, doc_tok));
 }
-int vb_mv_delete(vb_mv* index, const char* id, size_t id_len) { return finish(index->impl->remove(id, id_len)); }
+int vb_mv_delete(vb_mv* index, const char* id, size_t id_len) {
+    return finish(index->sharded ? index->sharded->remove(id, id_len) : index->impl->remove(id, id_len));
+}
 int vb_mv_search(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, vb_hits** out) {
     *out = nullptr;
     vb::Hits hits;
-    vb::Status s = index->impl->search(q_vals, q_off, tq, limit, &hits);
+    vb::Status s = index->sharded ? index->sharded->search(q_vals, q_off, tq, limit, &hits)
+                                  : index->impl->search(q_vals, q_off, tq, limit, &hits);
     if (!s.ok()) return finish(s);
     *out = new vb_hits{std::move(hits)};
     return VB_OK;
@@ -628,6 +652,7 @@ int vb_mv_search(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_
 int vb_mv_search_packed_device(vb_mv* index, const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit,
                                uint64_t* d_keys, float* d_values, uint32_t* d_rows, uint32_t* d_counts, vb_hits** out) {
     *out = nullptr;
+    VB_MV_SINGLE_GPU_ONLY(index);
     vb::Hits hits;
     vb::Status s = index->impl->search_packed_device(q_vals, q_off, tq, limit, reinterpret_cast<vb::u64*>(d_keys), d_values,
                                                      d_rows, d_counts, &hits);
@@ -636,10 +661,12 @@ int vb_mv_search_packed_device(vb_mv* index, const float* q_vals, const uint64_t
     return VB_OK;
 }
 int vb_mv_set_id_ranks(vb_mv* index, const uint32_t* ranks, size_t n) {
+    VB_MV_SINGLE_GPU_ONLY(index);
     return finish(index->impl->set_id_ranks(ranks, n));
 }
 int vb_mv_info(vb_mv* index, size_t* docs, size_t* tokens, size_t* dimension) {
-    index->impl->info(docs, tokens, dimension);
+    if (index->sharded) index->sharded->info(docs, tokens, dimension);
+    else index->impl->info(docs, tokens, dimension);
     return VB_OK;
 }
 

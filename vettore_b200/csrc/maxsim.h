@@ -116,6 +116,10 @@ class MvIndex {
 
 }  // namespace vb
 
+namespace vb { class ShardedMvIndex; }
+
+// The C ABI handle: a single-GPU collection (impl) or a multi-GPU one in the same process (sharded).
 struct vb_mv {
     vb::MvIndex* impl;
+    vb::ShardedMvIndex* sharded;
 };

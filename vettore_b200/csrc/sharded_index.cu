@@ -324,4 +324,143 @@ Status ShardedFlatIndex::quantized_search(const float* query, size_t len, int me
     return stage_top_k(&cand, query, len, metric_code, len, limit, out);   // exact rerank on the owners
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Multi-vector collection over several GPUs (see sharded_index.h)
+ShardedMvIndex::ShardedMvIndex(int metric, const std::vector<int>& devices) {
+    for (size_t s = 0; s < devices.size(); ++s) {
+        shards_.emplace_back(new MvIndex(metric, devices[s]));
+        if (s > 0) workers_.emplace_back(new ShardWorker());
+    }
+}
+
+ShardedMvIndex::~ShardedMvIndex() {
+    workers_.clear();
+    shards_.clear();
+}
+
+size_t ShardedMvIndex::shard_of(const char* id, size_t len) const {
+    uint64_t h = 1469598103934665603ull;   // FNV-1a over the id bytes (as ShardedFlatIndex)
+    for (size_t i = 0; i < len; ++i) { h ^= (unsigned char)id[i]; h *= 1099511628211ull; }
+    h ^= h >> 32;
+    return (size_t)(h % shards_.size());
+}
+
+void ShardedMvIndex::for_each_shard(const std::function<void(size_t)>& fn) {
+    const size_t g = shards_.size();
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t pending = g - 1;
+    for (size_t s = 1; s < g; ++s) {
+        workers_[s - 1]->post([&, s] {
+            fn(s);
+            std::lock_guard<std::mutex> lk(mu);
+            if (--pending == 0) cv.notify_one();
+        });
+    }
+    fn(0);
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return pending == 0; });
+}
+
+void ShardedMvIndex::refresh_totals() {
+    docs_ = tokens_ = 0;
+    for (auto& sh : shards_) {
+        size_t d = 0, t = 0, dm = 0;
+        sh->info(&d, &t, &dm);
+        docs_ += d;
+        tokens_ += t;
+    }
+    if (docs_ == 0) dim_ = 0;   // like MvIndex: an empty collection forgets its dimension
+}
+
+void ShardedMvIndex::info(size_t* docs, size_t* tokens, size_t* dim) {
+    std::shared_lock<std::shared_mutex> g(mu_);
+    *docs = docs_;
+    *tokens = tokens_;
+    *dim = dim_;
+}
+
+Status ShardedMvIndex::insert_many(size_t ndocs, const char* ids, const uint64_t* id_off, const float* tok_vals,
+                                   const uint64_t* tok_off, const uint64_t* doc_tok) {
+    std::unique_lock<std::shared_mutex> g(mu_);
+    // multi_vector.rs:134-152 over the WHOLE batch against the collection's dimension before any shard is touched
+    size_t expected = dim_;
+    for (size_t d = 0; d < ndocs; ++d) {
+        for (size_t t = doc_tok[d]; t < doc_tok[d + 1]; ++t) {
+            const size_t len = tok_off[t + 1] - tok_off[t];
+            if (len == 0) return Status::Ref("vectors must not be empty");
+            if (expected == 0) expected = len;
+            if (len != expected) return Status::Ref("dimension mismatch");
+            for (size_t c = 0; c < len; ++c)
+                if (!std::isfinite(tok_vals[tok_off[t] + c])) return Status::Ref("vector contains a non-finite value");
+        }
+    }
+    if (ndocs == 0) return Status::Ok();
+    const size_t G = shards_.size();
+    struct Part { std::string ids; std::vector<uint64_t> id_off{0}, tok_off{0}, doc_tok{0}; std::vector<float> vals; size_t n = 0; };
+    std::vector<Part> parts(G);
+    for (size_t d = 0; d < ndocs; ++d) {
+        const char* id = ids + id_off[d];
+        const size_t il = id_off[d + 1] - id_off[d];
+        Part& p = parts[shard_of(id, il)];
+        p.ids.append(id, il);
+        p.id_off.push_back(p.ids.size());
+        for (size_t t = doc_tok[d]; t < doc_tok[d + 1]; ++t) {
+            p.vals.insert(p.vals.end(), tok_vals + tok_off[t], tok_vals + tok_off[t + 1]);
+            p.tok_off.push_back(p.vals.size());
+        }
+        p.doc_tok.push_back(p.tok_off.size() - 1);
+        ++p.n;
+    }
+    std::vector<Status> st(G);
+    for_each_shard([&](size_t s) {
+        Part& p = parts[s];
+        if (p.n == 0) return;
+        st[s] = shards_[s]->insert_many(p.n, p.ids.data(), p.id_off.data(), p.vals.data(), p.tok_off.data(), p.doc_tok.data());
+    });
+    if (expected != 0) dim_ = expected;
+    refresh_totals();
+    for (auto& x : st) VB_TRY(x);
+    return Status::Ok();
+}
+
+Status ShardedMvIndex::remove(const char* id, size_t id_len) {
+    std::unique_lock<std::shared_mutex> g(mu_);
+    VB_TRY(shards_[shard_of(id, id_len)]->remove(id, id_len));
+    refresh_totals();
+    return Status::Ok();
+}
+
+Status ShardedMvIndex::search(const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, Hits* out) {
+    *out = Hits{};
+    // multi_vector.rs:96-97: the query is validated on its own first
+    size_t qdim = 0;
+    for (size_t t = 0; t < tq; ++t) {
+        const size_t len = q_off[t + 1] - q_off[t];
+        if (t == 0) {
+            if (len == 0) return Status::Ref("vectors must not be empty");
+            qdim = len;
+        }
+        if (len != qdim) return Status::Ref("dimension mismatch");
+        for (size_t c = 0; c < len; ++c)
+            if (!std::isfinite(q_vals[q_off[t] + c])) return Status::Ref("vector contains a non-finite value");
+    }
+    std::shared_lock<std::shared_mutex> g(mu_);
+    if (docs_ == 0) return Status::Ok();
+    if (tq > 0 && tokens_ > 0 && qdim != dim_) return Status::Ref("dimension mismatch");   // :108
+    if (limit == 0) return Status::Ok();
+    const size_t G = shards_.size();
+    std::vector<Hits> part(G);
+    std::vector<Status> st(G);
+    for_each_shard([&](size_t s) {
+        size_t d = 0, t = 0, dm = 0;
+        shards_[s]->info(&d, &t, &dm);
+        if (d == 0) return;
+        st[s] = shards_[s]->search(q_vals, q_off, tq, limit, &part[s]);   // a shard of empty documents scores 0.0 for all (:102-106)
+    });
+    for (auto& x : st) VB_TRY(x);   // "score overflow" / "metric overflow" of any shard aborts the search
+    merge_parts(part, limit, [](float score) { return -score; }, out);   // descending score, ascending id (:22-31)
+    return Status::Ok();
+}
+
 }  // namespace vb

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "flat_index.h"
+#include "maxsim.h"
 
 namespace vb {
 
@@ -73,6 +74,30 @@ class ShardedFlatIndex {
     std::shared_mutex mu_;      // searches share, mutations exclude (nifs.rs:266-309) — across ALL shards
     size_t dim_ = 0;            // 0 == None (flat.rs:16): the dimension of the whole index
     size_t rows_ = 0;
+};
+
+// The multi-vector (MaxSim) collection spread over several GPUs in one process, behind the same vb_mv handle: a
+// document lives on shard fnv1a(id) % G, every shard scores its own documents (K5) on its own GPU and thread, and
+// the G sorted lists are merged on the calling thread by (score descending, id bytes) — multi_vector.rs:22-31.
+class ShardedMvIndex {
+  public:
+    ShardedMvIndex(int metric, const std::vector<int>& devices);
+    ~ShardedMvIndex();
+    Status insert_many(size_t ndocs, const char* ids, const uint64_t* id_off, const float* tok_vals,
+                       const uint64_t* tok_off, const uint64_t* doc_tok);
+    Status remove(const char* id, size_t id_len);
+    Status search(const float* q_vals, const uint64_t* q_off, size_t tq, size_t limit, Hits* out);
+    void info(size_t* docs, size_t* tokens, size_t* dim);
+
+  private:
+    size_t shard_of(const char* id, size_t len) const;
+    void for_each_shard(const std::function<void(size_t)>& fn);
+    void refresh_totals();
+
+    std::vector<std::unique_ptr<MvIndex>> shards_;
+    std::vector<std::unique_ptr<ShardWorker>> workers_;
+    std::shared_mutex mu_;
+    size_t dim_ = 0, docs_ = 0, tokens_ = 0;   // of the whole collection (dimension 0 == none yet)
 };
 
 }  // namespace vb

@@ -391,9 +391,14 @@ def multi_vector_top_k(documents: Sequence[tuple], query_vectors, metric_code: i
 class MvRef:
     """Handle of an HBM-resident multi-vector collection (additive; see include/vettore_b200.h)."""
 
-    def __init__(self, metric: str):
+    def __init__(self, metric: str, n_shards: int = 0, devices: Sequence[int] | None = None):
         h = C.c_void_p()
-        if lib().vb_mv_new(METRIC_CODE[metric], C.byref(h)):
+        if n_shards:
+            devs = (C.c_int * n_shards)(*devices) if devices is not None else None
+            rc = lib().vb_mv_new_sharded(METRIC_CODE[metric], int(n_shards), devs, C.byref(h))
+        else:
+            rc = lib().vb_mv_new(METRIC_CODE[metric], C.byref(h))
+        if rc:
             raise RuntimeError(_lib.last_error())
         self._h, self.metric = h, metric
 
@@ -412,6 +417,11 @@ class MvRef:
 
 def mv_new(metric: str) -> MvRef:
     return MvRef(metric)
+
+
+def mv_new_sharded(metric: str, n_shards: int, devices: Sequence[int] | None = None) -> MvRef:
+    """Additive: one multi-vector collection over several GPUs in this process (vb_mv_new_sharded)."""
+    return MvRef(metric, n_shards, devices)
 
 
 def mv_insert_many(index: MvRef, documents: Sequence[tuple]):
