@@ -430,7 +430,12 @@ static ERL_NIF_TERM mv_new(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) 
     int metric; vb_mv* index = NULL;
     (void)argc;
     if (!get_metric(env, argv[0], &metric)) return enif_make_badarg(env);
-    if (vb_mv_new(metric, &index) != VB_OK) return mk_error(env);
+    {   /* VETTORE_B200_GPUS=N (N > 1): the collection spread over N GPUs, like flat_new */
+        const char* gpus = getenv("VETTORE_B200_GPUS");
+        const int n_gpus = gpus ? atoi(gpus) : 1;
+        const int rc = n_gpus > 1 ? vb_mv_new_sharded(metric, n_gpus, NULL, &index) : vb_mv_new(metric, &index);
+        if (rc != VB_OK) return mk_error(env);
+    }
     mv_res* r = (mv_res*)enif_alloc_resource(MV_TYPE, sizeof(mv_res));
     r->index = index;
     ERL_NIF_TERM t = enif_make_resource(env, r);
