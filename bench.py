@@ -563,8 +563,9 @@ def headline(run: Run, args, pk):
                          "frac": achieved / pk["hbm"],
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full
                          # capture of this shape (profiles/r1_flat_stream_ncu_summary.txt: 3.073186 GB + 6.35 MB)
-                         "traffic": 3.0795e9 if (n, d, k) == (1_000_000, 768, 10) else None,
-                         "traffic_source": "profiles/r1_flat_stream_ncu_summary.txt",
+                         "traffic": 3.078051e9 if (n, d, k) == (1_000_000, 768, 10) else None,
+                         "traffic_source": "profiles/r2_flat_stream_ncu_summary.txt (ncu --set full of this kernel inside this command, "
+                                           "round 2: dram__bytes_read 3.073062 GB + dram__bytes_write 4.99 MB per launch)",
                          "peak_source": pk["hbm_src"],
                          "kernel": "vb::flat_stream_kernel<cosine, NV=6, RPW=1, W=16> (TMA-staged ring; the timed "
                                    "launch pair also holds the ~3 us unpack kernel)",
