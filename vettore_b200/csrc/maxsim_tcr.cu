@@ -46,6 +46,7 @@ struct MaxSimTcrParams {
     uint32_t cap, stages;
     uint32_t ckpt_tiles, slack;   // both epilogue groups meet every ckpt_tiles tiles (even); pushes in between <= slack
     uint32_t has_empty;           // some document has no token
+    uint32_t no_scan;             // timing experiments (VB_MAXSIM_NO_SCAN): masked butterflies instead of the transposition tile
     u64* dump_keys;               // limit beyond the fused collector: every live document's key / payload goes to
     u64* dump_pays;               // [ndocs] arrays (pre-filled with kKeyMax) and the host radix-sorts them
     uint32_t* err;
@@ -121,6 +122,8 @@ maxsim_tcr_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcrParam
     unsigned char* b_hi = ring + (size_t)stages * kTcChunkBytes;   // KB x [N rows x 128 B]
     unsigned char* b_lo = b_hi + (size_t)KB * kBBlock;
     unsigned char* col_mem = b_lo + (size_t)KB * kBBlock;
+    // N = 32 only: one [32 queries][33] transposition tile per epilogue warp, behind the collector (multi-segment chunks)
+    float* scan_tiles = reinterpret_cast<float*>(col_mem + (size_t)p.cap * 16);
 
     Collector col;
     col.init(col_mem, &s_thresh, &s_count, p.cap, p.ws.k, kTcEpiWarps * 32, 2);
@@ -283,6 +286,7 @@ maxsim_tcr_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcrParam
         const bool cosine = p.metric == kCosineTrue;
         const uint32_t C = p.ckpt_tiles;
         float* fin = s_fin[warp];
+        float* tile = scan_tiles + (size_t)warp * (32 * 33);
         u64 g_prefetch = kKeyMax;
         uint32_t d_next = 0, before_next = 0xFFFFFFFFu, after_next = 0xFFFFFFFFu;
         {
@@ -364,12 +368,30 @@ maxsim_tcr_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcrParam
                 // Segments are taken LAST to FIRST: the chunk's open last segment is published before the first
                 // segment waits for the previous chunk, so only chunks that lie wholly inside one document (wait ->
                 // max -> publish) are links of the serial carry chain; every butterfly stays off it.
+                // A chunk cut by document boundaries (N = 32): instead of one masked butterfly per segment, the warp
+                // transposes its 32 x 32 scores through shared memory once; lane q then walks ITS query's column
+                // segment by segment (32 loads in all, whatever the number of segments), parks the maxima of the
+                // documents that end here in the columns it has already consumed, and after the loop lane j adds the
+                // 32 maxima of segment j in query order — every finished document of the chunk in parallel.
+                const bool scan = N == 32 && (heads & (heads - 1u)) != 0u && !p.no_scan;
+                uint32_t final_mask = 0u;
+                if (scan) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) tile[q * 33 + lane] = v[q];
+                    __syncwarp();
+                }
                 uint32_t hm = heads, j = 0, l1 = 32u;
                 while (hm) {                                                  // warp-uniform: one round per segment
                     const uint32_t l0 = 31u - (uint32_t)__clz(hm);
                     hm &= ~(1u << l0);
-                    float m = heads == 1u ? warp_transpose_max(v, lane)
-                                          : warp_transpose_max_masked(v, (uint32_t)lane >= l0 && (uint32_t)lane < l1, lane);
+                    float m;
+                    if (scan) {
+                        m = -INFINITY;
+                        for (uint32_t t = l0; t < l1; ++t) m = fmaxf(m, tile[lane * 33 + t]);
+                    } else {
+                        m = heads == 1u ? warp_transpose_max(v, lane)
+                                        : warp_transpose_max_masked(v, (uint32_t)lane >= l0 && (uint32_t)lane < l1, lane);
+                    }
                     const uint32_t sd = __shfl_sync(0xffffffffu, d, l0), srank = __shfl_sync(0xffffffffu, rank, l0);
                     const bool starts_here = l0 != 0u || !first_continues, ends_here = l1 != 32u || !last_continues;
                     l1 = l0;
@@ -384,6 +406,11 @@ maxsim_tcr_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcrParam
                         s_carry[slot][h * 32u + lane] = m;
                         __syncwarp();
                         if (lane == 0) st_release_smem(&s_flag[slot][h], chunk + 1u);
+                    } else if (scan) {
+                        if (cosine) m = fminf(1.0f, fmaxf(-1.0f, m * s_invq[lane]));
+                        tile[lane * 33 + (31u - j)] = m;                       // column 31 - j >= l0: already consumed by this lane
+                        final_mask |= 1u << j;
+                        if ((uint32_t)lane == j) { my_doc = sd; my_rank = srank; my_final = true; }
                     } else {
                         if (cosine) m = fminf(1.0f, fmaxf(-1.0f, m * s_invq[h * 32u + lane]));
                         fin[lane] = m;
@@ -407,6 +434,16 @@ maxsim_tcr_kernel(const __grid_constant__ CUtensorMap tmap, const MaxSimTcrParam
                         __syncwarp();
                     }
                     ++j;
+                }
+                if (scan) {
+                    __syncwarp();
+                    if ((final_mask >> lane) & 1u) {                         // lane j: the document that closed segment j
+                        float total = 0.0f;
+                        const float* colp = tile + (31 - lane);
+                        for (uint32_t q = 0; q < p.tq; ++q) total += colp[q * 33];   // query order (multi_vector.rs:81-84)
+                        my_total = total;
+                    }
+                    __syncwarp();
                 }
             }
             if (my_final && my_rank != 0xFFFFFFFFu) {
@@ -493,7 +530,7 @@ Status maxsim_tcr_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out)
     uint32_t ckpt = 2;
     while (ckpt < 16 && k + 2 * ckpt * ends_per_tile <= cap) ckpt *= 2;
     const uint32_t slack = ckpt * ends_per_tile;
-    const size_t fixed = 2 * (size_t)KB * N * 128 + (size_t)cap * 16 + 1024;
+    const size_t fixed = 2 * (size_t)KB * N * 128 + (size_t)cap * 16 + 1024 + (N == 32 ? (size_t)kTcEpiWarps * 32 * 33 * 4 : 0);
     uint32_t stages = kTcStages;
     while (stages > 2 && (size_t)stages * kTcChunkBytes + fixed > 208 * 1024) --stages;
     const size_t smem = (size_t)stages * kTcChunkBytes + fixed;
@@ -533,6 +570,7 @@ Status maxsim_tcr_top_k(SearchCtx& ctx, const MaxSimJob& job, MaxSimResult* out)
     p.ckpt_tiles = ckpt;
     p.slack = slack;
     p.has_empty = job.has_empty ? 1u : 0u;
+    p.no_scan = std::getenv("VB_MAXSIM_NO_SCAN") ? 1u : 0u;
     p.err = ctx.err_row();
     p.ws.k = k;
     p.ws.cand_keys = ctx.cand_keys.as<u64>();
