@@ -192,3 +192,25 @@ def test_batched_search_keeps_the_overflow_semantics(metric):
     assert got[0] == exp[0]
     if exp[0] == "error":
         assert got[1] == exp[1]
+
+
+@pytest.mark.parametrize("metric,k,dup", [("cosine", 100, False), ("l2", 40, False), ("inner_product", 100, True)])
+def test_long_pre_pass_sample_two_phase_select(monkeypatch, metric, k, dup):
+    """The dense pre-pass with a sample longer than the select kernel's shared-memory head (32 768 scores): the tail of
+    the sample is streamed and filtered against the head's bound. `dup`: every sample score equal (the survivor list
+    overflows, the head's bound stands) — either way the bound only filters, the answers stay exact."""
+    monkeypatch.setenv("VB_GEMM_TERMS", "1")
+    monkeypatch.setenv("VB_GEMM_SAMPLE", "60000")
+    n, d, nq = 90000, 64, 40
+    rows = _rows(n, d, 77)
+    if dup:
+        rows[:70000] = rows[0]
+    if metric == "l2":
+        rows = (rows * np.linspace(0.5, 2.0, n, dtype=np.float32)[:, None]).astype(np.float32)
+    ids = [f"{(i * 7919) % n:06d}" for i in range(n)]
+    queries = _rows(nq, d, 78)
+    idx = getattr(nifs, f"flat_new_{metric}")()
+    ok(nifs.flat_insert_matrix(idx, ids, rows))
+    got = ok(nifs.flat_search_batch(idx, queries, k))
+    for qi in (0, 7, nq - 1):
+        assert_hits_match(got[qi], ok(oracle.flat_search_dense(metric, rows, ids, queries[qi], k)))

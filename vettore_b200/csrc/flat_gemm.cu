@@ -722,32 +722,71 @@ __global__ void pack_queries_kernel(const float* q, uint32_t nq, uint32_t qblock
     }
 }
 
-// Pre-pass select (single-pass kernel): the k-th smallest rank among a query's `n` sample scores, by bisection on the
-// order key with the scores held in shared memory. One CTA per query. Fewer than k sample rows: no bound (+inf).
-__global__ void __launch_bounds__(128) gemm1_sample_select_kernel(const float* dump, uint32_t stride, uint32_t n, uint32_t k,
-                                                                  float* out_rank) {
-    extern __shared__ __align__(1024) unsigned char gsmem[];
-    __shared__ uint32_t s_part[4];
-    uint32_t* keys = reinterpret_cast<uint32_t*>(gsmem);
-    const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* src = dump + (size_t)q * stride;
-    for (uint32_t i = tid; i < n; i += 128) keys[i] = order_key(src[i]);
-    __syncthreads();
-    if (n < k) { if (tid == 0) out_rank[q] = INFINITY; return; }
-    uint32_t lo = 0u, hi = 0xFFFFFFFFu;
+// Pre-pass select (single-pass kernel): the k-th smallest rank among a query's `n` sample scores. One CTA per query.
+// Phase 1 bisects the order keys of the first kSelHead scores in shared memory (bound t0); phase 2 streams the rest of
+// the sample once from L2 / HBM and keeps what is <= t0 (about k * n / kSelHead keys) in a short list next to the
+// phase-1 keys <= t0; the k-th smallest of that list is the k-th smallest of the whole sample. A list that overflows
+// (ties, or a sample sorted best-last) leaves t0, which is still a valid bound. Fewer than k sample rows: +inf.
+constexpr uint32_t kSelHead = 32768, kSelList = 8192, kSelThreads = 256;
+constexpr size_t kSelSmem = (size_t)(kSelHead + kSelList) * sizeof(uint32_t);
+
+__device__ __forceinline__ uint32_t select_kth_key(const uint32_t* keys, uint32_t n, uint32_t k, uint32_t hi, uint32_t* s_part) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t lo = 0u;
     while (lo < hi) {                          // smallest H with #(key <= H) >= k
         const uint32_t mid = lo + ((hi - lo) >> 1);
         uint32_t c = 0;
-        for (uint32_t i = tid; i < n; i += 128) c += keys[i] <= mid ? 1u : 0u;
+        for (uint32_t i = tid; i < n; i += kSelThreads) c += keys[i] <= mid ? 1u : 0u;
         c = __reduce_add_sync(0xffffffffu, c);
         if (lane == 0) s_part[warp] = c;
         __syncthreads();
-        c = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+        c = (s_part[0] + s_part[1] + s_part[2] + s_part[3]) + (s_part[4] + s_part[5] + s_part[6] + s_part[7]);
         __syncthreads();
         if (c >= k) hi = mid; else lo = mid + 1u;
     }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kSelThreads) gemm1_sample_select_kernel(const float* dump, uint32_t stride, uint32_t n, uint32_t k,
+                                                                          float* out_rank) {
+    extern __shared__ __align__(1024) unsigned char gsmem[];
+    __shared__ uint32_t s_part[8];
+    __shared__ uint32_t s_cnt;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(gsmem);
+    uint32_t* list = keys + kSelHead;
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    const float* src = dump + (size_t)q * stride;
+    const uint32_t n1 = min(n, kSelHead);
+    for (uint32_t i = tid; i < n1; i += kSelThreads) keys[i] = order_key(src[i]);
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    if (n < k) { if (tid == 0) out_rank[q] = INFINITY; return; }
+    uint32_t t = select_kth_key(keys, n1, k, 0xFFFFFFFFu, s_part);
+    if (n > n1) {
+        for (uint32_t i = tid; i < n1; i += kSelThreads) {
+            const uint32_t key = keys[i];
+            if (key <= t) { const uint32_t at = atomicAdd(&s_cnt, 1u); if (at < kSelList) list[at] = key; }
+        }
+        const uint4* src4 = reinterpret_cast<const uint4*>(src + n1);   // n1 and stride are multiples of 4
+        const uint32_t n4 = (n - n1) / 4u;
+        for (uint32_t i = tid; i < n4; i += kSelThreads) {
+            const uint4 v = __ldcs(src4 + i);
+            const uint32_t kk[4] = {order_key(__uint_as_float(v.x)), order_key(__uint_as_float(v.y)),
+                                    order_key(__uint_as_float(v.z)), order_key(__uint_as_float(v.w))};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (kk[j] <= t) { const uint32_t at = atomicAdd(&s_cnt, 1u); if (at < kSelList) list[at] = kk[j]; }
+        }
+        for (uint32_t i = n1 + n4 * 4u + tid; i < n; i += kSelThreads) {
+            const uint32_t key = order_key(src[i]);
+            if (key <= t) { const uint32_t at = atomicAdd(&s_cnt, 1u); if (at < kSelList) list[at] = key; }
+        }
+        __syncthreads();
+        const uint32_t cnt = s_cnt;
+        if (cnt <= kSelList) t = select_kth_key(list, cnt, k, t, s_part);
+    }
     if (tid == 0) {
-        const uint32_t bits = (lo & 0x80000000u) ? (lo ^ 0x80000000u) : ~lo;   // inverse of order_key
+        const uint32_t bits = (t & 0x80000000u) ? (t ^ 0x80000000u) : ~t;   // inverse of order_key
         out_rank[q] = __uint_as_float(bits);
     }
 }
@@ -1045,12 +1084,17 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     // (measured at 1M x 768, Q = 1024: 9.5k rows 313k queries/s, 19k 287k, 33k 282k, 66k 272k).
     const uint32_t ranges_full = std::max<uint32_t>(1, workers / group);
     size_t sample = std::min<size_t>(n / 8, (size_t)ranges_full * (pair ? 512 : 256));   // one work unit per CTA / CTA pair
+    // Single-pass kernel with long lists (k' > 64): the dense pre-pass costs only sample / n of the main launch, and the
+    // appends it saves grow with k' — n / 32 rows, at most 151 552 (measured, Q = 1024, k = 100: 1M rows 4.62 -> 3.61 ms
+    // at 37 888; 12.5M rows 40.9 -> 37.9 / 35.2 / 34.1 / 34.4 ms at 37 888 / 75 776 / 151 552 / 303 104; k = 10 is
+    // fastest with the short sample).
+    if (terms == 1 && kprime > 64) sample = std::max(sample, std::min<size_t>((n / 32) & ~(size_t)255, 151552));
     if (const char* e = std::getenv("VB_GEMM_SAMPLE")) sample = std::min<size_t>(n, std::max<size_t>(1024, (size_t)std::atol(e)));
     const bool prepass = n >= 65536 && sample >= 2048 && !std::getenv("VB_GEMM_NO_PREPASS");
     // Single-pass kernel: the pre-pass is a dense dump — ranks of [queries x sample rows] straight to HBM (coalesced, no
     // lists), then one small CTA per query bisects its k'-th smallest. (Through the list machinery the same pass cost
     // 290 us + a 70 us merge per 1024-query batch: with the bounds open every score took the append path.)
-    const bool dense_prepass = prepass && terms == 1 && sample <= 12288 && !std::getenv("VB_GEMM_LIST_PREPASS");
+    const bool dense_prepass = prepass && terms == 1 && sample <= 524288 && !std::getenv("VB_GEMM_LIST_PREPASS");
     u64* pre_keys = nullptr;
     uint32_t* pre_counts = nullptr;
     float* pre_dump = nullptr;
@@ -1061,7 +1105,7 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
         VB_TRY(ctx.hist.reserve(nq_pad * sizeof(float)));
         pre_dump = ctx.dump_keys2.as<float>();
         pre_rank = ctx.hist.as<float>();
-        VB_TRY(ensure_dynamic_smem_for(gemm1_sample_select_kernel, (size_t)dump_stride * sizeof(uint32_t)));
+        VB_TRY(ensure_dynamic_smem_for(gemm1_sample_select_kernel, kSelSmem));
     } else if (prepass) {
         VB_TRY(ctx.dump_keys2.reserve(nq_pad * kprime * sizeof(u64)));
         VB_TRY(ctx.dump_pays2.reserve(nq_pad * kprime * sizeof(u64)));
@@ -1121,7 +1165,7 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
             }
             VB_CUDA(cudaGetLastError());
             if (pass == 0 && dense_prepass)
-                gemm1_sample_select_kernel<<<nq_here, 128, (size_t)dump_stride * sizeof(uint32_t), stream>>>(
+                gemm1_sample_select_kernel<<<nq_here, kSelThreads, kSelSmem, stream>>>(
                     pre_dump + q0 * dump_stride, dump_stride, (uint32_t)sample, (uint32_t)kprime, pre_rank + q0);
             else if (pass == 0)
                 flat_gemm_merge_kernel<<<nq_here, 128, (size_t)cap * 16, stream>>>(p, cap, pre_keys + q0 * kprime,
