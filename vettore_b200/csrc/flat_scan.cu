@@ -48,6 +48,11 @@ static StreamKernel lookup_stream(int metric, int nv, int rpw, int warps) {
     return nullptr;
 }
 
+StreamKernel prefix_lane_kernel_entry();
+int prefix_lane_max_warps();
+int prefix_lane_max_stages();
+int prefix_lane_sync_rounds();
+
 int device_sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;
@@ -72,6 +77,13 @@ static uint32_t next_pow2(uint32_t v) {
     return p;
 }
 
+// Collector capacity for k results with up to `slack` pushes between two checkpoints: room for k kept entries plus
+// the pushes between two compactions; beyond k = 256 the launch-wide bound (pivot ladder) keeps pushes rare, so half
+// of k again is plenty and the ring keeps its stages. (More head-room — 4k, 8k — measured no faster at any k.)
+static uint32_t collector_cap(uint32_t k, uint32_t slack) {
+    return next_pow2(k <= 256 ? 2 * k + slack : k + k / 2 + slack);
+}
+
 // Kernel B: whole contiguous rows streamed through a shared-memory ring by TMA bulk copies.
 static Status plan_stream(int metric, int nv, size_t row_stride, uint32_t row_floats, uint32_t tail_rem, bool use_tmap,
                           uint32_t n, uint32_t k, ScanPlan* plan, bool* taken) {
@@ -93,7 +105,7 @@ static Status plan_stream(int metric, int nv, size_t row_stride, uint32_t row_fl
     const uint32_t slack = groups_per_sync * kGroupRows * warps;
     // room for k kept entries plus the pushes between two compactions; beyond k = 256 the launch-wide bound
     // (pivot ladder) keeps pushes rare, so half of k again is plenty and the ring keeps its stages
-    const uint32_t cap = next_pow2(k <= 256 ? 2 * k + slack : k + k / 2 + slack);
+    const uint32_t cap = collector_cap(k, slack);
     const size_t budget = 200 * 1024;
     if ((size_t)cap * 16 + 2 * (size_t)tile_bytes > budget) return Status::Ok();
     uint32_t stages = (uint32_t)std::min<size_t>(kStreamMaxStages, (budget - (size_t)cap * 16) / tile_bytes);
@@ -117,6 +129,54 @@ static Status plan_stream(int metric, int nv, size_t row_stride, uint32_t row_fl
     plan->tail_rem = tail_rem;
     plan->tile_rows = tile_rows;
     plan->use_tmap = use_tmap;
+    *taken = true;
+    return Status::Ok();
+}
+
+// Kernel C (prefix_lane.cu): true-cosine prefix scoring of every row, one row per lane, tiles of 32 rows as
+// ceil(dims / 32) swizzled TMA boxes. Ring slots are a multiple of the consumer warps (a slot belongs to one warp).
+static Status plan_lane(uint32_t dims, uint32_t n, uint32_t k, ScanPlan* plan, bool* taken) {
+    *taken = false;
+    const uint32_t nb = (dims + 31) / 32;
+    const uint32_t tile_bytes = nb * 32 * 128;
+    const size_t budget = 214 * 1024;
+    // consumer warps: as many as the ring can give one tile each (the per-row dependency chain is long — conversions,
+    // f64 FMAs — and only other warps hide it), at most kLaneMaxWarps; what is left deepens the ring
+    uint32_t warps = (uint32_t)prefix_lane_max_warps();
+    const int warps_env = env_int("VB_LANE_WARPS", 0);
+    if (warps_env > 0 && (uint32_t)warps_env < warps) warps = warps_env;
+    uint32_t cap = 0;
+    for (;; --warps) {
+        if (warps < 2) return Status::Ok();
+        const uint32_t slack = (uint32_t)prefix_lane_sync_rounds() * warps * 32;
+        cap = collector_cap(k, slack);
+        if ((size_t)cap * 16 + (size_t)warps * tile_bytes <= budget) break;
+    }
+    uint32_t depth = (uint32_t)std::min<size_t>((budget - (size_t)cap * 16) / ((size_t)warps * tile_bytes),
+                                                (size_t)prefix_lane_max_stages() / (warps * nb));
+    const int depth_env = env_int("VB_LANE_DEPTH", 0);
+    if (depth_env >= 1 && (uint32_t)depth_env < depth) depth = depth_env;
+    if (depth < 1) return Status::Ok();
+    const uint32_t stages = depth;   // StreamGeom.stages carries the ring depth in tiles per consumer warp
+    StreamKernel kernel = prefix_lane_kernel_entry();
+    VB_TRY(ensure_dynamic_smem_for(kernel, budget));
+    const int sms = device_sm_count();
+    if (sms <= 0) return Status::Cuda("no CUDA device");
+    plan->stream_kernel = kernel;
+    plan->nv = 1;
+    plan->r = 32;
+    plan->stream_threads = warps * 32 + 32;
+    plan->grid_x = std::min<uint32_t>((n + 31) / 32, (uint32_t)sms);
+    plan->cap = cap;
+    plan->smem = (size_t)warps * stages * tile_bytes + (size_t)cap * 16;
+    plan->stages = stages;
+    plan->tile_bytes = tile_bytes;
+    plan->row_floats = nb * 32;
+    plan->tail_rem = 4;
+    plan->tile_rows = 32;
+    plan->use_tmap = true;
+    plan->lane_rows = true;
+    plan->lane_cols = dims;
     *taken = true;
     return Status::Ok();
 }
@@ -145,7 +205,14 @@ Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, int layout, 
     *plan = ScanPlan{};
     if (!dump && nv > 0 && !env_int("VB_SCAN_NO_STREAM", 0)) {
         bool taken = false;
-        if (layout == kScanWholeRows && (size_t)nvec * 4 == row_stride) {
+        const bool whole_rows = layout == kScanWholeRows && (size_t)nvec * 4 == row_stride;
+        if (layout != kScanRowList && metric == kCosineTrue && dims <= 128 && (row_stride & 3) == 0 && n >= 4096 &&
+            !env_int("VB_SCAN_NO_LANE", 0)) {
+            // true-cosine prefix (or a narrow whole row, e.g. the dense prefix mirror) of every row: one row per lane
+            VB_TRY(plan_lane(dims, n, k, plan, &taken));
+        }
+        if (taken) return Status::Ok();
+        if (whole_rows) {
             VB_TRY(plan_stream(metric, nv, row_stride, /*row_floats=*/(uint32_t)row_stride, 4, false, n, k, plan, &taken));
         } else if (layout != kScanRowList && nvec * 4 <= 256 && (row_stride & 3) == 0 && !env_int("VB_SCAN_NO_PREFIX_STREAM", 0)) {
             // every row, only its first columns: a 2D tensor map moves just those columns (box <= 256 floats wide)
@@ -155,7 +222,7 @@ Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, int layout, 
     }
     const uint32_t slack = kSyncEvery * kScanWarps * r;
     const uint32_t kk = dump ? 1 : k;
-    const uint32_t cap = next_pow2(kk <= 256 ? 2 * kk + slack : kk + kk / 2 + slack);   // as in plan_stream
+    const uint32_t cap = collector_cap(kk, slack);
     const size_t smem = (size_t)cap * 16;
 
     VB_TRY(ensure_dynamic_smem_for(kernel, smem));      // cached per (device, kernel); occupancy is device independent here
@@ -189,14 +256,22 @@ Status plan_flat_scan(int metric, uint32_t dims, size_t row_stride, int layout, 
     return Status::Ok();
 }
 
+// Which kernel the calling thread's last scan launched (tests, tuning): 0 kernel A, 1 kernel B over whole rows,
+// 2 kernel B over a prefix box, 3 kernel C (one row per lane).
+static thread_local int t_last_scan = 0;
+extern "C" int vb_debug_scan_path() { return t_last_scan; }
+
 Status run_flat_scan(const ScanPlan& plan, ScanParams params, uint32_t nq, cudaStream_t stream) {
     params.cap = plan.cap;
+    t_last_scan = plan.lane_rows ? 3 : plan.stream_kernel ? (plan.use_tmap ? 2 : 1) : 0;
     dim3 grid(plan.grid_x, nq);
     if (plan.stream_kernel) {
         StreamGeom geom{plan.stages, plan.tile_bytes, plan.row_floats, plan.tail_rem, plan.use_tmap ? 1u : 0u};
         CUtensorMap tmap;
         std::memset(&tmap, 0, sizeof(tmap));
-        if (plan.use_tmap)
+        if (plan.lane_rows)
+            VB_TRY(make_tmap_rows_sw128_cols(params.rows, params.n, params.row_stride, plan.lane_cols, plan.tile_rows, &tmap));
+        else if (plan.use_tmap)
             VB_TRY(make_tmap_rows_prefix(params.rows, params.n, params.row_stride, plan.row_floats, plan.tile_rows, &tmap));
         plan.stream_kernel<<<grid, plan.stream_threads, plan.smem, stream>>>(params, geom, tmap);
     } else {

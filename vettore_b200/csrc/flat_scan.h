@@ -23,6 +23,9 @@ struct ScanPlan {
     // kernel B geometry in shared memory; use_tmap: prefix scan fed by a 2D tensor map (built at launch)
     uint32_t row_floats = 0, tail_rem = 4, tile_rows = 0;
     bool use_tmap = false;
+    // kernel C (prefix_lane.cu): one row per lane, 128-byte swizzled boxes, tensor map `lane_cols` columns wide
+    bool lane_rows = false;
+    uint32_t lane_cols = 0;
 };
 
 // Picks the kernel variant, grid and collector capacity for `n` rows of `dims` scored

@@ -216,6 +216,10 @@ __device__ __forceinline__ float tf32_lo(float x) {
 // runtime so the library does not link libcuda directly.
 Status make_tmap_rows_sw128(const float* base, uint64_t rows, uint64_t row_stride_floats, uint32_t box_rows,
                             CUtensorMap* out);
+// The first `cols` columns of the same matrix as a tensor `cols` wide (columns beyond are out of bounds: zero filled),
+// box = 32 floats x box_rows, 128-byte swizzle. Feeds the lane-per-row prefix kernel (prefix_lane.cu).
+Status make_tmap_rows_sw128_cols(const float* base, uint64_t rows, uint64_t row_stride_floats, uint32_t cols,
+                                 uint32_t box_rows, CUtensorMap* out);
 // Same matrix, no swizzle: box = the first `box_cols` floats (<= 256, multiple of 4) x box_rows (<= 256) rows,
 // landing densely packed in shared memory. Feeds the prefix scans (only the scored columns leave HBM).
 Status make_tmap_rows_prefix(const float* base, uint64_t rows, uint64_t row_stride_floats, uint32_t box_cols,

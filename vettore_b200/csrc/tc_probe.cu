@@ -46,6 +46,22 @@ Status make_tmap_rows_sw128(const float* base, uint64_t rows, uint64_t row_strid
     return make_tmap_rows(base, rows, row_stride_floats, 32, box_rows, CU_TENSOR_MAP_SWIZZLE_128B, out);
 }
 
+Status make_tmap_rows_sw128_cols(const float* base, uint64_t rows, uint64_t row_stride_floats, uint32_t cols,
+                                 uint32_t box_rows, CUtensorMap* out) {
+    TmapEncodeFn encode = tmap_encode_fn();
+    if (!encode) return Status::Cuda("cuTensorMapEncodeTiled unavailable");
+    if (cols == 0 || cols > row_stride_floats || box_rows == 0 || box_rows > 256) return Status::Cuda("tensor map: box out of range");
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {row_stride_floats * sizeof(float)};
+    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint32_t estride[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return Status::Cuda("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return Status::Ok();
+}
+
 Status make_tmap_rows_prefix(const float* base, uint64_t rows, uint64_t row_stride_floats, uint32_t box_cols,
                              uint32_t box_rows, CUtensorMap* out) {
     if (box_cols == 0 || box_cols > 256 || (box_cols & 3) || box_rows == 0 || box_rows > 256)

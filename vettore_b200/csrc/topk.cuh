@@ -82,6 +82,11 @@ struct Collector {
 
     // Block-wide (every thread of the CTA must call). Sorts the buffer ascending, keeps the
     // best k and tightens the threshold. Returns the number of retained entries.
+    // Bitonic network in shared memory. A power-of-two number of warps each own an aligned segment of the array:
+    // every step whose stride is shorter than a segment only touches pairs inside one segment, so it needs a
+    // __syncwarp, not a block barrier — 1024 entries on 8 warps take 9 block barriers instead of 55 (a barrier round
+    // of 12-16 warps costs ~0.2 us, and with k = 100 a short scan pays for several sorts: measured on the 1M-row
+    // prefix scan).
     __device__ uint32_t compact() {
         sync();
         uint32_t n = min(*count, cap);
@@ -89,21 +94,38 @@ struct Collector {
         while (p2 < n) p2 <<= 1;
         for (uint32_t i = n + threadIdx.x; i < p2; i += nthreads) { keys[i] = kKeyMax; pays[i] = 0; }
         sync();
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+        uint32_t aw = 1;                                   // warps that own a segment: power of two, >= 64 entries each
+        while (aw * 2u <= (nthreads >> 5) && p2 / (aw * 2u) >= 64u) aw <<= 1;
+        const uint32_t seg = p2 / aw;
+        auto exchange = [this](uint32_t t, uint32_t stride, uint32_t size) {
+            const uint32_t lo = 2 * t - (t & (stride - 1));
+            const uint32_t hi = lo + stride;
+            const bool up = (lo & size) == 0;
+            const u64 a = keys[lo], b = keys[hi];
+            if ((a > b) == up) {
+                keys[lo] = b; keys[hi] = a;
+                const u64 pa = pays[lo]; pays[lo] = pays[hi]; pays[hi] = pa;
+            }
+        };
+        bool local = false;                                // the previous step was warp-local
         for (uint32_t size = 2; size <= p2; size <<= 1) {
             for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-                for (uint32_t t = threadIdx.x; t < (p2 >> 1); t += nthreads) {
-                    uint32_t lo = 2 * t - (t & (stride - 1));
-                    uint32_t hi = lo + stride;
-                    bool up = (lo & size) == 0;
-                    u64 a = keys[lo], b = keys[hi];
-                    if ((a > b) == up) {
-                        keys[lo] = b; keys[hi] = a;
-                        u64 pa = pays[lo]; pays[lo] = pays[hi]; pays[hi] = pa;
+                if (stride < seg) {
+                    if (warp < aw) {
+                        for (uint32_t t = lane; t < (seg >> 1); t += 32u) exchange(warp * (seg >> 1) + t, stride, size);
+                        __syncwarp();
                     }
+                    local = true;
+                } else {
+                    if (local) sync();
+                    for (uint32_t t = threadIdx.x; t < (p2 >> 1); t += nthreads) exchange(t, stride, size);
+                    sync();
+                    local = false;
                 }
-                sync();
             }
         }
+        if (local) sync();
         uint32_t kept = min(n, k);
         if (threadIdx.x == 0) {
             *count = kept;
