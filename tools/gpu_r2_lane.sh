@@ -1,8 +1,7 @@
 #!/bin/bash
-# Merge-tree threshold sweep: K1 over k, prefix scan over k (the static is read once per process).
+# Kernel C: checkpoint cadence sweep (rounds between collector checkpoints), parity first.
 mkdir -p gpurun_out
-for m in 16384 4096 1024; do
-  export VB_MERGE_TREE_MIN=$m
-  echo "tree above $m: $(timeout 300 python tools/bench_k_sweep.py 2>&1 | tail -1 | cut -c1-600)"
-  timeout 300 python tools/bench_prefix_dbg.py 2>&1 | grep "debug 0"
+timeout 200 python -m pytest tests/test_prefix_lane_gpu.py -x -q 2>&1 | tail -2
+for r in 1 2 4 8; do
+  echo "sync rounds $r: $(VB_LANE_SYNC_ROUNDS=$r timeout 100 python tools/bench_funnel.py --stages 128,384 --candidates 100 --iters 200 2>&1 | tail -1 | cut -c150-330)"
 done

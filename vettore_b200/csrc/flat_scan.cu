@@ -145,10 +145,11 @@ static Status plan_lane(uint32_t dims, uint32_t n, uint32_t k, ScanPlan* plan, b
     uint32_t warps = (uint32_t)prefix_lane_max_warps();
     const int warps_env = env_int("VB_LANE_WARPS", 0);
     if (warps_env > 0 && (uint32_t)warps_env < warps) warps = warps_env;
+    const uint32_t sync_rounds = (uint32_t)std::min(std::max(env_int("VB_LANE_SYNC_ROUNDS", prefix_lane_sync_rounds()), 1), 8);
     uint32_t cap = 0;
     for (;; --warps) {
         if (warps < 2) return Status::Ok();
-        const uint32_t slack = (uint32_t)prefix_lane_sync_rounds() * warps * 32;
+        const uint32_t slack = sync_rounds * warps * 32;
         cap = collector_cap(k, slack);
         if ((size_t)cap * 16 + (size_t)warps * tile_bytes <= budget) break;
     }
@@ -172,7 +173,7 @@ static Status plan_lane(uint32_t dims, uint32_t n, uint32_t k, ScanPlan* plan, b
     plan->stages = stages;
     plan->tile_bytes = tile_bytes;
     plan->row_floats = nb * 32;
-    plan->tail_rem = 4;
+    plan->tail_rem = sync_rounds;   // kernel C reads StreamGeom.tail_rem as its checkpoint cadence (it masks no tail)
     plan->tile_rows = 32;
     plan->use_tmap = true;
     plan->lane_rows = true;

@@ -27,7 +27,7 @@ namespace vb {
 
 constexpr int kLaneMaxWarps = 12;       // consumer warps (runtime choice, blockDim.x / 32 - 1)
 constexpr int kLaneMaxStages = 48;
-constexpr int kLaneSyncRounds = 2;      // rounds (one tile per consumer warp) between collector checkpoints
+constexpr int kLaneSyncRounds = 2;      // default rounds (one tile per consumer warp) between collector checkpoints
 constexpr uint32_t kLaneBoxBytes = 32 * 128;
 
 __global__ void __launch_bounds__(kLaneMaxWarps * 32 + 32, 1)
@@ -90,6 +90,7 @@ prefix_lane_kernel(const ScanParams p, const StreamGeom geom, const __grid_const
     // ===== consumers: warp w takes tiles w, w + W, ... of this CTA; lane L owns row L of the tile =====
     const double q_norm = p.q_norms[qi];
     const uint32_t rounds = (iters + W - 1u) / W;
+    const uint32_t sync_rounds = geom.tail_rem;          // kernel C: rounds between collector checkpoints (plan_lane)
     const uint32_t my_off = lane * 128u, my_x = lane & 7u;
     u64 g_prefetch = kKeyMax;
     for (uint32_t r = 0; r < rounds; ++r) {
@@ -125,8 +126,8 @@ prefix_lane_kernel(const ScanParams p, const StreamGeom geom, const __grid_const
                 emit_row<kCosineTrue>(p, col, qi, false, col.threshold(), raw, row, row);
             }
         }
-        if (!(p.debug & 4u) && (r & (kLaneSyncRounds - 1)) == kLaneSyncRounds - 1)
-            collector_checkpoint(col, p.ws, qi, kLaneSyncRounds * W * 32u, g_prefetch);
+        if (!(p.debug & 4u) && (r + 1u) % sync_rounds == 0u)
+            collector_checkpoint(col, p.ws, qi, sync_rounds * W * 32u, g_prefetch);
     }
     // every tile was consumed, so the ring is idle: the last CTA merges in ring + collector memory
     const uint32_t total_smem = W * geom.stages * geom.tile_bytes + p.cap * 16u;
