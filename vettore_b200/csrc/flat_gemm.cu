@@ -1088,7 +1088,9 @@ Status flat_gemm_search_device(SearchCtx& ctx, int metric, const float* d_rows, 
     // appends it saves grow with k' — n / 32 rows, at most 151 552 (measured, Q = 1024, k = 100: 1M rows 4.62 -> 3.61 ms
     // at 37 888; 12.5M rows 40.9 -> 37.9 / 35.2 / 34.1 / 34.4 ms at 37 888 / 75 776 / 151 552 / 303 104; k = 10 is
     // fastest with the short sample).
-    if (terms == 1 && kprime > 64) sample = std::max(sample, std::min<size_t>((n / 32) & ~(size_t)255, 151552));
+    // The dump is [queries x sample] floats: the long sample stays under 1 GiB of workspace whatever the batch size.
+    if (terms == 1 && kprime > 64)
+        sample = std::max(sample, std::min<size_t>({(n / 32) & ~(size_t)255, (size_t)151552, (((size_t)1 << 28) / nq_pad) & ~(size_t)255}));
     if (const char* e = std::getenv("VB_GEMM_SAMPLE")) sample = std::min<size_t>(n, std::max<size_t>(1024, (size_t)std::atol(e)));
     const bool prepass = n >= 65536 && sample >= 2048 && !std::getenv("VB_GEMM_NO_PREPASS");
     // Single-pass kernel: the pre-pass is a dense dump — ranks of [queries x sample rows] straight to HBM (coalesced, no
