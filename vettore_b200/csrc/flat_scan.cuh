@@ -523,10 +523,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 
 struct StreamGeom {
-    uint32_t stages;      // ring depth
+    uint32_t stages;      // ring depth (kernel C, prefix_lane.cu: tiles per consumer warp)
     uint32_t tile_bytes;  // bytes per stage (tile_rows * row_floats * 4), multiple of 128
     uint32_t row_floats;  // floats per row IN SHARED MEMORY: the row stride (whole rows) or the padded prefix
-    uint32_t tail_rem;    // valid components of the last float4 of a row (4 = nothing to mask)
+    uint32_t tail_rem;    // valid components of the last float4 of a row (4 = nothing to mask); kernel C masks no
+                          // tail (its tensor map is `dims` wide) and reads this word as its checkpoint cadence
     uint32_t use_tmap;    // 1: prefix scan, tiles arrive through the 2D tensor map (only the scored columns)
 };
 
